@@ -135,9 +135,9 @@ def test_smpl_invariants(smpl_model):
     # (1e-7, not 1e-12: the fp32 skinning weights sum to 1 only to ~6e-8)
     assert (r0['vertices'] - r0['v_shaped']).abs().max() < 1e-7
     assert (r0['joints24'] - r0['J']).abs().max() < 1e-12
-    # axis-angle zero: smplx's ||theta + 1e-8|| leaves an O(1e-8) rad rotation, not identity
+    # axis-angle zero: the 1e-8 only enters the norm, rot_dir = 0/angle = 0 => exactly identity
     rz = o(b['betas'], np.zeros((B, 69)), zg, pose2rot=True)
-    assert 0 < (rz['vertices'] - r0['vertices']).abs().max() < 1e-7
+    assert (rz['vertices'] - r0['vertices']).abs().max() == 0
     # global rotation equivariance about the root joint
     r = o(b['betas'], b['pose_aa'][:, 3:], zg, pose2rot=True)
     rg = o(b['betas'], b['pose_aa'][:, 3:], b['pose_aa'][:, :3], pose2rot=True)
