@@ -144,7 +144,7 @@ def test_smpl_invariants(smpl_model):
     R = torch.from_numpy(syn.rodrigues_np(b['pose_aa'][:, :3]))
     root = r['J'][:, :1]
     expect = torch.einsum('bij,bvj->bvi', R, r['vertices'] - root) + root
-    assert (rg['vertices'] - expect).abs().max() < 1e-9
+    assert (rg['vertices'] - expect).abs().max() < 1e-7   # weights sum to 1 only to ~6e-8
     # joints output: 49 entries assembled per models/smpl.py:66-76
     assert rg['joints'].shape == (B, 49, 3)
     assert torch.equal(rg['joints'][:, 8], rg['joints24'][:, 0])          # 'OP MidHip' -> joint 0
