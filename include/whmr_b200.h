@@ -1,0 +1,198 @@
+/*
+ * whmr_b200.h -- C ABI of the B200-native W-HMR body-model hot path (libwhmr_b200.so).
+ *
+ * The reference (yw0208/W-HMR) has no FFI: the path is reached through Python attributes and
+ * module-level functions.  Each entry point below names the reference
+ * interface it replaces (file:line under the reference tree).  Conventions:
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures (`stream` is a
+ *     cudaStream_t passed as void*; NULL = the legacy default stream);
+ *   - unless a name ends in `_host`, every data pointer is a DEVICE pointer owned by the
+ *     caller; nothing is allocated after the `*_create` / `*_reserve` calls;
+ *   - all tensors are contiguous row-major float32 unless stated;
+ *   - return value: 0 = ok, non-zero = WHMR_E_* ; whmr_last_error() gives the message of the
+ *     calling thread's last failure.  No exception ever crosses the ABI;
+ *   - kernels are launched asynchronously on `stream`; the caller synchronises.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns WHMR_E_CUDA.
+ */
+#ifndef WHMR_B200_H_
+#define WHMR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WHMR_ABI_VERSION 1
+
+enum {
+  WHMR_OK = 0,
+  WHMR_E_INVALID = 1,  /* bad argument (null pointer, negative size, unsupported shape) */
+  WHMR_E_CUDA = 2,     /* CUDA runtime / driver error (message has cudaGetErrorString) */
+  WHMR_E_WORKSPACE = 3 /* caller workspace too small */
+};
+
+enum { WHMR_LAYOUT_NCHW = 0, WHMR_LAYOUT_NHWC = 1 };
+
+/* pose-blend GEMM arithmetic (the one dense contraction) */
+enum {
+  WHMR_GEMM_FP32_SIMT = 0, /* CUDA-core FFMA, exact fp32 products (bring-up / error apportioning) */
+  WHMR_GEMM_TC_BF16X3 = 1, /* tcgen05 kind::f16, 3 bf16 products of a hi/lo split (~2^-16 rel) */
+  WHMR_GEMM_TC_3XTF32 = 2  /* tcgen05 kind::tf32, 3 tf32 products of a hi/lo split (~2^-21 rel) */
+};
+
+int whmr_abi_version(void);
+const char* whmr_last_error(void);
+/* number of kernels this library has launched from the calling process since load (bench.py's
+ * `gpu_launches`); whmr_launch_count_reset() zeroes it. */
+uint64_t whmr_launch_count(void);
+void whmr_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------
+ * SMPL body model.  Replaces pare.models.SMPL / smplx.SMPL as constructed at
+ * models/whmr.py:59 and core/trainer.py:54-64 (commented twin of the wrapper: models/smpl.py:61-83;
+ * in-tree statement of the math: models/smpl_webuser/lbs.py:27-79, verts.py:42-50).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct whmr_smpl_s* whmr_smpl_t;
+
+typedef struct {
+  int32_t n_verts;          /* V, 6890 */
+  int32_t n_joints;         /* J, 24 (<= 32) */
+  int32_t n_betas;          /* 10 (<= 16) */
+  const float* v_template;  /* HOST [V,3] */
+  const float* shapedirs;   /* HOST [V,3,n_betas] */
+  const float* posedirs;    /* HOST [(J-1)*9, V*3]  (smplx in-memory layout) */
+  const float* J_regressor; /* HOST [J,V] dense */
+  const float* lbs_weights; /* HOST [V,J] dense; any sparsity is detected and exploited */
+  const int64_t* parents;   /* HOST [J], parents[0] = -1, parents[i] < i */
+} whmr_smpl_model_desc;
+
+/* Uploads and pre-arranges the model on the current device (planar padded layouts, ELL skinning
+ * weights, pre-contracted rest-joint regressor, hi/lo-split tensor-core operand of posedirs). */
+int whmr_smpl_create(const whmr_smpl_model_desc* desc, int gemm_mode, whmr_smpl_t* out);
+int whmr_smpl_destroy(whmr_smpl_t h);
+int whmr_smpl_set_gemm_mode(whmr_smpl_t h, int gemm_mode);
+int whmr_smpl_get_info(whmr_smpl_t h, int32_t* n_verts, int32_t* n_joints, int32_t* n_betas,
+                       int32_t* ell_width, int32_t* gemm_mode);
+
+/* bytes of scratch whmr_smpl_forward needs for a batch of B bodies */
+size_t whmr_smpl_workspace_bytes(whmr_smpl_t h, int B);
+
+/* SMPL.forward(betas, body_pose, global_orient, pose2rot, transl) -- call sites
+ * models/whmr.py:132-137,227-232,641-644; core/trainer.py:415,420,781,787-790; evaluate/eval.py:159,200.
+ *   betas [B,n_betas]; pose: pose_is_rotmat ? [B,J,3,3] : [B,J*3] axis-angle (global_orient first);
+ *   transl [B,3] or NULL.
+ * Outputs: verts [B,V,3]; joints [B,J,3] = posed kinematic-chain joints (smplx J_transformed);
+ *   rel_transforms [B,J,12] (rows of the 3x4 skinning transforms A_j) or NULL.
+ * Internally: chain kernel -> pose-blend GEMM -> skinning kernel, all on `stream`. */
+int whmr_smpl_forward(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                      const float* transl, int B, float* verts, float* joints,
+                      float* rel_transforms, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The three stages individually (same workspace; used by bench.py for per-kernel CUDA-event
+ * timing and by the tests).  whmr_smpl_forward == chain; pose_blend; skin. */
+int whmr_smpl_stage_chain(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                          const float* transl, int B, float* joints, float* rel_transforms,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int whmr_smpl_stage_pose_blend(whmr_smpl_t h, int B, void* workspace, size_t workspace_bytes,
+                               void* stream);
+int whmr_smpl_stage_skin(whmr_smpl_t h, const float* betas, int B, float* verts, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* Host-buffer variant (bench.py `e2e`): pinned or pageable HOST pointers in and out; H2D copies,
+ * the three kernels and the D2H copies are enqueued on `stream` and the call returns after
+ * cudaStreamSynchronize.  Device staging comes from whmr_smpl_reserve (grow-only, inside h). */
+int whmr_smpl_reserve(whmr_smpl_t h, int max_B);
+int whmr_smpl_forward_host(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                           int B, float* verts, float* joints, void* stream);
+
+/* batch_rodrigues, smplx variant used inside SMPL.forward (angle = ||v+1e-8||,
+ * R = I + sin K + (1-cos) K K).  aa [n,3] -> R [n,3,3]. */
+int whmr_batch_rodrigues(const float* aa, int n, float* R, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse linear read-out of the posed vertices.  Replaces every "matrix x vertices" and
+ * vertex-pick on the path: J_regressor_extra + joint_map (models/smpl.py:66-76), VertexJointSelector
+ * (models/whmr.py:60,187,251), H36M regression + pelvis centring (models/whmr.py:176-180,240-244,647-651;
+ * evaluate/eval.py:198-219), dense Dmap0/Dmap1 (models/whmr.py:182-183,246-247) and the SSM marker
+ * pick (models/whmr.py:184,248).
+ *   out[b,r,:] = sum_k vals[k] * src[b, col_idx[k], :]   for k in [row_ptr[r], row_ptr[r+1])
+ *               - (sub_row[r] >= 0 ? same sum over row sub_row[r] : 0)
+ * where src is the virtual concatenation [verts (V rows) ; joints (n_joints rows)].
+ * Rows may be partitioned into consecutive groups (group_sizes, summing to n_rows); the output is
+ * then group-major: group g occupies a contiguous [B, group_sizes[g], 3] block, blocks in group
+ * order, so each read-out (joints, markers, sub-sampled meshes ...) is its own contiguous tensor
+ * while all of them come from one launch pair.  n_groups == 0: a single [B, n_rows, 3] block.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct whmr_readout_s* whmr_readout_t;
+int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* row_ptr /*HOST [n_rows+1]*/,
+                        const int32_t* col_idx /*HOST [nnz]*/, const float* vals /*HOST [nnz]*/,
+                        const int32_t* sub_row /*HOST [n_rows] or NULL*/, int n_groups,
+                        const int32_t* group_sizes /*HOST [n_groups] or NULL*/, whmr_readout_t* out);
+int whmr_readout_destroy(whmr_readout_t r);
+int whmr_readout_apply(whmr_readout_t r, const float* verts /*[B,V,3]*/, const float* joints /*[B,J,3] or NULL*/,
+                       int B, float* out /*[B*n_rows*3], group-major*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Projection.
+ * ------------------------------------------------------------------------------------------ */
+/* utils/geometry.py:289-307 projection(pred_joints, pred_camera): t = [tx, ty, 2*focal/(img_h*s + 1e-9)],
+ * u = focal*(X+t)_xy/(X+t)_z, out = u / (img_w/2, img_h/2).  points [B,N,3], cam [B,3] -> out [B,N,2]. */
+int whmr_project_weak(const float* points, const float* cam, int B, int N, float focal, float img_w,
+                      float img_h, float* out, void* stream);
+
+/* utils/geometry.py:310-341 perspective_projection(points, rotation, translation, focal_length,
+ * camera_center, retain_z) and its sibling models/maf_extractor.py:192-235 (optional rotation /
+ * translation / 5-coefficient distortion).  rotation: [rot_batch,3,3] with rot_batch in
+ * {0 (NULL: identity), 1, B}; translation [B,3] or NULL; focal: per-sample [B] if focal_dev != NULL
+ * else the scalar focal_scalar; distortion [B,5] or NULL; out [B,N,2] or [B,N,3] when retain_z. */
+int whmr_perspective_projection(const float* points, const float* rotation, int rot_batch,
+                                const float* translation, const float* focal_dev, float focal_scalar,
+                                const float* camera_center, const float* distortion, int B, int N,
+                                int retain_z, float* out, void* stream);
+
+/* The predicted-focal block of Regressor.forward, models/whmr.py:147-173, fused:
+ * focal = s*bbox_h*Tz/2; cam_t = convert_pare_to_full_img_cam(...) (utils/geometry.py:139-157);
+ * kp = perspective_projection(...); kp_norm = kp/center - 1.
+ * orig_shape [B,2] = (h,w); center [B,2] = bbox centre (x,y).  Any of kp_px / focal_out / cam_t_out may be NULL. */
+int whmr_project_full(const float* points, const float* cam, const float* bbox_height,
+                      const float* center, const float* orig_shape, const float* Tz, int B, int N,
+                      float* kp_norm, float* kp_px, float* focal_out, float* cam_t_out, void* stream);
+
+/* models/maf_extractor.py:145-235 MAF_Extractor.project (+get_trans, perspective_projection with the
+ * optional 5-coefficient distortion): full-frame pixels and crop-normalised [-1,1] coordinates. */
+int whmr_project_crop(const float* points, const float* cam, const float* center, const float* scale,
+                      const float* img_focal, const float* img_center, const float* distortion /*[B,5] or NULL*/,
+                      int B, int N, float crop_size, float img_w, float img_h, float* full_out /*or NULL*/,
+                      float* crop_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mesh-aligned feature sampling: models/maf_extractor.py:103-124 (the grid_sample inside
+ * MAF_Extractor.sampling): bilinear, zero padding, align_corners=True, points[...,0] <-> W.
+ *   feat [B,C,H,W] (NCHW) or [B,H,W,C] (NHWC); points [B,N,2]; out [B,C,N].
+ * ------------------------------------------------------------------------------------------ */
+int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int W,
+                         const float* points, int N, float* out, void* stream);
+/* MAF_Extractor.forward (models/maf_extractor.py:126-143) = projection (weak) + sampling, fused:
+ * p [B,N,3], cam [B,3]; also writes the 2-D points if points2d_out != NULL. */
+int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int W, const float* p,
+                        const float* cam, int N, float focal, float img_w, float img_h,
+                        float* points2d_out, float* out, void* stream);
+
+/* verts[:, idx] (models/whmr.py:184 markers) -- verts [B,V,3], idx [n_idx] int32 DEVICE -> out [B,n_idx,3] */
+int whmr_gather_vertices(const float* verts, const int32_t* idx, int B, int V, int n_idx, float* out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation metrics (BASELINE config 5): evaluate/eval.py:208-223 and utils/pose_utils.py:10-75.
+ *   pred, gt [n,J,3].  mpjpe[n] = mean_j ||pred-gt||; pa_mpjpe[n] = same after the similarity
+ *   (Procrustes) alignment of pred onto gt (3x3 SVD per sample, on device).
+ * ------------------------------------------------------------------------------------------ */
+int whmr_joint_errors(const float* pred, const float* gt, int n, int J, float* mpjpe /*or NULL*/,
+                      float* pa_mpjpe /*or NULL*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHMR_B200_H_ */

@@ -1,0 +1,356 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference-generated
+golden fixtures.  Tolerances are the north star's: vertices/joints <= 1e-5 m max-abs, projected
+keypoints <= 1e-3 px, sampled features <= 1e-4 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+VERT_TOL = 1e-5      # metres
+PX_TOL = 1e-3        # pixels
+FEAT_RTOL = 1e-4     # relative
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _oracle(model, dtype=torch.float32):
+    from oracle.smpl_oracle import SMPLOracle
+    return SMPLOracle(model, dtype)
+
+
+def _smpl(model, dev, gemm_mode):
+    from whmr_b200.smpl import SMPL
+    return SMPL(model=model, gemm_mode=gemm_mode).to(dev)
+
+
+def _bodies(B, seed=1):
+    import whmr_b200.synthetic as syn
+    return syn.make_bodies(B, seed=seed)
+
+
+def _maxabs(a, b):
+    return float((a.detach().double().cpu() - torch.as_tensor(b).double()).abs().max())
+
+
+GEMM_MODES = ["fp32_simt", "bf16x3", "3xtf32"]
+
+
+# ------------------------------------------------------------------------------------------ SMPL
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+@pytest.mark.parametrize("weights", ["random", "skeleton", "dense"])
+def test_smpl_forward_config1(dev, weights, gemm_mode):
+    """BASELINE config 1: B=64, axis-angle and rotmat modes, vs the fp32 and fp64 oracle."""
+    import whmr_b200.synthetic as syn
+    model = syn.make_smpl_model(seed={"random": 0, "skeleton": 3, "dense": 5}[weights], weights=weights)
+    b = _bodies(64)
+    smpl = _smpl(model, dev, gemm_mode)
+    o32, o64 = _oracle(model), _oracle(model, torch.float64)
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    # axis-angle mode (core/trainer.py:415)
+    out = smpl(betas=T(b['betas']), body_pose=T(b['pose_aa'][:, 3:]), global_orient=T(b['pose_aa'][:, :3]),
+               pose2rot=True)
+    ref = o32(b['betas'], b['pose_aa'][:, 3:], b['pose_aa'][:, :3], pose2rot=True)
+    ref64 = o64(b['betas'], b['pose_aa'][:, 3:], b['pose_aa'][:, :3], pose2rot=True)
+    assert out.vertices.shape == (64, 6890, 3) and out.joints.shape == (64, 49, 3)
+    assert _maxabs(out.vertices, ref['vertices']) <= VERT_TOL
+    assert _maxabs(out.joints, ref['joints']) <= VERT_TOL
+    assert _maxabs(out.smpl_joints, ref['joints45']) <= VERT_TOL
+    assert _maxabs(out.vertices, ref64['vertices']) <= VERT_TOL
+    # rotation-matrix mode (models/whmr.py:132-137)
+    out = smpl(betas=T(b['betas']), body_pose=T(b['rotmat'][:, 1:]), global_orient=T(b['rotmat'][:, :1]),
+               pose2rot=False, return_transforms=True)
+    ref = o32(b['betas'], b['rotmat'][:, 1:], b['rotmat'][:, :1], pose2rot=False)
+    assert _maxabs(out.vertices, ref['vertices']) <= VERT_TOL
+    assert _maxabs(out.joints, ref['joints']) <= VERT_TOL
+    assert _maxabs(out.rel_transforms.view(64, 24, 3, 4), ref['A'][:, :, :3, :]) <= VERT_TOL
+
+
+def test_smpl_simt_error_budget(dev, smpl_model):
+    """The exact-fp32 GEMM path should sit ~1e-6 from the fp64 oracle (summation order only)."""
+    b = _bodies(32)
+    smpl = _smpl(smpl_model, dev, "fp32_simt")
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    out = smpl(betas=T(b['betas']), body_pose=T(b['rotmat'][:, 1:]), global_orient=T(b['rotmat'][:, :1]), pose2rot=False)
+    ref64 = _oracle(smpl_model, torch.float64)(b['betas'], b['rotmat'][:, 1:].astype(np.float64),
+                                               b['rotmat'][:, :1].astype(np.float64), pose2rot=False)
+    assert _maxabs(out.vertices, ref64['vertices']) <= 3e-6
+
+
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+@pytest.mark.parametrize("B", [0, 1, 3, 65, 257])
+def test_smpl_ragged_batches(dev, smpl_model, B, gemm_mode):
+    """empty, single and tile-straddling batches (the vendored smplx test also drives batch 0:
+    models/ViTPose/tests/test_external/test_smpl.py:60-78)."""
+    smpl = _smpl(smpl_model, dev, gemm_mode)
+    b = _bodies(max(B, 1), seed=7)
+    T = lambda a: torch.from_numpy(a[:B]).to(dev)  # noqa: E731
+    out = smpl(betas=T(b['betas']), body_pose=T(b['rotmat'][:, 1:]), global_orient=T(b['rotmat'][:, :1]), pose2rot=False)
+    assert out.vertices.shape == (B, 6890, 3) and out.joints.shape == (B, 49, 3)
+    if B:
+        ref = _oracle(smpl_model)(b['betas'][:B], b['rotmat'][:B, 1:], b['rotmat'][:B, :1], pose2rot=False)
+        assert _maxabs(out.vertices, ref['vertices']) <= VERT_TOL
+        assert _maxabs(out.joints, ref['joints']) <= VERT_TOL
+
+
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+def test_smpl_chunked_large_batch_properties(dev, smpl_model, gemm_mode):
+    """Full-size property checks (no oracle at this size): chunk boundaries must be invisible, the
+    identity pose returns v_shaped, bodies are independent of their batch position."""
+    from whmr_b200 import ops
+    B = 2048 + 37
+    b = _bodies(B, seed=11)
+    smpl = _smpl(smpl_model, dev, gemm_mode)
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    betas, rot = T(b['betas']), T(b['rotmat'])
+    big = smpl(betas=betas, body_pose=rot[:, 1:], global_orient=rot[:, :1], pose2rot=False)
+    # same bodies in a different order / batch size -> bitwise identical per body
+    perm = torch.randperm(B, device=dev)[:300]
+    small = smpl(betas=betas[perm], body_pose=rot[perm, 1:], global_orient=rot[perm, :1], pose2rot=False)
+    assert torch.equal(big.vertices[perm], small.vertices)
+    assert torch.equal(big.joints[perm], small.joints)
+    # spot-check 16 bodies straddling chunk boundaries against the oracle
+    idx = [0, 1, 255, 256, 511, 512, 767, 768, 769, 1023, 1535, 1536, 2047, 2048, B - 2, B - 1]
+    ref = _oracle(smpl_model)(b['betas'][idx], b['rotmat'][idx, 1:], b['rotmat'][idx, :1], pose2rot=False)
+    assert _maxabs(big.vertices[idx], ref['vertices']) <= VERT_TOL
+    # identity pose => v_shaped
+    eye = torch.eye(3, device=dev).expand(B, 24, 3, 3).contiguous()
+    ident = smpl(betas=betas, body_pose=eye[:, 1:], global_orient=eye[:, :1], pose2rot=False)
+    vs = torch.from_numpy(smpl_model['v_template']).to(dev)[None] + torch.einsum(
+        'bl,mkl->bmk', betas, torch.from_numpy(smpl_model['shapedirs']).to(dev))
+    assert float((ident.vertices - vs).abs().max()) <= 2e-6
+    assert ops is not None
+
+
+def test_smpl_transl_and_default_params(dev, smpl_model):
+    from whmr_b200.smpl import SMPL
+    smpl = SMPL(model=smpl_model, batch_size=4, create_transl=True, gemm_mode="fp32_simt").to(dev)
+    b = _bodies(4)
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    tr = torch.tensor([[0.1, -0.2, 0.3]] * 4, device=dev)
+    out = smpl(betas=T(b['betas']), body_pose=T(b['pose_aa'][:, 3:]), global_orient=T(b['pose_aa'][:, :3]), transl=tr)
+    ref = _oracle(smpl_model)(b['betas'], b['pose_aa'][:, 3:], b['pose_aa'][:, :3], pose2rot=True, transl=tr.cpu())
+    assert _maxabs(out.vertices, ref['vertices']) <= VERT_TOL
+    assert _maxabs(out.joints, ref['joints']) <= VERT_TOL
+    out0 = smpl()      # all-default parameters: zero pose, zero betas, zero transl
+    assert out0.vertices.shape == (4, 6890, 3)
+    assert _maxabs(out0.vertices[0], smpl_model['v_template']) <= 2e-6
+
+
+def test_smpl_host_buffer_entry(dev, smpl_model):
+    """whmr_smpl_forward_host: pinned host buffers in/out (the bench's e2e leg)."""
+    smpl = _smpl(smpl_model, dev, "fp32_simt")
+    h, _ = smpl._state(dev)
+    b = _bodies(33)
+    betas = torch.from_numpy(b['betas']).pin_memory()
+    rot = torch.from_numpy(b['rotmat']).pin_memory()
+    verts = torch.empty(33, 6890, 3).pin_memory()
+    joints = torch.empty(33, 24, 3).pin_memory()
+    h.forward_host(betas, rot, True, verts, joints)
+    ref = _oracle(smpl_model)(b['betas'], b['rotmat'][:, 1:], b['rotmat'][:, :1], pose2rot=False)
+    assert _maxabs(verts, ref['vertices']) <= VERT_TOL
+    assert _maxabs(joints, ref['joints24']) <= VERT_TOL
+
+
+def test_batch_rodrigues(dev):
+    from oracle.smpl_oracle import batch_rodrigues
+    from whmr_b200.geometry import batch_rodrigues as gpu_rod
+    g = torch.Generator().manual_seed(0)
+    aa = torch.randn(500, 3, generator=g) * 1.5
+    aa[0] = 0
+    aa[1] = torch.tensor([np.pi, 0, 0])
+    assert _maxabs(gpu_rod(aa.to(dev)), batch_rodrigues(aa)) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------ read-outs
+@pytest.mark.parametrize("gemm_mode", ["fp32_simt", "bf16x3"])
+def test_body_model_head_matches_regressor_forward(dev, smpl_model, gemm_mode):
+    """All tensors of Regressor.forward's dict that come from the body model (models/whmr.py:189-208)."""
+    from oracle import geometry_oracle as G
+    from oracle.smpl_oracle import regressor_readouts
+    from whmr_b200.regressor import BodyModelHead
+    B = 40
+    b = _bodies(B, seed=3)
+    smpl = _smpl(smpl_model, dev, gemm_mode)
+    head = BodyModelHead(smpl, smpl_model['Dmap0'], smpl_model['Dmap1'], smpl_model['ssm'],
+                         smpl_model['J_regressor_h36m'])
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    out = head(T(b['rotmat']), T(b['betas']), T(b['cam']), T(b['bbox_height']), T(b['center']), T(b['orig_shape']),
+               T(b['Tz']), J_regressor=True)
+    ref = _oracle(smpl_model)(b['betas'], b['rotmat'][:, 1:], b['rotmat'][:, :1], pose2rot=False)
+    rr = regressor_readouts(smpl_model, ref['vertices'])
+    assert _maxabs(out['verts'], ref['vertices']) <= VERT_TOL
+    assert _maxabs(out['joints49'], ref['joints']) <= VERT_TOL
+    for k_gpu, k_ref in (('sub_verts', 'sub_verts'), ('temp_verts', 'temp_verts'), ('markers', 'markers'),
+                         ('smpl_kp_3d', 'smpl_kp_3d'), ('kp_3d', 'kp_3d_h36m')):
+        assert out[k_gpu].is_contiguous()
+        assert _maxabs(out[k_gpu], rr[k_ref]) <= VERT_TOL, k_gpu
+    assert _maxabs(out['pelvis'], rr['smpl_kp_3d'][:, :1]) <= VERT_TOL
+    # projections of the GPU joints, checked against the oracle applied to the same joints
+    j = out['joints49'].cpu()
+    kp = G.projection(j, T(b['cam']).cpu())
+    assert _maxabs(out['kp_2d'], kp) * 128.0 <= PX_TOL            # normalised by 256/2 -> pixels
+    kpn, focal, cam_t, kp_px = G.full_projection(j, *[torch.from_numpy(b[k]) for k in
+                                                      ('cam', 'bbox_height', 'center', 'orig_shape', 'Tz')])
+    np.testing.assert_allclose(out['focal_length'].cpu().numpy(), focal.numpy(), rtol=1e-6)
+    assert _maxabs(out['pred_cam_t'], cam_t) <= 1e-5
+    half = torch.from_numpy(b['orig_shape'][:, ::-1].copy()).unsqueeze(1) / 2
+    assert float(((out['kp_2d_w'].cpu() - kpn).abs() * half).max()) <= PX_TOL * 4   # px, large focal => 4e-3
+    # without H36M regressor 'kp_3d' is the 49 joints (models/whmr.py:140)
+    out2 = head(T(b['rotmat']), T(b['betas']), T(b['cam']))
+    assert out2['kp_3d'].shape == (B, 49, 3) and 'kp_2d_w' not in out2
+
+
+def test_readout_generic_csr(dev):
+    """long rows, short rows, sub_row, chain-joint sources, group-major output."""
+    import scipy.sparse as sp
+    from whmr_b200 import ops
+    rng = np.random.default_rng(0)
+    V, J, B = 500, 24, 9
+    dense = rng.random((7, V + J)) * (rng.random((7, V + J)) < 0.2)
+    picks = rng.integers(0, V + J, size=11)
+    groups = [('dense', sp.csr_matrix(dense)), ('picks', picks), ('empty', sp.csr_matrix((2, V + J)))]
+    sub = np.full(7 + 11 + 2, -1, dtype=np.int32)
+    sub[3] = 0
+    sub[8] = 7
+    ro = ops.Readout(groups, V, J, dev, sub_rows=sub)
+    verts = torch.randn(B, V, 3, device=dev)
+    joints = torch.randn(B, J, 3, device=dev)
+    r = ro.apply(verts, joints)
+    src = torch.cat([verts, joints], 1).double().cpu()
+    d = torch.einsum('rs,bsc->brc', torch.from_numpy(dense), src)
+    d[:, 3] -= d[:, 0].clone()
+    p = src[:, picks]
+    p[:, 1] -= p[:, 0].clone()
+    assert _maxabs(r['dense'], d) <= 1e-5
+    assert _maxabs(r['picks'], p) <= 1e-6
+    assert float(r['empty'].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------ projection
+def test_projection_matches_reference_golden(dev, golden):
+    from whmr_b200 import geometry as geo
+    g = golden
+    T = lambda k: torch.from_numpy(g[k]).to(dev)  # noqa: E731
+    assert _maxabs(geo.projection(T('proj_points'), T('proj_cam')), g['proj_out']) * 128 <= PX_TOL
+    kpn, focal, cam_t, px = geo.full_image_projection(T('proj_points'), T('proj_cam'), T('full_bbox_h'), T('full_center'),
+                                                      T('full_orig_shape'), T('full_Tz'), want_px=True)
+    assert _maxabs(px, g['full_kp_px']) <= 4 * PX_TOL      # pixel coords ~2e3, fp32 ulp 2.4e-4
+    assert _maxabs(cam_t, g['full_cam_t']) <= 1e-5
+    np.testing.assert_allclose(focal.cpu().numpy(), g['full_focal'], rtol=1e-6)
+    assert _maxabs(kpn, g['full_kp_norm']) <= 1e-5
+    cc = T('full_orig_shape')[:, [1, 0]] / 2.
+    pp = geo.perspective_projection(T('proj_points'), T('pp_rot'), T('full_cam_t'), T('full_focal'), cc, retain_z=True)
+    assert _maxabs(pp, g['pp_retain_z']) <= 4 * PX_TOL
+    # keyword use + broadcast eye, exactly as models/whmr.py:157-163
+    pp2 = geo.perspective_projection(T('proj_points'), rotation=torch.eye(3, device=dev).unsqueeze(0).expand(1, -1, -1),
+                                     translation=T('full_cam_t'), focal_length=T('full_focal'), camera_center=cc)
+    assert _maxabs(pp2, g['full_kp_px']) <= 4 * PX_TOL
+    ct = geo.convert_pare_to_full_img_cam(T('proj_cam'), T('full_bbox_h'), T('full_center'), T('full_orig_shape')[:, 1],
+                                          T('full_orig_shape')[:, 0], focal_length=5000.)
+    assert _maxabs(ct, g['full_cam_t_f5000']) <= 1e-5
+    with pytest.raises(RuntimeError):
+        geo.projection(T('proj_points'), T('proj_cam'), retain_z=True)
+
+
+def test_projection_large_random(dev):
+    from oracle import geometry_oracle as G
+    from whmr_b200 import geometry as geo
+    b = _bodies(1000, seed=5)
+    g = torch.Generator().manual_seed(1)
+    pts = torch.randn(1000, 49, 3, generator=g) * 0.4
+    kp = geo.projection(pts.to(dev), torch.from_numpy(b['cam']).to(dev))
+    assert _maxabs(kp, G.projection(pts, torch.from_numpy(b['cam']))) * 128 <= PX_TOL
+
+
+# ------------------------------------------------------------------------------------------ sampling
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_sampling_matches_reference_golden(dev, golden, tag):
+    from whmr_b200.maf_extractor import MAF_Extractor
+    g = golden
+    ext = MAF_Extractor(mesh_downsampling=None).to(dev)
+    sd = {k: torch.from_numpy(g['maf_' + k.replace('.', '_')]) for k in
+          ('conv0.weight', 'conv0.bias', 'conv1.weight', 'conv1.bias', 'conv2.weight', 'conv2.bias')}
+    ext.load_state_dict(sd, strict=False)
+    feat = torch.from_numpy(g['samp_%s_feat' % tag]).to(dev)
+    pts = torch.from_numpy(g['samp_%s_points' % tag]).to(dev)
+    maf, pf = ext.sampling(pts, im_feat=feat)
+    ref = g['samp_%s_point_feat' % tag]
+    assert _maxabs(pf, ref) <= FEAT_RTOL * np.abs(ref).max()
+    assert _maxabs(maf, g['samp_%s_mesh_align' % tag]) <= 1e-3    # PyTorch Conv1d MLP (may use TF32 convs)
+    # state-driven forward (self.im_feat / self.cam), models/maf_extractor.py:126-143
+    ext.im_feat = torch.from_numpy(g['fwd_feat']).to(dev)
+    ext.cam = torch.from_numpy(g['fwd_cam']).to(dev)
+    _, pf2 = ext(torch.from_numpy(g['fwd_p']).to(dev), None, None, None, None)
+    assert _maxabs(pf2, g['fwd_point_feat']) <= FEAT_RTOL * np.abs(g['fwd_point_feat']).max() * 4
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("H,W,N,C", [(32, 24, 63, 256), (64, 48, 67, 256), (128, 96, 67, 256), (14, 14, 431, 256),
+                                      (28, 28, 431, 256), (56, 56, 431, 256), (7, 5, 1, 3), (16, 16, 6890, 8)])
+def test_sampling_vs_grid_sample(dev, layout, H, W, N, C):
+    from oracle.sampling_oracle import grid_sample_points
+    from whmr_b200 import ops
+    import whmr_b200.synthetic as syn
+    B = 3
+    g = torch.Generator().manual_seed(H * 1000 + N)
+    feat = torch.randn(B, C, H, W, generator=g)
+    pts = torch.from_numpy(syn.make_sample_points(B, N, seed=H))
+    pts[0, 0] = torch.tensor([-1.0, -1.0])
+    pts[1, 0] = torch.tensor([1.0, 1.0])
+    pts[2, 0] = torch.tensor([float('inf'), 0.0]) if N > 1 else pts[2, 0]
+    ref = grid_sample_points(feat, pts.clone().nan_to_num(posinf=5.0))
+    if layout == "nchw":
+        out = ops.sample_bilinear(feat.to(dev), pts.to(dev), ops.LAYOUT_NCHW)
+    else:
+        out = ops.sample_bilinear(feat.permute(0, 2, 3, 1).contiguous().to(dev), pts.to(dev), ops.LAYOUT_NHWC)
+    assert out.shape == (B, C, N)
+    assert _maxabs(out, ref) <= FEAT_RTOL * float(ref.abs().max())
+
+
+def test_maf_project_matches_reference_golden(dev, golden):
+    from whmr_b200.maf_extractor import MAF_Extractor
+    g = golden
+    T = lambda k: torch.from_numpy(g[k]).to(dev)  # noqa: E731
+    ext = MAF_Extractor(mesh_downsampling=None).to(dev)
+    full, crop = ext.project(T('fwd_p'), T('fwd_cam'), T('mproj_center'), T('mproj_scale'), T('mproj_focal'),
+                             T('mproj_img_center'), return_full=True)
+    assert _maxabs(full, g['mproj_full']) <= 4 * PX_TOL
+    assert _maxabs(crop, g['mproj_crop']) * 128 <= 20 * PX_TOL     # crop coords are scaled by 256/b (up to ~2.5x)
+    tr = ext.get_trans(T('fwd_cam'), T('mproj_center'), T('mproj_scale'), T('mproj_focal'), T('mproj_img_center'))
+    d = ext.perspective_projection(T('fwd_p') + tr, None, None, T('mproj_focal'), T('mproj_img_center'),
+                                   distortion=T('mproj_kc'))
+    assert _maxabs(d, g['mproj_distorted']) <= 4 * PX_TOL
+
+
+# ------------------------------------------------------------------------------------------ metrics
+def test_joint_errors_match_reference_golden(dev, golden):
+    from oracle import metrics_oracle as M
+    from whmr_b200 import ops
+    g = golden
+    mp, pa = ops.joint_errors(torch.from_numpy(g['pa_S1']).to(dev), torch.from_numpy(g['pa_S2']).to(dev))
+    assert _maxabs(pa, g['pa_err']) <= 1e-6
+    assert _maxabs(mp, M.mpjpe(g['pa_S1'], g['pa_S2'])) <= 1e-6
+    rng = np.random.default_rng(3)
+    S1 = rng.normal(0, 0.3, size=(2000, 14, 3)).astype(np.float32)
+    S2 = (S1 + rng.normal(0, 0.05, size=S1.shape)).astype(np.float32)
+    S2[:5] = S1[:5] * 0.5 + 0.3          # vendored KAT: exact similarity => zero error
+    S1[5] = 0; S1[5, :, 0] = np.linspace(0, 1, 14); S2[5] = S1[5] * 2     # rank-1 (collinear) input
+    mp, pa = ops.joint_errors(torch.from_numpy(S1).to(dev), torch.from_numpy(S2).to(dev))
+    assert _maxabs(pa, M.pa_mpjpe(S1, S2)) <= 2e-6
+    assert float(pa[:5].max()) <= 1e-6
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of routing anywhere else."""
+    from whmr_b200 import ops
+    from whmr_b200._lib import WhmrError
+    with pytest.raises(WhmrError):
+        ops.project_weak(torch.zeros(1, 2, 3), torch.ones(1, 3), 1000., 256., 256.)
+    assert os.path.exists(os.path.join(os.path.dirname(ops.__file__), "libwhmr_b200.so"))

@@ -1,0 +1,141 @@
+// Projection kernels.  One thread per (body, point); the reference's ~12 tiny
+// launches per call (zeros, 4 indexed writes into K, 2 einsums, div, slice, div) become one.
+// Operation order follows the reference so fp32 rounding matches: rotate -> translate -> divide
+// by z -> intrinsics -> normalise.  These kernels move ~1 KB per body: they are launch-latency
+// bound at any realistic batch and exist to take launches off the critical path, not for bandwidth.
+#pragma once
+#include "common.cuh"
+
+namespace whmr {
+
+// utils/geometry.py:289-307
+__global__ void __launch_bounds__(256)
+project_weak_kernel(const float* __restrict__ points, const float* __restrict__ cam, int B, int N,
+                    float focal, float img_w, float img_h, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int b = (int)(i / N);
+  const float s = cam[b * 3 + 0];
+  const float tz = 2.0f * focal / (img_h * s + 1e-9f);
+  const float px = points[i * 3 + 0] + cam[b * 3 + 1];
+  const float py = points[i * 3 + 1] + cam[b * 3 + 2];
+  const float pz = points[i * 3 + 2] + tz;
+  const float qx = px / pz, qy = py / pz;
+  out[i * 2 + 0] = (focal * qx) / (img_w * 0.5f);
+  out[i * 2 + 1] = (focal * qy) / (img_h * 0.5f);
+}
+
+// utils/geometry.py:310-341
+__global__ void __launch_bounds__(256)
+perspective_projection_kernel(const float* __restrict__ points, const float* __restrict__ rotation,
+                              int rot_batch, const float* __restrict__ translation,
+                              const float* __restrict__ focal_dev, float focal_scalar,
+                              const float* __restrict__ camera_center,
+                              const float* __restrict__ distortion, int B, int N, int retain_z,
+                              float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int b = (int)(i / N);
+  float x = points[i * 3 + 0], y = points[i * 3 + 1], z = points[i * 3 + 2];
+  if (rotation) {
+    const float* R = rotation + (rot_batch > 1 ? (size_t)b * 9 : 0);
+    const float rx = R[0] * x + R[1] * y + R[2] * z;
+    const float ry = R[3] * x + R[4] * y + R[5] * z;
+    const float rz = R[6] * x + R[7] * y + R[8] * z;
+    x = rx; y = ry; z = rz;
+  }
+  if (translation) { x += translation[b * 3 + 0]; y += translation[b * 3 + 1]; z += translation[b * 3 + 2]; }
+  if (distortion) {   // models/maf_extractor.py:212-225 (5-coefficient radial + tangential)
+    const float* kc = distortion + (size_t)b * 5;
+    const float px = x / z, py = y / z;
+    const float r2 = px * px + py * py;
+    const float dx = 2.0f * kc[2] * px * py + kc[3] * (r2 + 2.0f * px * px);
+    const float dy = 2.0f * kc[3] * px * py + kc[2] * (r2 + 2.0f * py * py);
+    const float rad = 1.0f + kc[0] * r2 + kc[1] * (r2 * r2) + kc[4] * (r2 * r2 * r2);
+    x = rad * px + dx; y = rad * py + dy; z = 1.0f;
+  }
+  const float qx = x / z, qy = y / z, qz = z / z;
+  const float f = focal_dev ? focal_dev[b] : focal_scalar;
+  const float cx = camera_center[b * 2 + 0], cy = camera_center[b * 2 + 1];
+  const float u = f * qx + cx * qz;
+  const float v = f * qy + cy * qz;
+  if (retain_z) {
+    out[i * 3 + 0] = u; out[i * 3 + 1] = v; out[i * 3 + 2] = qz;
+  } else {
+    out[i * 2 + 0] = u; out[i * 2 + 1] = v;
+  }
+}
+
+// models/whmr.py:147-173 (+ utils/geometry.py:139-157)
+__global__ void __launch_bounds__(256)
+project_full_kernel(const float* __restrict__ points, const float* __restrict__ cam,
+                    const float* __restrict__ bbox_height, const float* __restrict__ center,
+                    const float* __restrict__ orig_shape, const float* __restrict__ Tz, int B, int N,
+                    float* __restrict__ kp_norm, float* __restrict__ kp_px,
+                    float* __restrict__ focal_out, float* __restrict__ cam_t_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int b = (int)(i / N);
+  const int n = (int)(i % N);
+  const float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+  const float h = bbox_height[b], tz = Tz[b];
+  const float img_h = orig_shape[b * 2 + 0], img_w = orig_shape[b * 2 + 1];
+  const float focal = s * h * tz / 2.0f;                       // whmr.py:149
+  const float ccx = img_w / 2.0f, ccy = img_h / 2.0f;          // :152-153
+  const float sh = s * h;
+  const float ctx = tx + 2.0f * (center[b * 2 + 0] - (img_w / 2.0f)) / sh;   // geometry.py:152-155
+  const float cty = ty + 2.0f * (center[b * 2 + 1] - (img_h / 2.0f)) / sh;
+  if (n == 0) {
+    if (focal_out) focal_out[b] = focal;
+    if (cam_t_out) { cam_t_out[b * 3 + 0] = ctx; cam_t_out[b * 3 + 1] = cty; cam_t_out[b * 3 + 2] = tz; }
+  }
+  const float x = points[i * 3 + 0] + ctx, y = points[i * 3 + 1] + cty, z = points[i * 3 + 2] + tz;
+  const float qx = x / z, qy = y / z, qz = z / z;
+  const float u = focal * qx + ccx * qz;
+  const float v = focal * qy + ccy * qz;
+  if (kp_px) { kp_px[i * 2 + 0] = u; kp_px[i * 2 + 1] = v; }
+  if (kp_norm) { kp_norm[i * 2 + 0] = u / ccx - 1.0f; kp_norm[i * 2 + 1] = v / ccy - 1.0f; }   // :173
+}
+
+// models/maf_extractor.py:145-235 (project + get_trans + perspective_projection w/ distortion)
+__global__ void __launch_bounds__(256)
+project_crop_kernel(const float* __restrict__ points, const float* __restrict__ cam,
+                    const float* __restrict__ center, const float* __restrict__ scale,
+                    const float* __restrict__ img_focal, const float* __restrict__ img_center,
+                    const float* __restrict__ distortion, int B, int N, float crop_size, float img_w,
+                    float img_h, float* __restrict__ full_out, float* __restrict__ crop_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int b = (int)(i / N);
+  const float bb = scale[b] * 200.0f;
+  const float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+  const float cx = center[b * 2 + 0], cy = center[b * 2 + 1];
+  const float icx = img_center[b * 2 + 0], icy = img_center[b * 2 + 1];
+  const float f = img_focal[b];
+  const float bs = bb * s;
+  float x = points[i * 3 + 0] + (tx + 2.0f * (cx - icx) / bs);
+  float y = points[i * 3 + 1] + (ty + 2.0f * (cy - icy) / bs);
+  float z = points[i * 3 + 2] + (2.0f * f / bs);
+  if (distortion) {
+    const float* kc = distortion + (size_t)b * 5;
+    const float px = x / z, py = y / z;
+    const float r2 = px * px + py * py;
+    const float dx = 2.0f * kc[2] * px * py + kc[3] * (r2 + 2.0f * px * px);
+    const float dy = 2.0f * kc[3] * px * py + kc[2] * (r2 + 2.0f * py * py);
+    const float rad = 1.0f + kc[0] * r2 + kc[1] * (r2 * r2) + kc[4] * (r2 * r2 * r2);
+    x = rad * px + dx; y = rad * py + dy; z = 1.0f;
+  }
+  const float qx = x / z, qy = y / z, qz = z / z;
+  const float u = f * qx + icx * qz;
+  const float v = f * qy + icy * qz;
+  if (full_out) { full_out[i * 2 + 0] = u; full_out[i * 2 + 1] = v; }
+  if (crop_out) {
+    const float hx = img_w * 0.5f, hy = img_h * 0.5f;
+    const float px = (u - (cx - bb / 2.0f)) * (crop_size / bb);
+    const float py = (v - (cy - bb / 2.0f)) * (crop_size / bb);
+    crop_out[i * 2 + 0] = (px - hx) / hx;
+    crop_out[i * 2 + 1] = (py - hy) / hy;
+  }
+}
+
+}  // namespace whmr

@@ -1,0 +1,121 @@
+// Sparse linear read-out of posed vertices: out[b,r,:] = sum_k vals[k] * src[b, col[k], :].
+//
+// One mechanism for every "regressor x vertices" / vertex-pick on the path:
+// J_regressor_extra + joint_map -> 49 joints (models/smpl.py:66-76), VertexJointSelector
+// (models/whmr.py:187,251), H36M 17 joints -> pelvis-centred 14 (models/whmr.py:176-180), the dense
+// [1723,6890] and [431,1723] down-sampling matmuls (models/whmr.py:182-183; 71+4.5 MFLOP/body in the
+// reference, a one-hot gather in fact) and the SSM marker pick (models/whmr.py:184).
+// src is the virtual concatenation [verts ; chain joints] so the 24 chain joints of smplx's
+// `joints` output can be routed through the same table.
+//
+// Rows are split by the host into "short" (<= kShortRow non-zeros: one thread per (body,row)) and
+// "long" (one warp per (body,row), shuffle reduction in a fixed order => deterministic).
+#pragma once
+#include "common.cuh"
+
+namespace whmr {
+
+constexpr int kShortRow = 4;
+
+struct ReadoutParams {
+  const int* row_ptr;   // [R+1]
+  const int* col_idx;   // [nnz]
+  const float* vals;    // [nnz]
+  const int* sub_row;   // [R] or null
+  const int* grp_prefix;  // [R] rows in all groups before this row's group
+  const int* grp_rows;    // [R] rows in this row's group
+  const int* rows;      // row ids handled by this launch
+  int n_rows_here;      // entries in `rows`
+  int R, V, J, B;
+  const float* verts;   // [B,V,3]
+  const float* joints;  // [B,J,3] or null
+  float* out;           // group-major: group g = [B, R_g, 3] at float offset 3*B*prefix_g
+};
+
+__device__ __forceinline__ float* readout_dst(const ReadoutParams& p, int b, int r) {
+  const int pre = p.grp_prefix[r], rg = p.grp_rows[r];
+  return p.out + 3 * ((size_t)p.B * pre + (size_t)b * rg + (r - pre));
+}
+
+__device__ __forceinline__ const float* readout_src(const ReadoutParams& p, int b, int col) {
+  return col < p.V ? p.verts + ((size_t)b * p.V + col) * 3
+                   : p.joints + ((size_t)b * p.J + (col - p.V)) * 3;
+}
+
+__device__ __forceinline__ void readout_row_serial(const ReadoutParams& p, int b, int r, float& x,
+                                                   float& y, float& z) {
+  x = y = z = 0.f;
+  for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; ++k) {
+    const float w = p.vals[k];
+    const float* s = readout_src(p, b, p.col_idx[k]);
+    x = fmaf(w, s[0], x); y = fmaf(w, s[1], y); z = fmaf(w, s[2], z);
+  }
+}
+
+__global__ void __launch_bounds__(256) readout_short_kernel(ReadoutParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.B * p.n_rows_here) return;
+  const int b = (int)(i / p.n_rows_here);
+  const int r = p.rows[(int)(i % p.n_rows_here)];
+  float x, y, z;
+  readout_row_serial(p, b, r, x, y, z);
+  const int sr = p.sub_row ? p.sub_row[r] : -1;
+  if (sr >= 0) {
+    float sx, sy, sz;
+    readout_row_serial(p, b, sr, sx, sy, sz);
+    x -= sx; y -= sy; z -= sz;
+  }
+  float* o = readout_dst(p, b, r);
+  o[0] = x; o[1] = y; o[2] = z;
+}
+
+__device__ __forceinline__ void readout_row_warp(const ReadoutParams& p, int b, int r, int lane,
+                                                 float& x, float& y, float& z) {
+  x = y = z = 0.f;
+  for (int k = p.row_ptr[r] + lane; k < p.row_ptr[r + 1]; k += 32) {
+    const float w = p.vals[k];
+    const float* s = readout_src(p, b, p.col_idx[k]);
+    x = fmaf(w, s[0], x); y = fmaf(w, s[1], y); z = fmaf(w, s[2], z);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, o);
+    y += __shfl_xor_sync(0xffffffffu, y, o);
+    z += __shfl_xor_sync(0xffffffffu, z, o);
+  }
+}
+
+__global__ void __launch_bounds__(256) readout_long_kernel(ReadoutParams p) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)p.B * p.n_rows_here) return;   // warp-uniform
+  const int b = (int)(w / p.n_rows_here);
+  const int r = p.rows[(int)(w % p.n_rows_here)];
+  float x, y, z;
+  readout_row_warp(p, b, r, lane, x, y, z);
+  const int sr = p.sub_row ? p.sub_row[r] : -1;
+  if (sr >= 0) {
+    float sx, sy, sz;
+    readout_row_warp(p, b, sr, lane, sx, sy, sz);
+    x -= sx; y -= sy; z -= sz;
+  }
+  if (lane == 0) {
+    float* o = readout_dst(p, b, r);
+    o[0] = x; o[1] = y; o[2] = z;
+  }
+}
+
+// verts[:, idx]
+__global__ void __launch_bounds__(256) gather_vertices_kernel(const float* __restrict__ verts,
+                                                              const int* __restrict__ idx, int B, int V,
+                                                              int n_idx, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over B*n_idx*3
+  if (i >= (long long)B * n_idx * 3) return;
+  const int c = (int)(i % 3);
+  const long long t = i / 3;
+  const int k = (int)(t % n_idx);
+  const int b = (int)(t / n_idx);
+  out[i] = verts[((size_t)b * V + idx[k]) * 3 + c];
+}
+
+}  // namespace whmr

@@ -1,0 +1,127 @@
+// Mesh-aligned feature sampling: F.grid_sample(im_feat, points[:, :, None, :],
+// align_corners=True)[..., 0] of models/maf_extractor.py:119 -- bilinear, zero padding,
+// pixel = (g + 1)/2 * (size - 1), points[...,0] <-> W.
+//
+// ATen's grid_sampler_2d assigns a thread per point and loops over C with stride H*W, so both its
+// reads and its [B,C,N] writes are uncoalesced.  Here:
+//  * NCHW (the contract layout): the output of one body is the flat array out_b[c*N + n]; threads
+//    walk that flat index, so every warp store is 128 contiguous bytes whatever N is (63, 67, 431,
+//    6890 ...), and the 4 taps of neighbouring lanes fall in the same channel plane (L1/L2 reuse).
+//    Each (point, channel, row) costs one 32 B sector -- the floor for a sparse gather from NCHW.
+//  * NHWC: lanes run over channels so every tap is a coalesced 128 B read; the [points x channels]
+//    tile is transposed through shared memory so the [B,C,N] store is coalesced too.
+#pragma once
+#include "common.cuh"
+
+namespace whmr {
+
+struct Taps {
+  int o00, o01, o10, o11;      // element offsets inside a plane (clamped, always valid)
+  float w00, w01, w10, w11;    // weights, zeroed for out-of-bounds taps
+};
+
+// PyTorch grid_sampler_2d semantics (align_corners=True, padding_mode=zeros, bilinear)
+__device__ __forceinline__ Taps make_taps(float gx, float gy, int H, int W) {
+  Taps t;
+  const float ix = ((gx + 1.0f) / 2.0f) * (float)(W - 1);
+  const float iy = ((gy + 1.0f) / 2.0f) * (float)(H - 1);
+  // keep the float->int conversion defined for far-away / non-finite points
+  const bool sane = (ix > -2.0f) && (ix < (float)W + 1.0f) && (iy > -2.0f) && (iy < (float)H + 1.0f);
+  const float fx = sane ? floorf(ix) : -2.0f;
+  const float fy = sane ? floorf(iy) : -2.0f;
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+  const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+  const bool vx0 = sane && x0 >= 0 && x0 < W, vx1 = sane && x1 >= 0 && x1 < W;
+  const bool vy0 = sane && y0 >= 0 && y0 < H, vy1 = sane && y1 >= 0 && y1 < H;
+  const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1);
+  const int cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+  t.o00 = cy0 * W + cx0; t.o01 = cy0 * W + cx1; t.o10 = cy1 * W + cx0; t.o11 = cy1 * W + cx1;
+  t.w00 = (vx0 && vy0) ? wx0 * wy0 : 0.0f;   // nw
+  t.w01 = (vx1 && vy0) ? wx1 * wy0 : 0.0f;   // ne
+  t.w10 = (vx0 && vy1) ? wx0 * wy1 : 0.0f;   // sw
+  t.w11 = (vx1 && vy1) ? wx1 * wy1 : 0.0f;   // se
+  return t;
+}
+
+constexpr int kSampleItems = 4;   // flat outputs per thread (independent gathers in flight)
+
+// grid = (ceil(C*N / (256*kSampleItems)), B)
+__global__ void __launch_bounds__(256)
+sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ points,
+                            float* __restrict__ out, int C, int H, int W, int N) {
+  const int b = blockIdx.y;
+  const int total = C * N;
+  const size_t plane = (size_t)H * W;
+  const float* fb = feat + (size_t)b * C * plane;
+  const float* pb = points + (size_t)b * N * 2;
+  float* ob = out + (size_t)b * total;
+  const int base = blockIdx.x * (256 * kSampleItems) + threadIdx.x;
+
+  float v00[kSampleItems], v01[kSampleItems], v10[kSampleItems], v11[kSampleItems];
+  Taps tp[kSampleItems];
+#pragma unroll
+  for (int it = 0; it < kSampleItems; ++it) {
+    const int i = base + it * 256;
+    if (i < total) {
+      const int c = i / N, n = i - c * N;
+      const float2 g = *reinterpret_cast<const float2*>(pb + (size_t)n * 2);
+      tp[it] = make_taps(g.x, g.y, H, W);
+      const float* pl = fb + (size_t)c * plane;
+      v00[it] = __ldg(pl + tp[it].o00); v01[it] = __ldg(pl + tp[it].o01);
+      v10[it] = __ldg(pl + tp[it].o10); v11[it] = __ldg(pl + tp[it].o11);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kSampleItems; ++it) {
+    const int i = base + it * 256;
+    if (i < total) {
+      float acc = v00[it] * tp[it].w00;
+      acc = fmaf(v01[it], tp[it].w01, acc);
+      acc = fmaf(v10[it], tp[it].w10, acc);
+      acc = fmaf(v11[it], tp[it].w11, acc);
+      ob[i] = acc;
+    }
+  }
+}
+
+// NHWC input: grid = (ceil(N/32), ceil(C/64), B), block 256 (8 warps x 4 points each)
+__global__ void __launch_bounds__(256)
+sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ points,
+                            float* __restrict__ out, int C, int H, int W, int N) {
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* fb = feat + (size_t)b * H * W * C;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int pt = warp * 4 + q;
+    const int n = n0 + pt;
+    if (n < N) {
+      const float2 g = *reinterpret_cast<const float2*>(points + ((size_t)b * N + n) * 2);
+      const Taps t = make_taps(g.x, g.y, H, W);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + h * 32 + lane;
+        float acc = 0.0f;
+        if (c < C) {
+          acc = __ldg(fb + (size_t)t.o00 * C + c) * t.w00;
+          acc = fmaf(__ldg(fb + (size_t)t.o01 * C + c), t.w01, acc);
+          acc = fmaf(__ldg(fb + (size_t)t.o10 * C + c), t.w10, acc);
+          acc = fmaf(__ldg(fb + (size_t)t.o11 * C + c), t.w11, acc);
+        }
+        tile[h * 32 + lane][pt] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // write [64 channels][32 points]: each warp handles 8 channels, lanes over points
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int cl = warp * 8 + q;
+    const int c = c0 + cl, n = n0 + lane;
+    if (c < C && n < N) out[((size_t)b * C + c) * N + n] = tile[cl][lane];
+  }
+}
+
+}  // namespace whmr

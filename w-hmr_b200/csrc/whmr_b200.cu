@@ -1,0 +1,619 @@
+// libwhmr_b200.so -- C ABI over the sm_100a kernels (see include/whmr_b200.h).
+#include <cuda_bf16.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "metrics.cuh"
+#include "pose_blend_simt.cuh"
+#include "pose_blend_tc.cuh"
+#include "projection.cuh"
+#include "readout.cuh"
+#include "sampling.cuh"
+#include "skinning.cuh"
+#include "smpl_chain.cuh"
+
+namespace whmr {
+
+std::atomic<uint64_t> g_launch_count{0};
+
+std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct DeviceArena {   // owns the cudaMalloc'ed constants of one handle
+  std::vector<void*> ptrs;
+  ~DeviceArena() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T>
+  cudaError_t upload(const std::vector<T>& h, T** out) {
+    void* d = nullptr;
+    const size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(d);
+    if (!h.empty()) {
+      e = cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return e;
+    }
+    *out = static_cast<T*>(d);
+    return cudaSuccess;
+  }
+  cudaError_t alloc(size_t bytes, void** out) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(d);
+    *out = d;
+    return cudaSuccess;
+  }
+};
+
+}  // namespace whmr
+
+using namespace whmr;
+
+struct whmr_smpl_s {
+  SmplDevice d{};
+  DeviceArena arena;
+  int gemm_mode = WHMR_GEMM_FP32_SIMT;
+  int chunk_bodies = 768;
+  TcPlan tc{};   // tensor maps etc. for the tcgen05 path
+  // host-buffer staging (whmr_smpl_reserve)
+  int reserved_B = 0;
+  float *st_betas = nullptr, *st_pose = nullptr, *st_verts = nullptr, *st_joints = nullptr;
+  void* st_ws = nullptr;
+  size_t st_ws_bytes = 0;
+};
+
+struct whmr_readout_s {
+  DeviceArena arena;
+  int R = 0, V = 0, J = 0, n_short = 0, n_long = 0;
+  int *row_ptr = nullptr, *col_idx = nullptr, *sub_row = nullptr, *rows_short = nullptr, *rows_long = nullptr;
+  int *grp_prefix = nullptr, *grp_rows = nullptr;
+  float* vals = nullptr;
+  bool needs_joints = false;
+};
+
+extern "C" {
+
+int whmr_abi_version(void) { return WHMR_ABI_VERSION; }
+const char* whmr_last_error(void) { return last_error_ref().c_str(); }
+uint64_t whmr_launch_count(void) { return g_launch_count.load(); }
+void whmr_launch_count_reset(void) { g_launch_count.store(0); }
+
+// =============================================================================================
+// SMPL
+// =============================================================================================
+int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* out) {
+  WHMR_CHECK_ARG(m && out, "whmr_smpl_create: null argument");
+  WHMR_CHECK_ARG(m->v_template && m->shapedirs && m->posedirs && m->J_regressor && m->lbs_weights && m->parents,
+                 "whmr_smpl_create: null model array");
+  const int V = m->n_verts, J = m->n_joints, NB = m->n_betas;
+  WHMR_CHECK_ARG(V > 0 && J >= 1 && J <= kMaxJoints && NB >= 0 && NB <= kMaxBetas,
+                 "whmr_smpl_create: unsupported sizes V=%d J=%d n_betas=%d (J<=%d, n_betas<=%d)", V, J, NB,
+                 kMaxJoints, kMaxBetas);
+  WHMR_CHECK_ARG(m->parents[0] < 0, "whmr_smpl_create: parents[0] must be -1");
+  for (int j = 1; j < J; ++j)
+    WHMR_CHECK_ARG(m->parents[j] >= 0 && m->parents[j] < j, "whmr_smpl_create: parents[%d]=%lld not in [0,%d)", j,
+                   (long long)m->parents[j], j);
+  WHMR_CHECK_ARG(gemm_mode >= WHMR_GEMM_FP32_SIMT && gemm_mode <= WHMR_GEMM_TC_3XTF32,
+                 "whmr_smpl_create: bad gemm_mode %d", gemm_mode);
+
+  whmr_smpl_s* h = new (std::nothrow) whmr_smpl_s();
+  if (!h) return set_error(WHMR_E_INVALID, "whmr_smpl_create: out of host memory");
+  SmplDevice& d = h->d;
+  d.V = V; d.J = J; d.NB = NB;
+  d.VP = ceil_div(V, kVertTile) * kVertTile;
+  d.NP = 3 * d.VP;
+  const int nfeat = (J - 1) * 9;
+  d.KP = std::max(16, ceil_div(nfeat, 16) * 16);
+  if (const char* e = getenv("WHMR_CHUNK_BODIES")) {
+    const int c = atoi(e);
+    if (c >= 8) h->chunk_bodies = c;
+  }
+
+  // kinematic tree depth
+  std::vector<int> parents(J), depth(J, 0);
+  int max_depth = 0;
+  for (int j = 0; j < J; ++j) {
+    parents[j] = (int)m->parents[j];
+    depth[j] = j == 0 ? 0 : depth[parents[j]] + 1;
+    max_depth = std::max(max_depth, depth[j]);
+  }
+  d.max_depth = max_depth;
+
+  // pre-contracted rest-joint regressor (fp64 accumulation): J = J_template + J_shapedirs . beta
+  std::vector<float> Jt((size_t)J * 3), Jd((size_t)J * 3 * std::max(NB, 1));
+  for (int j = 0; j < J; ++j) {
+    double t[3] = {0, 0, 0};
+    std::vector<double> dd((size_t)3 * std::max(NB, 1), 0.0);
+    const float* row = m->J_regressor + (size_t)j * V;
+    for (int v = 0; v < V; ++v) {
+      const double w = row[v];
+      if (w == 0.0) continue;
+      for (int c = 0; c < 3; ++c) {
+        t[c] += w * m->v_template[(size_t)v * 3 + c];
+        for (int k = 0; k < NB; ++k) dd[(size_t)c * NB + k] += w * m->shapedirs[((size_t)v * 3 + c) * NB + k];
+      }
+    }
+    for (int c = 0; c < 3; ++c) {
+      Jt[(size_t)j * 3 + c] = (float)t[c];
+      for (int k = 0; k < NB; ++k) Jd[((size_t)j * 3 + c) * NB + k] = (float)dd[(size_t)c * NB + k];
+    }
+  }
+
+  // planar padded per-vertex constants
+  const int VP = d.VP;
+  std::vector<float> vt((size_t)3 * VP, 0.f), sdp((size_t)3 * std::max(NB, 1) * VP, 0.f);
+  for (int v = 0; v < V; ++v)
+    for (int c = 0; c < 3; ++c) {
+      vt[(size_t)c * VP + v] = m->v_template[(size_t)v * 3 + c];
+      for (int k = 0; k < NB; ++k)
+        sdp[((size_t)c * NB + k) * VP + v] = m->shapedirs[((size_t)v * 3 + c) * NB + k];
+    }
+
+  // ELL skinning weights (joint order ascending, like the dense matmul's summation order).  The
+  // table width is rounded up to 4 or 8 (zero-weight padding) so the register-resident
+  // specialisations of the skinning kernel apply; wider models take the generic path.
+  int ell_k = 1;
+  for (int v = 0; v < V; ++v) {
+    int nnz = 0;
+    for (int j = 0; j < J; ++j) nnz += m->lbs_weights[(size_t)v * J + j] != 0.0f;
+    ell_k = std::max(ell_k, nnz);
+  }
+  if (ell_k <= 4) ell_k = 4; else if (ell_k <= 8) ell_k = 8;
+  d.ell_k = ell_k;
+  std::vector<int> eidx((size_t)ell_k * VP, 0);
+  std::vector<float> ew((size_t)ell_k * VP, 0.f);
+  for (int v = 0; v < V; ++v) {
+    int k = 0;
+    for (int j = 0; j < J; ++j) {
+      const float w = m->lbs_weights[(size_t)v * J + j];
+      if (w != 0.0f) { eidx[(size_t)k * VP + v] = j; ew[(size_t)k * VP + v] = w; ++k; }
+    }
+  }
+
+  // posedirs, planar padded [KP, NP]
+  std::vector<float> pp((size_t)d.KP * d.NP, 0.f);
+  for (int k = 0; k < nfeat; ++k) {
+    const float* src = m->posedirs + (size_t)k * V * 3;
+    float* dst = pp.data() + (size_t)k * d.NP;
+    for (int v = 0; v < V; ++v)
+      for (int c = 0; c < 3; ++c) dst[(size_t)c * VP + v] = src[(size_t)v * 3 + c];
+  }
+
+  cudaError_t e = cudaSuccess;
+  auto up = [&](auto& vec, auto** dst) { if (e == cudaSuccess) e = h->arena.upload(vec, dst); };
+  up(Jt, &d.J_template); up(Jd, &d.J_shapedirs); up(parents, &d.parents); up(depth, &d.depth);
+  up(vt, &d.v_template_p); up(sdp, &d.shapedirs_p); up(eidx, &d.ell_idx); up(ew, &d.ell_w);
+  up(pp, &d.posedirs_p);
+  if (e != cudaSuccess) {
+    delete h;
+    return set_error(WHMR_E_CUDA, "whmr_smpl_create: device upload failed: %s", cudaGetErrorString(e));
+  }
+  // tensor-core operand (hi|lo split of posedirs, K-major) + TMA descriptors
+  int rc = tc_plan_create(d, pp, h->arena, &h->tc);
+  if (rc != WHMR_OK) { delete h; return rc; }
+  h->gemm_mode = gemm_mode;
+  *out = h;
+  return WHMR_OK;
+}
+
+int whmr_smpl_destroy(whmr_smpl_t h) {
+  if (!h) return WHMR_OK;
+  cudaFree(h->st_betas); cudaFree(h->st_pose); cudaFree(h->st_verts); cudaFree(h->st_joints); cudaFree(h->st_ws);
+  delete h;
+  return WHMR_OK;
+}
+
+int whmr_smpl_set_gemm_mode(whmr_smpl_t h, int gemm_mode) {
+  WHMR_CHECK_ARG(h, "whmr_smpl_set_gemm_mode: null handle");
+  WHMR_CHECK_ARG(gemm_mode >= WHMR_GEMM_FP32_SIMT && gemm_mode <= WHMR_GEMM_TC_3XTF32, "bad gemm_mode %d", gemm_mode);
+  h->gemm_mode = gemm_mode;
+  return WHMR_OK;
+}
+
+int whmr_smpl_get_info(whmr_smpl_t h, int32_t* n_verts, int32_t* n_joints, int32_t* n_betas, int32_t* ell_width,
+                       int32_t* gemm_mode) {
+  WHMR_CHECK_ARG(h, "whmr_smpl_get_info: null handle");
+  if (n_verts) *n_verts = h->d.V;
+  if (n_joints) *n_joints = h->d.J;
+  if (n_betas) *n_betas = h->d.NB;
+  if (ell_width) *ell_width = h->d.ell_k;
+  if (gemm_mode) *gemm_mode = h->gemm_mode;
+  return WHMR_OK;
+}
+
+// ---- workspace carving --------------------------------------------------------------------
+static size_t carve(const whmr_smpl_s* h, int B, void* base, SmplWorkspace* ws) {
+  const SmplDevice& d = h->d;
+  const int chunk = std::min(B, h->chunk_bodies);
+  const int Bpad = ceil_div(std::max(B, 1), kTcBodyTile) * kTcBodyTile;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  const size_t oA = take((size_t)B * d.J * 12 * sizeof(float));
+  const size_t oPf = take((size_t)B * d.KP * sizeof(float));
+  const size_t oSplit = take((size_t)Bpad * 2 * d.KP * sizeof(float));   // sized for the tf32 variant
+  const size_t oOff = take((size_t)chunk * d.NP * sizeof(float));
+  if (ws) {
+    char* p = static_cast<char*>(base);
+    ws->A = reinterpret_cast<float*>(p + oA);
+    ws->pf = reinterpret_cast<float*>(p + oPf);
+    ws->pf_split = p + oSplit;
+    ws->offsets = reinterpret_cast<float*>(p + oOff);
+    ws->chunk = chunk;
+  }
+  return off;
+}
+
+size_t whmr_smpl_workspace_bytes(whmr_smpl_t h, int B) {
+  if (!h || B < 0) return 0;
+  return carve(h, B, nullptr, nullptr) + 1024;
+}
+
+static int get_ws(whmr_smpl_t h, int B, void* workspace, size_t bytes, SmplWorkspace* ws) {
+  WHMR_CHECK_ARG(h, "null SMPL handle");
+  WHMR_CHECK_ARG(B >= 0, "negative batch %d", B);
+  WHMR_CHECK_ARG(workspace || B == 0, "null workspace");
+  const size_t need = whmr_smpl_workspace_bytes(h, B);
+  if (bytes < need) return set_error(WHMR_E_WORKSPACE, "workspace too small: %zu < %zu bytes for B=%d", bytes, need, B);
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 1024));
+  carve(h, B, base, ws);
+  return WHMR_OK;
+}
+
+int whmr_smpl_stage_chain(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                          const float* transl, int B, float* joints, float* rel_transforms, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  SmplWorkspace ws;
+  int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(betas && pose, "whmr_smpl_stage_chain: null betas/pose");
+  const SmplDevice& d = h->d;
+  ChainParams p{};
+  p.betas = betas; p.pose = pose; p.transl = transl; p.pose_is_rotmat = pose_is_rotmat;
+  p.B = B; p.J = d.J; p.NB = d.NB; p.KP = d.KP; p.max_depth = d.max_depth;
+  p.J_template = d.J_template; p.J_shapedirs = d.J_shapedirs; p.parents = d.parents; p.depth = d.depth;
+  p.A = ws.A; p.joints = joints; p.A_user = rel_transforms;
+  p.pf = h->gemm_mode == WHMR_GEMM_FP32_SIMT ? ws.pf : nullptr;
+  p.pf_split = h->gemm_mode == WHMR_GEMM_TC_BF16X3 ? static_cast<__nv_bfloat16*>(ws.pf_split) : nullptr;
+  p.pf_tf32 = h->gemm_mode == WHMR_GEMM_TC_3XTF32 ? static_cast<float*>(ws.pf_split) : nullptr;
+  smpl_chain_kernel<<<ceil_div(B, kChainWarpsPerBlock), kChainWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p);
+  WHMR_LAUNCHED("smpl_chain_kernel");
+  return WHMR_OK;
+}
+
+// pose offsets for bodies [b0, b0+nb) -> ws.offsets[0..nb)
+static int launch_pose_blend(whmr_smpl_t h, const SmplWorkspace& ws, int B, int b0, int nb, cudaStream_t st) {
+  const SmplDevice& d = h->d;
+  if (h->gemm_mode == WHMR_GEMM_FP32_SIMT) {
+    dim3 grid(d.NP / kSimtBN, ceil_div(nb, kSimtBM));
+    pose_blend_simt_kernel<<<grid, 256, 0, st>>>(ws.pf + (size_t)b0 * d.KP, d.posedirs_p, ws.offsets, nb, d.KP, d.NP);
+    WHMR_LAUNCHED("pose_blend_simt_kernel");
+    return WHMR_OK;
+  }
+  return tc_pose_blend_launch(h->tc, d, h->gemm_mode, ws.pf_split, B, b0, nb, ws.offsets, st);
+}
+
+static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* betas, const float* transl, int b0,
+                       int nb, float* verts, cudaStream_t st) {
+  const SmplDevice& d = h->d;
+  SkinParams p{};
+  p.offsets = ws.offsets;
+  p.A = ws.A + (size_t)b0 * d.J * 12;
+  p.betas = betas + (size_t)b0 * d.NB;
+  p.transl = transl ? transl + (size_t)b0 * 3 : nullptr;
+  p.v_template_p = d.v_template_p; p.shapedirs_p = d.shapedirs_p; p.ell_idx = d.ell_idx; p.ell_w = d.ell_w;
+  p.verts = verts + (size_t)b0 * d.V * 3;
+  p.B = nb; p.V = d.V; p.VP = d.VP; p.NP = d.NP; p.J = d.J; p.NB = d.NB; p.ell_k = d.ell_k;
+  dim3 grid(d.VP / kVertTile, ceil_div(nb, kSkinBodies));
+  const size_t smem = skin_smem_bytes(d.J);
+  if (d.NB == 10 && d.ell_k == 4) skin_kernel<4, 10><<<grid, kVertTile, smem, st>>>(p);
+  else if (d.NB == 10 && d.ell_k == 8) skin_kernel<8, 10><<<grid, kVertTile, smem, st>>>(p);
+  else if (d.NB == 10) skin_kernel<0, 10><<<grid, kVertTile, smem, st>>>(p);
+  else skin_kernel<0, 0><<<grid, kVertTile, smem, st>>>(p);
+  WHMR_LAUNCHED("skin_kernel");
+  return WHMR_OK;
+}
+
+int whmr_smpl_stage_pose_blend(whmr_smpl_t h, int B, void* workspace, size_t workspace_bytes, void* stream) {
+  SmplWorkspace ws;
+  int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(B <= ws.chunk, "whmr_smpl_stage_pose_blend: B=%d exceeds the chunk size %d (stage calls are per chunk)", B,
+                 ws.chunk);
+  return launch_pose_blend(h, ws, B, 0, B, (cudaStream_t)stream);
+}
+
+int whmr_smpl_stage_skin(whmr_smpl_t h, const float* betas, int B, float* verts, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  SmplWorkspace ws;
+  int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(betas && verts, "whmr_smpl_stage_skin: null betas/verts");
+  WHMR_CHECK_ARG(B <= ws.chunk, "whmr_smpl_stage_skin: B=%d exceeds the chunk size %d", B, ws.chunk);
+  return launch_skin(h, ws, betas, nullptr, 0, B, verts, (cudaStream_t)stream);
+}
+
+int whmr_smpl_forward(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat, const float* transl,
+                      int B, float* verts, float* joints, float* rel_transforms, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  SmplWorkspace ws;
+  int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(betas && pose && verts, "whmr_smpl_forward: null betas/pose/verts");
+  rc = whmr_smpl_stage_chain(h, betas, pose, pose_is_rotmat, transl, B, joints, rel_transforms, workspace,
+                             workspace_bytes, stream);
+  if (rc) return rc;
+  // chunked so the [chunk, NP] pose-offset intermediate stays L2-resident between the two kernels
+  for (int b0 = 0; b0 < B; b0 += ws.chunk) {
+    const int nb = std::min(ws.chunk, B - b0);
+    rc = launch_pose_blend(h, ws, B, b0, nb, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = launch_skin(h, ws, betas, transl, b0, nb, verts, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return WHMR_OK;
+}
+
+int whmr_smpl_reserve(whmr_smpl_t h, int max_B) {
+  WHMR_CHECK_ARG(h && max_B > 0, "whmr_smpl_reserve: bad arguments");
+  if (max_B <= h->reserved_B) return WHMR_OK;
+  cudaFree(h->st_betas); cudaFree(h->st_pose); cudaFree(h->st_verts); cudaFree(h->st_joints); cudaFree(h->st_ws);
+  h->st_betas = h->st_pose = h->st_verts = h->st_joints = nullptr; h->st_ws = nullptr; h->reserved_B = 0;
+  const SmplDevice& d = h->d;
+  h->st_ws_bytes = whmr_smpl_workspace_bytes(h, max_B);
+  WHMR_CUDA(cudaMalloc(&h->st_betas, (size_t)max_B * std::max(d.NB, 1) * sizeof(float)));
+  WHMR_CUDA(cudaMalloc(&h->st_pose, (size_t)max_B * d.J * 9 * sizeof(float)));
+  WHMR_CUDA(cudaMalloc(&h->st_verts, (size_t)max_B * d.V * 3 * sizeof(float)));
+  WHMR_CUDA(cudaMalloc(&h->st_joints, (size_t)max_B * d.J * 3 * sizeof(float)));
+  WHMR_CUDA(cudaMalloc(&h->st_ws, h->st_ws_bytes));
+  h->reserved_B = max_B;
+  return WHMR_OK;
+}
+
+int whmr_smpl_forward_host(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat, int B,
+                           float* verts, float* joints, void* stream) {
+  WHMR_CHECK_ARG(h && betas && pose && verts, "whmr_smpl_forward_host: null argument");
+  WHMR_CHECK_ARG(B > 0, "whmr_smpl_forward_host: B must be positive");
+  if (B > h->reserved_B) {
+    int rc = whmr_smpl_reserve(h, B);
+    if (rc) return rc;
+  }
+  const SmplDevice& d = h->d;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pose_elems = (size_t)B * d.J * (pose_is_rotmat ? 9 : 3);
+  WHMR_CUDA(cudaMemcpyAsync(h->st_betas, betas, (size_t)B * d.NB * sizeof(float), cudaMemcpyHostToDevice, st));
+  WHMR_CUDA(cudaMemcpyAsync(h->st_pose, pose, pose_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = whmr_smpl_forward(h, h->st_betas, h->st_pose, pose_is_rotmat, nullptr, B, h->st_verts, h->st_joints, nullptr,
+                             h->st_ws, h->st_ws_bytes, stream);
+  if (rc) return rc;
+  WHMR_CUDA(cudaMemcpyAsync(verts, h->st_verts, (size_t)B * d.V * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (joints)
+    WHMR_CUDA(cudaMemcpyAsync(joints, h->st_joints, (size_t)B * d.J * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  WHMR_CUDA(cudaStreamSynchronize(st));
+  return WHMR_OK;
+}
+
+int whmr_batch_rodrigues(const float* aa, int n, float* R, void* stream) {
+  WHMR_CHECK_ARG(n >= 0, "whmr_batch_rodrigues: negative n");
+  if (n == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(aa && R, "whmr_batch_rodrigues: null pointer");
+  rodrigues_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(aa, n, R);
+  WHMR_LAUNCHED("rodrigues_kernel");
+  return WHMR_OK;
+}
+
+// =============================================================================================
+// read-out
+// =============================================================================================
+int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* row_ptr, const int32_t* col_idx,
+                        const float* vals, const int32_t* sub_row, int n_groups, const int32_t* group_sizes,
+                        whmr_readout_t* out) {
+  WHMR_CHECK_ARG(out && row_ptr && n_rows >= 0 && n_verts > 0 && n_joints >= 0, "whmr_readout_create: bad arguments");
+  WHMR_CHECK_ARG(n_groups >= 0 && (n_groups == 0 || group_sizes), "whmr_readout_create: bad groups");
+  std::vector<int> gpre(n_rows, 0), grows(n_rows, n_rows);
+  if (n_groups > 0) {
+    int r = 0;
+    for (int g = 0; g < n_groups; ++g) {
+      WHMR_CHECK_ARG(group_sizes[g] >= 0 && r + group_sizes[g] <= n_rows, "whmr_readout_create: group sizes exceed n_rows");
+      for (int k = 0; k < group_sizes[g]; ++k) { gpre[r + k] = r; grows[r + k] = group_sizes[g]; }
+      r += group_sizes[g];
+    }
+    WHMR_CHECK_ARG(r == n_rows, "whmr_readout_create: group sizes sum to %d, expected %d", r, n_rows);
+  }
+  const int nnz = row_ptr[n_rows];
+  WHMR_CHECK_ARG(row_ptr[0] == 0 && nnz >= 0, "whmr_readout_create: malformed row_ptr");
+  WHMR_CHECK_ARG(nnz == 0 || (col_idx && vals), "whmr_readout_create: null col_idx/vals");
+  bool needs_joints = false;
+  for (int r = 0; r < n_rows; ++r) WHMR_CHECK_ARG(row_ptr[r + 1] >= row_ptr[r], "whmr_readout_create: row_ptr not monotone");
+  for (int k = 0; k < nnz; ++k) {
+    WHMR_CHECK_ARG(col_idx[k] >= 0 && col_idx[k] < n_verts + n_joints, "whmr_readout_create: col_idx[%d]=%d out of range", k,
+                   col_idx[k]);
+    needs_joints |= col_idx[k] >= n_verts;
+  }
+  std::vector<int> rp(row_ptr, row_ptr + n_rows + 1), ci(col_idx, col_idx + nnz), sr, rs, rl;
+  std::vector<float> vv(vals, vals + nnz);
+  if (sub_row) {
+    sr.assign(sub_row, sub_row + n_rows);
+    for (int r = 0; r < n_rows; ++r) WHMR_CHECK_ARG(sr[r] < n_rows, "whmr_readout_create: sub_row[%d] out of range", r);
+  }
+  for (int r = 0; r < n_rows; ++r) {
+    int len = rp[r + 1] - rp[r];
+    if (sub_row && sr[r] >= 0) len = std::max(len, rp[sr[r] + 1] - rp[sr[r]]);
+    (len <= kShortRow ? rs : rl).push_back(r);
+  }
+  whmr_readout_s* h = new (std::nothrow) whmr_readout_s();
+  if (!h) return set_error(WHMR_E_INVALID, "whmr_readout_create: out of host memory");
+  h->R = n_rows; h->V = n_verts; h->J = n_joints; h->n_short = (int)rs.size(); h->n_long = (int)rl.size();
+  h->needs_joints = needs_joints;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](auto& vec, auto** dst) { if (e == cudaSuccess) e = h->arena.upload(vec, dst); };
+  up(rp, &h->row_ptr); up(ci, &h->col_idx); up(vv, &h->vals); up(rs, &h->rows_short); up(rl, &h->rows_long);
+  up(gpre, &h->grp_prefix); up(grows, &h->grp_rows);
+  if (sub_row) up(sr, &h->sub_row);
+  if (e != cudaSuccess) {
+    delete h;
+    return set_error(WHMR_E_CUDA, "whmr_readout_create: device upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return WHMR_OK;
+}
+
+int whmr_readout_destroy(whmr_readout_t r) { delete r; return WHMR_OK; }
+
+int whmr_readout_apply(whmr_readout_t r, const float* verts, const float* joints, int B, float* out, void* stream) {
+  WHMR_CHECK_ARG(r && B >= 0, "whmr_readout_apply: bad arguments");
+  if (B == 0 || r->R == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(verts && out, "whmr_readout_apply: null verts/out");
+  WHMR_CHECK_ARG(joints || !r->needs_joints, "whmr_readout_apply: table references chain joints but joints == NULL");
+  ReadoutParams p{};
+  p.row_ptr = r->row_ptr; p.col_idx = r->col_idx; p.vals = r->vals; p.sub_row = r->sub_row;
+  p.grp_prefix = r->grp_prefix; p.grp_rows = r->grp_rows;
+  p.R = r->R; p.V = r->V; p.J = r->J; p.B = B; p.verts = verts; p.joints = joints; p.out = out;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (r->n_short) {
+    p.rows = r->rows_short; p.n_rows_here = r->n_short;
+    const long long n = (long long)B * r->n_short;
+    readout_short_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    WHMR_LAUNCHED("readout_short_kernel");
+  }
+  if (r->n_long) {
+    p.rows = r->rows_long; p.n_rows_here = r->n_long;
+    const long long n = (long long)B * r->n_long * 32;
+    readout_long_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    WHMR_LAUNCHED("readout_long_kernel");
+  }
+  return WHMR_OK;
+}
+
+int whmr_gather_vertices(const float* verts, const int32_t* idx, int B, int V, int n_idx, float* out, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && V > 0 && n_idx >= 0, "whmr_gather_vertices: bad sizes");
+  if (B == 0 || n_idx == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(verts && idx && out, "whmr_gather_vertices: null pointer");
+  const long long n = (long long)B * n_idx * 3;
+  gather_vertices_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(verts, idx, B, V, n_idx, out);
+  WHMR_LAUNCHED("gather_vertices_kernel");
+  return WHMR_OK;
+}
+
+// =============================================================================================
+// projection
+// =============================================================================================
+#define WHMR_BN_GRID(B, N) (unsigned)(((long long)(B) * (N) + 255) / 256)
+
+int whmr_project_weak(const float* points, const float* cam, int B, int N, float focal, float img_w, float img_h,
+                      float* out, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_weak: negative size");
+  if (B == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(points && cam && out, "whmr_project_weak: null pointer");
+  project_weak_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(points, cam, B, N, focal, img_w, img_h, out);
+  WHMR_LAUNCHED("project_weak_kernel");
+  return WHMR_OK;
+}
+
+int whmr_perspective_projection(const float* points, const float* rotation, int rot_batch, const float* translation,
+                                const float* focal_dev, float focal_scalar, const float* camera_center,
+                                const float* distortion, int B, int N, int retain_z, float* out, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_perspective_projection: negative size");
+  if (B == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(points && camera_center && out, "whmr_perspective_projection: null pointer");
+  WHMR_CHECK_ARG(rot_batch == 0 || rot_batch == 1 || rot_batch == B,
+                 "whmr_perspective_projection: rotation batch %d must be 0, 1 or B=%d", rot_batch, B);
+  WHMR_CHECK_ARG((rot_batch == 0) == (rotation == nullptr), "whmr_perspective_projection: rotation/rot_batch mismatch");
+  perspective_projection_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(
+      points, rotation, rot_batch, translation, focal_dev, focal_scalar, camera_center, distortion, B, N, retain_z, out);
+  WHMR_LAUNCHED("perspective_projection_kernel");
+  return WHMR_OK;
+}
+
+int whmr_project_full(const float* points, const float* cam, const float* bbox_height, const float* center,
+                      const float* orig_shape, const float* Tz, int B, int N, float* kp_norm, float* kp_px,
+                      float* focal_out, float* cam_t_out, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_full: negative size");
+  if (B == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(points && cam && bbox_height && center && orig_shape && Tz, "whmr_project_full: null input");
+  project_full_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(points, cam, bbox_height, center, orig_shape,
+                                                                           Tz, B, N, kp_norm, kp_px, focal_out, cam_t_out);
+  WHMR_LAUNCHED("project_full_kernel");
+  return WHMR_OK;
+}
+
+int whmr_project_crop(const float* points, const float* cam, const float* center, const float* scale,
+                      const float* img_focal, const float* img_center, const float* distortion, int B, int N,
+                      float crop_size, float img_w, float img_h, float* full_out, float* crop_out, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_crop: negative size");
+  if (B == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(points && cam && center && scale && img_focal && img_center, "whmr_project_crop: null input");
+  project_crop_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(
+      points, cam, center, scale, img_focal, img_center, distortion, B, N, crop_size, img_w, img_h, full_out, crop_out);
+  WHMR_LAUNCHED("project_crop_kernel");
+  return WHMR_OK;
+}
+
+// =============================================================================================
+// sampling
+// =============================================================================================
+int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int W, const float* points, int N,
+                         float* out, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && H > 0 && W > 0, "whmr_sample_bilinear: bad sizes");
+  WHMR_CHECK_ARG(layout == WHMR_LAYOUT_NCHW || layout == WHMR_LAYOUT_NHWC, "whmr_sample_bilinear: bad layout %d", layout);
+  if (B == 0 || C == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(feat && points && out, "whmr_sample_bilinear: null pointer");
+  WHMR_CHECK_ARG((reinterpret_cast<size_t>(points) & 7) == 0, "whmr_sample_bilinear: points must be 8-byte aligned");
+  WHMR_CHECK_ARG((long long)C * N < (1ll << 31) && B < 65536, "whmr_sample_bilinear: C*N or B too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layout == WHMR_LAYOUT_NCHW) {
+    dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
+    sample_bilinear_nchw_kernel<<<grid, 256, 0, st>>>(feat, points, out, C, H, W, N);
+    WHMR_LAUNCHED("sample_bilinear_nchw_kernel");
+  } else {
+    dim3 grid(ceil_div(N, 32), ceil_div(C, 64), B);
+    sample_bilinear_nhwc_kernel<<<grid, 256, 0, st>>>(feat, points, out, C, H, W, N);
+    WHMR_LAUNCHED("sample_bilinear_nhwc_kernel");
+  }
+  return WHMR_OK;
+}
+
+int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int W, const float* p, const float* cam,
+                        int N, float focal, float img_w, float img_h, float* points2d_out, float* out, void* stream) {
+  WHMR_CHECK_ARG(points2d_out, "whmr_project_sample: points2d_out scratch [B,N,2] is required");
+  int rc = whmr_project_weak(p, cam, B, N, focal, img_w, img_h, points2d_out, stream);
+  if (rc) return rc;
+  return whmr_sample_bilinear(feat, layout, B, C, H, W, points2d_out, N, out, stream);
+}
+
+// =============================================================================================
+// metrics
+// =============================================================================================
+int whmr_joint_errors(const float* pred, const float* gt, int n, int J, float* mpjpe, float* pa_mpjpe, void* stream) {
+  WHMR_CHECK_ARG(n >= 0 && J > 0 && J <= kMaxEvalJoints, "whmr_joint_errors: bad sizes n=%d J=%d", n, J);
+  if (n == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(pred && gt, "whmr_joint_errors: null pointer");
+  joint_errors_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(pred, gt, n, J, mpjpe, pa_mpjpe);
+  WHMR_LAUNCHED("joint_errors_kernel");
+  return WHMR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,400 @@
+"""Tensor-level entry points over the C ABI + their `torch.library` custom-op registrations.
+
+Everything here takes/returns CUDA float32 torch tensors, launches on torch's current stream and
+allocates outputs / scratch through torch's caching allocator (so the C side never allocates).
+No function in this file has a CPU or PyTorch-eager fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+GEMM_FP32_SIMT, GEMM_TC_BF16X3, GEMM_TC_3XTF32 = 0, 1, 2
+GEMM_MODES = {"fp32_simt": 0, "bf16x3": 1, "3xtf32": 2}
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, name, dtype=torch.float32, align=4):
+    """contiguous CUDA tensor of `dtype`; copies only when the caller's view is not already so."""
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise _lib.WhmrError("%s is on %s: whmr_b200 ops run on CUDA only (no CPU fallback)" % (name, t.device))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % align:
+        t = t.clone()
+    return t
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------------
+# SMPL handle
+# ----------------------------------------------------------------------------------------------
+_HANDLES = {}
+
+
+class SmplHandle:
+    """Device-resident, pre-arranged SMPL model (whmr_smpl_create)."""
+
+    def __init__(self, v_template, shapedirs, posedirs, J_regressor, lbs_weights, parents,
+                 device, gemm_mode=GEMM_TC_BF16X3):
+        f = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32))  # noqa: E731
+        self._arrs = [f(v_template), f(shapedirs), f(posedirs), f(J_regressor), f(lbs_weights),
+                      np.ascontiguousarray(np.asarray(parents, dtype=np.int64))]
+        vt, sd, pd, jr, w, par = self._arrs
+        V, J = vt.shape[0], jr.shape[0]
+        NB = sd.shape[-1]
+        assert sd.shape == (V, 3, NB) and pd.shape == ((J - 1) * 9, V * 3) and w.shape == (V, J)
+        desc = _lib.SmplModelDesc(V, J, NB, vt.ctypes.data, sd.ctypes.data, pd.ctypes.data,
+                                  jr.ctypes.data, w.ctypes.data, par.ctypes.data)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.WhmrError("SMPL handle needs a CUDA device, got %s (no CPU fallback)" % (self.device,))
+        self.V, self.J, self.NB = V, J, NB
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().whmr_smpl_create(C.byref(desc), int(gemm_mode), C.byref(self._h)))
+        self.gemm_mode = int(gemm_mode)
+        self.id = id(self)
+        _HANDLES[self.id] = self
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().whmr_smpl_destroy(self._h)
+            self._h = C.c_void_p()
+        _HANDLES.pop(getattr(self, "id", None), None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_gemm_mode(self, mode):
+        check(_lib.lib().whmr_smpl_set_gemm_mode(self._h, int(mode)))
+        self.gemm_mode = int(mode)
+
+    def info(self):
+        v = [C.c_int32() for _ in range(5)]
+        check(_lib.lib().whmr_smpl_get_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("n_verts", "n_joints", "n_betas", "ell_width", "gemm_mode"), [x.value for x in v]))
+
+    def workspace(self, B):
+        n = int(_lib.lib().whmr_smpl_workspace_bytes(self._h, int(B)))
+        return torch.empty(n, dtype=torch.uint8, device=self.device), n
+
+    def forward(self, betas, pose, pose_is_rotmat, transl=None, want_transforms=False):
+        betas = _req(betas, "betas", align=16)
+        pose = _req(pose, "pose", align=16)
+        transl = _req(transl, "transl")
+        B = betas.shape[0]
+        exp = self.J * (9 if pose_is_rotmat else 3)
+        if pose.numel() != B * exp or betas.numel() != B * self.NB:
+            raise ValueError("smpl forward: betas %s / pose %s do not match B=%d, J=%d, n_betas=%d, rotmat=%s"
+                             % (tuple(betas.shape), tuple(pose.shape), B, self.J, self.NB, pose_is_rotmat))
+        verts = torch.empty(B, self.V, 3, dtype=torch.float32, device=self.device)
+        joints = torch.empty(B, self.J, 3, dtype=torch.float32, device=self.device)
+        A = torch.empty(B, self.J, 12, dtype=torch.float32, device=self.device) if want_transforms else None
+        ws, n = self.workspace(B)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().whmr_smpl_forward(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl),
+                                               B, _p(verts), _p(joints), _p(A), _p(ws), n, _stream()))
+        return verts, joints, A
+
+    # per-stage launches (bench.py per-kernel timing, tests)
+    def stage_chain(self, betas, pose, pose_is_rotmat, ws, n, joints=None, A=None, transl=None):
+        check(_lib.lib().whmr_smpl_stage_chain(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl),
+                                               betas.shape[0], _p(joints), _p(A), _p(ws), n, _stream()))
+
+    def stage_pose_blend(self, B, ws, n):
+        check(_lib.lib().whmr_smpl_stage_pose_blend(self._h, int(B), _p(ws), n, _stream()))
+
+    def stage_skin(self, betas, verts, ws, n):
+        check(_lib.lib().whmr_smpl_stage_skin(self._h, _p(betas), betas.shape[0], _p(verts), _p(ws), n, _stream()))
+
+    def forward_host(self, betas_h, pose_h, pose_is_rotmat, verts_h, joints_h=None):
+        """HOST (ideally pinned) tensors in and out; synchronous (bench.py e2e leg)."""
+        B = betas_h.shape[0]
+        with torch.cuda.device(self.device):
+            check(_lib.lib().whmr_smpl_forward_host(self._h, betas_h.data_ptr(), pose_h.data_ptr(),
+                                                    int(bool(pose_is_rotmat)), B, verts_h.data_ptr(),
+                                                    None if joints_h is None else joints_h.data_ptr(), _stream()))
+
+
+def batch_rodrigues(aa):
+    """smplx-variant Rodrigues (the one inside SMPL.forward). aa [n,3] -> [n,3,3]."""
+    aa = _req(aa, "rot_vecs")
+    n = aa.shape[0]
+    out = torch.empty(n, 3, 3, dtype=torch.float32, device=aa.device)
+    with torch.cuda.device(aa.device):
+        check(_lib.lib().whmr_batch_rodrigues(_p(aa), n, _p(out), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# read-out
+# ----------------------------------------------------------------------------------------------
+class Readout:
+    """Sparse linear read-out table (whmr_readout_create).  Built from named groups; each group
+    is a dense [R_g, n_src] matrix, a list of source indices (picks) or a scipy CSR matrix, over
+    the source set [V vertices ; J chain joints]."""
+
+    def __init__(self, groups, n_verts, n_joints, device, sub_rows=None):
+        import scipy.sparse as sp
+        self.names, self.sizes = [], []
+        mats = []
+        n_src = n_verts + n_joints
+        for name, g in groups:
+            if sp.issparse(g):
+                m = sp.csr_matrix(g, dtype=np.float64)
+                if m.shape[1] < n_src:
+                    m = sp.hstack([m, sp.csr_matrix((m.shape[0], n_src - m.shape[1]))]).tocsr()
+            else:
+                g = np.asarray(g)
+                if g.ndim == 1:   # index picks
+                    m = sp.csr_matrix((np.ones(len(g)), (np.arange(len(g)), g.astype(np.int64))),
+                                      shape=(len(g), n_src))
+                else:
+                    d = np.zeros((g.shape[0], n_src), dtype=np.float64)
+                    d[:, :g.shape[1]] = g
+                    m = sp.csr_matrix(d)
+            m.sort_indices()
+            mats.append(m)
+            self.names.append(name)
+            self.sizes.append(m.shape[0])
+        full = sp.vstack(mats).tocsr() if mats else sp.csr_matrix((0, n_src))
+        full.sort_indices()
+        self.R = full.shape[0]
+        self.csr = full
+        row_ptr = np.ascontiguousarray(full.indptr.astype(np.int32))
+        col = np.ascontiguousarray(full.indices.astype(np.int32))
+        vals = np.ascontiguousarray(full.data.astype(np.float32))
+        sub = None
+        if sub_rows is not None:
+            sub = np.ascontiguousarray(np.asarray(sub_rows, dtype=np.int32))
+            assert sub.shape[0] == self.R
+        gs = np.ascontiguousarray(np.asarray(self.sizes, dtype=np.int32))
+        self.device = torch.device(device)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().whmr_readout_create(self.R, n_verts, n_joints, row_ptr.ctypes.data,
+                                                 col.ctypes.data if len(col) else None,
+                                                 vals.ctypes.data if len(vals) else None,
+                                                 None if sub is None else sub.ctypes.data,
+                                                 len(gs), gs.ctypes.data if len(gs) else None, C.byref(self._h)))
+        self.V, self.J = n_verts, n_joints
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                _lib.lib().whmr_readout_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def apply(self, verts, joints=None):
+        """-> dict name -> contiguous [B, R_g, 3] tensor (all from one launch pair)."""
+        verts = _req(verts, "verts")
+        joints = _req(joints, "joints")
+        B = verts.shape[0]
+        out = torch.empty(B * self.R * 3, dtype=torch.float32, device=verts.device)
+        with torch.cuda.device(verts.device):
+            check(_lib.lib().whmr_readout_apply(self._h, _p(verts), _p(joints), B, _p(out), _stream()))
+        res, off = {}, 0
+        for name, r in zip(self.names, self.sizes):
+            res[name] = out[off:off + B * r * 3].view(B, r, 3)
+            off += B * r * 3
+        return res
+
+
+def gather_vertices(verts, idx):
+    verts = _req(verts, "verts")
+    idx = _req(idx, "idx", dtype=torch.int32)
+    B, V = verts.shape[0], verts.shape[1]
+    out = torch.empty(B, idx.numel(), 3, dtype=torch.float32, device=verts.device)
+    with torch.cuda.device(verts.device):
+        check(_lib.lib().whmr_gather_vertices(_p(verts), _p(idx), B, V, idx.numel(), _p(out), _stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# projection
+# ----------------------------------------------------------------------------------------------
+def project_weak(points, cam, focal, img_w, img_h):
+    points = _req(points, "points")
+    cam = _req(cam, "cam")
+    B, N = points.shape[0], points.shape[1]
+    out = torch.empty(B, N, 2, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().whmr_project_weak(_p(points), _p(cam), B, N, float(focal), float(img_w), float(img_h),
+                                           _p(out), _stream()))
+    return out
+
+
+def perspective_projection(points, rotation, translation, focal_length, camera_center, retain_z=False,
+                           distortion=None):
+    points = _req(points, "points")
+    B, N = points.shape[0], points.shape[1]
+    dev = points.device
+    rot_batch = 0
+    if rotation is not None:
+        rotation = _req(rotation, "rotation")
+        rot_batch = rotation.shape[0] if rotation.dim() == 3 else 1
+        if rot_batch not in (1, B):
+            raise ValueError("rotation batch %d must be 1 or %d" % (rot_batch, B))
+    translation = _req(translation, "translation")
+    distortion = _req(distortion, "distortion")
+    focal_dev, focal_scalar = None, 0.0
+    if torch.is_tensor(focal_length) and focal_length.numel() > 1:
+        focal_dev = _req(focal_length.reshape(-1), "focal_length")
+    else:
+        focal_scalar = float(focal_length)
+    if not torch.is_tensor(camera_center):
+        camera_center = torch.as_tensor(camera_center, dtype=torch.float32)
+    camera_center = _req(camera_center.to(dev), "camera_center")
+    out = torch.empty(B, N, 3 if retain_z else 2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().whmr_perspective_projection(_p(points), _p(rotation), rot_batch, _p(translation),
+                                                     _p(focal_dev), focal_scalar, _p(camera_center),
+                                                     _p(distortion), B, N, int(bool(retain_z)), _p(out),
+                                                     _stream()))
+    return out
+
+
+def project_full(points, cam, bbox_height, center, orig_shape, Tz, want_px=False):
+    """models/whmr.py:147-173 fused.  -> (kp_norm [B,N,2], focal [B], cam_t [B,3], kp_px or None)"""
+    points = _req(points, "points")
+    B, N = points.shape[0], points.shape[1]
+    dev = points.device
+    cam, bbox_height, center = _req(cam, "cam"), _req(bbox_height, "bbox_height"), _req(center, "center")
+    orig_shape, Tz = _req(orig_shape, "orig_shape"), _req(Tz, "Tz")
+    kp = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+    px = torch.empty(B, N, 2, dtype=torch.float32, device=dev) if want_px else None
+    focal = torch.empty(B, dtype=torch.float32, device=dev)
+    cam_t = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().whmr_project_full(_p(points), _p(cam), _p(bbox_height), _p(center), _p(orig_shape), _p(Tz),
+                                           B, N, _p(kp), _p(px), _p(focal), _p(cam_t), _stream()))
+    return kp, focal, cam_t, px
+
+
+def project_crop(points, cam, center, scale, img_focal, img_center, crop_size, img_w, img_h, distortion=None):
+    points = _req(points, "points")
+    B, N = points.shape[0], points.shape[1]
+    dev = points.device
+    args = [_req(x, n) for x, n in ((cam, "cam"), (center, "center"), (scale, "scale"),
+                                    (img_focal, "img_focal"), (img_center, "img_center"))]
+    distortion = _req(distortion, "distortion")
+    full = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+    crop = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().whmr_project_crop(_p(points), *[_p(a) for a in args], _p(distortion), B, N,
+                                           float(crop_size), float(img_w), float(img_h), _p(full), _p(crop), _stream()))
+    return full, crop
+
+
+# ----------------------------------------------------------------------------------------------
+# sampling
+# ----------------------------------------------------------------------------------------------
+def sample_bilinear(feat, points, layout=LAYOUT_NCHW):
+    """grid_sample(feat, points[:, :, None, :], align_corners=True)[..., 0]  ->  [B,C,N]"""
+    feat = _req(feat, "im_feat")
+    points = _req(points, "points", align=8)
+    if layout == LAYOUT_NCHW:
+        B, Cc, H, W = feat.shape
+    else:
+        B, H, W, Cc = feat.shape
+    N = points.shape[1]
+    if points.shape[0] != B or points.shape[-1] != 2:
+        raise ValueError("points %s do not match feature batch %d" % (tuple(points.shape), B))
+    out = torch.empty(B, Cc, N, dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        check(_lib.lib().whmr_sample_bilinear(_p(feat), int(layout), B, Cc, H, W, _p(points), N, _p(out), _stream()))
+    return out
+
+
+def project_sample(feat, p, cam, focal, img_w, img_h, layout=LAYOUT_NCHW):
+    """MAF_Extractor.forward's projection + sampling.  -> (point_feat [B,C,N], points2d [B,N,2])"""
+    feat = _req(feat, "im_feat")
+    p = _req(p, "p")
+    cam = _req(cam, "cam")
+    if layout == LAYOUT_NCHW:
+        B, Cc, H, W = feat.shape
+    else:
+        B, H, W, Cc = feat.shape
+    N = p.shape[1]
+    pts2d = torch.empty(B, N, 2, dtype=torch.float32, device=feat.device)
+    out = torch.empty(B, Cc, N, dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        check(_lib.lib().whmr_project_sample(_p(feat), int(layout), B, Cc, H, W, _p(p), _p(cam), N, float(focal),
+                                             float(img_w), float(img_h), _p(pts2d), _p(out), _stream()))
+    return out, pts2d
+
+
+# ----------------------------------------------------------------------------------------------
+# metrics
+# ----------------------------------------------------------------------------------------------
+def joint_errors(pred, gt, want_pa=True):
+    """-> (mpjpe [n], pa_mpjpe [n] or None) in the units of the inputs."""
+    pred, gt = _req(pred, "pred"), _req(gt, "gt")
+    n, J = pred.shape[0], pred.shape[1]
+    mp = torch.empty(n, dtype=torch.float32, device=pred.device)
+    pa = torch.empty(n, dtype=torch.float32, device=pred.device) if want_pa else None
+    with torch.cuda.device(pred.device):
+        check(_lib.lib().whmr_joint_errors(_p(pred), _p(gt), n, J, _p(mp), _p(pa), _stream()))
+    return mp, pa
+
+
+# ----------------------------------------------------------------------------------------------
+# torch.library custom ops (the "PyTorch custom op" boundary named by the north star).  The
+# module-level drop-ins (smpl.SMPL, geometry.projection, maf_extractor.MAF_Extractor) call these,
+# so the ops show up by name in profiler traces and can be captured in CUDA graphs.
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op("whmr::smpl_lbs", mutates_args=(), device_types="cuda")
+def smpl_lbs(handle: int, betas: torch.Tensor, pose: torch.Tensor, pose_is_rotmat: bool) -> \
+        tuple[torch.Tensor, torch.Tensor]:
+    v, j, _ = _HANDLES[handle].forward(betas, pose, pose_is_rotmat)
+    return v, j
+
+
+@smpl_lbs.register_fake
+def _(handle, betas, pose, pose_is_rotmat):
+    h = _HANDLES[handle]
+    B = betas.shape[0]
+    return betas.new_empty(B, h.V, 3), betas.new_empty(B, h.J, 3)
+
+
+@torch.library.custom_op("whmr::sample_bilinear", mutates_args=(), device_types="cuda")
+def sample_bilinear_op(feat: torch.Tensor, points: torch.Tensor, layout: int) -> torch.Tensor:
+    return sample_bilinear(feat, points, layout)
+
+
+@sample_bilinear_op.register_fake
+def _(feat, points, layout):
+    Cc = feat.shape[1] if layout == LAYOUT_NCHW else feat.shape[3]
+    return feat.new_empty(feat.shape[0], Cc, points.shape[1])
+
+
+@torch.library.custom_op("whmr::project_weak", mutates_args=(), device_types="cuda")
+def project_weak_op(points: torch.Tensor, cam: torch.Tensor, focal: float, img_w: float, img_h: float) -> torch.Tensor:
+    return project_weak(points, cam, focal, img_w, img_h)
+
+
+@project_weak_op.register_fake
+def _(points, cam, focal, img_w, img_h):
+    return points.new_empty(points.shape[0], points.shape[1], 2)
