@@ -126,7 +126,7 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
   d.KP = std::max(16, ceil_div(nfeat, 16) * 16);
   if (const char* e = getenv("WHMR_CHUNK_BODIES")) {
     const int c = atoi(e);
-    if (c >= 8) h->chunk_bodies = c;
+    if (c >= 8) h->chunk_bodies = std::max(kTcBodyTile, c / kTcBodyTile * kTcBodyTile);   // whole 256-body tiles
   }
 
   // kinematic tree depth
