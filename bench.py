@@ -1,0 +1,469 @@
+#!/usr/bin/env python
+"""bench.py -- W-HMR regressor-loop hot path on N B200s (BASELINE.json configs[1]).
+
+One step = one pass of the body-model hot path of WHMR.forward's loop over a batch of B=256 bodies
+per GPU (whmr_b200.loop.RegressorLoop.step): init SMPL, 3 x {MAF sampling, SMPL, read-outs, weak +
+predicted-focal projection}, global SMPL -- 5 SMPL forwards, 3 samplings, 7 projections per body.
+metric = SMPL bodies/s (batch rows through the whole loop), whole job over all N GPUs.
+
+  value     : inputs resident in HBM, the step replayed as one CUDA graph, CUDA-event timed.
+  e2e       : through the host-buffer path -- every step copies ALL step inputs (feature maps 4.2 GB
+              + parameters) from pinned host memory, runs the step, and copies the results the
+              reference's caller reads (demo/tester.py:164-165) back to pinned host memory.
+  roofline  : dominant kernel of the step, timed inside the timed region with external CUDA events
+              recorded as graph nodes; algorithmic bytes/flops per DESIGN.md.
+  cpu_baseline : the oracle (CPU restatement of the reference's path, torch CPU kernels, all host
+              threads) on a bounded sample of the same workload (rank 0, N=1 only).
+`--impl reference` times that CPU path alone, same metric/config.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "smpl_bodies_per_sec"
+UNIT = "bodies/s"
+V, J, NBETA, KPOSE = 6890, 24, 10, 207
+VP = 6912
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.stop_flag, self.region = index, period, [], False, "idle"
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((self.region, sm, int(r)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvml unavailable: %s" % getattr(self, "err", "")}
+        load = [s for s in self.samples if s[0] != "idle"]
+        timed = [s for s in load if s[0] == "timed"] or load
+        sm = sorted(s[1] for s in timed)
+        reasons = set()
+        for s in load:
+            for bit, name in self.REASONS.items():
+                if s[2] & bit:
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm, "reasons": sorted(reasons),
+                "samples_under_load": len(load), "samples_timed": len([s for s in load if s[0] == "timed"])}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes / flops per launch (DESIGN.md section "Kernels")
+# ------------------------------------------------------------------------------------------------
+def algorithmic(kind, B, ctx):
+    C = 256
+    if kind == "chain":
+        return {"bytes": B * (4 * (NBETA + 216) + 4 * (J * 12 + J * 3) + ctx["pf_bytes"]), "bound": "hbm"}
+    if kind == "pose_blend":
+        return {"flops": B * 2.0 * KPOSE * 3 * V, "bound": "tensor"}
+    if kind == "skin":
+        return {"bytes": B * (4 * 3 * VP + 4 * 3 * V + 4 * J * 12 + 4 * NBETA), "bound": "hbm"}
+    if kind == "readout":
+        return {"bytes": B * 12 * (ctx["readout_nnz"] + ctx["readout_rows"]), "bound": "hbm"}
+    if kind.startswith("sample_l"):
+        lvl = int(kind[-1])
+        H, W = ctx["levels"][lvl]
+        N = 63 if lvl == 0 else 67
+        return {"bytes": B * (4 * C * (min(4 * N, H * W) + N) + 8 * N), "bound": "hbm"}
+    if kind == "project_weak":
+        return {"bytes": B * (4 * 5 * 49 + 12), "bound": "hbm"}
+    if kind == "project_markers":
+        return {"bytes": B * (4 * 5 * 67 + 12), "bound": "hbm"}
+    if kind == "project_full":
+        return {"bytes": B * (4 * 5 * 49 + 36 + 16), "bound": "hbm"}
+    return {"bytes": 0, "bound": "hbm"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import whmr_b200.synthetic as syn
+    from whmr_b200 import _lib, ops
+    from whmr_b200.loop import RegressorLoop, make_loop_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    gemm_mode = args.gemm_mode
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    model = syn.make_smpl_model(seed=0, weights="random")
+    loop = RegressorLoop(model, dev, backbone=args.backbone, gemm_mode=gemm_mode)
+    feats, params, bbox = make_loop_inputs(B, dev, backbone=args.backbone, seed=1, rank=rank)
+
+    # ---- parity gate on this rank's own data before anything is timed (16 bodies vs the oracle) ----
+    parity = None
+    if rank == 0 and not args.skip_parity:
+        from oracle.loop_oracle import LoopOracle, to_cpu_inputs
+        n = 16
+        sub = ([f[:n].contiguous() for f in feats], [{k: v[:n].contiguous() for k, v in q.items()} for q in params],
+               {k: v[:n].contiguous() for k, v in bbox.items()})
+        got = loop.step(*sub)
+        torch.cuda.synchronize()
+        ref = LoopOracle(model, args.backbone).step(*to_cpu_inputs(*sub))
+        e_v = float((got["verts"].cpu() - ref["verts"]).abs().max())
+        e_g = float((got["global_verts"].cpu() - ref["global_verts"]).abs().max())
+        e_k = float(((got["kp_2d_w"].cpu() - ref["kp_2d_w"]).abs() * (sub[2]["orig_shape"].cpu()[:, [1, 0]] / 2).unsqueeze(1)).max())
+        e_f = max(float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(got["point_feats"], ref["point_feats"]))
+        parity = {"verts_m": max(e_v, e_g), "kp2d_px": e_k, "sampled_rel": e_f, "bodies": n}
+        if not (parity["verts_m"] <= 1e-5 and e_f <= 1e-4 and e_k <= 4e-3):
+            raise SystemExit("bench.py: parity gate failed: %s" % parity)
+
+    # ---- device-resident timing: the step as one CUDA graph ----------------------------------------
+    n0 = _lib.launch_count()
+    loop.step(feats, params, bbox)
+    launches_per_step = _lib.launch_count() - n0
+    graph, outs = loop.capture(feats, params, bbox)
+    for _ in range(W):
+        graph.replay()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.region = "timed"
+    ev0.record()
+    for _ in range(K):
+        graph.replay()
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.region = "load"
+    if world > 1:
+        dist.barrier()
+    ms_total = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total) / K
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- per-kernel timing inside the (instrumented) graph, same K steps ---------------------------
+    marks = []
+
+    def probe(name):
+        e = torch.cuda.Event(enable_timing=True, external=True)
+        if name == "pre_smpl":
+            a = torch.cuda.Event(enable_timing=True, external=True)
+            b = torch.cuda.Event(enable_timing=True, external=True)
+            h.set_probe_events(a, b)
+            e.record()
+            marks.append(("start", e))
+            marks.append(("chain", a))
+            marks.append(("pose_blend", b))
+        else:
+            e.record()
+            marks.append((name, e))
+
+    h, _ = loop.smpl._state(dev)
+    kern = {}
+    if rank == 0:
+        loop.head.probe = probe
+        marks.clear()
+        igraph, _ = loop.capture(feats, params, bbox, warmup=0)
+        loop.head.probe = None
+        h.set_probe_events(None, None)
+        mk = list(marks)
+        for _ in range(3):
+            igraph.replay()
+        torch.cuda.synchronize()
+        acc = {}
+        reps = min(K, 200)
+        for _ in range(reps):
+            igraph.replay()
+            torch.cuda.synchronize()
+            for (n_prev, e_prev), (name, e) in zip(mk[:-1], mk[1:]):
+                if name == "start":
+                    continue
+                t = e_prev.elapsed_time(e)
+                a = acc.setdefault(name, [0.0, 0])
+                a[0] += t
+                a[1] += 1
+        ro = loop.head._readout(dev, loop.with_h36m)
+        ctx = {"pf_bytes": 2 * 208 * (2 if loop.smpl.gemm_mode == ops.GEMM_TC_BF16X3 else 4),
+               "readout_nnz": int(ro.csr.nnz), "readout_rows": int(ro.R), "levels": loop.levels}
+        for name, (tot, cnt) in acc.items():
+            per_launch_ms = tot / cnt
+            launches = cnt // reps
+            a = algorithmic(name, B, ctx)
+            k = {"launches_per_step": launches, "ms_per_launch": per_launch_ms, "ms_per_step": per_launch_ms * launches,
+                 "bound": a["bound"]}
+            if a["bound"] == "tensor":
+                mode_peak = peaks["bf16_tflops_sustained"] / 3.0 if loop.smpl.gemm_mode == ops.GEMM_TC_BF16X3 \
+                    else peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+                k.update(achieved=a["flops"] / (per_launch_ms * 1e-3) / 1e12, peak=mode_peak, unit="TFLOP/s")
+            else:
+                k.update(achieved=a["bytes"] / (per_launch_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
+            k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
+            kern[name] = k
+
+    # ---- end to end through host buffers ------------------------------------------------------------
+    e2e = None
+    e2e_resident = None
+    if not args.skip_e2e:
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)  # noqa: E731
+        h_feats = [pin(f) for f in feats]
+        h_params = [{k: pin(v) for k, v in q.items()} for q in params]
+        h_bbox = {k: pin(v) for k, v in bbox.items()}
+        out_keys = ["verts", "global_verts", "pred_cam_t", "focal_length", "kp_2d_w", "global_kp_3d"]
+        h_out = {k: torch.empty(outs[k].shape, dtype=outs[k].dtype, pin_memory=True) for k in out_keys}
+        h2d_small = sum(v.numel() * 4 for q in h_params for v in q.values()) + sum(v.numel() * 4 for v in h_bbox.values())
+        h2d_feat = sum(f.numel() * 4 for f in h_feats)
+        d2h = sum(v.numel() * 4 for v in h_out.values())
+
+        def e2e_step(with_feats):
+            if with_feats:
+                for d, s in zip(feats, h_feats):
+                    d.copy_(s, non_blocking=True)
+            for dq, sq in zip(params, h_params):
+                for k in dq:
+                    dq[k].copy_(sq[k], non_blocking=True)
+            for k in bbox:
+                bbox[k].copy_(h_bbox[k], non_blocking=True)
+            graph.replay()
+            for k in out_keys:
+                h_out[k].copy_(outs[k], non_blocking=True)
+
+        def time_e2e(with_feats, steps):
+            for _ in range(2):
+                e2e_step(with_feats)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                e2e_step(with_feats)
+                torch.cuda.current_stream().synchronize()    # the caller reads the result every step
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t) / steps
+
+        ke = max(3, min(K, args.e2e_steps))
+        ms_e2e = time_e2e(True, ke)
+        ms_e2e_res = time_e2e(False, max(ke, min(K, 200)))
+        e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_small + h2d_feat,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": ke,
+               "note": "ALL step inputs from pinned host memory, incl. the 3 feature-map levels (in the reference "
+                       "these are produced on the device by the backbone and never cross PCIe)"}
+        e2e_resident = {"value": world * B / (ms_e2e_res * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_small,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_res,
+                        "note": "same, feature maps device-resident as in the reference (backbone output)"}
+    sampler.region = "idle"
+
+    # ---- kernel quality at scale: one SMPL forward at 16k bodies (BASELINE configs[2]) -------------
+    scale = None
+    if rank == 0 and not args.skip_sweep:
+        scale = smpl_sweep(loop, dev, peaks, [4096, 16384] if not args.quick else [4096])
+
+    # ---- CPU baseline (oracle on host cores), rank 0, N == 1 ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_loop_baseline(args.backbone, args.cpu_sample, reps=3)
+
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    clocks = sampler.summary()
+
+    if rank == 0:
+        dom = max(kern.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if kern else None
+        roof = None
+        if dom:
+            k = kern[dom]
+            roof = {"kernel": dom, "bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"], "unit": k["unit"],
+                    "frac": k["frac"], "traffic": None, "peak_source": peaks["source"] + (
+                        " (sustained bf16 / 3 MMAs per product)" if k["bound"] == "tensor" else " hbm copy"),
+                    "ms_per_launch": k["ms_per_launch"], "launches_per_step": k["launches_per_step"],
+                    "share_of_step": k["ms_per_step"] / sum(x["ms_per_step"] for x in kern.values())}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "whmr_regressor_loop_B256 (BASELINE configs[1]): init SMPL + 3 x (MAF sampling + SMPL + "
+                                   "read-outs + weak/full projection) + global SMPL; %s feature levels %s x 256 ch"
+                                   % (args.backbone, list(loop.levels)),
+                       "batch_per_gpu": B, "global_batch": B * world, "smpl_forwards_per_step": 5,
+                       "samplings_per_step": 3, "pose_blend_arithmetic": {0: "fp32_simt", 1: "tcgen05 bf16x3", 2: "tcgen05 3xtf32"}[loop.smpl.gemm_mode],
+                       "parallelism": "dp%d (bodies sharded by rank, no data-path collective)" % world,
+                       "l2": "inputs larger than L2: feature maps 4.2 GB/step/GPU + ~0.2 GB of outputs vs 126 MB L2",
+                       "launch": "one CUDA graph replay per step"},
+            "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident,
+            "gpu_launches": int(launches_per_step) * K, "gpu_launches_per_step": int(launches_per_step),
+            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "smpl_at_scale": scale, "parity": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def smpl_sweep(loop, dev, peaks, sizes):
+    """SMPL forward alone at large batch: per-kernel CUDA-event times via the stage entry points."""
+    import torch
+    import whmr_b200.synthetic as syn
+    from whmr_b200 import ops
+    h, _ = loop.smpl._state(dev)
+    res = {}
+    for Bs in sizes:
+        b = syn.make_bodies(Bs, seed=5)
+        betas = torch.from_numpy(b["betas"]).to(dev)
+        rot = torch.from_numpy(b["rotmat"]).to(dev)
+        for _ in range(3):
+            h.forward(betas, rot, True)
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 10
+        e[0].record()
+        for _ in range(reps):
+            h.forward(betas, rot, True)
+        e[1].record()
+        torch.cuda.synchronize()
+        ms = e[0].elapsed_time(e[1]) / reps
+        bytes_alg = Bs * (4 * (NBETA + 216) + 4 * (3 * V + 3 * J))
+        gb = bytes_alg / (ms * 1e-3) / 1e9
+        mode = loop.smpl.gemm_mode
+        tpeak = peaks["bf16_tflops_sustained"] / (3.0 if mode == ops.GEMM_TC_BF16X3 else 6.0)
+        tf = Bs * 2.0 * KPOSE * 3 * V / (ms * 1e-3) / 1e12
+        res[str(Bs)] = {"ms": ms, "bodies_per_s": Bs / (ms * 1e-3), "hbm_GBs_algorithmic": gb,
+                        "hbm_frac": gb / peaks["hbm_gbs"], "pose_blend_TFLOPs_algorithmic_if_alone": tf,
+                        "tensor_frac_lower_bound": tf / tpeak}
+    return res
+
+
+def cpu_loop_baseline(backbone, n_bodies, reps=3):
+    import torch
+    import whmr_b200.synthetic as syn
+    from oracle.loop_oracle import LoopOracle, make_cpu_inputs
+    model = syn.make_smpl_model(seed=0, weights="random")
+    orc = LoopOracle(model, backbone)
+    f, p, bb = make_cpu_inputs(n_bodies, backbone)
+    orc.step(f, p, bb)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.step(f, p, bb)
+        ts.append(time.perf_counter() - t0)
+    t = sorted(ts)[len(ts) // 2]
+    return {"value": n_bodies / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d bodies of the same loop workload (same generators), median of %d passes, %.2f s/pass; "
+                      "oracle = CPU restatement of the reference path (dense SMPL + dense Dmap matmuls + grid_sample), "
+                      "torch %s CPU kernels, os.cpu_count()=%d" % (n_bodies, reps, t, torch.__version__, os.cpu_count())}
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path = the oracle port (smplx / pare / the SMPL
+    weights are not installable offline, so the reference itself cannot run)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import whmr_b200.synthetic as syn
+    from oracle.loop_oracle import LoopOracle, make_cpu_inputs
+    n = args.cpu_sample
+    K, W = args.steps if args.steps_given else 10, max(1, min(args.warmup, 3))
+    K = min(K, 40)
+    model = syn.make_smpl_model(seed=0, weights="random")
+    orc = LoopOracle(model, args.backbone)
+    f, p, bb = make_cpu_inputs(n, args.backbone)
+    for _ in range(W):
+        orc.step(f, p, bb)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        orc.step(f, p, bb)
+    t = (time.perf_counter() - t0) / K
+    v = n / t
+    sample = ("each step = one loop pass over a %d-body sample of the B=256 workload on the host CPU "
+              "(torch %s, %d threads)" % (n, torch.__version__, torch.get_num_threads()))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": K, "warmup": W, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "whmr_regressor_loop_B256 (BASELINE configs[1]), CPU arm on a %d-body sample" % n,
+                       "batch_per_gpu": args.batch, "parallelism": "cpu"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--backbone", default="vitpose", choices=["vitpose", "res50"])
+    ap.add_argument("--gemm-mode", default=None, choices=[None, "fp32_simt", "bf16x3", "3xtf32"])
+    ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-sweep", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 1000
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

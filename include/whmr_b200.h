@@ -100,6 +100,12 @@ int whmr_smpl_stage_pose_blend(whmr_smpl_t h, int B, void* workspace, size_t wor
 int whmr_smpl_stage_skin(whmr_smpl_t h, const float* betas, int B, float* verts, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Profiling hook: two cudaEvent_t (passed as void*, NULL clears) that the next whmr_smpl_forward
+ * calls record on their stream right after the chain kernel and right after the (last chunk's)
+ * pose-blend kernel, with cudaEventRecordExternal so they become event-record nodes when the call is
+ * being captured into a CUDA graph.  bench.py uses them to time each kernel inside the timed region. */
+int whmr_smpl_set_probe_events(whmr_smpl_t h, void* after_chain, void* after_pose_blend);
+
 /* Host-buffer variant (bench.py `e2e`): pinned or pageable HOST pointers in and out; H2D copies,
  * the three kernels and the D2H copies are enqueued on `stream` and the call returns after
  * cudaStreamSynchronize.  Device staging comes from whmr_smpl_reserve (grow-only, inside h). */
@@ -170,10 +176,11 @@ int whmr_project_crop(const float* points, const float* cam, const float* center
 /* ------------------------------------------------------------------------------------------
  * Mesh-aligned feature sampling: models/maf_extractor.py:103-124 (the grid_sample inside
  * MAF_Extractor.sampling): bilinear, zero padding, align_corners=True, points[...,0] <-> W.
- *   feat [B,C,H,W] (NCHW) or [B,H,W,C] (NHWC); points [B,N,2]; out [B,C,N].
+ *   feat [B,C,H,W] (NCHW) or [B,H,W,C] (NHWC); points [B,N,2], or [N,2] shared by every body when
+ *   points_shared != 0 (the iteration-0 grid of models/whmr.py:338-347,596); out [B,C,N].
  * ------------------------------------------------------------------------------------------ */
 int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int W,
-                         const float* points, int N, float* out, void* stream);
+                         const float* points, int points_shared, int N, float* out, void* stream);
 /* MAF_Extractor.forward (models/maf_extractor.py:126-143) = projection (weak) + sampling, fused:
  * p [B,N,3], cam [B,3]; also writes the 2-D points if points2d_out != NULL. */
 int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int W, const float* p,

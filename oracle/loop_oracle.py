@@ -1,0 +1,84 @@
+"""CPU restatement of the body-model part of WHMR.forward's regressor loop -- TEST INFRASTRUCTURE
+(also the `cpu_baseline` / `--impl reference` arm of bench.py: it executes the path the way the
+reference does on its CPU code path -- dense SMPL matmuls, dense [1723,6890] / [431,1723] Dmap
+matmuls, expanded H36M regressor, F.grid_sample -- with torch CPU kernels on all host threads).
+
+Follows models/whmr.py:550-651 with the MLPs factored out exactly as whmr_b200.loop.RegressorLoop
+does: per iteration the regressor outputs (rotmat, betas, cam) are inputs."""
+import numpy as np
+import torch
+
+from . import geometry_oracle as G
+from .sampling_oracle import grid_sample_points
+from .smpl_oracle import SMPLOracle, regressor_readouts
+
+
+class LoopOracle:
+    def __init__(self, model, backbone='vitpose', with_h36m=True):
+        import importlib
+        syn = importlib.import_module('whmr_b200.synthetic')
+        self.model = model
+        self.smpl = SMPLOracle(model, torch.float32)
+        self.grid = torch.from_numpy(syn.grid_points(backbone))
+        self.with_h36m = with_h36m
+
+    def regressor_outputs(self, p, bbox=None):
+        """Regressor.forward / forward_init after the MLP (models/whmr.py:128-209, 225-269)."""
+        o = self.smpl(p['betas'], p['rotmat'][:, 1:], p['rotmat'][:, :1], pose2rot=False)
+        verts, joints = o['vertices'], o['joints']
+        r = regressor_readouts(self.model, verts)
+        out = {'verts': verts, 'joints49': joints, 'kp_2d': G.projection(joints, p['cam']),
+               'sub_verts': r['sub_verts'], 'temp_verts': r['temp_verts'], 'markers': r['markers'],
+               'smpl_kp_3d': r['smpl_kp_3d'], 'kp_3d': r['kp_3d_h36m'] if self.with_h36m else joints}
+        if bbox is not None:
+            kpn, focal, cam_t, _ = G.full_projection(joints, p['cam'], bbox['bbox_height'], bbox['center'],
+                                                     bbox['orig_shape'], bbox['Tz'])
+            out.update(kp_2d_w=kpn, focal_length=focal, pred_cam_t=cam_t)
+        return out
+
+    def step(self, feats, params, bbox):
+        B = feats[0].shape[0]
+        out = self.regressor_outputs(params[0])
+        point_feats = []
+        for it in range(3):
+            if it == 0:
+                pts = self.grid.unsqueeze(0).expand(B, -1, -1)
+            else:
+                pts = G.projection(out['markers'], params[it]['cam'])
+            point_feats.append(grid_sample_points(feats[it], pts))
+            out = self.regressor_outputs(params[it + 1], bbox)
+        g = self.smpl(params[4]['betas'], params[4]['rotmat'][:, 1:], params[4]['rotmat'][:, :1], pose2rot=False)
+        res = dict(out)
+        res['point_feats'] = point_feats
+        res['global_verts'] = g['vertices']
+        if self.with_h36m:
+            res['global_kp_3d'] = regressor_readouts(self.model, g['vertices'])['kp_3d_h36m']
+        else:
+            res['global_kp_3d'] = g['joints']
+        return res
+
+
+def to_cpu_inputs(feats, params, bbox, n=None):
+    """first n bodies of device inputs -> CPU tensors"""
+    s = slice(0, n)
+    f = [x[s].detach().cpu() for x in feats]
+    p = [{k: v[s].detach().cpu() for k, v in q.items()} for q in params]
+    b = {k: v[s].detach().cpu() for k, v in bbox.items()}
+    return f, p, b
+
+
+def make_cpu_inputs(B, backbone='vitpose', seed=1, channels=256):
+    """CPU-only twin of whmr_b200.loop.make_loop_inputs (same parameter streams; feature maps from a
+    CPU generator) for boxes without a GPU (`bench.py --impl reference`)."""
+    import importlib
+    syn = importlib.import_module('whmr_b200.synthetic')
+    levels = ((32, 24), (64, 48), (128, 96)) if backbone == 'vitpose' else ((14, 14), (28, 28), (56, 56))
+    g = torch.Generator().manual_seed(1000 * seed)
+    feats = [torch.randn(B, channels, h, w, generator=g) for h, w in levels]
+    base = syn.make_bodies(B, seed=seed)
+    params = []
+    for i in range(5):
+        b = syn.make_bodies(B, seed=seed + 17 * (i + 1), with_real_rows=(i == 0))
+        params.append({k: torch.from_numpy(b[k]) for k in ('rotmat', 'betas', 'cam')})
+    bbox = {k: torch.from_numpy(np.ascontiguousarray(base[k])) for k in ('bbox_height', 'center', 'orig_shape', 'Tz')}
+    return feats, params, bbox

@@ -67,6 +67,7 @@ SIGNATURES = {
     "whmr_smpl_stage_chain": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "whmr_smpl_stage_pose_blend": (C.c_int, [_vp, _i, _vp, _sz, _vp]),
     "whmr_smpl_stage_skin": (C.c_int, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "whmr_smpl_set_probe_events": (C.c_int, [_vp, _vp, _vp]),
     "whmr_smpl_reserve": (C.c_int, [_vp, _i]),
     "whmr_smpl_forward_host": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "whmr_batch_rodrigues": (C.c_int, [_vp, _i, _vp, _vp]),
@@ -77,7 +78,7 @@ SIGNATURES = {
     "whmr_perspective_projection": (C.c_int, [_vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "whmr_project_full": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "whmr_project_crop": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
-    "whmr_sample_bilinear": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    "whmr_sample_bilinear": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "whmr_project_sample": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _f, _vp, _vp, _vp]),
     "whmr_gather_vertices": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "whmr_joint_errors": (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

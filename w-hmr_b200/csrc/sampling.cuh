@@ -48,13 +48,13 @@ constexpr int kSampleItems = 4;   // flat outputs per thread (independent gather
 
 // grid = (ceil(C*N / (256*kSampleItems)), B)
 __global__ void __launch_bounds__(256)
-sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ points,
+sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
                             float* __restrict__ out, int C, int H, int W, int N) {
   const int b = blockIdx.y;
   const int total = C * N;
   const size_t plane = (size_t)H * W;
   const float* fb = feat + (size_t)b * C * plane;
-  const float* pb = points + (size_t)b * N * 2;
+  const float* pb = points + (size_t)b * pts_bstride;
   float* ob = out + (size_t)b * total;
   const int base = blockIdx.x * (256 * kSampleItems) + threadIdx.x;
 
@@ -87,7 +87,7 @@ sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restr
 
 // NHWC input: grid = (ceil(N/32), ceil(C/64), B), block 256 (8 warps x 4 points each)
 __global__ void __launch_bounds__(256)
-sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ points,
+sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
                             float* __restrict__ out, int C, int H, int W, int N) {
   __shared__ float tile[64][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
@@ -98,7 +98,7 @@ sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restr
     const int pt = warp * 4 + q;
     const int n = n0 + pt;
     if (n < N) {
-      const float2 g = *reinterpret_cast<const float2*>(points + ((size_t)b * N + n) * 2);
+      const float2 g = *reinterpret_cast<const float2*>(points + (size_t)b * pts_bstride + (size_t)n * 2);
       const Taps t = make_taps(g.x, g.y, H, W);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {

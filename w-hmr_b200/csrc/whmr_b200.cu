@@ -75,6 +75,7 @@ struct whmr_smpl_s {
   int gemm_mode = WHMR_GEMM_FP32_SIMT;
   int chunk_bodies = 768;
   TcPlan tc{};   // tensor maps etc. for the tcgen05 path
+  cudaEvent_t probe_chain = nullptr, probe_blend = nullptr;
   // host-buffer staging (whmr_smpl_reserve)
   int reserved_B = 0;
   float *st_betas = nullptr, *st_pose = nullptr, *st_verts = nullptr, *st_joints = nullptr;
@@ -366,14 +367,24 @@ int whmr_smpl_forward(whmr_smpl_t h, const float* betas, const float* pose, int 
   rc = whmr_smpl_stage_chain(h, betas, pose, pose_is_rotmat, transl, B, joints, rel_transforms, workspace,
                              workspace_bytes, stream);
   if (rc) return rc;
+  if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, (cudaStream_t)stream, cudaEventRecordExternal));
   // chunked so the [chunk, NP] pose-offset intermediate stays L2-resident between the two kernels
   for (int b0 = 0; b0 < B; b0 += ws.chunk) {
     const int nb = std::min(ws.chunk, B - b0);
     rc = launch_pose_blend(h, ws, B, b0, nb, (cudaStream_t)stream);
     if (rc) return rc;
+    if (h->probe_blend && b0 + nb >= B)
+      WHMR_CUDA(cudaEventRecordWithFlags(h->probe_blend, (cudaStream_t)stream, cudaEventRecordExternal));
     rc = launch_skin(h, ws, betas, transl, b0, nb, verts, (cudaStream_t)stream);
     if (rc) return rc;
   }
+  return WHMR_OK;
+}
+
+int whmr_smpl_set_probe_events(whmr_smpl_t h, void* after_chain, void* after_pose_blend) {
+  WHMR_CHECK_ARG(h, "whmr_smpl_set_probe_events: null handle");
+  h->probe_chain = (cudaEvent_t)after_chain;
+  h->probe_blend = (cudaEvent_t)after_pose_blend;
   return WHMR_OK;
 }
 
@@ -575,8 +586,9 @@ int whmr_project_crop(const float* points, const float* cam, const float* center
 // =============================================================================================
 // sampling
 // =============================================================================================
-int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int W, const float* points, int N,
-                         float* out, void* stream) {
+int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int W, const float* points,
+                         int points_shared, int N, float* out, void* stream) {
+  const int pts_bstride = points_shared ? 0 : N * 2;
   WHMR_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && H > 0 && W > 0, "whmr_sample_bilinear: bad sizes");
   WHMR_CHECK_ARG(layout == WHMR_LAYOUT_NCHW || layout == WHMR_LAYOUT_NHWC, "whmr_sample_bilinear: bad layout %d", layout);
   if (B == 0 || C == 0 || N == 0) return WHMR_OK;
@@ -586,11 +598,11 @@ int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int
   cudaStream_t st = (cudaStream_t)stream;
   if (layout == WHMR_LAYOUT_NCHW) {
     dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
-    sample_bilinear_nchw_kernel<<<grid, 256, 0, st>>>(feat, points, out, C, H, W, N);
+    sample_bilinear_nchw_kernel<<<grid, 256, 0, st>>>(feat, points, pts_bstride, out, C, H, W, N);
     WHMR_LAUNCHED("sample_bilinear_nchw_kernel");
   } else {
     dim3 grid(ceil_div(N, 32), ceil_div(C, 64), B);
-    sample_bilinear_nhwc_kernel<<<grid, 256, 0, st>>>(feat, points, out, C, H, W, N);
+    sample_bilinear_nhwc_kernel<<<grid, 256, 0, st>>>(feat, points, pts_bstride, out, C, H, W, N);
     WHMR_LAUNCHED("sample_bilinear_nhwc_kernel");
   }
   return WHMR_OK;
@@ -601,7 +613,7 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
   WHMR_CHECK_ARG(points2d_out, "whmr_project_sample: points2d_out scratch [B,N,2] is required");
   int rc = whmr_project_weak(p, cam, B, N, focal, img_w, img_h, points2d_out, stream);
   if (rc) return rc;
-  return whmr_sample_bilinear(feat, layout, B, C, H, W, points2d_out, N, out, stream);
+  return whmr_sample_bilinear(feat, layout, B, C, H, W, points2d_out, 0, N, out, stream);
 }
 
 // =============================================================================================

@@ -1,0 +1,107 @@
+"""The body-model hot path of `WHMR.forward`'s iterative regressor loop (models/whmr.py:550-651)
+with the unchanged PyTorch parts (backbone, deconvs, Tz head, regressor / reduce_dim MLPs) factored
+out: per iteration the caller supplies what those MLPs would produce (rotmats, betas, camera) and
+gets back what they would consume (sampled point features) plus the Regressor result tensors.
+
+    init      : forward_init        -> SMPL + read-outs + weak projection                 (:550)
+    iter 0    : grid sampling of the 7x9 grid on feature level 0, then Regressor.forward  (:596-602)
+    iter 1, 2 : MAF_Extractor.forward(markers of the previous output, previous camera) on level i,
+                then Regressor.forward                                                     (:604-612)
+    global    : 5th SMPL call with the re-estimated global orientation + H36M joints       (:641-651)
+
+`RegressorLoop.step` launches 41 kernels (5 x {chain, pose-blend, skin}, 4+1 x read-out pairs,
+4 weak + 3 full projections, 1 + 2x2 sampling); `capture()` wraps the step in a CUDA graph so a
+replay costs one launch from the host.
+"""
+import numpy as np
+import torch
+
+from . import constants, ops
+from .regressor import BodyModelHead
+from .smpl import SMPL
+from .synthetic import grid_points
+
+VITPOSE_LEVELS = ((32, 24), (64, 48), (128, 96))   # models/whmr.py:325-331,543 deconv outputs @256 ch
+RES50_LEVELS = ((14, 14), (28, 28), (56, 56))
+
+
+class RegressorLoop:
+    def __init__(self, model, device, backbone='vitpose', gemm_mode=None, with_h36m=True):
+        self.device = torch.device(device)
+        self.smpl = SMPL(model=model, gemm_mode=gemm_mode).to(self.device)
+        self.head = BodyModelHead(self.smpl, model['Dmap0'], model['Dmap1'], model['ssm'],
+                                  model.get('J_regressor_h36m'))
+        self.with_h36m = bool(with_h36m) and model.get('J_regressor_h36m') is not None
+        self.grid = torch.from_numpy(grid_points(backbone)).to(self.device)   # [63,2] shared by all bodies
+        self.backbone = backbone
+        self.levels = VITPOSE_LEVELS if backbone == 'vitpose' else RES50_LEVELS
+        self.layout = ops.LAYOUT_NCHW
+        self._graph = None
+
+    def step(self, feats, params, bbox):
+        """feats: 3 feature maps [B,256,H_i,W_i]; params: 5 dicts {rotmat [B,24,3,3], betas [B,10],
+        cam [B,3]} (init, iter0, iter1, iter2, global); bbox: {bbox_height, center, orig_shape, Tz}.
+        Returns the last Regressor output dict + 'point_feats' (3 x [B,256,N]) + global outputs."""
+        J = True if self.with_h36m else None
+        p = params
+        out = self.head(p[0]['rotmat'], p[0]['betas'], p[0]['cam'], J_regressor=J)           # forward_init
+        point_feats = []
+        for it in range(3):
+            if it == 0:
+                pf = ops.sample_bilinear_op(feats[0], self.grid, self.layout)                # :596-597
+            else:                                                                            # :606
+                pts = ops.project_weak_op(out['markers'], p[it]['cam'], constants.FOCAL_LENGTH,
+                                          float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
+                self.head._mark('project_markers')
+                pf = ops.sample_bilinear_op(feats[it], pts, self.layout)
+            self.head._mark('sample_l%d' % it)
+            point_feats.append(pf)
+            q = p[it + 1]
+            out = self.head(q['rotmat'], q['betas'], q['cam'], bbox['bbox_height'], bbox['center'],
+                            bbox['orig_shape'], bbox['Tz'], J_regressor=J)                   # :598 / :608
+        g = p[4]
+        h, _ = self.smpl._state(self.device)
+        self.head._mark('pre_smpl')
+        gverts, gjoints24 = ops.smpl_lbs(h.id, g['betas'], g['rotmat'], True)               # :641-644
+        self.head._mark('skin')
+        r = self.head._readout(self.device, self.with_h36m).apply(gverts, gjoints24)
+        self.head._mark('readout')
+        res = dict(out)
+        res['point_feats'] = point_feats
+        res['global_verts'] = gverts
+        res['global_kp_3d'] = r['kp_3d_h36m'] if self.with_h36m else r['joints']            # :646-651
+        return res
+
+    # ---- CUDA-graph replay ------------------------------------------------------------------------
+    def capture(self, feats, params, bbox, warmup=2):
+        """Capture `step` on static input tensors; returns (graph, static outputs dict)."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.step(feats, params, bbox)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.step(feats, params, bbox)
+        return g, out
+
+
+def make_loop_inputs(B, device, backbone='vitpose', seed=1, rank=0, channels=256, dtype=torch.float32):
+    """Synthetic inputs of one loop pass: feature maps ~ N(0,1) generated on the device,
+    5 parameter sets, bbox quantities.  Reproducible per (seed, rank)."""
+    from . import synthetic as syn
+    dev = torch.device(device)
+    levels = VITPOSE_LEVELS if backbone == 'vitpose' else RES50_LEVELS
+    g = torch.Generator(device=dev).manual_seed(1000 * seed + rank)
+    feats = [torch.randn(B, channels, h, w, generator=g, device=dev, dtype=dtype) for h, w in levels]
+    params = []
+    base = syn.make_bodies(B, seed=seed, rank=rank)
+    for i in range(5):
+        b = syn.make_bodies(B, seed=seed + 17 * (i + 1), rank=rank, with_real_rows=(i == 0))
+        params.append({'rotmat': torch.from_numpy(b['rotmat']).to(dev), 'betas': torch.from_numpy(b['betas']).to(dev),
+                       'cam': torch.from_numpy(b['cam']).to(dev)})
+    bbox = {k: torch.from_numpy(np.ascontiguousarray(base[k])).to(dev)
+            for k in ('bbox_height', 'center', 'orig_shape', 'Tz')}
+    return feats, params, bbox

@@ -89,6 +89,15 @@ class SmplHandle:
         check(_lib.lib().whmr_smpl_set_gemm_mode(self._h, int(mode)))
         self.gemm_mode = int(mode)
 
+    def set_probe_events(self, after_chain=None, after_pose_blend=None):
+        """torch.cuda.Event(enable_timing=True, external=True) pair recorded inside the next forward calls."""
+        for e in (after_chain, after_pose_blend):
+            if e is not None:
+                e.record()           # materialise the lazily created cudaEvent_t
+        check(_lib.lib().whmr_smpl_set_probe_events(
+            self._h, None if after_chain is None else after_chain.cuda_event,
+            None if after_pose_blend is None else after_pose_blend.cuda_event))
+
     def info(self):
         v = [C.c_int32() for _ in range(5)]
         check(_lib.lib().whmr_smpl_get_info(self._h, *[C.byref(x) for x in v]))
@@ -319,12 +328,14 @@ def sample_bilinear(feat, points, layout=LAYOUT_NCHW):
         B, Cc, H, W = feat.shape
     else:
         B, H, W, Cc = feat.shape
-    N = points.shape[1]
-    if points.shape[0] != B or points.shape[-1] != 2:
+    shared = points.dim() == 2 or (points.shape[0] == 1 and B != 1)   # one [N,2] grid for every body
+    N = points.shape[-2]
+    if (not shared and points.shape[0] != B) or points.shape[-1] != 2:
         raise ValueError("points %s do not match feature batch %d" % (tuple(points.shape), B))
     out = torch.empty(B, Cc, N, dtype=torch.float32, device=feat.device)
     with torch.cuda.device(feat.device):
-        check(_lib.lib().whmr_sample_bilinear(_p(feat), int(layout), B, Cc, H, W, _p(points), N, _p(out), _stream()))
+        check(_lib.lib().whmr_sample_bilinear(_p(feat), int(layout), B, Cc, H, W, _p(points), int(shared), N,
+                                              _p(out), _stream()))
     return out
 
 
@@ -387,7 +398,7 @@ def sample_bilinear_op(feat: torch.Tensor, points: torch.Tensor, layout: int) ->
 @sample_bilinear_op.register_fake
 def _(feat, points, layout):
     Cc = feat.shape[1] if layout == LAYOUT_NCHW else feat.shape[3]
-    return feat.new_empty(feat.shape[0], Cc, points.shape[1])
+    return feat.new_empty(feat.shape[0], Cc, points.shape[-2])
 
 
 @torch.library.custom_op("whmr::project_weak", mutates_args=(), device_types="cuda")

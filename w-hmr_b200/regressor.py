@@ -29,6 +29,11 @@ class BodyModelHead(nn.Module):
         self._ssm = np.asarray(ssm, dtype=np.int64)
         self._h36m = None if J_regressor_h36m is None else np.asarray(J_regressor_h36m, dtype=np.float64)
         self._ro = {}
+        self.probe = None    # bench.py: callable(name) recording a CUDA event after each enqueued op
+
+    def _mark(self, name):
+        if self.probe is not None:
+            self.probe(name)
 
     def set_h36m_regressor(self, J_regressor):
         J = J_regressor.detach().cpu().numpy() if torch.is_tensor(J_regressor) else np.asarray(J_regressor)
@@ -86,13 +91,17 @@ class BodyModelHead(nn.Module):
         dev = pred_rotmat.device
         h, _ = self.smpl._state(dev)
         rot = pred_rotmat.reshape(B, -1, 3, 3)
+        self._mark('pre_smpl')
         verts, joints24 = ops.smpl_lbs(h.id, pred_shape, rot, True)
+        self._mark('skin')
         r = self._readout(dev, bool(J_regressor)).apply(verts, joints24)
+        self._mark('readout')
         pred_joints = r['joints']
+        kp_2d = ops.project_weak_op(pred_joints, pred_cam, constants.FOCAL_LENGTH,
+                                    float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
+        self._mark('project_weak')
         out = {
-            'verts': verts, 'sub_verts': r['sub_verts'], 'temp_verts': r['temp_verts'],
-            'kp_2d': ops.project_weak_op(pred_joints, pred_cam, constants.FOCAL_LENGTH,
-                                         float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT)),
+            'verts': verts, 'sub_verts': r['sub_verts'], 'temp_verts': r['temp_verts'], 'kp_2d': kp_2d,
             'kp_3d': r['kp_3d_h36m'] if J_regressor else pred_joints,
             'smpl_kp_3d': r['smpl_kp_3d'], 'rotmat': rot, 'pred_cam': pred_cam, 'pred_shape': pred_shape,
             'pred_pose': pred_rotmat.reshape(B, -1), 'pelvis': r['smpl_kp_3d'][:, :1, :], 'markers': r['markers'],
@@ -100,5 +109,6 @@ class BodyModelHead(nn.Module):
         }
         if bbox_height is not None:
             kp_w, focal, cam_t, _ = ops.project_full(pred_joints, pred_cam, bbox_height, center, orig_shape, Tz)
+            self._mark('project_full')
             out.update(kp_2d_w=kp_w, focal_length=focal, pred_cam_t=cam_t, scale=scale)
         return out
