@@ -65,6 +65,8 @@ class SmplHandle:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.WhmrError("SMPL handle needs a CUDA device, got %s (no CPU fallback)" % (self.device,))
+        if not torch.cuda.is_available():
+            raise _lib.WhmrError("no CUDA device is available: whmr_b200 has no CPU fallback")
         self.V, self.J, self.NB = V, J, NB
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
