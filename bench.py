@@ -103,6 +103,9 @@ def algorithmic(kind, B, ctx):
         return {"bytes": B * (4 * 3 * VP + 4 * 3 * V + 4 * J * 12 + 4 * NBETA), "bound": "hbm"}
     if kind == "readout":
         return {"bytes": B * 12 * (ctx["readout_nnz"] + ctx["readout_rows"]), "bound": "hbm"}
+    if kind == "skin_readout":   # skinning kernel (with the one-hot read-outs in its epilogue) + regressor rows
+        return {"bytes": B * (4 * 3 * VP + 4 * 3 * V + 4 * J * 12 + 4 * NBETA + 12 * (ctx["readout_nnz"] + ctx["readout_rows"])),
+                "bound": "hbm"}
     if kind.startswith("sample_l"):
         lvl = int(kind[-1])
         H, W = ctx["levels"][lvl]

@@ -140,6 +140,15 @@ int whmr_readout_destroy(whmr_readout_t r);
 int whmr_readout_apply(whmr_readout_t r, const float* verts /*[B,V,3]*/, const float* joints /*[B,J,3] or NULL*/,
                        int B, float* out /*[B*n_rows*3], group-major*/, void* stream);
 
+/* SMPL forward and its read-outs in one call (what Regressor.forward does back to back,
+ * models/whmr.py:132-187): same as whmr_smpl_forward followed by whmr_readout_apply(ro, verts, joints),
+ * but per 768-body chunk -- the one-hot rows (vertex picks, markers, mesh down-sampling) are written
+ * by the skinning kernel's epilogue and the regressor rows read the chunk's vertices out of L2. */
+int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                              const float* transl, int B, float* verts, float* joints, float* rel_transforms,
+                              whmr_readout_t ro, float* ro_out /*[B*n_rows*3], group-major*/, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Projection.
  * ------------------------------------------------------------------------------------------ */

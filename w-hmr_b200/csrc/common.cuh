@@ -66,6 +66,7 @@ struct SmplDevice {
   // pose-blend operands
   float* posedirs_p;             // [KP,NP] fp32 planar padded (SIMT path)
   void* posedirs_split;          // tensor-core A operand: [NP, 2, KP] bf16 hi|lo, K-major (TC paths)
+  int nfeat;                     // (J-1)*9 pose-feature terms; K = nfeat + NB (shape blend folded in), padded to KP
 };
 
 // scratch carved from the caller's workspace for one chunk of bodies
@@ -73,7 +74,10 @@ struct SmplWorkspace {
   float* A;          // [B,J,12]
   float* pf;         // [B,KP]       fp32 pose feature (R_j - I), zero padded
   void* pf_split;    // [Bpad,2,KP]  bf16 hi|lo split of pf  (TC paths)
-  float* offsets;    // [chunk,NP]   pose offsets, planar per body
+  float* offsets;    // [chunk,NP]   pose offsets + shape blend, planar per body
+  float* At;         // [2, Bpad*12, 32] tf32 hi|lo of the skinning transforms, transposed (TC skinning)
+  size_t At_part_stride;   // floats
+  int Bpad;
   int chunk;         // bodies per GEMM/skin chunk
 };
 

@@ -49,6 +49,9 @@ struct TcPlan {
   CUtensorMap tmapA_bf16, tmapA_tf32;
   void* encode_fn = nullptr;   // cuTensorMapEncodeTiled
   int num_sms = 148;
+  // tensor-core skinning: dense tf32 hi|lo weights [2, VP, 32 joints]
+  void* W_tf32 = nullptr;
+  CUtensorMap tmapW;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -301,6 +304,23 @@ static inline float f32_to_tf32_rna(float f) {   // cvt.rna.tf32.f32
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D map {32 floats of K, rows, 2 parts} over a part-major [2, part_rows, 32] tf32 operand (128 B rows)
+static inline int tc_encode_rows32(void* fn, CUtensorMap* map, void* base, size_t rows, size_t part_stride_bytes,
+                                   int box_rows) {
+  cuuint64_t dims[3] = {32, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {128, (cuuint64_t)part_stride_bytes};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill)>(fn)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(WHMR_E_CUDA, "cuTensorMapEncodeTiled (rows32) failed with CUresult %d", (int)r);
+  return WHMR_OK;
+}
 
 // 3-D map over a [rows, 2, KP] hi|lo operand: box = (128 bytes of K, 1 part, box_rows rows), 128B swizzle
 static inline int tc_encode(void* fn, CUtensorMap* map, int kind, void* base, int KP, int rows, int box_rows) {

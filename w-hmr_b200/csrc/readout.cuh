@@ -26,15 +26,16 @@ struct ReadoutParams {
   const int* grp_rows;    // [R] rows in this row's group
   const int* rows;      // row ids handled by this launch
   int n_rows_here;      // entries in `rows`
-  int R, V, J, B;
-  const float* verts;   // [B,V,3]
-  const float* joints;  // [B,J,3] or null
-  float* out;           // group-major: group g = [B, R_g, 3] at float offset 3*B*prefix_g
+  int R, V, J, B;       // B = bodies handled by this launch (a chunk)
+  int B_total, b0;      // batch of the output buffer, first body of the chunk
+  const float* verts;   // [B,V,3]  (chunk base)
+  const float* joints;  // [B,J,3] or null (chunk base)
+  float* out;           // group-major: group g = [B_total, R_g, 3] at float offset 3*B_total*prefix_g
 };
 
 __device__ __forceinline__ float* readout_dst(const ReadoutParams& p, int b, int r) {
   const int pre = p.grp_prefix[r], rg = p.grp_rows[r];
-  return p.out + 3 * ((size_t)p.B * pre + (size_t)b * rg + (r - pre));
+  return p.out + 3 * ((size_t)p.B_total * pre + (size_t)(p.b0 + b) * rg + (r - pre));
 }
 
 __device__ __forceinline__ const float* readout_src(const ReadoutParams& p, int b, int col) {

@@ -1,7 +1,7 @@
 // Linear blend skinning with sparse weights, fused with the shape blend.
 //
-//   v_shaped = v_template + shapedirs . beta                   (smplx blend_shapes)
-//   v_posed  = pose_offsets + v_shaped                         (pose_offsets from the pose-blend GEMM)
+//   v_posed  = v_template + (shapedirs . beta + pose_offsets)  (the bracket comes out of the pose-blend
+//              contraction, whose K dimension carries the 10 shape coefficients after the 207 pose terms)
 //   T_v      = sum_j w_vj A_j ;  v' = T_v . [v_posed ; 1]      (SURVEY K6 + K7; lbs.py:63-79)
 //
 // The reference materialises T as a dense [B,6890,24]x[B,24,16] matmul (441 KB/body of
@@ -71,13 +71,6 @@ __global__ void __launch_bounds__(kVertTile) skin_kernel(SkinParams p) {
   float tmpl[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) tmpl[c] = p.v_template_p[c * p.VP + v];
-  float sd[3][NBT > 0 ? NBT : 1];
-  if (NBT > 0) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int k = 0; k < NBT; ++k) sd[c][k] = p.shapedirs_p[((size_t)c * NBT + k) * p.VP + v];
-  }
   int jid[ELLK > 0 ? ELLK : 1];
   float jw[ELLK > 0 ? ELLK : 1];
   if (ELLK > 0) {
@@ -107,24 +100,8 @@ __global__ void __launch_bounds__(kVertTile) skin_kernel(SkinParams p) {
       const float* o = p.offsets + (size_t)(b + 1) * p.NP + v;
       ox = o[0]; oy = o[p.VP]; oz = o[2 * p.VP];
     }
-    // shape blend (einsum 'bl,mkl->bmk'), then v_template +, then pose offsets +  (smplx order)
-    float bx = 0.f, by = 0.f, bz = 0.f;
-    const float* be = beta_s + bi * kMaxBetas;
-    if (NBT > 0) {
-#pragma unroll
-      for (int k = 0; k < NBT; ++k) {
-        const float bk = be[k];
-        bx = fmaf(bk, sd[0][k], bx); by = fmaf(bk, sd[1][k], by); bz = fmaf(bk, sd[2][k], bz);
-      }
-    } else {
-      for (int k = 0; k < NB; ++k) {
-        const float bk = be[k];
-        bx = fmaf(bk, p.shapedirs_p[((size_t)0 * NB + k) * p.VP + v], bx);
-        by = fmaf(bk, p.shapedirs_p[((size_t)1 * NB + k) * p.VP + v], by);
-        bz = fmaf(bk, p.shapedirs_p[((size_t)2 * NB + k) * p.VP + v], bz);
-      }
-    }
-    const float px = cx + (tmpl[0] + bx), py = cy + (tmpl[1] + by), pz = cz + (tmpl[2] + bz);
+    // offsets already hold pose offsets + shape blend (both come out of the pose-blend contraction)
+    const float px = cx + tmpl[0], py = cy + tmpl[1], pz = cz + tmpl[2];
 
     // blended transform T = sum_k w_k A_{j_k}
     float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0;

@@ -34,6 +34,8 @@ struct ChainParams {
   float* pf;                 // [B,KP] or null
   __nv_bfloat16* pf_split;   // [B,2,KP] hi|lo or null
   float* pf_tf32;            // [B,2,KP] hi|lo tf32-valued floats or null
+  float* At;                 // [2, At_rows, 32] tf32 hi|lo of A transposed: row (b*12+e), column = joint; or null
+  size_t At_part_stride;     // floats between the hi and lo parts (= At_rows*32)
 };
 
 // smplx.lbs.batch_rodrigues for one vector: angle = ||v + 1e-8||, R = I + sin*K + (1-cos)*K*K
@@ -133,6 +135,28 @@ __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(Ch
     }
   }
 
+  // ---- skinning operand for the tensor-core kernel: A_j (with rest pose removed) transposed so that
+  //      joints run along K: At[part][(b*12+e)*32 + j], zero for j >= J (lanes >= J write the padding)
+  float Arow[12];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float t = G[r * 4 + 0] * Jr[0];
+    t = fmaf(G[r * 4 + 1], Jr[1], t);
+    t = fmaf(G[r * 4 + 2], Jr[2], t);
+    Arow[r * 4 + 0] = G[r * 4 + 0]; Arow[r * 4 + 1] = G[r * 4 + 1]; Arow[r * 4 + 2] = G[r * 4 + 2];
+    Arow[r * 4 + 3] = G[r * 4 + 3] - t;
+  }
+  if (p.At) {
+    float* a0 = p.At + ((size_t)b * 12) * 32 + lane;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      const float x = active ? Arow[e] : 0.0f;
+      const float hi = tf32_round(x);
+      a0[(size_t)e * 32] = hi;
+      a0[(size_t)e * 32 + p.At_part_stride] = tf32_round(x - hi);
+    }
+  }
+
   if (!active) return;
 
   // ---- outputs ----------------------------------------------------------------------------
@@ -151,12 +175,7 @@ __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(Ch
   // A_j = G_j with translation  t - R_g . J_j   (rest-pose removal, lbs.py:49-58)
   float4 row[3];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    float t = G[r * 4 + 0] * Jr[0];
-    t = fmaf(G[r * 4 + 1], Jr[1], t);
-    t = fmaf(G[r * 4 + 2], Jr[2], t);
-    row[r] = make_float4(G[r * 4 + 0], G[r * 4 + 1], G[r * 4 + 2], G[r * 4 + 3] - t);
-  }
+  for (int r = 0; r < 3; ++r) row[r] = make_float4(Arow[r * 4 + 0], Arow[r * 4 + 1], Arow[r * 4 + 2], Arow[r * 4 + 3]);
   float4* Ao = reinterpret_cast<float4*>(p.A + ((size_t)b * p.J + j) * 12);
   Ao[0] = row[0]; Ao[1] = row[1]; Ao[2] = row[2];
   if (p.A_user) {
@@ -189,15 +208,20 @@ __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(Ch
       }
     }
   }
+  // K tail: the NB shape coefficients (the shape blend is folded into the same contraction:
+  // rows nfeat..nfeat+NB-1 of the posedirs operand hold shapedirs), then zero padding up to KP
   for (int o = nfeat + j; o < p.KP; o += p.J) {
-    if (p.pf) p.pf[(size_t)b * p.KP + o] = 0.0f;
+    const float f = (o - nfeat) < p.NB ? p.betas[(size_t)b * p.NB + (o - nfeat)] : 0.0f;
+    if (p.pf) p.pf[(size_t)b * p.KP + o] = f;
     if (p.pf_split) {
-      p.pf_split[((size_t)b * 2 + 0) * p.KP + o] = __float2bfloat16_rn(0.0f);
-      p.pf_split[((size_t)b * 2 + 1) * p.KP + o] = __float2bfloat16_rn(0.0f);
+      const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+      p.pf_split[((size_t)b * 2 + 0) * p.KP + o] = hi;
+      p.pf_split[((size_t)b * 2 + 1) * p.KP + o] = __float2bfloat16_rn(f - __bfloat162float(hi));
     }
     if (p.pf_tf32) {
-      p.pf_tf32[((size_t)b * 2 + 0) * p.KP + o] = 0.0f;
-      p.pf_tf32[((size_t)b * 2 + 1) * p.KP + o] = 0.0f;
+      const float hi = tf32_round(f);
+      p.pf_tf32[((size_t)b * 2 + 0) * p.KP + o] = hi;
+      p.pf_tf32[((size_t)b * 2 + 1) * p.KP + o] = tf32_round(f - hi);
     }
   }
 }

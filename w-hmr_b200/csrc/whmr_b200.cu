@@ -15,6 +15,7 @@
 #include "projection.cuh"
 #include "readout.cuh"
 #include "sampling.cuh"
+#include "skin_tc.cuh"
 #include "skinning.cuh"
 #include "smpl_chain.cuh"
 
@@ -76,6 +77,7 @@ struct whmr_smpl_s {
   int chunk_bodies = 768;
   TcPlan tc{};   // tensor maps etc. for the tcgen05 path
   cudaEvent_t probe_chain = nullptr, probe_blend = nullptr;
+  bool skin_tc = true;   // tensor-core skinning (WHMR_SKIN=simt selects the CUDA-core kernel)
   // host-buffer staging (whmr_smpl_reserve)
   int reserved_B = 0;
   float *st_betas = nullptr, *st_pose = nullptr, *st_verts = nullptr, *st_joints = nullptr;
@@ -85,9 +87,15 @@ struct whmr_smpl_s {
 
 struct whmr_readout_s {
   DeviceArena arena;
-  int R = 0, V = 0, J = 0, n_short = 0, n_long = 0;
+  int R = 0, V = 0, J = 0;
+  // row classes: one-hot rows (weight 1 on a single vertex: picks, markers, down-sampling), other
+  // short rows (<= kShortRow non-zeros, one thread each) and long rows (one warp each)
+  int n_onehot = 0, n_short = 0, n_long = 0, n_short_all = 0;
   int *row_ptr = nullptr, *col_idx = nullptr, *sub_row = nullptr, *rows_short = nullptr, *rows_long = nullptr;
+  int *rows_short_all = nullptr;    // one-hot + short: used when the read-out runs stand-alone
   int *grp_prefix = nullptr, *grp_rows = nullptr;
+  int *dst_ptr = nullptr, *dst_row = nullptr;   // vertex -> one-hot destination rows (CSC), [VP+1] / [n_onehot]
+  int dst_VP = 0;
   float* vals = nullptr;
   bool needs_joints = false;
 };
@@ -124,7 +132,8 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
   d.VP = ceil_div(V, kVertTile) * kVertTile;
   d.NP = 3 * d.VP;
   const int nfeat = (J - 1) * 9;
-  d.KP = std::max(16, ceil_div(nfeat, 16) * 16);
+  d.nfeat = nfeat;
+  d.KP = std::max(16, ceil_div(nfeat + NB, 16) * 16);   // pose terms, then the NB shape coefficients, zero padded
   if (const char* e = getenv("WHMR_CHUNK_BODIES")) {
     const int c = atoi(e);
     if (c >= 8) h->chunk_bodies = std::max(kTcBodyTile, c / kTcBodyTile * kTcBodyTile);   // whole 256-body tiles
@@ -199,6 +208,20 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
     for (int v = 0; v < V; ++v)
       for (int c = 0; c < 3; ++c) dst[(size_t)c * VP + v] = src[(size_t)v * 3 + c];
   }
+  for (int k = 0; k < NB; ++k) {   // shape blend rides in the same contraction (rows nfeat..nfeat+NB-1)
+    float* dst = pp.data() + (size_t)(nfeat + k) * d.NP;
+    for (int v = 0; v < V; ++v)
+      for (int c = 0; c < 3; ++c) dst[(size_t)c * VP + v] = m->shapedirs[((size_t)v * 3 + c) * NB + k];
+  }
+  // dense tf32 hi|lo skinning weights [2, VP, 32] for the tensor-core skinning kernel
+  std::vector<float> wsplit((size_t)2 * VP * 32, 0.f);
+  for (int v = 0; v < V; ++v)
+    for (int j = 0; j < J; ++j) {
+      const float w = m->lbs_weights[(size_t)v * J + j];
+      const float hi = f32_to_tf32_rna(w);
+      wsplit[((size_t)0 * VP + v) * 32 + j] = hi;
+      wsplit[((size_t)1 * VP + v) * 32 + j] = f32_to_tf32_rna(w - hi);
+    }
 
   cudaError_t e = cudaSuccess;
   auto up = [&](auto& vec, auto** dst) { if (e == cudaSuccess) e = h->arena.upload(vec, dst); };
@@ -212,6 +235,17 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
   // tensor-core operand (hi|lo split of posedirs, K-major) + TMA descriptors
   int rc = tc_plan_create(d, pp, h->arena, &h->tc);
   if (rc != WHMR_OK) { delete h; return rc; }
+  {
+    float* dw = nullptr;
+    e = h->arena.upload(wsplit, &dw);
+    if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "weight split upload failed: %s", cudaGetErrorString(e)); }
+    h->tc.W_tf32 = dw;
+    rc = tc_encode_rows32(h->tc.encode_fn, &h->tc.tmapW, dw, (size_t)VP, (size_t)VP * 128, kTcM);
+    if (rc != WHMR_OK) { delete h; return rc; }
+    e = cudaFuncSetAttribute(skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinSmem);
+    if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "cudaFuncSetAttribute(skin_tc) failed: %s", cudaGetErrorString(e)); }
+  }
+  if (const char* s = getenv("WHMR_SKIN")) h->skin_tc = strcmp(s, "simt") != 0;
   h->gemm_mode = gemm_mode;
   *out = h;
   return WHMR_OK;
@@ -253,12 +287,16 @@ static size_t carve(const whmr_smpl_s* h, int B, void* base, SmplWorkspace* ws) 
   const size_t oPf = take((size_t)B * d.KP * sizeof(float));
   const size_t oSplit = take((size_t)Bpad * 2 * d.KP * sizeof(float));   // sized for the tf32 variant
   const size_t oOff = take((size_t)chunk * d.NP * sizeof(float));
+  const size_t oAt = take((size_t)2 * Bpad * 12 * 32 * sizeof(float));
   if (ws) {
     char* p = static_cast<char*>(base);
     ws->A = reinterpret_cast<float*>(p + oA);
     ws->pf = reinterpret_cast<float*>(p + oPf);
     ws->pf_split = p + oSplit;
     ws->offsets = reinterpret_cast<float*>(p + oOff);
+    ws->At = reinterpret_cast<float*>(p + oAt);
+    ws->At_part_stride = (size_t)Bpad * 12 * 32;
+    ws->Bpad = Bpad;
     ws->chunk = chunk;
   }
   return off;
@@ -297,6 +335,8 @@ int whmr_smpl_stage_chain(whmr_smpl_t h, const float* betas, const float* pose, 
   p.pf = h->gemm_mode == WHMR_GEMM_FP32_SIMT ? ws.pf : nullptr;
   p.pf_split = h->gemm_mode == WHMR_GEMM_TC_BF16X3 ? static_cast<__nv_bfloat16*>(ws.pf_split) : nullptr;
   p.pf_tf32 = h->gemm_mode == WHMR_GEMM_TC_3XTF32 ? static_cast<float*>(ws.pf_split) : nullptr;
+  p.At = h->skin_tc ? ws.At : nullptr;
+  p.At_part_stride = ws.At_part_stride;
   smpl_chain_kernel<<<ceil_div(B, kChainWarpsPerBlock), kChainWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p);
   WHMR_LAUNCHED("smpl_chain_kernel");
   return WHMR_OK;
@@ -314,9 +354,54 @@ static int launch_pose_blend(whmr_smpl_t h, const SmplWorkspace& ws, int B, int 
   return tc_pose_blend_launch(h->tc, d, h->gemm_mode, ws.pf_split, B, b0, nb, ws.offsets, st);
 }
 
-static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* betas, const float* transl, int b0,
-                       int nb, float* verts, cudaStream_t st) {
+static int launch_readout_rows(whmr_readout_t r, const int* rows, int n_rows_here, bool warp_per_row, const float* verts,
+                               const float* joints, int nb, int B_total, int b0, float* out, cudaStream_t st) {
+  if (n_rows_here == 0 || nb == 0) return WHMR_OK;
+  ReadoutParams p{};
+  p.row_ptr = r->row_ptr; p.col_idx = r->col_idx; p.vals = r->vals; p.sub_row = r->sub_row;
+  p.grp_prefix = r->grp_prefix; p.grp_rows = r->grp_rows;
+  p.R = r->R; p.V = r->V; p.J = r->J; p.B = nb; p.B_total = B_total; p.b0 = b0;
+  p.verts = verts; p.joints = joints; p.out = out;
+  p.rows = rows; p.n_rows_here = n_rows_here;
+  if (warp_per_row) {
+    const long long n = (long long)nb * n_rows_here * 32;
+    readout_long_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    WHMR_LAUNCHED("readout_long_kernel");
+  } else {
+    const long long n = (long long)nb * n_rows_here;
+    readout_short_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    WHMR_LAUNCHED("readout_short_kernel");
+  }
+  return WHMR_OK;
+}
+
+// skinning of bodies [b0, b0+nb); with `ro` the one-hot read-out rows are written by the same kernel
+static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* betas, const float* transl, int B, int b0,
+                       int nb, float* verts, whmr_readout_t ro, float* ro_out, cudaStream_t st) {
   const SmplDevice& d = h->d;
+  if (h->skin_tc) {
+    SkinTcParams p{};
+    p.offsets = ws.offsets;
+    p.v_template_p = d.v_template_p;
+    p.transl = transl ? transl + (size_t)b0 * 3 : nullptr;
+    p.verts = verts + (size_t)b0 * d.V * 3;
+    if (ro && ro->n_onehot) {
+      p.dst_ptr = ro->dst_ptr; p.dst_row = ro->dst_row; p.grp_prefix = ro->grp_prefix; p.grp_rows = ro->grp_rows;
+      p.ro_out = ro_out; p.ro_B = B; p.ro_b0 = b0;
+    }
+    p.nb = nb; p.V = d.V; p.VP = d.VP; p.NP = d.NP;
+    p.n_groups = ceil_div(nb, kSkinGB);
+    p.n_items = (d.VP / kTcM) * p.n_groups;
+    p.ksteps = ceil_div(d.J, 8);
+    CUtensorMap tmapAt;
+    int rc = tc_encode_rows32(h->tc.encode_fn, &tmapAt, ws.At + (size_t)b0 * 12 * 32, (size_t)(ws.Bpad - b0) * 12,
+                              ws.At_part_stride * sizeof(float), kSkinN);
+    if (rc) return rc;
+    const int grid = std::min(h->tc.num_sms, p.n_items);
+    skin_tc_kernel<<<grid, kSkinThreads, kSkinSmem, st>>>(h->tc.tmapW, tmapAt, p);
+    WHMR_LAUNCHED("skin_tc_kernel");
+    return WHMR_OK;
+  }
   SkinParams p{};
   p.offsets = ws.offsets;
   p.A = ws.A + (size_t)b0 * d.J * 12;
@@ -327,9 +412,8 @@ static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* beta
   p.B = nb; p.V = d.V; p.VP = d.VP; p.NP = d.NP; p.J = d.J; p.NB = d.NB; p.ell_k = d.ell_k;
   dim3 grid(d.VP / kVertTile, ceil_div(nb, kSkinBodies));
   const size_t smem = skin_smem_bytes(d.J);
-  if (d.NB == 10 && d.ell_k == 4) skin_kernel<4, 10><<<grid, kVertTile, smem, st>>>(p);
-  else if (d.NB == 10 && d.ell_k == 8) skin_kernel<8, 10><<<grid, kVertTile, smem, st>>>(p);
-  else if (d.NB == 10) skin_kernel<0, 10><<<grid, kVertTile, smem, st>>>(p);
+  if (d.ell_k == 4) skin_kernel<4, 0><<<grid, kVertTile, smem, st>>>(p);
+  else if (d.ell_k == 8) skin_kernel<8, 0><<<grid, kVertTile, smem, st>>>(p);
   else skin_kernel<0, 0><<<grid, kVertTile, smem, st>>>(p);
   WHMR_LAUNCHED("skin_kernel");
   return WHMR_OK;
@@ -353,32 +437,56 @@ int whmr_smpl_stage_skin(whmr_smpl_t h, const float* betas, int B, float* verts,
   if (B == 0) return WHMR_OK;
   WHMR_CHECK_ARG(betas && verts, "whmr_smpl_stage_skin: null betas/verts");
   WHMR_CHECK_ARG(B <= ws.chunk, "whmr_smpl_stage_skin: B=%d exceeds the chunk size %d", B, ws.chunk);
-  return launch_skin(h, ws, betas, nullptr, 0, B, verts, (cudaStream_t)stream);
+  return launch_skin(h, ws, betas, nullptr, B, 0, B, verts, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-int whmr_smpl_forward(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat, const float* transl,
-                      int B, float* verts, float* joints, float* rel_transforms, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                              const float* transl, int B, float* verts, float* joints, float* rel_transforms,
+                              whmr_readout_t ro, float* ro_out, void* workspace, size_t workspace_bytes, void* stream) {
   SmplWorkspace ws;
   int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
   if (rc) return rc;
   if (B == 0) return WHMR_OK;
   WHMR_CHECK_ARG(betas && pose && verts, "whmr_smpl_forward: null betas/pose/verts");
+  if (ro) {
+    WHMR_CHECK_ARG(ro_out, "whmr_smpl_forward_readout: null read-out buffer");
+    WHMR_CHECK_ARG(ro->V == h->d.V && ro->J == h->d.J, "whmr_smpl_forward_readout: read-out table built for V=%d J=%d", ro->V,
+                   ro->J);
+    WHMR_CHECK_ARG(joints || !ro->needs_joints, "whmr_smpl_forward_readout: table references chain joints but joints == NULL");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
   rc = whmr_smpl_stage_chain(h, betas, pose, pose_is_rotmat, transl, B, joints, rel_transforms, workspace,
                              workspace_bytes, stream);
   if (rc) return rc;
-  if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, (cudaStream_t)stream, cudaEventRecordExternal));
-  // chunked so the [chunk, NP] pose-offset intermediate stays L2-resident between the two kernels
+  if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, st, cudaEventRecordExternal));
+  // chunked so the [chunk, NP] pose-offset intermediate (and the chunk's vertices, for the read-outs)
+  // stay L2-resident between the kernels
+  const bool fused_onehot = ro && h->skin_tc && ro->dst_VP == h->d.VP;
   for (int b0 = 0; b0 < B; b0 += ws.chunk) {
     const int nb = std::min(ws.chunk, B - b0);
-    rc = launch_pose_blend(h, ws, B, b0, nb, (cudaStream_t)stream);
+    rc = launch_pose_blend(h, ws, B, b0, nb, st);
     if (rc) return rc;
-    if (h->probe_blend && b0 + nb >= B)
-      WHMR_CUDA(cudaEventRecordWithFlags(h->probe_blend, (cudaStream_t)stream, cudaEventRecordExternal));
-    rc = launch_skin(h, ws, betas, transl, b0, nb, verts, (cudaStream_t)stream);
+    if (h->probe_blend && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_blend, st, cudaEventRecordExternal));
+    rc = launch_skin(h, ws, betas, transl, B, b0, nb, verts, fused_onehot ? ro : nullptr, ro_out, st);
     if (rc) return rc;
+    if (ro) {
+      const float* vch = verts + (size_t)b0 * h->d.V * 3;
+      const float* jch = joints ? joints + (size_t)b0 * h->d.J * 3 : nullptr;
+      if (fused_onehot) rc = launch_readout_rows(ro, ro->rows_short, ro->n_short, false, vch, jch, nb, B, b0, ro_out, st);
+      else rc = launch_readout_rows(ro, ro->rows_short_all, ro->n_short_all, false, vch, jch, nb, B, b0, ro_out, st);
+      if (rc) return rc;
+      rc = launch_readout_rows(ro, ro->rows_long, ro->n_long, true, vch, jch, nb, B, b0, ro_out, st);
+      if (rc) return rc;
+    }
   }
   return WHMR_OK;
+}
+
+int whmr_smpl_forward(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat, const float* transl,
+                      int B, float* verts, float* joints, float* rel_transforms, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return whmr_smpl_forward_readout(h, betas, pose, pose_is_rotmat, transl, B, verts, joints, rel_transforms, nullptr,
+                                   nullptr, workspace, workspace_bytes, stream);
 }
 
 int whmr_smpl_set_probe_events(whmr_smpl_t h, void* after_chain, void* after_pose_blend) {
@@ -470,18 +578,38 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
     sr.assign(sub_row, sub_row + n_rows);
     for (int r = 0; r < n_rows; ++r) WHMR_CHECK_ARG(sr[r] < n_rows, "whmr_readout_create: sub_row[%d] out of range", r);
   }
+  // row classes
+  std::vector<int> ro1, rs_all;
+  std::vector<char> used_as_sub(n_rows, 0);
+  if (sub_row) for (int r = 0; r < n_rows; ++r) if (sr[r] >= 0) used_as_sub[sr[r]] = 1;
   for (int r = 0; r < n_rows; ++r) {
     int len = rp[r + 1] - rp[r];
-    if (sub_row && sr[r] >= 0) len = std::max(len, rp[sr[r] + 1] - rp[sr[r]]);
-    (len <= kShortRow ? rs : rl).push_back(r);
+    const bool has_sub = sub_row && sr[r] >= 0;
+    if (has_sub) len = std::max(len, rp[sr[r] + 1] - rp[sr[r]]);
+    const bool onehot = !has_sub && len == 1 && vv[rp[r]] == 1.0f && ci[rp[r]] < n_verts;
+    if (onehot) { ro1.push_back(r); rs_all.push_back(r); }
+    else if (len <= kShortRow) { rs.push_back(r); rs_all.push_back(r); }
+    else rl.push_back(r);
+  }
+  // vertex -> one-hot destination rows (CSC over the padded vertex range of the skinning kernel)
+  const int VP = ceil_div(n_verts, kVertTile) * kVertTile;
+  std::vector<int> dptr(VP + 1, 0), drow(ro1.size());
+  for (int r : ro1) dptr[ci[rp[r]] + 1]++;
+  for (int v = 0; v < VP; ++v) dptr[v + 1] += dptr[v];
+  {
+    std::vector<int> fill(dptr.begin(), dptr.end() - 1);
+    for (int r : ro1) drow[fill[ci[rp[r]]]++] = r;
   }
   whmr_readout_s* h = new (std::nothrow) whmr_readout_s();
   if (!h) return set_error(WHMR_E_INVALID, "whmr_readout_create: out of host memory");
-  h->R = n_rows; h->V = n_verts; h->J = n_joints; h->n_short = (int)rs.size(); h->n_long = (int)rl.size();
+  h->R = n_rows; h->V = n_verts; h->J = n_joints;
+  h->n_onehot = (int)ro1.size(); h->n_short = (int)rs.size(); h->n_long = (int)rl.size(); h->n_short_all = (int)rs_all.size();
+  h->dst_VP = VP;
   h->needs_joints = needs_joints;
   cudaError_t e = cudaSuccess;
   auto up = [&](auto& vec, auto** dst) { if (e == cudaSuccess) e = h->arena.upload(vec, dst); };
   up(rp, &h->row_ptr); up(ci, &h->col_idx); up(vv, &h->vals); up(rs, &h->rows_short); up(rl, &h->rows_long);
+  up(rs_all, &h->rows_short_all); up(dptr, &h->dst_ptr); up(drow, &h->dst_row);
   up(gpre, &h->grp_prefix); up(grows, &h->grp_rows);
   if (sub_row) up(sr, &h->sub_row);
   if (e != cudaSuccess) {
@@ -499,24 +627,10 @@ int whmr_readout_apply(whmr_readout_t r, const float* verts, const float* joints
   if (B == 0 || r->R == 0) return WHMR_OK;
   WHMR_CHECK_ARG(verts && out, "whmr_readout_apply: null verts/out");
   WHMR_CHECK_ARG(joints || !r->needs_joints, "whmr_readout_apply: table references chain joints but joints == NULL");
-  ReadoutParams p{};
-  p.row_ptr = r->row_ptr; p.col_idx = r->col_idx; p.vals = r->vals; p.sub_row = r->sub_row;
-  p.grp_prefix = r->grp_prefix; p.grp_rows = r->grp_rows;
-  p.R = r->R; p.V = r->V; p.J = r->J; p.B = B; p.verts = verts; p.joints = joints; p.out = out;
   cudaStream_t st = (cudaStream_t)stream;
-  if (r->n_short) {
-    p.rows = r->rows_short; p.n_rows_here = r->n_short;
-    const long long n = (long long)B * r->n_short;
-    readout_short_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
-    WHMR_LAUNCHED("readout_short_kernel");
-  }
-  if (r->n_long) {
-    p.rows = r->rows_long; p.n_rows_here = r->n_long;
-    const long long n = (long long)B * r->n_long * 32;
-    readout_long_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
-    WHMR_LAUNCHED("readout_long_kernel");
-  }
-  return WHMR_OK;
+  int rc = launch_readout_rows(r, r->rows_short_all, r->n_short_all, false, verts, joints, B, B, 0, out, st);
+  if (rc) return rc;
+  return launch_readout_rows(r, r->rows_long, r->n_long, true, verts, joints, B, B, 0, out, st);
 }
 
 int whmr_gather_vertices(const float* verts, const int32_t* idx, int B, int V, int n_idx, float* out, void* stream) {

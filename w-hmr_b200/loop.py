@@ -62,10 +62,10 @@ class RegressorLoop:
         g = p[4]
         h, _ = self.smpl._state(self.device)
         self.head._mark('pre_smpl')
-        gverts, gjoints24 = ops.smpl_lbs(h.id, g['betas'], g['rotmat'], True)               # :641-644
-        self.head._mark('skin')
-        r = self.head._readout(self.device, self.with_h36m).apply(gverts, gjoints24)
-        self.head._mark('readout')
+        ro = self.head._readout(self.device, self.with_h36m)
+        gverts, gjoints24, flat = ops.smpl_lbs_readout(h.id, ro.id, g['betas'], g['rotmat'], True)  # :641-644
+        r = ro.split(flat, gverts.shape[0])
+        self.head._mark('skin_readout')
         res = dict(out)
         res['point_feats'] = point_feats
         res['global_verts'] = gverts

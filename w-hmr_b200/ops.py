@@ -109,7 +109,8 @@ class SmplHandle:
         n = int(_lib.lib().whmr_smpl_workspace_bytes(self._h, int(B)))
         return torch.empty(n, dtype=torch.uint8, device=self.device), n
 
-    def forward(self, betas, pose, pose_is_rotmat, transl=None, want_transforms=False):
+    def forward(self, betas, pose, pose_is_rotmat, transl=None, want_transforms=False, readout=None):
+        """-> (verts [B,V,3], chain joints [B,J,3], A [B,J,12] or None[, flat read-out buffer])"""
         betas = _req(betas, "betas", align=16)
         pose = _req(pose, "pose", align=16)
         transl = _req(transl, "transl")
@@ -122,10 +123,17 @@ class SmplHandle:
         joints = torch.empty(B, self.J, 3, dtype=torch.float32, device=self.device)
         A = torch.empty(B, self.J, 12, dtype=torch.float32, device=self.device) if want_transforms else None
         ws, n = self.workspace(B)
+        if readout is None:
+            with torch.cuda.device(self.device):
+                check(_lib.lib().whmr_smpl_forward(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl),
+                                                   B, _p(verts), _p(joints), _p(A), _p(ws), n, _stream()))
+            return verts, joints, A
+        ro_flat = torch.empty(B * readout.R * 3, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(_lib.lib().whmr_smpl_forward(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl),
-                                               B, _p(verts), _p(joints), _p(A), _p(ws), n, _stream()))
-        return verts, joints, A
+            check(_lib.lib().whmr_smpl_forward_readout(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)),
+                                                       _p(transl), B, _p(verts), _p(joints), _p(A), readout._h,
+                                                       _p(ro_flat), _p(ws), n, _stream()))
+        return verts, joints, A, ro_flat
 
     # per-stage launches (bench.py per-kernel timing, tests)
     def stage_chain(self, betas, pose, pose_is_rotmat, ws, n, joints=None, A=None, transl=None):
@@ -160,6 +168,9 @@ def batch_rodrigues(aa):
 # ----------------------------------------------------------------------------------------------
 # read-out
 # ----------------------------------------------------------------------------------------------
+_READOUTS = {}
+
+
 class Readout:
     """Sparse linear read-out table (whmr_readout_create).  Built from named groups; each group
     is a dense [R_g, n_src] matrix, a list of source indices (picks) or a scipy CSR matrix, over
@@ -209,14 +220,25 @@ class Readout:
                                                  None if sub is None else sub.ctypes.data,
                                                  len(gs), gs.ctypes.data if len(gs) else None, C.byref(self._h)))
         self.V, self.J = n_verts, n_joints
+        self.id = id(self)
+        _READOUTS[self.id] = self
 
     def __del__(self):
         try:
+            _READOUTS.pop(self.id, None)
             if self._h.value:
                 _lib.lib().whmr_readout_destroy(self._h)
                 self._h = C.c_void_p()
         except Exception:
             pass
+
+    def split(self, flat, B):
+        """group-major flat buffer -> dict name -> contiguous [B, R_g, 3] view"""
+        res, off = {}, 0
+        for name, r in zip(self.names, self.sizes):
+            res[name] = flat[off:off + B * r * 3].view(B, r, 3)
+            off += B * r * 3
+        return res
 
     def apply(self, verts, joints=None):
         """-> dict name -> contiguous [B, R_g, 3] tensor (all from one launch pair)."""
@@ -226,11 +248,7 @@ class Readout:
         out = torch.empty(B * self.R * 3, dtype=torch.float32, device=verts.device)
         with torch.cuda.device(verts.device):
             check(_lib.lib().whmr_readout_apply(self._h, _p(verts), _p(joints), B, _p(out), _stream()))
-        res, off = {}, 0
-        for name, r in zip(self.names, self.sizes):
-            res[name] = out[off:off + B * r * 3].view(B, r, 3)
-            off += B * r * 3
-        return res
+        return self.split(out, B)
 
 
 def gather_vertices(verts, idx):
@@ -390,6 +408,21 @@ def _(handle, betas, pose, pose_is_rotmat):
     h = _HANDLES[handle]
     B = betas.shape[0]
     return betas.new_empty(B, h.V, 3), betas.new_empty(B, h.J, 3)
+
+
+@torch.library.custom_op("whmr::smpl_lbs_readout", mutates_args=(), device_types="cuda")
+def smpl_lbs_readout(handle: int, readout: int, betas: torch.Tensor, pose: torch.Tensor, pose_is_rotmat: bool) -> \
+        tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """SMPL forward + all read-outs of a Readout table (flat, group-major) in one chunked pass."""
+    v, j, _, flat = _HANDLES[handle].forward(betas, pose, pose_is_rotmat, readout=_READOUTS[readout])
+    return v, j, flat
+
+
+@smpl_lbs_readout.register_fake
+def _(handle, readout, betas, pose, pose_is_rotmat):
+    h, ro = _HANDLES[handle], _READOUTS[readout]
+    B = betas.shape[0]
+    return betas.new_empty(B, h.V, 3), betas.new_empty(B, h.J, 3), betas.new_empty(B * ro.R * 3)
 
 
 @torch.library.custom_op("whmr::sample_bilinear", mutates_args=(), device_types="cuda")

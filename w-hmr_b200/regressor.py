@@ -92,10 +92,10 @@ class BodyModelHead(nn.Module):
         h, _ = self.smpl._state(dev)
         rot = pred_rotmat.reshape(B, -1, 3, 3)
         self._mark('pre_smpl')
-        verts, joints24 = ops.smpl_lbs(h.id, pred_shape, rot, True)
-        self._mark('skin')
-        r = self._readout(dev, bool(J_regressor)).apply(verts, joints24)
-        self._mark('readout')
+        ro = self._readout(dev, bool(J_regressor))
+        verts, joints24, flat = ops.smpl_lbs_readout(h.id, ro.id, pred_shape, rot, True)
+        r = ro.split(flat, B)
+        self._mark('skin_readout')
         pred_joints = r['joints']
         kp_2d = ops.project_weak_op(pred_joints, pred_cam, constants.FOCAL_LENGTH,
                                     float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
