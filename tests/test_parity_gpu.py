@@ -124,7 +124,9 @@ def test_smpl_chunked_large_batch_properties(dev, smpl_model, gemm_mode):
     ident = smpl(betas=betas, body_pose=eye[:, 1:], global_orient=eye[:, :1], pose2rot=False)
     vs = torch.from_numpy(smpl_model['v_template']).to(dev)[None] + torch.einsum(
         'bl,mkl->bmk', betas, torch.from_numpy(smpl_model['shapedirs']).to(dev))
-    assert float((ident.vertices - vs).abs().max()) <= 2e-6
+    # the shape blend rides in the pose-blend contraction: bf16x3 carries 2^-16 relative error on
+    # |S.beta| <= ~0.1 m (measured 2.1e-6), the fp32 / 3xtf32 paths stay below 1e-6
+    assert float((ident.vertices - vs).abs().max()) <= (4e-6 if gemm_mode == "bf16x3" else 1.5e-6)
     assert ops is not None
 
 
