@@ -27,7 +27,7 @@ constexpr int kSkinThreads = 320;
 constexpr int kSkinWPart = kTcM * 128;      // 16 KB: 128 vertices x 32 joints (tf32)
 constexpr int kSkinAtPart = kSkinN * 128;   // 24 KB: 192 rows x 32 joints
 constexpr int kSkinStageBytes = 2 * kSkinAtPart;
-constexpr int kSkinSmem = 2 * kSkinWPart + kSkinStages * kSkinStageBytes + 8 * 96 * 4 + 256 + 1024;
+constexpr int kSkinSmem = 2 * kSkinWPart + kSkinStages * kSkinStageBytes + 8 * 192 * 4 + 256 + 1024;
 constexpr int kSkinTmemStage = 256;         // column stride between the two accumulator stages
 
 struct SkinTcParams {
@@ -61,8 +61,8 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_smem = smem;                                   // [2][16 KB]
   uint8_t* at_smem = smem + 2 * kSkinWPart;                 // [stages][2][24 KB]
-  float* stage_out = reinterpret_cast<float*>(at_smem + kSkinStages * kSkinStageBytes);   // [8 warps][96]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 8 * 96);
+  float* stage_out = reinterpret_cast<float*>(at_smem + kSkinStages * kSkinStageBytes);   // [8 warps][2][96]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 8 * 192);
   uint64_t* w_full = bars;
   uint64_t* w_empty = bars + 1;
   uint64_t* at_full = bars + 2;                  // [stages]
@@ -151,68 +151,100 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     // ===================================== epilogue =========================================
     const int q = warp & 3;            // TMEM lane quarter
     const int hb = (warp - 2) >> 2;    // which 8 bodies of the 16-body group
-    float* stg = stage_out + (warp - 2) * 96;
+    float* stg = stage_out + (warp - 2) * 192;   // two 96-float transpose buffers, alternated per body
     int acc = 0; uint32_t acc_phase = 0;
     int cur_vt = -1;
     float tx = 0.f, ty = 0.f, tz = 0.f;
     int v = 0, d0 = 0, d1 = 0;
+    // one-hot read-out destinations of this thread's vertex: element offset of body 0 + per-body stride
+    long long db0 = 0, db1 = 0, db2 = 0;
+    int ds0 = 0, ds1 = 0, ds2 = 0, nd = 0;
+    auto dest = [&](int d, long long& base, int& stride) {
+      const int row = p.dst_row[d];
+      const int pre = p.grp_prefix[row], rg = p.grp_rows[row];
+      base = 3LL * ((long long)p.ro_B * pre + (long long)p.ro_b0 * rg + (row - pre));
+      stride = 3 * rg;
+    };
+    int parity = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int vt = t / p.n_groups, g = t % p.n_groups;
       if (vt != cur_vt) {
         cur_vt = vt;
         v = vt * kTcM + q * 32 + lane;                        // < VP
         tx = p.v_template_p[v]; ty = p.v_template_p[p.VP + v]; tz = p.v_template_p[2 * p.VP + v];
-        if (p.dst_ptr) { d0 = p.dst_ptr[v]; d1 = p.dst_ptr[v + 1]; }
+        nd = 0;
+        if (p.dst_ptr) {
+          d0 = p.dst_ptr[v]; d1 = p.dst_ptr[v + 1]; nd = d1 - d0;
+          if (nd > 0) dest(d0, db0, ds0);
+          if (nd > 1) dest(d0 + 1, db1, ds1);
+          if (nd > 2) dest(d0 + 2, db2, ds2);
+        }
       }
       const int body_base = g * kSkinGB + hb * 8;
+      // the pose offsets do not depend on the MMA: get all 8 bodies' loads in flight before waiting on it
+      float ox[8], oy[8], oz[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int b = min(body_base + i, p.nb - 1);
+        const float* o = p.offsets + (size_t)b * p.NP + v;
+        ox[i] = o[0]; oy[i] = o[p.VP]; oz[i] = o[2 * p.VP];
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kSkinTmemStage + hb * 96);
       const size_t out_base = (size_t)(vt * kTcM + q * 32) * 3;   // float index of this warp's first vertex in a body
-#pragma unroll 1
+#pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int b4 = body_base + half * 4;
-        if (b4 >= p.nb) break;                                  // warp-uniform
-        float ox[4], oy[4], oz[4];
+        if (b4 < p.nb) {                                        // warp-uniform
+          uint32_t T[48];
+          tmem_ld_32x32b_x32(taddr + half * 48, T);
+          tmem_ld_32x32b_x16(taddr + half * 48 + 32, T + 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int b = min(b4 + i, p.nb - 1);
-          const float* o = p.offsets + (size_t)b * p.NP + v;
-          ox[i] = o[0]; oy[i] = o[p.VP]; oz[i] = o[2 * p.VP];
-        }
-        uint32_t T[48];
-        tmem_ld_32x32b_x32(taddr + half * 48, T);
-        tmem_ld_32x32b_x16(taddr + half * 48 + 32, T + 32);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int b = b4 + i;
-          if (b < p.nb) {                                       // warp-uniform
-            const float px = ox[i] + tx, py = oy[i] + ty, pz = oz[i] + tz;
+          for (int i = 0; i < 4; ++i) {
+            const int b = b4 + i;
+            if (b < p.nb) {                                     // warp-uniform
+              const float px = ox[half * 4 + i] + tx, py = oy[half * 4 + i] + ty, pz = oz[half * 4 + i] + tz;
 #define WHMR_T(k) __uint_as_float(T[i * 12 + (k)])
-            float rx = fmaf(WHMR_T(0), px, fmaf(WHMR_T(1), py, fmaf(WHMR_T(2), pz, WHMR_T(3))));
-            float ry = fmaf(WHMR_T(4), px, fmaf(WHMR_T(5), py, fmaf(WHMR_T(6), pz, WHMR_T(7))));
-            float rz = fmaf(WHMR_T(8), px, fmaf(WHMR_T(9), py, fmaf(WHMR_T(10), pz, WHMR_T(11))));
+              float rx = fmaf(WHMR_T(0), px, fmaf(WHMR_T(1), py, fmaf(WHMR_T(2), pz, WHMR_T(3))));
+              float ry = fmaf(WHMR_T(4), px, fmaf(WHMR_T(5), py, fmaf(WHMR_T(6), pz, WHMR_T(7))));
+              float rz = fmaf(WHMR_T(8), px, fmaf(WHMR_T(9), py, fmaf(WHMR_T(10), pz, WHMR_T(11))));
 #undef WHMR_T
-            if (p.transl) {
-              rx += p.transl[(size_t)b * 3 + 0]; ry += p.transl[(size_t)b * 3 + 1]; rz += p.transl[(size_t)b * 3 + 2];
-            }
-            // transpose through smem: 3 coalesced 128-byte rows per warp and body
-            stg[lane * 3 + 0] = rx; stg[lane * 3 + 1] = ry; stg[lane * 3 + 2] = rz;
-            __syncwarp();
-            float* ob = p.verts + (size_t)b * p.V * 3;
+              if (p.transl) {
+                rx += p.transl[(size_t)b * 3 + 0]; ry += p.transl[(size_t)b * 3 + 1]; rz += p.transl[(size_t)b * 3 + 2];
+              }
+              // transpose through smem (double-buffered: one __syncwarp per body): lane l holds xyz of
+              // vertex l -> 3 coalesced 128-byte rows per warp and body
+              float* sb = stg + parity * 96;
+              parity ^= 1;
+              sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz;
+              __syncwarp();
+              float* ob = p.verts + (size_t)b * p.V * 3;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const size_t idx = out_base + r * 32 + lane;
-              if (idx < (size_t)p.V * 3) ob[idx] = stg[r * 32 + lane];
-            }
-            __syncwarp();
-            // fused one-hot read-outs (vertex picks, markers, mesh down-sampling)
-            for (int d = d0; d < d1; ++d) {
-              const int row = p.dst_row[d];
-              const int pre = p.grp_prefix[row], rg = p.grp_rows[row];
-              float* o = p.ro_out + 3 * ((size_t)p.ro_B * pre + (size_t)(p.ro_b0 + b) * rg + (row - pre));
-              o[0] = rx; o[1] = ry; o[2] = rz;
+              for (int r = 0; r < 3; ++r) {
+                const size_t idx = out_base + r * 32 + lane;
+                if (idx < (size_t)p.V * 3) ob[idx] = sb[r * 32 + lane];
+              }
+              // fused one-hot read-outs (vertex picks, markers, mesh down-sampling)
+              if (nd > 0) {
+                float* o = p.ro_out + db0 + (long long)b * ds0;
+                o[0] = rx; o[1] = ry; o[2] = rz;
+                if (nd > 1) {
+                  o = p.ro_out + db1 + (long long)b * ds1;
+                  o[0] = rx; o[1] = ry; o[2] = rz;
+                  if (nd > 2) {
+                    o = p.ro_out + db2 + (long long)b * ds2;
+                    o[0] = rx; o[1] = ry; o[2] = rz;
+                    for (int d = d0 + 3; d < d1; ++d) {   // rare: a vertex feeding more than 3 read-out rows
+                      long long bb; int ss;
+                      dest(d, bb, ss);
+                      o = p.ro_out + bb + (long long)b * ss;
+                      o[0] = rx; o[1] = ry; o[2] = rz;
+                    }
+                  }
+                }
+              }
             }
           }
         }
