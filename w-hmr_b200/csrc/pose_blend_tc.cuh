@@ -158,7 +158,7 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
   constexpr int kElem = kKind == 0 ? 2 : 4;
   constexpr int kChunkElems = 128 / kElem;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + S::kStages;         // [kStages]

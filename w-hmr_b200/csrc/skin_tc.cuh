@@ -16,6 +16,8 @@
 // vertex-major, so a CTA reloads the weight tile only when its vertex tile changes.
 // HBM/L2 traffic per body: 4*NP (offsets, L2-resident) + 4*3V (out) + 54 * 3 KB of At from L2.
 #pragma once
+#include <cuda/std/type_traits>
+
 #include "pose_blend_tc.cuh"
 
 namespace whmr {
@@ -58,7 +60,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) 
 __global__ void __launch_bounds__(kSkinThreads, 1)
 skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapAt, SkinTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by OFFSET (not by integer round-trip) so the compiler keeps the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* w_smem = smem;                                   // [2][16 KB]
   uint8_t* at_smem = smem + 2 * kSkinWPart;                 // [stages][2][24 KB]
   float* stage_out = reinterpret_cast<float*>(at_smem + kSkinStages * kSkinStageBytes);   // [8 warps][2][96]
@@ -155,16 +158,18 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     int acc = 0; uint32_t acc_phase = 0;
     int cur_vt = -1;
     float tx = 0.f, ty = 0.f, tz = 0.f;
-    int v = 0, d0 = 0, d1 = 0;
-    // one-hot read-out destinations of this thread's vertex: element offset of body 0 + per-body stride
-    long long db0 = 0, db1 = 0, db2 = 0;
-    int ds0 = 0, ds1 = 0, ds2 = 0, nd = 0;
-    auto dest = [&](int d, long long& base, int& stride) {
+    int v = 0, d0 = 0, d1 = 0, nd = 0;
+    // one-hot read-out destinations of this thread's vertex: element offset for body 0 of the chunk and
+    // per-body stride (elements); 32-bit is enough (the host checks 3*B*R < 2^31)
+    int db0 = 0, db1 = 0, db2 = 0, ds0 = 0, ds1 = 0, ds2 = 0;
+    auto dest = [&](int d, int& base, int& stride) {
       const int row = p.dst_row[d];
       const int pre = p.grp_prefix[row], rg = p.grp_rows[row];
-      base = 3LL * ((long long)p.ro_B * pre + (long long)p.ro_b0 * rg + (row - pre));
+      base = 3 * (p.ro_B * pre + p.ro_b0 * rg + (row - pre));
       stride = 3 * rg;
     };
+    const int V3 = p.V * 3;
+    const bool has_transl = p.transl != nullptr;
     int parity = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int vt = t / p.n_groups, g = t % p.n_groups;
@@ -181,73 +186,86 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         }
       }
       const int body_base = g * kSkinGB + hb * 8;
+      const int n_valid = min(8, p.nb - body_base);             // bodies this warp really has (may be <= 0)
+      const int out_col = (vt * kTcM + q * 32) * 3 + lane;      // float index inside a body row
       // the pose offsets do not depend on the MMA: get all 8 bodies' loads in flight before waiting on it
       float ox[8], oy[8], oz[8];
+      {
+        const float* offp = p.offsets + (size_t)min(body_base, p.nb - 1) * p.NP + v;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int b = min(body_base + i, p.nb - 1);
-        const float* o = p.offsets + (size_t)b * p.NP + v;
-        ox[i] = o[0]; oy[i] = o[p.VP]; oz[i] = o[2 * p.VP];
+        for (int i = 0; i < 8; ++i) {
+          const float* o = offp + (size_t)(i < n_valid ? i : 0) * p.NP;
+          ox[i] = o[0]; oy[i] = o[p.VP]; oz[i] = o[2 * p.VP];
+        }
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kSkinTmemStage + hb * 96);
-      const size_t out_base = (size_t)(vt * kTcM + q * 32) * 3;   // float index of this warp's first vertex in a body
+      float* outp = p.verts + (size_t)max(body_base, 0) * V3 + out_col;
+      // guarded (ragged last group / last vertex tile / transl) and unguarded instantiations of the same body
+      auto run = [&](auto guard_tag) {
+        constexpr bool G = decltype(guard_tag)::value;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int b4 = body_base + half * 4;
-        if (b4 < p.nb) {                                        // warp-uniform
+        for (int half = 0; half < 2; ++half) {
+          if (G && half * 4 >= n_valid) continue;               // warp-uniform
           uint32_t T[48];
           tmem_ld_32x32b_x32(taddr + half * 48, T);
           tmem_ld_32x32b_x16(taddr + half * 48 + 32, T + 32);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int b = b4 + i;
-            if (b < p.nb) {                                     // warp-uniform
-              const float px = ox[half * 4 + i] + tx, py = oy[half * 4 + i] + ty, pz = oz[half * 4 + i] + tz;
+            const int bi = half * 4 + i;
+            if (G && bi >= n_valid) continue;                   // warp-uniform
+            const float px = ox[bi] + tx, py = oy[bi] + ty, pz = oz[bi] + tz;
 #define WHMR_T(k) __uint_as_float(T[i * 12 + (k)])
-              float rx = fmaf(WHMR_T(0), px, fmaf(WHMR_T(1), py, fmaf(WHMR_T(2), pz, WHMR_T(3))));
-              float ry = fmaf(WHMR_T(4), px, fmaf(WHMR_T(5), py, fmaf(WHMR_T(6), pz, WHMR_T(7))));
-              float rz = fmaf(WHMR_T(8), px, fmaf(WHMR_T(9), py, fmaf(WHMR_T(10), pz, WHMR_T(11))));
+            float rx = fmaf(WHMR_T(0), px, fmaf(WHMR_T(1), py, fmaf(WHMR_T(2), pz, WHMR_T(3))));
+            float ry = fmaf(WHMR_T(4), px, fmaf(WHMR_T(5), py, fmaf(WHMR_T(6), pz, WHMR_T(7))));
+            float rz = fmaf(WHMR_T(8), px, fmaf(WHMR_T(9), py, fmaf(WHMR_T(10), pz, WHMR_T(11))));
 #undef WHMR_T
-              if (p.transl) {
-                rx += p.transl[(size_t)b * 3 + 0]; ry += p.transl[(size_t)b * 3 + 1]; rz += p.transl[(size_t)b * 3 + 2];
-              }
-              // transpose through smem (double-buffered: one __syncwarp per body): lane l holds xyz of
-              // vertex l -> 3 coalesced 128-byte rows per warp and body
-              float* sb = stg + parity * 96;
-              parity ^= 1;
-              sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz;
-              __syncwarp();
-              float* ob = p.verts + (size_t)b * p.V * 3;
+            if (G && has_transl) {
+              const float* tr = p.transl + (size_t)(body_base + bi) * 3;
+              rx += tr[0]; ry += tr[1]; rz += tr[2];
+            }
+            // transpose through smem (double-buffered: one __syncwarp per body): lane l holds xyz of
+            // vertex l -> 3 coalesced 128-byte rows per warp and body
+            float* sb = stg + parity * 96;
+            parity ^= 1;
+            sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz;
+            __syncwarp();
+            float* ob = outp + (size_t)bi * V3;
+            if (G) {
 #pragma unroll
-              for (int r = 0; r < 3; ++r) {
-                const size_t idx = out_base + r * 32 + lane;
-                if (idx < (size_t)p.V * 3) ob[idx] = sb[r * 32 + lane];
-              }
-              // fused one-hot read-outs (vertex picks, markers, mesh down-sampling)
-              if (nd > 0) {
-                float* o = p.ro_out + db0 + (long long)b * ds0;
+              for (int r = 0; r < 3; ++r)
+                if (out_col + r * 32 < V3) ob[r * 32] = sb[r * 32 + lane];
+            } else {
+              ob[0] = sb[lane]; ob[32] = sb[32 + lane]; ob[64] = sb[64 + lane];
+            }
+            // fused one-hot read-outs (vertex picks, markers, mesh down-sampling)
+            if (nd > 0) {
+              const int b = body_base + bi;
+              float* o = p.ro_out + (db0 + b * ds0);
+              o[0] = rx; o[1] = ry; o[2] = rz;
+              if (nd > 1) {
+                o = p.ro_out + (db1 + b * ds1);
                 o[0] = rx; o[1] = ry; o[2] = rz;
-                if (nd > 1) {
-                  o = p.ro_out + db1 + (long long)b * ds1;
+                if (nd > 2) {
+                  o = p.ro_out + (db2 + b * ds2);
                   o[0] = rx; o[1] = ry; o[2] = rz;
-                  if (nd > 2) {
-                    o = p.ro_out + db2 + (long long)b * ds2;
+                  for (int d = d0 + 3; d < d1; ++d) {   // rare: a vertex feeding more than 3 read-out rows
+                    int bb, ss;
+                    dest(d, bb, ss);
+                    o = p.ro_out + (bb + b * ss);
                     o[0] = rx; o[1] = ry; o[2] = rz;
-                    for (int d = d0 + 3; d < d1; ++d) {   // rare: a vertex feeding more than 3 read-out rows
-                      long long bb; int ss;
-                      dest(d, bb, ss);
-                      o = p.ro_out + bb + (long long)b * ss;
-                      o[0] = rx; o[1] = ry; o[2] = rz;
-                    }
                   }
                 }
               }
             }
           }
         }
+      };
+      if (n_valid > 0) {
+        const bool fast = n_valid == 8 && !has_transl && (vt + 1) * kTcM <= p.V;
+        if (fast) run(cuda::std::false_type{}); else run(cuda::std::true_type{});
       }
       tcgen05_fence_before();
       __syncwarp();

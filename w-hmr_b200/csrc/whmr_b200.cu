@@ -461,7 +461,9 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
   if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, st, cudaEventRecordExternal));
   // chunked so the [chunk, NP] pose-offset intermediate (and the chunk's vertices, for the read-outs)
   // stay L2-resident between the kernels
-  const bool fused_onehot = ro && h->skin_tc && ro->dst_VP == h->d.VP;
+  static const bool fuse_env = !(getenv("WHMR_FUSE_ONEHOT") && atoi(getenv("WHMR_FUSE_ONEHOT")) == 0);
+  const bool fused_onehot = ro && h->skin_tc && fuse_env && ro->dst_VP == h->d.VP &&
+                            3LL * B * ro->R < (1LL << 31);   // 32-bit element offsets in the epilogue
   for (int b0 = 0; b0 < B; b0 += ws.chunk) {
     const int nb = std::min(ws.chunk, B - b0);
     rc = launch_pose_blend(h, ws, B, b0, nb, st);
