@@ -24,12 +24,15 @@ namespace whmr {
 
 constexpr int kSkinGB = 16;                 // bodies per MMA tile
 constexpr int kSkinN = kSkinGB * 12;        // 192 accumulator columns per tile
-constexpr int kSkinStages = 3;
+constexpr int kSkinStages = 2;               // At ring (released by the MMA's commit)
+constexpr int kSkinOffStages = 3;            // pose-offset ring (released by the epilogue warps)
+constexpr int kSkinOffBytes = kSkinGB * 3 * kTcM * 4;   // 24 KB: [16 bodies][3 planes][128 vertices] fp32
 constexpr int kSkinThreads = 320;
 constexpr int kSkinWPart = kTcM * 128;      // 16 KB: 128 vertices x 32 joints (tf32)
 constexpr int kSkinAtPart = kSkinN * 128;   // 24 KB: 192 rows x 32 joints
 constexpr int kSkinStageBytes = 2 * kSkinAtPart;
-constexpr int kSkinSmem = 2 * kSkinWPart + kSkinStages * kSkinStageBytes + 8 * 192 * 4 + 256 + 1024;
+constexpr int kSkinSmem = 2 * kSkinWPart + kSkinStages * kSkinStageBytes + kSkinOffStages * kSkinOffBytes +
+                          8 * 192 * 4 + 256 + 1024;
 constexpr int kSkinTmemStage = 256;         // column stride between the two accumulator stages
 
 struct SkinTcParams {
@@ -58,19 +61,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) 
 }
 
 __global__ void __launch_bounds__(kSkinThreads, 1)
-skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapAt, SkinTcParams p) {
+skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant__ CUtensorMap tmapAt,
+               const __grid_constant__ CUtensorMap tmapOff, SkinTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSET (not by integer round-trip) so the compiler keeps the shared address space
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* w_smem = smem;                                   // [2][16 KB]
   uint8_t* at_smem = smem + 2 * kSkinWPart;                 // [stages][2][24 KB]
-  float* stage_out = reinterpret_cast<float*>(at_smem + kSkinStages * kSkinStageBytes);   // [8 warps][2][96]
+  float* off_smem = reinterpret_cast<float*>(at_smem + kSkinStages * kSkinStageBytes);    // [off stages][16][3][128]
+  float* stage_out = off_smem + kSkinOffStages * (kSkinOffBytes / 4);                     // [8 warps][2][96]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 8 * 192);
   uint64_t* w_full = bars;
   uint64_t* w_empty = bars + 1;
   uint64_t* at_full = bars + 2;                  // [stages]
   uint64_t* at_empty = at_full + kSkinStages;    // [stages]
-  uint64_t* tmem_full = at_empty + kSkinStages;  // [2]
+  uint64_t* off_full = at_empty + kSkinStages;   // [off stages]
+  uint64_t* off_empty = off_full + kSkinOffStages;
+  uint64_t* tmem_full = off_empty + kSkinOffStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -82,6 +89,7 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
     for (int s = 0; s < kSkinStages; ++s) { mbar_init(&at_full[s], 1); mbar_init(&at_empty[s], 1); }
+    for (int s = 0; s < kSkinOffStages; ++s) { mbar_init(&off_full[s], 1); mbar_init(&off_empty[s], 8); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -99,6 +107,7 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, w_par = 1;
+      int ostage = 0; uint32_t ophase = 0;
       int cur_vt = -1;
       for (int t = t_begin; t < t_end; ++t) {
         const int vt = t / p.n_groups, g = t % p.n_groups;
@@ -116,6 +125,11 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         tma_load_3d(st, &tmapAt, &at_full[stage], 0, g * kSkinN, 0);
         tma_load_3d(st + kSkinAtPart, &tmapAt, &at_full[stage], 0, g * kSkinN, 1);
         if (++stage == kSkinStages) { stage = 0; phase ^= 1; }
+        // pose offsets of the item: [16 bodies][3 planes][128 vertices]
+        mbar_wait(&off_empty[ostage], ophase ^ 1);
+        mbar_arrive_expect_tx(&off_full[ostage], kSkinOffBytes);
+        tma_load_3d(off_smem + ostage * (kSkinOffBytes / 4), &tmapOff, &off_full[ostage], vt * kTcM, 0, g * kSkinGB);
+        if (++ostage == kSkinOffStages) { ostage = 0; ophase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -171,6 +185,7 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     const int V3 = p.V * 3;
     const bool has_transl = p.transl != nullptr;
     int parity = 0;
+    int ostage = 0; uint32_t ophase = 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int vt = t / p.n_groups, g = t % p.n_groups;
       if (vt != cur_vt) {
@@ -188,16 +203,9 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
       const int body_base = g * kSkinGB + hb * 8;
       const int n_valid = min(8, p.nb - body_base);             // bodies this warp really has (may be <= 0)
       const int out_col = (vt * kTcM + q * 32) * 3 + lane;      // float index inside a body row
-      // the pose offsets do not depend on the MMA: get all 8 bodies' loads in flight before waiting on it
-      float ox[8], oy[8], oz[8];
-      {
-        const float* offp = p.offsets + (size_t)min(body_base, p.nb - 1) * p.NP + v;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float* o = offp + (size_t)(i < n_valid ? i : 0) * p.NP;
-          ox[i] = o[0]; oy[i] = o[p.VP]; oz[i] = o[2 * p.VP];
-        }
-      }
+      // pose offsets of this item were put in shared memory by the TMA producer
+      const float* offs = off_smem + ostage * (kSkinOffBytes / 4) + (hb * 8) * (3 * kTcM) + q * 32 + lane;
+      mbar_wait(&off_full[ostage], ophase);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kSkinTmemStage + hb * 96);
@@ -216,7 +224,8 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
           for (int i = 0; i < 4; ++i) {
             const int bi = half * 4 + i;
             if (G && bi >= n_valid) continue;                   // warp-uniform
-            const float px = ox[bi] + tx, py = oy[bi] + ty, pz = oz[bi] + tz;
+            const float px = offs[bi * 3 * kTcM] + tx, py = offs[bi * 3 * kTcM + kTcM] + ty,
+                        pz = offs[bi * 3 * kTcM + 2 * kTcM] + tz;
 #define WHMR_T(k) __uint_as_float(T[i * 12 + (k)])
             float rx = fmaf(WHMR_T(0), px, fmaf(WHMR_T(1), py, fmaf(WHMR_T(2), pz, WHMR_T(3))));
             float ry = fmaf(WHMR_T(4), px, fmaf(WHMR_T(5), py, fmaf(WHMR_T(6), pz, WHMR_T(7))));
@@ -269,8 +278,9 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) { mbar_arrive(&tmem_empty[acc]); mbar_arrive(&off_empty[ostage]); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++ostage == kSkinOffStages) { ostage = 0; ophase ^= 1; }
     }
   }
 

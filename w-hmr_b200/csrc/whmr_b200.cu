@@ -397,8 +397,20 @@ static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* beta
     int rc = tc_encode_rows32(h->tc.encode_fn, &tmapAt, ws.At + (size_t)b0 * 12 * 32, (size_t)(ws.Bpad - b0) * 12,
                               ws.At_part_stride * sizeof(float), kSkinN);
     if (rc) return rc;
+    // pose offsets: 3-D map {VP vertices, 3 planes, chunk bodies} over the planar [chunk, NP] buffer
+    CUtensorMap tmapOff;
+    {
+      cuuint64_t dims[3] = {(cuuint64_t)d.VP, 3, (cuuint64_t)ws.chunk};
+      cuuint64_t strides[2] = {(cuuint64_t)d.VP * 4, (cuuint64_t)d.NP * 4};
+      cuuint32_t box[3] = {(cuuint32_t)kTcM, 3, (cuuint32_t)kSkinGB};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = reinterpret_cast<PFN_encodeTiled>(h->tc.encode_fn)(
+          &tmapOff, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ws.offsets, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return set_error(WHMR_E_CUDA, "cuTensorMapEncodeTiled (offsets) failed with CUresult %d", (int)r);
+    }
     const int grid = std::min(h->tc.num_sms, p.n_items);
-    skin_tc_kernel<<<grid, kSkinThreads, kSkinSmem, st>>>(h->tc.tmapW, tmapAt, p);
+    skin_tc_kernel<<<grid, kSkinThreads, kSkinSmem, st>>>(h->tc.tmapW, tmapAt, tmapOff, p);
     WHMR_LAUNCHED("skin_tc_kernel");
     return WHMR_OK;
   }
@@ -461,7 +473,9 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
   if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, st, cudaEventRecordExternal));
   // chunked so the [chunk, NP] pose-offset intermediate (and the chunk's vertices, for the read-outs)
   // stay L2-resident between the kernels
-  static const bool fuse_env = !(getenv("WHMR_FUSE_ONEHOT") && atoi(getenv("WHMR_FUSE_ONEHOT")) == 0);
+  // measured (profiles/r01_notes.md): per-thread scattered stores in the epilogue cost more than the separate
+  // L2-resident gather kernel, so the fusion is opt-in until the epilogue scatters warp-cooperatively
+  static const bool fuse_env = getenv("WHMR_FUSE_ONEHOT") && atoi(getenv("WHMR_FUSE_ONEHOT")) == 1;
   const bool fused_onehot = ro && h->skin_tc && fuse_env && ro->dst_VP == h->d.VP &&
                             3LL * B * ro->R < (1LL << 31);   // 32-bit element offsets in the epilogue
   for (int b0 = 0; b0 < B; b0 += ws.chunk) {
