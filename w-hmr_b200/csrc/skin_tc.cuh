@@ -11,8 +11,8 @@
 // numbers per body.  Dense in J, so any weight sparsity (incl. fully dense weights) costs the same.
 // fp32 accuracy: w and A are split x = hi + lo into tf32-exact halves, 3 MMAs (hi.hi + hi.lo + lo.hi).
 //
-// CTA = 320 threads: warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2-9 epilogue
-// (2 warps per TMEM lane quarter, 8 bodies each).  Persistent over (vertex tile x 16-body group) items,
+// CTA = 576 threads: warp 0 TMA producer, warp 1 TMEM alloc + MMA issue, warps 2-17 epilogue
+// (4 warps per TMEM lane quarter, 4 bodies each).  Persistent over (vertex tile x 16-body group) items,
 // vertex-major, so a CTA reloads the weight tile only when its vertex tile changes.
 // HBM/L2 traffic per body: 4*NP (offsets, L2-resident) + 4*3V (out) + 54 * 3 KB of At from L2.
 #pragma once
@@ -27,12 +27,13 @@ constexpr int kSkinN = kSkinGB * 12;        // 192 accumulator columns per tile
 constexpr int kSkinStages = 2;               // At ring (released by the MMA's commit)
 constexpr int kSkinOffStages = 3;            // pose-offset ring (released by the epilogue warps)
 constexpr int kSkinOffBytes = kSkinGB * 3 * kTcM * 4;   // 24 KB: [16 bodies][3 planes][128 vertices] fp32
-constexpr int kSkinThreads = 320;
+constexpr int kSkinEpiWarps = 16;            // 4 per TMEM lane quarter, 4 bodies each
+constexpr int kSkinThreads = (2 + kSkinEpiWarps) * 32;
 constexpr int kSkinWPart = kTcM * 128;      // 16 KB: 128 vertices x 32 joints (tf32)
 constexpr int kSkinAtPart = kSkinN * 128;   // 24 KB: 192 rows x 32 joints
 constexpr int kSkinStageBytes = 2 * kSkinAtPart;
 constexpr int kSkinSmem = 2 * kSkinWPart + kSkinStages * kSkinStageBytes + kSkinOffStages * kSkinOffBytes +
-                          8 * 192 * 4 + 256 + 1024;
+                          kSkinEpiWarps * 192 * 4 + 256 + 1024;
 constexpr int kSkinTmemStage = 256;         // column stride between the two accumulator stages
 
 struct SkinTcParams {
@@ -70,7 +71,7 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
   uint8_t* at_smem = smem + 2 * kSkinWPart;                 // [stages][2][24 KB]
   float* off_smem = reinterpret_cast<float*>(at_smem + kSkinStages * kSkinStageBytes);    // [off stages][16][3][128]
   float* stage_out = off_smem + kSkinOffStages * (kSkinOffBytes / 4);                     // [8 warps][2][96]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 8 * 192);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kSkinEpiWarps * 192);
   uint64_t* w_full = bars;
   uint64_t* w_empty = bars + 1;
   uint64_t* at_full = bars + 2;                  // [stages]
@@ -89,8 +90,8 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
     for (int s = 0; s < kSkinStages; ++s) { mbar_init(&at_full[s], 1); mbar_init(&at_empty[s], 1); }
-    for (int s = 0; s < kSkinOffStages; ++s) { mbar_init(&off_full[s], 1); mbar_init(&off_empty[s], 8); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 8); }
+    for (int s = 0; s < kSkinOffStages; ++s) { mbar_init(&off_full[s], 1); mbar_init(&off_empty[s], kSkinEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kSkinEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -167,7 +168,7 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
   } else {
     // ===================================== epilogue =========================================
     const int q = warp & 3;            // TMEM lane quarter
-    const int hb = (warp - 2) >> 2;    // which 8 bodies of the 16-body group
+    const int hb = (warp - 2) >> 2;    // which 4 bodies of the 16-body group
     float* stg = stage_out + (warp - 2) * 192;   // two 96-float transpose buffers, alternated per body
     int acc = 0; uint32_t acc_phase = 0;
     int cur_vt = -1;
@@ -200,25 +201,24 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
           if (nd > 2) dest(d0 + 2, db2, ds2);
         }
       }
-      const int body_base = g * kSkinGB + hb * 8;
-      const int n_valid = min(8, p.nb - body_base);             // bodies this warp really has (may be <= 0)
+      const int body_base = g * kSkinGB + hb * 4;
+      const int n_valid = min(4, p.nb - body_base);             // bodies this warp really has (may be <= 0)
       const int out_col = (vt * kTcM + q * 32) * 3 + lane;      // float index inside a body row
       // pose offsets of this item were put in shared memory by the TMA producer
-      const float* offs = off_smem + ostage * (kSkinOffBytes / 4) + (hb * 8) * (3 * kTcM) + q * 32 + lane;
+      const float* offs = off_smem + ostage * (kSkinOffBytes / 4) + (hb * 4) * (3 * kTcM) + q * 32 + lane;
       mbar_wait(&off_full[ostage], ophase);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kSkinTmemStage + hb * 96);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kSkinTmemStage + hb * 48);
       float* outp = p.verts + (size_t)max(body_base, 0) * V3 + out_col;
       // guarded (ragged last group / last vertex tile / transl) and unguarded instantiations of the same body
       auto run = [&](auto guard_tag) {
         constexpr bool G = decltype(guard_tag)::value;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (G && half * 4 >= n_valid) continue;               // warp-uniform
+        {
+          constexpr int half = 0;
           uint32_t T[48];
-          tmem_ld_32x32b_x32(taddr + half * 48, T);
-          tmem_ld_32x32b_x16(taddr + half * 48 + 32, T + 32);
+          tmem_ld_32x32b_x32(taddr, T);
+          tmem_ld_32x32b_x16(taddr + 32, T + 32);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -273,7 +273,7 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         }
       };
       if (n_valid > 0) {
-        const bool fast = n_valid == 8 && !has_transl && (vt + 1) * kTcM <= p.V;
+        const bool fast = n_valid == 4 && !has_transl && (vt + 1) * kTcM <= p.V;
         if (fast) run(cuda::std::false_type{}); else run(cuda::std::true_type{});
       }
       tcgen05_fence_before();
