@@ -153,7 +153,8 @@ struct TcSmem {
 template <int kKind, int NB>
 __global__ void __launch_bounds__(kTcThreads, 1)
 pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                     float* __restrict__ out, int nb, int NP, int n_body_tiles, int n_items, int ksteps) {
+                     float* __restrict__ out, int nb, int NP, int n_body_tiles, int n_items, int ksteps,
+                     long long* __restrict__ dbg) {
   using S = TcSmem<NB>;
   constexpr int kElem = kKind == 0 ? 2 : 4;
   constexpr int kChunkElems = 128 / kElem;
@@ -190,11 +191,15 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      long long dbg_wait = 0;
+      const long long k0 = dbg ? clock64() : 0;
       for (int t = t_begin; t < t_end; ++t) {
         const int coord0 = (t / n_body_tiles) * kTcM;
         const int body0 = (t % n_body_tiles) * NB;
         for (int kc = 0; kc < kch; ++kc) {
+          const long long w0 = dbg ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);
+          if (dbg) dbg_wait += clock64() - w0;
           uint8_t* st = smem + stage * S::kStageBytes;
           mbar_arrive_expect_tx(&full[stage], S::kStageBytes);
           tma_load_3d(st, &tmapA, &full[stage], kc * kChunkElems, 0, coord0);
@@ -204,6 +209,7 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
           if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (dbg) { dbg[blockIdx.x * 8 + 0] = dbg_wait; dbg[blockIdx.x * 8 + 1] = clock64() - k0; }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
@@ -214,12 +220,18 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
                                  ((uint32_t)(kTcM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      long long dbg_full = 0, dbg_tm = 0;
+      const long long k0 = dbg ? clock64() : 0;
       for (int t = t_begin; t < t_end; ++t) {
+        long long w0 = dbg ? clock64() : 0;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (dbg) dbg_tm += clock64() - w0;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NB);
         for (int kc = 0; kc < kch; ++kc) {
+          w0 = dbg ? clock64() : 0;
           mbar_wait(&full[stage], phase);
+          if (dbg) dbg_full += clock64() - w0;
           tcgen05_fence_after();
           const uint32_t a_hi = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t a_lo = a_hi + S::kABytes;
@@ -239,15 +251,20 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
         tcgen05_commit(&tmem_full[acc]);   // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (dbg) { dbg[blockIdx.x * 8 + 2] = dbg_full; dbg[blockIdx.x * 8 + 3] = dbg_tm; dbg[blockIdx.x * 8 + 4] = clock64() - k0; }
     }
   } else {
     // ===================================== epilogue =========================================
     const int q = warp & 3;   // TMEM lane quarter this warp may access
     int acc = 0; uint32_t acc_phase = 0;
+    long long dbg_w = 0;
+    const long long k0 = dbg ? clock64() : 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int coord = (t / n_body_tiles) * kTcM + q * 32 + lane;
       const int body0 = (t % n_body_tiles) * NB;
+      const long long w0 = dbg ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (dbg) dbg_w += clock64() - w0;
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NB);
 #pragma unroll 1
@@ -266,6 +283,7 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (dbg && warp == 2 && lane == 0) { dbg[blockIdx.x * 8 + 5] = dbg_w; dbg[blockIdx.x * 8 + 6] = clock64() - k0; }
   }
 
   tcgen05_fence_before();
@@ -408,15 +426,29 @@ static inline int tc_pose_blend_launch(const TcPlan& plan, const SmplDevice& d, 
   if (rc) return rc;
   const int grid = std::min(plan.num_sms, n_items);
   const CUtensorMap& tmapA = kind == 0 ? plan.tmapA_bf16 : plan.tmapA_tf32;
+  long long* dbg = nullptr;
+  static const bool dbg_on = getenv("WHMR_TC_DEBUG") != nullptr;
+  if (dbg_on) { cudaMalloc(&dbg, sizeof(long long) * 8 * grid); cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, st); }
   if (kind == 0 && NB == 256)
-    pose_blend_tc_kernel<0, 256><<<grid, kTcThreads, TcSmem<256>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps);
+    pose_blend_tc_kernel<0, 256><<<grid, kTcThreads, TcSmem<256>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps, dbg);
   else if (kind == 0)
-    pose_blend_tc_kernel<0, 128><<<grid, kTcThreads, TcSmem<128>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps);
+    pose_blend_tc_kernel<0, 128><<<grid, kTcThreads, TcSmem<128>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps, dbg);
   else if (NB == 256)
-    pose_blend_tc_kernel<1, 256><<<grid, kTcThreads, TcSmem<256>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps);
+    pose_blend_tc_kernel<1, 256><<<grid, kTcThreads, TcSmem<256>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps, dbg);
   else
-    pose_blend_tc_kernel<1, 128><<<grid, kTcThreads, TcSmem<128>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps);
+    pose_blend_tc_kernel<1, 128><<<grid, kTcThreads, TcSmem<128>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps, dbg);
   WHMR_LAUNCHED("pose_blend_tc_kernel");
+  if (dbg) {   // WHMR_TC_DEBUG: per-role wait/total cycles, averaged over CTAs (debug only: synchronises)
+    cudaStreamSynchronize(st);
+    std::vector<long long> hd((size_t)8 * grid);
+    cudaMemcpy(hd.data(), dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dbg);
+    double a[8] = {0};
+    for (int c = 0; c < grid; ++c) for (int k = 0; k < 8; ++k) a[k] += (double)hd[(size_t)c * 8 + k] / grid;
+    fprintf(stderr, "[whmr tc dbg] NB=%d nb=%d items=%d grid=%d | producer wait_empty %.0f of %.0f | mma wait_full %.0f "
+            "wait_tmem %.0f of %.0f | epi wait_full %.0f of %.0f cycles\n", NB, nb, n_items, grid, a[0], a[1], a[2], a[3], a[4],
+            a[5], a[6]);
+  }
   return WHMR_OK;
 }
 
