@@ -145,7 +145,8 @@ struct TcSmem {
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
   static constexpr int kStages = NB == 256 ? 2 : 3;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;   // + alignment slack
+  static constexpr int kOutTile = 32 * kTcM * 4;      // epilogue staging: [32 bodies][128 coords] fp32, x2 buffers
+  static constexpr int kTotal = kStages * kStageBytes + 2 * kOutTile + kBarrierBytes + 1024;   // + alignment slack
 };
 
 // kKind 0: bf16 operands (2 B), 1: tf32 operands (4 B).  K is walked in 128-byte chunks (one TMA box
@@ -153,14 +154,15 @@ struct TcSmem {
 template <int kKind, int NB>
 __global__ void __launch_bounds__(kTcThreads, 1)
 pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                     float* __restrict__ out, int nb, int NP, int n_body_tiles, int n_items, int ksteps,
-                     long long* __restrict__ dbg) {
+                     const __grid_constant__ CUtensorMap tmapOut, int nb, int NP, int n_body_tiles, int n_items, int ksteps,
+                     long long* __restrict__ dbg, int dbg_mode) {
   using S = TcSmem<NB>;
   constexpr int kElem = kKind == 0 ? 2 : 4;
   constexpr int kChunkElems = 128 / kElem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  float* out_smem = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes);   // [2][32][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes + 2 * S::kOutTile);
   uint64_t* full = bars;                       // [kStages]
   uint64_t* empty = bars + S::kStages;         // [kStages]
   uint64_t* tmem_full = bars + 2 * S::kStages; // [2]
@@ -255,12 +257,16 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
     }
   } else {
     // ===================================== epilogue =========================================
+    // TMEM -> registers -> shared staging tile [32 bodies][128 coords] -> TMA store.  (Per-thread global
+    // stores from 4 warps topped out at ~2 TB/s here; the bulk store keeps the LSU out of the way.)
     const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const bool issuer = (warp == 2 && lane == 0);
     int acc = 0; uint32_t acc_phase = 0;
+    int buf = 0;
     long long dbg_w = 0;
     const long long k0 = dbg ? clock64() : 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const int coord = (t / n_body_tiles) * kTcM + q * 32 + lane;
+      const int coord0 = (t / n_body_tiles) * kTcM;
       const int body0 = (t % n_body_tiles) * NB;
       const long long w0 = dbg ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -269,20 +275,32 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NB);
 #pragma unroll 1
       for (int c0 = 0; c0 < NB; c0 += 32) {
-        if (body0 + c0 >= nb) break;   // warp-uniform
+        if (body0 + c0 >= nb) break;   // warp-uniform (and uniform across the 4 epilogue warps)
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + c0, v);
+        // the staging buffer we are about to overwrite was handed to a bulk store two blocks ago
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float* o = out + (size_t)(body0 + c0) * NP + coord;
+        float* tile = out_smem + buf * (32 * kTcM) + q * 32 + lane;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (body0 + c0 + j < nb) o[(size_t)j * NP] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) tile[j * kTcM] = __uint_as_float(v[j]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer && dbg_mode == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&tmapOut)), "r"(smem_u32(out_smem + buf * (32 * kTcM))),
+                         "r"(coord0), "r"(body0 + c0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        buf ^= 1;
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (dbg && warp == 2 && lane == 0) { dbg[blockIdx.x * 8 + 5] = dbg_w; dbg[blockIdx.x * 8 + 6] = clock64() - k0; }
   }
 
@@ -426,17 +444,30 @@ static inline int tc_pose_blend_launch(const TcPlan& plan, const SmplDevice& d, 
   if (rc) return rc;
   const int grid = std::min(plan.num_sms, n_items);
   const CUtensorMap& tmapA = kind == 0 ? plan.tmapA_bf16 : plan.tmapA_tf32;
+  // output: 2-D map {NP coords, nb bodies} over the planar pose-offset buffer, box {128, 32}; rows >= nb are clipped
+  CUtensorMap tmapOut;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.NP, (cuuint64_t)nb};
+    cuuint64_t strides[1] = {(cuuint64_t)d.NP * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kTcM, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<PFN_encodeTiled>(plan.encode_fn)(
+        &tmapOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(WHMR_E_CUDA, "cuTensorMapEncodeTiled (out) failed with CUresult %d", (int)r);
+  }
   long long* dbg = nullptr;
+  static const int dbg_mode = getenv("WHMR_TC_DEBUG_MODE") ? atoi(getenv("WHMR_TC_DEBUG_MODE")) : 0;
   static const bool dbg_on = getenv("WHMR_TC_DEBUG") != nullptr;
   if (dbg_on) { cudaMalloc(&dbg, sizeof(long long) * 8 * grid); cudaMemsetAsync(dbg, 0, sizeof(long long) * 8 * grid, st); }
   if (kind == 0 && NB == 256)
-    pose_blend_tc_kernel<0, 256><<<grid, kTcThreads, TcSmem<256>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps, dbg);
+    pose_blend_tc_kernel<0, 256><<<grid, kTcThreads, TcSmem<256>::kTotal, st>>>(tmapA, tmapB, tmapOut, nb, d.NP, n_body_tiles, n_items, ksteps, dbg, dbg_mode);
   else if (kind == 0)
-    pose_blend_tc_kernel<0, 128><<<grid, kTcThreads, TcSmem<128>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps, dbg);
+    pose_blend_tc_kernel<0, 128><<<grid, kTcThreads, TcSmem<128>::kTotal, st>>>(tmapA, tmapB, tmapOut, nb, d.NP, n_body_tiles, n_items, ksteps, dbg, dbg_mode);
   else if (NB == 256)
-    pose_blend_tc_kernel<1, 256><<<grid, kTcThreads, TcSmem<256>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps, dbg);
+    pose_blend_tc_kernel<1, 256><<<grid, kTcThreads, TcSmem<256>::kTotal, st>>>(tmapA, tmapB, tmapOut, nb, d.NP, n_body_tiles, n_items, ksteps, dbg, dbg_mode);
   else
-    pose_blend_tc_kernel<1, 128><<<grid, kTcThreads, TcSmem<128>::kTotal, st>>>(tmapA, tmapB, out, nb, d.NP, n_body_tiles, n_items, ksteps, dbg);
+    pose_blend_tc_kernel<1, 128><<<grid, kTcThreads, TcSmem<128>::kTotal, st>>>(tmapA, tmapB, tmapOut, nb, d.NP, n_body_tiles, n_items, ksteps, dbg, dbg_mode);
   WHMR_LAUNCHED("pose_blend_tc_kernel");
   if (dbg) {   // WHMR_TC_DEBUG: per-role wait/total cycles, averaged over CTAs (debug only: synchronises)
     cudaStreamSynchronize(st);
