@@ -106,6 +106,81 @@ __global__ void __launch_bounds__(256) readout_long_kernel(ReadoutParams p) {
   }
 }
 
+// One-hot rows (vertex picks, SSM markers, mesh down-sampling): compact table, one thread per (body,row).
+//   tab[r] = {source vertex, rows of all groups before this row's group, rows in its group, row - prefix}
+__global__ void __launch_bounds__(256)
+readout_onehot_kernel(const int4* __restrict__ tab, int n_rows, const float* __restrict__ verts, int V, int nb,
+                      int B_total, int b0, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nb * n_rows) return;
+  const int b = (int)(i / n_rows);
+  const int4 t = tab[(int)(i - (long long)b * n_rows)];
+  const float* s = verts + ((size_t)b * V + t.x) * 3;
+  const float x = s[0], y = s[1], z = s[2];
+  float* o = out + 3 * ((size_t)B_total * t.y + (size_t)(b0 + b) * t.z + t.w);
+  o[0] = x; o[1] = y; o[2] = z;
+}
+
+// Regressor rows: one warp per (row, block of kLongBodies bodies).  The lanes fetch the row's (column,
+// weight) pairs once, then every lane gathers its vertex for each body (kLongBodies independent
+// loads in flight) and the warp reduces in a fixed butterfly order => deterministic.
+constexpr int kLongBodies = 8;
+
+__device__ __forceinline__ void readout_rows_warp8(const ReadoutParams& p, int r, int bbase, int nvalid, int lane,
+                                                   float (&x)[kLongBodies], float (&y)[kLongBodies],
+                                                   float (&z)[kLongBodies]) {
+#pragma unroll
+  for (int i = 0; i < kLongBodies; ++i) x[i] = y[i] = z[i] = 0.f;
+  const int k1 = p.row_ptr[r + 1];
+  for (int k = p.row_ptr[r] + lane; k < k1; k += 32) {
+    const float w = p.vals[k];
+    const int col = p.col_idx[k];
+#pragma unroll
+    for (int i = 0; i < kLongBodies; ++i) {
+      const int b = bbase + (i < nvalid ? i : 0);
+      const float* s = readout_src(p, b, col);
+      x[i] = fmaf(w, s[0], x[i]); y[i] = fmaf(w, s[1], y[i]); z[i] = fmaf(w, s[2], z[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLongBodies; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      x[i] += __shfl_xor_sync(0xffffffffu, x[i], o);
+      y[i] += __shfl_xor_sync(0xffffffffu, y[i], o);
+      z[i] += __shfl_xor_sync(0xffffffffu, z[i], o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) readout_long8_kernel(ReadoutParams p) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_bblocks = (p.B + kLongBodies - 1) / kLongBodies;
+  if (w >= (long long)n_bblocks * p.n_rows_here) return;   // warp-uniform
+  const int bb = (int)(w / p.n_rows_here);
+  const int r = p.rows[(int)(w % p.n_rows_here)];
+  const int bbase = bb * kLongBodies;
+  const int nvalid = min(kLongBodies, p.B - bbase);
+  float x[kLongBodies], y[kLongBodies], z[kLongBodies];
+  readout_rows_warp8(p, r, bbase, nvalid, lane, x, y, z);
+  const int sr = p.sub_row ? p.sub_row[r] : -1;
+  if (sr >= 0) {
+    float sx[kLongBodies], sy[kLongBodies], sz[kLongBodies];
+    readout_rows_warp8(p, sr, bbase, nvalid, lane, sx, sy, sz);
+#pragma unroll
+    for (int i = 0; i < kLongBodies; ++i) { x[i] -= sx[i]; y[i] -= sy[i]; z[i] -= sz[i]; }
+  }
+  // lane i writes body i
+#pragma unroll
+  for (int i = 0; i < kLongBodies; ++i) {
+    if (lane == i && i < nvalid) {
+      float* o = readout_dst(p, bbase + i, r);
+      o[0] = x[i]; o[1] = y[i]; o[2] = z[i];
+    }
+  }
+}
+
 // verts[:, idx]
 __global__ void __launch_bounds__(256) gather_vertices_kernel(const float* __restrict__ verts,
                                                               const int* __restrict__ idx, int B, int V,

@@ -95,6 +95,7 @@ struct whmr_readout_s {
   int *rows_short_all = nullptr;    // one-hot + short: used when the read-out runs stand-alone
   int *grp_prefix = nullptr, *grp_rows = nullptr;
   int *dst_ptr = nullptr, *dst_row = nullptr;   // vertex -> one-hot destination rows (CSC), [VP+1] / [n_onehot]
+  int4* onehot_tab = nullptr;                   // [n_onehot] {src vertex, group prefix, group rows, row - prefix}
   int dst_VP = 0;
   float* vals = nullptr;
   bool needs_joints = false;
@@ -364,14 +365,24 @@ static int launch_readout_rows(whmr_readout_t r, const int* rows, int n_rows_her
   p.verts = verts; p.joints = joints; p.out = out;
   p.rows = rows; p.n_rows_here = n_rows_here;
   if (warp_per_row) {
-    const long long n = (long long)nb * n_rows_here * 32;
-    readout_long_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
-    WHMR_LAUNCHED("readout_long_kernel");
+    const long long n = (long long)ceil_div(nb, kLongBodies) * n_rows_here * 32;
+    readout_long8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    WHMR_LAUNCHED("readout_long8_kernel");
   } else {
     const long long n = (long long)nb * n_rows_here;
     readout_short_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
     WHMR_LAUNCHED("readout_short_kernel");
   }
+  return WHMR_OK;
+}
+
+static int launch_readout_onehot(whmr_readout_t r, const float* verts, int nb, int B_total, int b0, float* out,
+                                 cudaStream_t st) {
+  if (r->n_onehot == 0 || nb == 0) return WHMR_OK;
+  const long long n = (long long)nb * r->n_onehot;
+  readout_onehot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r->onehot_tab, r->n_onehot, verts, r->V, nb, B_total,
+                                                                    b0, out);
+  WHMR_LAUNCHED("readout_onehot_kernel");
   return WHMR_OK;
 }
 
@@ -488,8 +499,8 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
     if (ro) {
       const float* vch = verts + (size_t)b0 * h->d.V * 3;
       const float* jch = joints ? joints + (size_t)b0 * h->d.J * 3 : nullptr;
-      if (fused_onehot) rc = launch_readout_rows(ro, ro->rows_short, ro->n_short, false, vch, jch, nb, B, b0, ro_out, st);
-      else rc = launch_readout_rows(ro, ro->rows_short_all, ro->n_short_all, false, vch, jch, nb, B, b0, ro_out, st);
+      if (!fused_onehot) { rc = launch_readout_onehot(ro, vch, nb, B, b0, ro_out, st); if (rc) return rc; }
+      rc = launch_readout_rows(ro, ro->rows_short, ro->n_short, false, vch, jch, nb, B, b0, ro_out, st);
       if (rc) return rc;
       rc = launch_readout_rows(ro, ro->rows_long, ro->n_long, true, vch, jch, nb, B, b0, ro_out, st);
       if (rc) return rc;
@@ -616,6 +627,11 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
     std::vector<int> fill(dptr.begin(), dptr.end() - 1);
     for (int r : ro1) drow[fill[ci[rp[r]]]++] = r;
   }
+  std::vector<int4> otab(ro1.size());
+  for (size_t i = 0; i < ro1.size(); ++i) {
+    const int r = ro1[i];
+    otab[i] = make_int4(ci[rp[r]], gpre[r], grows[r], r - gpre[r]);
+  }
   whmr_readout_s* h = new (std::nothrow) whmr_readout_s();
   if (!h) return set_error(WHMR_E_INVALID, "whmr_readout_create: out of host memory");
   h->R = n_rows; h->V = n_verts; h->J = n_joints;
@@ -625,7 +641,7 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   cudaError_t e = cudaSuccess;
   auto up = [&](auto& vec, auto** dst) { if (e == cudaSuccess) e = h->arena.upload(vec, dst); };
   up(rp, &h->row_ptr); up(ci, &h->col_idx); up(vv, &h->vals); up(rs, &h->rows_short); up(rl, &h->rows_long);
-  up(rs_all, &h->rows_short_all); up(dptr, &h->dst_ptr); up(drow, &h->dst_row);
+  up(rs_all, &h->rows_short_all); up(dptr, &h->dst_ptr); up(drow, &h->dst_row); up(otab, &h->onehot_tab);
   up(gpre, &h->grp_prefix); up(grows, &h->grp_rows);
   if (sub_row) up(sr, &h->sub_row);
   if (e != cudaSuccess) {
@@ -644,7 +660,9 @@ int whmr_readout_apply(whmr_readout_t r, const float* verts, const float* joints
   WHMR_CHECK_ARG(verts && out, "whmr_readout_apply: null verts/out");
   WHMR_CHECK_ARG(joints || !r->needs_joints, "whmr_readout_apply: table references chain joints but joints == NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_readout_rows(r, r->rows_short_all, r->n_short_all, false, verts, joints, B, B, 0, out, st);
+  int rc = launch_readout_onehot(r, verts, B, B, 0, out, st);
+  if (rc) return rc;
+  rc = launch_readout_rows(r, r->rows_short, r->n_short, false, verts, joints, B, B, 0, out, st);
   if (rc) return rc;
   return launch_readout_rows(r, r->rows_long, r->n_long, true, verts, joints, B, B, 0, out, st);
 }
