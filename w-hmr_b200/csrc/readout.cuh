@@ -109,13 +109,14 @@ __global__ void __launch_bounds__(256) readout_long_kernel(ReadoutParams p) {
 // One-hot rows (vertex picks, SSM markers, mesh down-sampling): compact table, one thread per (body,row).
 //   tab[r] = {source vertex, rows of all groups before this row's group, rows in its group, row - prefix}
 __global__ void __launch_bounds__(256)
-readout_onehot_kernel(const int4* __restrict__ tab, int n_rows, const float* __restrict__ verts, int V, int nb,
-                      int B_total, int b0, float* __restrict__ out) {
+readout_onehot_kernel(const int4* __restrict__ tab, int n_rows, const float* __restrict__ verts,
+                      const float* __restrict__ joints, int V, int J, int nb, int B_total, int b0,
+                      float* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)nb * n_rows) return;
   const int b = (int)(i / n_rows);
   const int4 t = tab[(int)(i - (long long)b * n_rows)];
-  const float* s = verts + ((size_t)b * V + t.x) * 3;
+  const float* s = t.x < V ? verts + ((size_t)b * V + t.x) * 3 : joints + ((size_t)b * J + (t.x - V)) * 3;
   const float x = s[0], y = s[1], z = s[2];
   float* o = out + 3 * ((size_t)B_total * t.y + (size_t)(b0 + b) * t.z + t.w);
   o[0] = x; o[1] = y; o[2] = z;

@@ -376,12 +376,12 @@ static int launch_readout_rows(whmr_readout_t r, const int* rows, int n_rows_her
   return WHMR_OK;
 }
 
-static int launch_readout_onehot(whmr_readout_t r, const float* verts, int nb, int B_total, int b0, float* out,
-                                 cudaStream_t st) {
+static int launch_readout_onehot(whmr_readout_t r, const float* verts, const float* joints, int nb, int B_total, int b0,
+                                 float* out, cudaStream_t st) {
   if (r->n_onehot == 0 || nb == 0) return WHMR_OK;
   const long long n = (long long)nb * r->n_onehot;
-  readout_onehot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r->onehot_tab, r->n_onehot, verts, r->V, nb, B_total,
-                                                                    b0, out);
+  readout_onehot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r->onehot_tab, r->n_onehot, verts, joints, r->V,
+                                                                    r->J, nb, B_total, b0, out);
   WHMR_LAUNCHED("readout_onehot_kernel");
   return WHMR_OK;
 }
@@ -499,7 +499,8 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
     if (ro) {
       const float* vch = verts + (size_t)b0 * h->d.V * 3;
       const float* jch = joints ? joints + (size_t)b0 * h->d.J * 3 : nullptr;
-      if (!fused_onehot) { rc = launch_readout_onehot(ro, vch, nb, B, b0, ro_out, st); if (rc) return rc; }
+      rc = launch_readout_onehot(ro, vch, jch, nb, B, b0, ro_out, st);   // (with the opt-in fused epilogue the vertex rows are simply rewritten with identical values)
+      if (rc) return rc;
       rc = launch_readout_rows(ro, ro->rows_short, ro->n_short, false, vch, jch, nb, B, b0, ro_out, st);
       if (rc) return rc;
       rc = launch_readout_rows(ro, ro->rows_long, ro->n_long, true, vch, jch, nb, B, b0, ro_out, st);
@@ -613,7 +614,7 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
     int len = rp[r + 1] - rp[r];
     const bool has_sub = sub_row && sr[r] >= 0;
     if (has_sub) len = std::max(len, rp[sr[r] + 1] - rp[sr[r]]);
-    const bool onehot = !has_sub && len == 1 && vv[rp[r]] == 1.0f && ci[rp[r]] < n_verts;
+    const bool onehot = !has_sub && len == 1 && vv[rp[r]] == 1.0f;   // source may be a vertex or a chain joint
     if (onehot) { ro1.push_back(r); rs_all.push_back(r); }
     else if (len <= kShortRow) { rs.push_back(r); rs_all.push_back(r); }
     else rl.push_back(r);
@@ -621,11 +622,11 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   // vertex -> one-hot destination rows (CSC over the padded vertex range of the skinning kernel)
   const int VP = ceil_div(n_verts, kVertTile) * kVertTile;
   std::vector<int> dptr(VP + 1, 0), drow(ro1.size());
-  for (int r : ro1) dptr[ci[rp[r]] + 1]++;
+  for (int r : ro1) if (ci[rp[r]] < n_verts) dptr[ci[rp[r]] + 1]++;
   for (int v = 0; v < VP; ++v) dptr[v + 1] += dptr[v];
   {
     std::vector<int> fill(dptr.begin(), dptr.end() - 1);
-    for (int r : ro1) drow[fill[ci[rp[r]]]++] = r;
+    for (int r : ro1) if (ci[rp[r]] < n_verts) drow[fill[ci[rp[r]]]++] = r;
   }
   std::vector<int4> otab(ro1.size());
   for (size_t i = 0; i < ro1.size(); ++i) {
@@ -660,7 +661,7 @@ int whmr_readout_apply(whmr_readout_t r, const float* verts, const float* joints
   WHMR_CHECK_ARG(verts && out, "whmr_readout_apply: null verts/out");
   WHMR_CHECK_ARG(joints || !r->needs_joints, "whmr_readout_apply: table references chain joints but joints == NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_readout_onehot(r, verts, B, B, 0, out, st);
+  int rc = launch_readout_onehot(r, verts, joints, B, B, 0, out, st);
   if (rc) return rc;
   rc = launch_readout_rows(r, r->rows_short, r->n_short, false, verts, joints, B, B, 0, out, st);
   if (rc) return rc;
