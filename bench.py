@@ -111,6 +111,8 @@ def algorithmic(kind, B, ctx):
         H, W = ctx["levels"][lvl]
         N = 63 if lvl == 0 else 67
         return {"bytes": B * (4 * C * (min(4 * N, H * W) + N) + 8 * N), "bound": "hbm"}
+    if kind == "project_weak_full":
+        return {"bytes": B * (4 * 7 * 49 + 12 + 36 + 16), "bound": "hbm"}
     if kind == "project_weak":
         return {"bytes": B * (4 * 5 * 49 + 12), "bound": "hbm"}
     if kind == "project_markers":

@@ -175,6 +175,13 @@ int whmr_project_full(const float* points, const float* cam, const float* bbox_h
                       const float* center, const float* orig_shape, const float* Tz, int B, int N,
                       float* kp_norm, float* kp_px, float* focal_out, float* cam_t_out, void* stream);
 
+/* whmr_project_weak + whmr_project_full on the same points in one launch (Regressor.forward evaluates
+ * both back to back, models/whmr.py:142-173).  kp_weak [B,N,2] as whmr_project_weak's out. */
+int whmr_project_weak_full(const float* points, const float* cam, const float* bbox_height, const float* center,
+                           const float* orig_shape, const float* Tz, int B, int N, float weak_focal,
+                           float weak_img_w, float weak_img_h, float* kp_weak, float* kp_norm, float* kp_px,
+                           float* focal_out, float* cam_t_out, void* stream);
+
 /* models/maf_extractor.py:145-235 MAF_Extractor.project (+get_trans, perspective_projection with the
  * optional 5-coefficient distortion): full-frame pixels and crop-normalised [-1,1] coordinates. */
 int whmr_project_crop(const float* points, const float* cam, const float* center, const float* scale,

@@ -78,6 +78,7 @@ SIGNATURES = {
     "whmr_project_weak": (C.c_int, [_vp, _vp, _i, _i, _f, _f, _f, _vp, _vp]),
     "whmr_perspective_projection": (C.c_int, [_vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "whmr_project_full": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "whmr_project_weak_full": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "whmr_project_crop": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
     "whmr_sample_bilinear": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "whmr_project_sample": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _f, _vp, _vp, _vp]),

@@ -72,7 +72,8 @@ project_full_kernel(const float* __restrict__ points, const float* __restrict__ 
                     const float* __restrict__ bbox_height, const float* __restrict__ center,
                     const float* __restrict__ orig_shape, const float* __restrict__ Tz, int B, int N,
                     float* __restrict__ kp_norm, float* __restrict__ kp_px,
-                    float* __restrict__ focal_out, float* __restrict__ cam_t_out) {
+                    float* __restrict__ focal_out, float* __restrict__ cam_t_out,
+                    float* __restrict__ kp_weak, float wfocal, float wimg_w, float wimg_h) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * N) return;
   const int b = (int)(i / N);
@@ -95,6 +96,12 @@ project_full_kernel(const float* __restrict__ points, const float* __restrict__ 
   const float v = focal * qy + ccy * qz;
   if (kp_px) { kp_px[i * 2 + 0] = u; kp_px[i * 2 + 1] = v; }
   if (kp_norm) { kp_norm[i * 2 + 0] = u / ccx - 1.0f; kp_norm[i * 2 + 1] = v / ccy - 1.0f; }   // :173
+  if (kp_weak) {   // utils/geometry.py:289-307 on the same points (Regressor.forward evaluates both, :142-173)
+    const float wtz = 2.0f * wfocal / (wimg_h * s + 1e-9f);
+    const float wx = points[i * 3 + 0] + tx, wy = points[i * 3 + 1] + ty, wz = points[i * 3 + 2] + wtz;
+    kp_weak[i * 2 + 0] = (wfocal * (wx / wz)) / (wimg_w * 0.5f);
+    kp_weak[i * 2 + 1] = (wfocal * (wy / wz)) / (wimg_h * 0.5f);
+  }
 }
 
 // models/maf_extractor.py:145-235 (project + get_trans + perspective_projection w/ distortion)

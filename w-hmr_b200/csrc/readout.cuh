@@ -182,6 +182,74 @@ __global__ void __launch_bounds__(256) readout_long8_kernel(ReadoutParams p) {
   }
 }
 
+// All row classes in ONE launch: blocks [0, n_blocks_onehot) gather the one-hot rows, the next
+// n_blocks_long blocks reduce the regressor rows (8 bodies per warp), the rest take the remaining short rows.
+struct ReadoutAllParams {
+  ReadoutParams rp;            // rows / n_rows_here are set per class below
+  const int4* onehot_tab; int n_onehot;
+  const int* rows_long; int n_long;
+  const int* rows_short; int n_short;
+  int n_blocks_onehot, n_blocks_long;
+};
+
+__global__ void __launch_bounds__(256) readout_all_kernel(ReadoutAllParams q) {
+  ReadoutParams& p = q.rp;
+  if ((int)blockIdx.x < q.n_blocks_onehot) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)p.B * q.n_onehot) return;
+    const int b = (int)(i / q.n_onehot);
+    const int4 t = q.onehot_tab[(int)(i - (long long)b * q.n_onehot)];
+    const float* s = readout_src(p, b, t.x);
+    const float x = s[0], y = s[1], z = s[2];
+    float* o = p.out + 3 * ((size_t)p.B_total * t.y + (size_t)(p.b0 + b) * t.z + t.w);
+    o[0] = x; o[1] = y; o[2] = z;
+    return;
+  }
+  if ((int)blockIdx.x < q.n_blocks_onehot + q.n_blocks_long) {
+    const long long w = ((long long)(blockIdx.x - q.n_blocks_onehot) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_bblocks = (p.B + kLongBodies - 1) / kLongBodies;
+    if (w >= (long long)n_bblocks * q.n_long) return;   // warp-uniform
+    const int bb = (int)(w / q.n_long);
+    const int r = q.rows_long[(int)(w % q.n_long)];
+    const int bbase = bb * kLongBodies;
+    const int nvalid = min(kLongBodies, p.B - bbase);
+    float x[kLongBodies], y[kLongBodies], z[kLongBodies];
+    readout_rows_warp8(p, r, bbase, nvalid, lane, x, y, z);
+    const int sr = p.sub_row ? p.sub_row[r] : -1;
+    if (sr >= 0) {
+      float sx[kLongBodies], sy[kLongBodies], sz[kLongBodies];
+      readout_rows_warp8(p, sr, bbase, nvalid, lane, sx, sy, sz);
+#pragma unroll
+      for (int i = 0; i < kLongBodies; ++i) { x[i] -= sx[i]; y[i] -= sy[i]; z[i] -= sz[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < kLongBodies; ++i) {
+      if (lane == i && i < nvalid) {
+        float* o = readout_dst(p, bbase + i, r);
+        o[0] = x[i]; o[1] = y[i]; o[2] = z[i];
+      }
+    }
+    return;
+  }
+  {
+    const long long i = (long long)(blockIdx.x - q.n_blocks_onehot - q.n_blocks_long) * blockDim.x + threadIdx.x;
+    if (i >= (long long)p.B * q.n_short) return;
+    const int b = (int)(i / q.n_short);
+    const int r = q.rows_short[(int)(i % q.n_short)];
+    float x, y, z;
+    readout_row_serial(p, b, r, x, y, z);
+    const int sr = p.sub_row ? p.sub_row[r] : -1;
+    if (sr >= 0) {
+      float sx, sy, sz;
+      readout_row_serial(p, b, sr, sx, sy, sz);
+      x -= sx; y -= sy; z -= sz;
+    }
+    float* o = readout_dst(p, b, r);
+    o[0] = x; o[1] = y; o[2] = z;
+  }
+}
+
 // verts[:, idx]
 __global__ void __launch_bounds__(256) gather_vertices_kernel(const float* __restrict__ verts,
                                                               const int* __restrict__ idx, int B, int V,

@@ -46,11 +46,25 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int H, int W) {
 
 constexpr int kSampleItems = 4;   // flat outputs per thread (independent gathers in flight)
 
+// Weak-perspective projection parameters for the fused MAF_Extractor.forward path (projection + sampling
+// in one launch): points are then [B,N,3] mesh points and the 2-D grid coordinate is computed on the fly.
+struct SampleProj {
+  const float* cam;     // [B,3] (s,tx,ty)
+  float focal, img_w, img_h;
+  float* pts2d_out;     // [B,N,2] or null
+};
+
 // grid = (ceil(C*N / (256*kSampleItems)), B)
+template <bool kProject>
 __global__ void __launch_bounds__(256)
 sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
-                            float* __restrict__ out, int C, int H, int W, int N) {
+                            float* __restrict__ out, int C, int H, int W, int N, SampleProj pj) {
   const int b = blockIdx.y;
+  float cs = 0.f, ctx = 0.f, cty = 0.f, ctz = 0.f;
+  if (kProject) {   // utils/geometry.py:289-307
+    cs = pj.cam[b * 3 + 0]; ctx = pj.cam[b * 3 + 1]; cty = pj.cam[b * 3 + 2];
+    ctz = 2.0f * pj.focal / (pj.img_h * cs + 1e-9f);
+  }
   const int total = C * N;
   const size_t plane = (size_t)H * W;
   const float* fb = feat + (size_t)b * C * plane;
@@ -65,7 +79,16 @@ sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restr
     const int i = base + it * 256;
     if (i < total) {
       const int c = i / N, n = i - c * N;
-      const float2 g = *reinterpret_cast<const float2*>(pb + (size_t)n * 2);
+      float2 g;
+      if (kProject) {
+        const float* q = pb + (size_t)n * 3;
+        const float px = q[0] + ctx, py = q[1] + cty, pz = q[2] + ctz;
+        g.x = (pj.focal * (px / pz)) / (pj.img_w * 0.5f);
+        g.y = (pj.focal * (py / pz)) / (pj.img_h * 0.5f);
+        if (pj.pts2d_out && c == 0) *reinterpret_cast<float2*>(pj.pts2d_out + ((size_t)b * N + n) * 2) = g;
+      } else {
+        g = *reinterpret_cast<const float2*>(pb + (size_t)n * 2);
+      }
       tp[it] = make_taps(g.x, g.y, H, W);
       const float* pl = fb + (size_t)c * plane;
       v00[it] = __ldg(pl + tp[it].o00); v01[it] = __ldg(pl + tp[it].o01);

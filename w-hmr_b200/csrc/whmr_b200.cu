@@ -355,34 +355,26 @@ static int launch_pose_blend(whmr_smpl_t h, const SmplWorkspace& ws, int B, int 
   return tc_pose_blend_launch(h->tc, d, h->gemm_mode, ws.pf_split, B, b0, nb, ws.offsets, st);
 }
 
-static int launch_readout_rows(whmr_readout_t r, const int* rows, int n_rows_here, bool warp_per_row, const float* verts,
-                               const float* joints, int nb, int B_total, int b0, float* out, cudaStream_t st) {
-  if (n_rows_here == 0 || nb == 0) return WHMR_OK;
-  ReadoutParams p{};
+// every row class of a read-out table for bodies [b0, b0+nb) in one launch
+static int launch_readout_all(whmr_readout_t r, const float* verts, const float* joints, int nb, int B_total, int b0,
+                              float* out, cudaStream_t st) {
+  if (nb == 0 || r->R == 0) return WHMR_OK;
+  ReadoutAllParams q{};
+  ReadoutParams& p = q.rp;
   p.row_ptr = r->row_ptr; p.col_idx = r->col_idx; p.vals = r->vals; p.sub_row = r->sub_row;
   p.grp_prefix = r->grp_prefix; p.grp_rows = r->grp_rows;
   p.R = r->R; p.V = r->V; p.J = r->J; p.B = nb; p.B_total = B_total; p.b0 = b0;
   p.verts = verts; p.joints = joints; p.out = out;
-  p.rows = rows; p.n_rows_here = n_rows_here;
-  if (warp_per_row) {
-    const long long n = (long long)ceil_div(nb, kLongBodies) * n_rows_here * 32;
-    readout_long8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
-    WHMR_LAUNCHED("readout_long8_kernel");
-  } else {
-    const long long n = (long long)nb * n_rows_here;
-    readout_short_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
-    WHMR_LAUNCHED("readout_short_kernel");
-  }
-  return WHMR_OK;
-}
-
-static int launch_readout_onehot(whmr_readout_t r, const float* verts, const float* joints, int nb, int B_total, int b0,
-                                 float* out, cudaStream_t st) {
-  if (r->n_onehot == 0 || nb == 0) return WHMR_OK;
-  const long long n = (long long)nb * r->n_onehot;
-  readout_onehot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(r->onehot_tab, r->n_onehot, verts, joints, r->V,
-                                                                    r->J, nb, B_total, b0, out);
-  WHMR_LAUNCHED("readout_onehot_kernel");
+  q.onehot_tab = r->onehot_tab; q.n_onehot = r->n_onehot;
+  q.rows_long = r->rows_long; q.n_long = r->n_long;
+  q.rows_short = r->rows_short; q.n_short = r->n_short;
+  q.n_blocks_onehot = (int)(((long long)nb * r->n_onehot + 255) / 256);
+  q.n_blocks_long = (int)(((long long)ceil_div(nb, kLongBodies) * r->n_long * 32 + 255) / 256);
+  const int n_blocks_short = (int)(((long long)nb * r->n_short + 255) / 256);
+  const int grid = q.n_blocks_onehot + q.n_blocks_long + n_blocks_short;
+  if (grid == 0) return WHMR_OK;
+  readout_all_kernel<<<grid, 256, 0, st>>>(q);
+  WHMR_LAUNCHED("readout_all_kernel");
   return WHMR_OK;
 }
 
@@ -499,11 +491,7 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
     if (ro) {
       const float* vch = verts + (size_t)b0 * h->d.V * 3;
       const float* jch = joints ? joints + (size_t)b0 * h->d.J * 3 : nullptr;
-      rc = launch_readout_onehot(ro, vch, jch, nb, B, b0, ro_out, st);   // (with the opt-in fused epilogue the vertex rows are simply rewritten with identical values)
-      if (rc) return rc;
-      rc = launch_readout_rows(ro, ro->rows_short, ro->n_short, false, vch, jch, nb, B, b0, ro_out, st);
-      if (rc) return rc;
-      rc = launch_readout_rows(ro, ro->rows_long, ro->n_long, true, vch, jch, nb, B, b0, ro_out, st);
+      rc = launch_readout_all(ro, vch, jch, nb, B, b0, ro_out, st);
       if (rc) return rc;
     }
   }
@@ -660,12 +648,7 @@ int whmr_readout_apply(whmr_readout_t r, const float* verts, const float* joints
   if (B == 0 || r->R == 0) return WHMR_OK;
   WHMR_CHECK_ARG(verts && out, "whmr_readout_apply: null verts/out");
   WHMR_CHECK_ARG(joints || !r->needs_joints, "whmr_readout_apply: table references chain joints but joints == NULL");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_readout_onehot(r, verts, joints, B, B, 0, out, st);
-  if (rc) return rc;
-  rc = launch_readout_rows(r, r->rows_short, r->n_short, false, verts, joints, B, B, 0, out, st);
-  if (rc) return rc;
-  return launch_readout_rows(r, r->rows_long, r->n_long, true, verts, joints, B, B, 0, out, st);
+  return launch_readout_all(r, verts, joints, B, B, 0, out, (cudaStream_t)stream);
 }
 
 int whmr_gather_vertices(const float* verts, const int32_t* idx, int B, int V, int n_idx, float* out, void* stream) {
@@ -715,7 +698,22 @@ int whmr_project_full(const float* points, const float* cam, const float* bbox_h
   if (B == 0 || N == 0) return WHMR_OK;
   WHMR_CHECK_ARG(points && cam && bbox_height && center && orig_shape && Tz, "whmr_project_full: null input");
   project_full_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(points, cam, bbox_height, center, orig_shape,
-                                                                           Tz, B, N, kp_norm, kp_px, focal_out, cam_t_out);
+                                                                           Tz, B, N, kp_norm, kp_px, focal_out, cam_t_out,
+                                                                           nullptr, 0.f, 0.f, 0.f);
+  WHMR_LAUNCHED("project_full_kernel");
+  return WHMR_OK;
+}
+
+int whmr_project_weak_full(const float* points, const float* cam, const float* bbox_height, const float* center,
+                           const float* orig_shape, const float* Tz, int B, int N, float weak_focal, float weak_img_w,
+                           float weak_img_h, float* kp_weak, float* kp_norm, float* kp_px, float* focal_out,
+                           float* cam_t_out, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_weak_full: negative size");
+  if (B == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(points && cam && bbox_height && center && orig_shape && Tz && kp_weak, "whmr_project_weak_full: null input");
+  project_full_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(points, cam, bbox_height, center, orig_shape,
+                                                                           Tz, B, N, kp_norm, kp_px, focal_out, cam_t_out,
+                                                                           kp_weak, weak_focal, weak_img_w, weak_img_h);
   WHMR_LAUNCHED("project_full_kernel");
   return WHMR_OK;
 }
@@ -747,7 +745,7 @@ int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int
   cudaStream_t st = (cudaStream_t)stream;
   if (layout == WHMR_LAYOUT_NCHW) {
     dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
-    sample_bilinear_nchw_kernel<<<grid, 256, 0, st>>>(feat, points, pts_bstride, out, C, H, W, N);
+    sample_bilinear_nchw_kernel<false><<<grid, 256, 0, st>>>(feat, points, pts_bstride, out, C, H, W, N, SampleProj{});
     WHMR_LAUNCHED("sample_bilinear_nchw_kernel");
   } else {
     dim3 grid(ceil_div(N, 32), ceil_div(C, 64), B);
@@ -759,7 +757,19 @@ int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int
 
 int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int W, const float* p, const float* cam,
                         int N, float focal, float img_w, float img_h, float* points2d_out, float* out, void* stream) {
-  WHMR_CHECK_ARG(points2d_out, "whmr_project_sample: points2d_out scratch [B,N,2] is required");
+  if (layout == WHMR_LAYOUT_NCHW) {   // one launch: the grid coordinate is computed per output element
+    WHMR_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && H > 0 && W > 0, "whmr_project_sample: bad sizes");
+    if (B == 0 || C == 0 || N == 0) return WHMR_OK;
+    WHMR_CHECK_ARG(feat && p && cam && out, "whmr_project_sample: null pointer");
+    WHMR_CHECK_ARG((long long)C * N < (1ll << 31) && B < 65536, "whmr_project_sample: C*N or B too large");
+    WHMR_CHECK_ARG(!points2d_out || (reinterpret_cast<size_t>(points2d_out) & 7) == 0, "whmr_project_sample: points2d_out must be 8-byte aligned");
+    dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
+    SampleProj pj{cam, focal, img_w, img_h, points2d_out};
+    sample_bilinear_nchw_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, p, N * 3, out, C, H, W, N, pj);
+    WHMR_LAUNCHED("sample_bilinear_nchw_kernel<project>");
+    return WHMR_OK;
+  }
+  WHMR_CHECK_ARG(points2d_out, "whmr_project_sample: points2d_out scratch [B,N,2] is required for NHWC");
   int rc = whmr_project_weak(p, cam, B, N, focal, img_w, img_h, points2d_out, stream);
   if (rc) return rc;
   return whmr_sample_bilinear(feat, layout, B, C, H, W, points2d_out, 0, N, out, stream);

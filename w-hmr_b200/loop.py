@@ -50,10 +50,9 @@ class RegressorLoop:
             if it == 0:
                 pf = ops.sample_bilinear_op(feats[0], self.grid, self.layout)                # :596-597
             else:                                                                            # :606
-                pts = ops.project_weak_op(out['markers'], p[it]['cam'], constants.FOCAL_LENGTH,
-                                          float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
-                self.head._mark('project_markers')
-                pf = ops.sample_bilinear_op(feats[it], pts, self.layout)
+                pf, _ = ops.project_sample(feats[it], out['markers'], p[it]['cam'], constants.FOCAL_LENGTH,
+                                           float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT),
+                                           self.layout)   # projection fused into the sampling launch
             self.head._mark('sample_l%d' % it)
             point_feats.append(pf)
             q = p[it + 1]

@@ -322,6 +322,24 @@ def project_full(points, cam, bbox_height, center, orig_shape, Tz, want_px=False
     return kp, focal, cam_t, px
 
 
+def project_weak_full(points, cam, bbox_height, center, orig_shape, Tz, focal, img_w, img_h):
+    """weak projection + predicted-focal block in one launch -> (kp_2d, kp_2d_w, focal_length, cam_t)"""
+    points = _req(points, "points")
+    B, N = points.shape[0], points.shape[1]
+    dev = points.device
+    cam, bbox_height, center = _req(cam, "cam"), _req(bbox_height, "bbox_height"), _req(center, "center")
+    orig_shape, Tz = _req(orig_shape, "orig_shape"), _req(Tz, "Tz")
+    kp = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+    kpw = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+    fl = torch.empty(B, dtype=torch.float32, device=dev)
+    cam_t = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().whmr_project_weak_full(_p(points), _p(cam), _p(bbox_height), _p(center), _p(orig_shape), _p(Tz),
+                                                B, N, float(focal), float(img_w), float(img_h), _p(kp), _p(kpw), None,
+                                                _p(fl), _p(cam_t), _stream()))
+    return kp, kpw, fl, cam_t
+
+
 def project_crop(points, cam, center, scale, img_focal, img_center, crop_size, img_w, img_h, distortion=None):
     points = _req(points, "points")
     B, N = points.shape[0], points.shape[1]

@@ -97,9 +97,15 @@ class BodyModelHead(nn.Module):
         r = ro.split(flat, B)
         self._mark('skin_readout')
         pred_joints = r['joints']
-        kp_2d = ops.project_weak_op(pred_joints, pred_cam, constants.FOCAL_LENGTH,
-                                    float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
-        self._mark('project_weak')
+        if bbox_height is not None:   # Regressor.forward: weak + predicted-focal projection, one launch
+            kp_2d, kp_w, focal, cam_t = ops.project_weak_full(
+                pred_joints, pred_cam, bbox_height, center, orig_shape, Tz, constants.FOCAL_LENGTH,
+                float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
+            self._mark('project_weak_full')
+        else:                         # forward_init: weak projection only
+            kp_2d = ops.project_weak_op(pred_joints, pred_cam, constants.FOCAL_LENGTH,
+                                        float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
+            self._mark('project_weak')
         out = {
             'verts': verts, 'sub_verts': r['sub_verts'], 'temp_verts': r['temp_verts'], 'kp_2d': kp_2d,
             'kp_3d': r['kp_3d_h36m'] if J_regressor else pred_joints,
@@ -108,7 +114,5 @@ class BodyModelHead(nn.Module):
             'joints49': pred_joints,
         }
         if bbox_height is not None:
-            kp_w, focal, cam_t, _ = ops.project_full(pred_joints, pred_cam, bbox_height, center, orig_shape, Tz)
-            self._mark('project_full')
             out.update(kp_2d_w=kp_w, focal_length=focal, pred_cam_t=cam_t, scale=scale)
         return out
