@@ -150,6 +150,8 @@ def run_ours(args):
     model = syn.make_smpl_model(seed=0, weights="random")
     loop = RegressorLoop(model, dev, backbone=args.backbone, gemm_mode=gemm_mode)
     feats, params, bbox = make_loop_inputs(B, dev, backbone=args.backbone, seed=1, rank=rank)
+    if args.channels_last:
+        feats = [f.contiguous(memory_format=torch.channels_last) for f in feats]
 
     # ---- parity gate on this rank's own data before anything is timed (16 bodies vs the oracle) ----
     parity = None
@@ -347,7 +349,8 @@ def run_ours(args):
                        "samplings_per_step": 3, "pose_blend_arithmetic": {0: "fp32_simt", 1: "tcgen05 bf16x3", 2: "tcgen05 3xtf32"}[loop.smpl.gemm_mode],
                        "parallelism": "dp%d (bodies sharded by rank, no data-path collective)" % world,
                        "l2": "inputs larger than L2: feature maps 4.2 GB/step/GPU + ~0.2 GB of outputs vs 126 MB L2",
-                       "launch": "one CUDA graph replay per step"},
+                       "launch": "one CUDA graph replay per step",
+                       "feature_layout": "channels_last (NHWC memory)" if args.channels_last else "NCHW contiguous (reference layout)"},
             "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident,
             "gpu_launches": int(launches_per_step) * K, "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "smpl_at_scale": scale, "parity": parity,
@@ -460,6 +463,8 @@ def main():
     ap.add_argument("--skip-sweep", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--channels-last", action="store_true",
+                    help="feature maps in torch.channels_last memory format (reported separately; the contract layout is NCHW)")
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:
