@@ -206,14 +206,16 @@ def run_ours(args):
         if name == "pre_smpl":
             a = torch.cuda.Event(enable_timing=True, external=True)
             b = torch.cuda.Event(enable_timing=True, external=True)
-            h.set_probe_events(a, b)
+            c = torch.cuda.Event(enable_timing=True, external=True)
+            h.set_probe_events(a, b, c)
             e.record()
             marks.append(("start", e))
             marks.append(("chain", a))
             marks.append(("pose_blend", b))
+            marks.append(("skin", c))
         else:
             e.record()
-            marks.append((name, e))
+            marks.append(("readout" if name == "skin_readout" else name, e))
 
     h, _ = loop.smpl._state(dev)
     kern = {}
@@ -222,7 +224,7 @@ def run_ours(args):
         marks.clear()
         igraph, _ = loop.capture(feats, params, bbox, warmup=0)
         loop.head.probe = None
-        h.set_probe_events(None, None)
+        h.set_probe_events(None, None, None)
         mk = list(marks)
         for _ in range(3):
             igraph.replay()

@@ -100,11 +100,11 @@ int whmr_smpl_stage_pose_blend(whmr_smpl_t h, int B, void* workspace, size_t wor
 int whmr_smpl_stage_skin(whmr_smpl_t h, const float* betas, int B, float* verts, void* workspace,
                          size_t workspace_bytes, void* stream);
 
-/* Profiling hook: two cudaEvent_t (passed as void*, NULL clears) that the next whmr_smpl_forward
- * calls record on their stream right after the chain kernel and right after the (last chunk's)
- * pose-blend kernel, with cudaEventRecordExternal so they become event-record nodes when the call is
- * being captured into a CUDA graph.  bench.py uses them to time each kernel inside the timed region. */
-int whmr_smpl_set_probe_events(whmr_smpl_t h, void* after_chain, void* after_pose_blend);
+/* Profiling hook: three cudaEvent_t (passed as void*, NULL clears) that the next whmr_smpl_forward[_readout]
+ * calls record on their stream right after the chain kernel, after the (last chunk's) pose-blend kernel and
+ * after the (last chunk's) skinning kernel, with cudaEventRecordExternal so they become event-record nodes
+ * when the call is captured into a CUDA graph.  bench.py uses them to time each kernel inside the timed region. */
+int whmr_smpl_set_probe_events(whmr_smpl_t h, void* after_chain, void* after_pose_blend, void* after_skin);
 
 /* Host-buffer variant (bench.py `e2e`): pinned or pageable HOST pointers in and out; H2D copies,
  * the three kernels and the D2H copies are enqueued on `stream` and the call returns after

@@ -68,7 +68,7 @@ SIGNATURES = {
     "whmr_smpl_stage_chain": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "whmr_smpl_stage_pose_blend": (C.c_int, [_vp, _i, _vp, _sz, _vp]),
     "whmr_smpl_stage_skin": (C.c_int, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
-    "whmr_smpl_set_probe_events": (C.c_int, [_vp, _vp, _vp]),
+    "whmr_smpl_set_probe_events": (C.c_int, [_vp, _vp, _vp, _vp]),
     "whmr_smpl_reserve": (C.c_int, [_vp, _i]),
     "whmr_smpl_forward_host": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "whmr_batch_rodrigues": (C.c_int, [_vp, _i, _vp, _vp]),

@@ -76,7 +76,7 @@ struct whmr_smpl_s {
   int gemm_mode = WHMR_GEMM_FP32_SIMT;
   int chunk_bodies = 768;
   TcPlan tc{};   // tensor maps etc. for the tcgen05 path
-  cudaEvent_t probe_chain = nullptr, probe_blend = nullptr;
+  cudaEvent_t probe_chain = nullptr, probe_blend = nullptr, probe_skin = nullptr;
   bool skin_tc = true;   // tensor-core skinning (WHMR_SKIN=simt selects the CUDA-core kernel)
   // host-buffer staging (whmr_smpl_reserve)
   int reserved_B = 0;
@@ -488,6 +488,7 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
     if (h->probe_blend && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_blend, st, cudaEventRecordExternal));
     rc = launch_skin(h, ws, betas, transl, B, b0, nb, verts, fused_onehot ? ro : nullptr, ro_out, st);
     if (rc) return rc;
+    if (h->probe_skin && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_skin, st, cudaEventRecordExternal));
     if (ro) {
       const float* vch = verts + (size_t)b0 * h->d.V * 3;
       const float* jch = joints ? joints + (size_t)b0 * h->d.J * 3 : nullptr;
@@ -505,10 +506,11 @@ int whmr_smpl_forward(whmr_smpl_t h, const float* betas, const float* pose, int 
                                    nullptr, workspace, workspace_bytes, stream);
 }
 
-int whmr_smpl_set_probe_events(whmr_smpl_t h, void* after_chain, void* after_pose_blend) {
+int whmr_smpl_set_probe_events(whmr_smpl_t h, void* after_chain, void* after_pose_blend, void* after_skin) {
   WHMR_CHECK_ARG(h, "whmr_smpl_set_probe_events: null handle");
   h->probe_chain = (cudaEvent_t)after_chain;
   h->probe_blend = (cudaEvent_t)after_pose_blend;
+  h->probe_skin = (cudaEvent_t)after_skin;
   return WHMR_OK;
 }
 

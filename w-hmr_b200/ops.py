@@ -91,14 +91,13 @@ class SmplHandle:
         check(_lib.lib().whmr_smpl_set_gemm_mode(self._h, int(mode)))
         self.gemm_mode = int(mode)
 
-    def set_probe_events(self, after_chain=None, after_pose_blend=None):
-        """torch.cuda.Event(enable_timing=True, external=True) pair recorded inside the next forward calls."""
-        for e in (after_chain, after_pose_blend):
+    def set_probe_events(self, after_chain=None, after_pose_blend=None, after_skin=None):
+        """torch.cuda.Event(enable_timing=True, external=True) triple recorded inside the next forward calls."""
+        evs = (after_chain, after_pose_blend, after_skin)
+        for e in evs:
             if e is not None:
                 e.record()           # materialise the lazily created cudaEvent_t
-        check(_lib.lib().whmr_smpl_set_probe_events(
-            self._h, None if after_chain is None else after_chain.cuda_event,
-            None if after_pose_blend is None else after_pose_blend.cuda_event))
+        check(_lib.lib().whmr_smpl_set_probe_events(self._h, *[None if e is None else e.cuda_event for e in evs]))
 
     def info(self):
         v = [C.c_int32() for _ in range(5)]
