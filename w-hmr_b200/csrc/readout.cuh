@@ -206,29 +206,48 @@ __global__ void __launch_bounds__(256) readout_all_kernel(ReadoutAllParams q) {
     return;
   }
   if ((int)blockIdx.x < q.n_blocks_onehot + q.n_blocks_long) {
+    // regressor rows: warp = (row, 32 consecutive bodies), thread = one body.  The row's (column, weight)
+    // pairs are warp-uniform loads; every thread sums its own body in the row's storage order, so the
+    // result is deterministic and independent of the batch composition; no shuffles.
     const long long w = ((long long)(blockIdx.x - q.n_blocks_onehot) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_bblocks = (p.B + kLongBodies - 1) / kLongBodies;
-    if (w >= (long long)n_bblocks * q.n_long) return;   // warp-uniform
-    const int bb = (int)(w / q.n_long);
+    const int n_bgroups = (p.B + 31) >> 5;
+    if (w >= (long long)n_bgroups * q.n_long) return;   // warp-uniform
     const int r = q.rows_long[(int)(w % q.n_long)];
-    const int bbase = bb * kLongBodies;
-    const int nvalid = min(kLongBodies, p.B - bbase);
-    float x[kLongBodies], y[kLongBodies], z[kLongBodies];
-    readout_rows_warp8(p, r, bbase, nvalid, lane, x, y, z);
+    const int b = (int)(w / q.n_long) * 32 + lane;
+    const int bc = min(b, p.B - 1);
+    auto row_dot = [&](int row, float& x, float& y, float& z) {
+      x = y = z = 0.f;
+      const int k1 = p.row_ptr[row + 1];
+      int k = p.row_ptr[row];
+      for (; k + 8 <= k1; k += 8) {
+        float wv[8], sx[8], sy[8], sz[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          wv[u] = p.vals[k + u];
+          const float* s = readout_src(p, bc, p.col_idx[k + u]);
+          sx[u] = s[0]; sy[u] = s[1]; sz[u] = s[2];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { x = fmaf(wv[u], sx[u], x); y = fmaf(wv[u], sy[u], y); z = fmaf(wv[u], sz[u], z); }
+      }
+      for (; k < k1; ++k) {
+        const float wv = p.vals[k];
+        const float* s = readout_src(p, bc, p.col_idx[k]);
+        x = fmaf(wv, s[0], x); y = fmaf(wv, s[1], y); z = fmaf(wv, s[2], z);
+      }
+    };
+    float x, y, z;
+    row_dot(r, x, y, z);
     const int sr = p.sub_row ? p.sub_row[r] : -1;
     if (sr >= 0) {
-      float sx[kLongBodies], sy[kLongBodies], sz[kLongBodies];
-      readout_rows_warp8(p, sr, bbase, nvalid, lane, sx, sy, sz);
-#pragma unroll
-      for (int i = 0; i < kLongBodies; ++i) { x[i] -= sx[i]; y[i] -= sy[i]; z[i] -= sz[i]; }
+      float sx, sy, sz;
+      row_dot(sr, sx, sy, sz);
+      x -= sx; y -= sy; z -= sz;
     }
-#pragma unroll
-    for (int i = 0; i < kLongBodies; ++i) {
-      if (lane == i && i < nvalid) {
-        float* o = readout_dst(p, bbase + i, r);
-        o[0] = x[i]; o[1] = y[i]; o[2] = z[i];
-      }
+    if (b < p.B) {
+      float* o = readout_dst(p, b, r);
+      o[0] = x; o[1] = y; o[2] = z;
     }
     return;
   }

@@ -369,7 +369,7 @@ static int launch_readout_all(whmr_readout_t r, const float* verts, const float*
   q.rows_long = r->rows_long; q.n_long = r->n_long;
   q.rows_short = r->rows_short; q.n_short = r->n_short;
   q.n_blocks_onehot = (int)(((long long)nb * r->n_onehot + 255) / 256);
-  q.n_blocks_long = (int)(((long long)ceil_div(nb, kLongBodies) * r->n_long * 32 + 255) / 256);
+  q.n_blocks_long = (int)(((long long)ceil_div(nb, 32) * r->n_long * 32 + 255) / 256);
   const int n_blocks_short = (int)(((long long)nb * r->n_short + 255) / 256);
   const int grid = q.n_blocks_onehot + q.n_blocks_long + n_blocks_short;
   if (grid == 0) return WHMR_OK;
