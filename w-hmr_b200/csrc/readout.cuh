@@ -1,4 +1,4 @@
-// Sparse linear read-out of posed vertices: out[b,r,:] = sum_k vals[k] * src[b, col[k], :].
+// Sparse linear read-out of posed vertices: out[b,r,:] = sum_k vals[k] * src[b, col[k], :]  (- sub row).
 //
 // One mechanism for every "regressor x vertices" / vertex-pick on the path:
 // J_regressor_extra + joint_map -> 49 joints (models/smpl.py:66-76), VertexJointSelector
@@ -8,8 +8,16 @@
 // src is the virtual concatenation [verts ; chain joints] so the 24 chain joints of smplx's
 // `joints` output can be routed through the same table.
 //
-// Rows are split by the host into "short" (<= kShortRow non-zeros: one thread per (body,row)) and
-// "long" (one warp per (body,row), shuffle reduction in a fixed order => deterministic).
+// Two execution paths:
+//  (1) stand-alone (`whmr_readout_apply`): readout_all_kernel gathers from the vertex array -- one-hot
+//      rows one thread each, other rows one warp per (row, 8 bodies) with a fixed butterfly reduction.
+//      2.5k random 12-byte gathers per body: measured latency/wavefront bound (profiles/r01_notes.md).
+//  (2) fused with the skinning kernel (`whmr_smpl_forward_readout`): the skinning epilogue already holds
+//      every vertex in registers/shared memory, so it EMITS  w * v  for every table entry that
+//      references the vertex (EmitEntry lists per group of 32 vertices): one-hot rows go straight to
+//      their output slot, regressor terms to a per-body partial buffer laid out in row order, which
+//      readout_reduce_kernel then sums sequentially (coalesced, deterministic) and finishes
+//      (sub rows, joint-sourced terms).
 #pragma once
 #include "common.cuh"
 
@@ -24,8 +32,6 @@ struct ReadoutParams {
   const int* sub_row;   // [R] or null
   const int* grp_prefix;  // [R] rows in all groups before this row's group
   const int* grp_rows;    // [R] rows in this row's group
-  const int* rows;      // row ids handled by this launch
-  int n_rows_here;      // entries in `rows`
   int R, V, J, B;       // B = bodies handled by this launch (a chunk)
   int B_total, b0;      // batch of the output buffer, first body of the chunk
   const float* verts;   // [B,V,3]  (chunk base)
@@ -53,78 +59,9 @@ __device__ __forceinline__ void readout_row_serial(const ReadoutParams& p, int b
   }
 }
 
-__global__ void __launch_bounds__(256) readout_short_kernel(ReadoutParams p) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)p.B * p.n_rows_here) return;
-  const int b = (int)(i / p.n_rows_here);
-  const int r = p.rows[(int)(i % p.n_rows_here)];
-  float x, y, z;
-  readout_row_serial(p, b, r, x, y, z);
-  const int sr = p.sub_row ? p.sub_row[r] : -1;
-  if (sr >= 0) {
-    float sx, sy, sz;
-    readout_row_serial(p, b, sr, sx, sy, sz);
-    x -= sx; y -= sy; z -= sz;
-  }
-  float* o = readout_dst(p, b, r);
-  o[0] = x; o[1] = y; o[2] = z;
-}
-
-__device__ __forceinline__ void readout_row_warp(const ReadoutParams& p, int b, int r, int lane,
-                                                 float& x, float& y, float& z) {
-  x = y = z = 0.f;
-  for (int k = p.row_ptr[r] + lane; k < p.row_ptr[r + 1]; k += 32) {
-    const float w = p.vals[k];
-    const float* s = readout_src(p, b, p.col_idx[k]);
-    x = fmaf(w, s[0], x); y = fmaf(w, s[1], y); z = fmaf(w, s[2], z);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    x += __shfl_xor_sync(0xffffffffu, x, o);
-    y += __shfl_xor_sync(0xffffffffu, y, o);
-    z += __shfl_xor_sync(0xffffffffu, z, o);
-  }
-}
-
-__global__ void __launch_bounds__(256) readout_long_kernel(ReadoutParams p) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= (long long)p.B * p.n_rows_here) return;   // warp-uniform
-  const int b = (int)(w / p.n_rows_here);
-  const int r = p.rows[(int)(w % p.n_rows_here)];
-  float x, y, z;
-  readout_row_warp(p, b, r, lane, x, y, z);
-  const int sr = p.sub_row ? p.sub_row[r] : -1;
-  if (sr >= 0) {
-    float sx, sy, sz;
-    readout_row_warp(p, b, sr, lane, sx, sy, sz);
-    x -= sx; y -= sy; z -= sz;
-  }
-  if (lane == 0) {
-    float* o = readout_dst(p, b, r);
-    o[0] = x; o[1] = y; o[2] = z;
-  }
-}
-
-// One-hot rows (vertex picks, SSM markers, mesh down-sampling): compact table, one thread per (body,row).
-//   tab[r] = {source vertex, rows of all groups before this row's group, rows in its group, row - prefix}
-__global__ void __launch_bounds__(256)
-readout_onehot_kernel(const int4* __restrict__ tab, int n_rows, const float* __restrict__ verts,
-                      const float* __restrict__ joints, int V, int J, int nb, int B_total, int b0,
-                      float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)nb * n_rows) return;
-  const int b = (int)(i / n_rows);
-  const int4 t = tab[(int)(i - (long long)b * n_rows)];
-  const float* s = t.x < V ? verts + ((size_t)b * V + t.x) * 3 : joints + ((size_t)b * J + (t.x - V)) * 3;
-  const float x = s[0], y = s[1], z = s[2];
-  float* o = out + 3 * ((size_t)B_total * t.y + (size_t)(b0 + b) * t.z + t.w);
-  o[0] = x; o[1] = y; o[2] = z;
-}
-
-// Regressor rows: one warp per (row, block of kLongBodies bodies).  The lanes fetch the row's (column,
-// weight) pairs once, then every lane gathers its vertex for each body (kLongBodies independent
-// loads in flight) and the warp reduces in a fixed butterfly order => deterministic.
+// ---------------------------------------------------------------------------------------------
+// (1) stand-alone gather path
+// ---------------------------------------------------------------------------------------------
 constexpr int kLongBodies = 8;
 
 __device__ __forceinline__ void readout_rows_warp8(const ReadoutParams& p, int r, int bbase, int nvalid, int lane,
@@ -154,39 +91,11 @@ __device__ __forceinline__ void readout_rows_warp8(const ReadoutParams& p, int r
   }
 }
 
-__global__ void __launch_bounds__(256) readout_long8_kernel(ReadoutParams p) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int n_bblocks = (p.B + kLongBodies - 1) / kLongBodies;
-  if (w >= (long long)n_bblocks * p.n_rows_here) return;   // warp-uniform
-  const int bb = (int)(w / p.n_rows_here);
-  const int r = p.rows[(int)(w % p.n_rows_here)];
-  const int bbase = bb * kLongBodies;
-  const int nvalid = min(kLongBodies, p.B - bbase);
-  float x[kLongBodies], y[kLongBodies], z[kLongBodies];
-  readout_rows_warp8(p, r, bbase, nvalid, lane, x, y, z);
-  const int sr = p.sub_row ? p.sub_row[r] : -1;
-  if (sr >= 0) {
-    float sx[kLongBodies], sy[kLongBodies], sz[kLongBodies];
-    readout_rows_warp8(p, sr, bbase, nvalid, lane, sx, sy, sz);
-#pragma unroll
-    for (int i = 0; i < kLongBodies; ++i) { x[i] -= sx[i]; y[i] -= sy[i]; z[i] -= sz[i]; }
-  }
-  // lane i writes body i
-#pragma unroll
-  for (int i = 0; i < kLongBodies; ++i) {
-    if (lane == i && i < nvalid) {
-      float* o = readout_dst(p, bbase + i, r);
-      o[0] = x[i]; o[1] = y[i]; o[2] = z[i];
-    }
-  }
-}
-
 // All row classes in ONE launch: blocks [0, n_blocks_onehot) gather the one-hot rows, the next
 // n_blocks_long blocks reduce the regressor rows (8 bodies per warp), the rest take the remaining short rows.
 struct ReadoutAllParams {
-  ReadoutParams rp;            // rows / n_rows_here are set per class below
-  const int4* onehot_tab; int n_onehot;
+  ReadoutParams rp;
+  const int4* onehot_tab; int n_onehot;   // {source index, group prefix, group rows, row - prefix}
   const int* rows_long; int n_long;
   const int* rows_short; int n_short;
   int n_blocks_onehot, n_blocks_long;
@@ -206,48 +115,29 @@ __global__ void __launch_bounds__(256) readout_all_kernel(ReadoutAllParams q) {
     return;
   }
   if ((int)blockIdx.x < q.n_blocks_onehot + q.n_blocks_long) {
-    // regressor rows: warp = (row, 32 consecutive bodies), thread = one body.  The row's (column, weight)
-    // pairs are warp-uniform loads; every thread sums its own body in the row's storage order, so the
-    // result is deterministic and independent of the batch composition; no shuffles.
     const long long w = ((long long)(blockIdx.x - q.n_blocks_onehot) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_bgroups = (p.B + 31) >> 5;
-    if (w >= (long long)n_bgroups * q.n_long) return;   // warp-uniform
+    const int n_bblocks = (p.B + kLongBodies - 1) / kLongBodies;
+    if (w >= (long long)n_bblocks * q.n_long) return;   // warp-uniform
+    const int bb = (int)(w / q.n_long);
     const int r = q.rows_long[(int)(w % q.n_long)];
-    const int b = (int)(w / q.n_long) * 32 + lane;
-    const int bc = min(b, p.B - 1);
-    auto row_dot = [&](int row, float& x, float& y, float& z) {
-      x = y = z = 0.f;
-      const int k1 = p.row_ptr[row + 1];
-      int k = p.row_ptr[row];
-      for (; k + 8 <= k1; k += 8) {
-        float wv[8], sx[8], sy[8], sz[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          wv[u] = p.vals[k + u];
-          const float* s = readout_src(p, bc, p.col_idx[k + u]);
-          sx[u] = s[0]; sy[u] = s[1]; sz[u] = s[2];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { x = fmaf(wv[u], sx[u], x); y = fmaf(wv[u], sy[u], y); z = fmaf(wv[u], sz[u], z); }
-      }
-      for (; k < k1; ++k) {
-        const float wv = p.vals[k];
-        const float* s = readout_src(p, bc, p.col_idx[k]);
-        x = fmaf(wv, s[0], x); y = fmaf(wv, s[1], y); z = fmaf(wv, s[2], z);
-      }
-    };
-    float x, y, z;
-    row_dot(r, x, y, z);
+    const int bbase = bb * kLongBodies;
+    const int nvalid = min(kLongBodies, p.B - bbase);
+    float x[kLongBodies], y[kLongBodies], z[kLongBodies];
+    readout_rows_warp8(p, r, bbase, nvalid, lane, x, y, z);
     const int sr = p.sub_row ? p.sub_row[r] : -1;
     if (sr >= 0) {
-      float sx, sy, sz;
-      row_dot(sr, sx, sy, sz);
-      x -= sx; y -= sy; z -= sz;
+      float sx[kLongBodies], sy[kLongBodies], sz[kLongBodies];
+      readout_rows_warp8(p, sr, bbase, nvalid, lane, sx, sy, sz);
+#pragma unroll
+      for (int i = 0; i < kLongBodies; ++i) { x[i] -= sx[i]; y[i] -= sy[i]; z[i] -= sz[i]; }
     }
-    if (b < p.B) {
-      float* o = readout_dst(p, b, r);
-      o[0] = x; o[1] = y; o[2] = z;
+#pragma unroll
+    for (int i = 0; i < kLongBodies; ++i) {
+      if (lane == i && i < nvalid) {
+        float* o = readout_dst(p, bbase + i, r);
+        o[0] = x[i]; o[1] = y[i]; o[2] = z[i];
+      }
     }
     return;
   }
@@ -267,6 +157,69 @@ __global__ void __launch_bounds__(256) readout_all_kernel(ReadoutAllParams q) {
     float* o = readout_dst(p, b, r);
     o[0] = x; o[1] = y; o[2] = z;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (2) fused path: entries emitted by the skinning epilogue + sequential reduction
+// ---------------------------------------------------------------------------------------------
+// One entry per table non-zero whose source is a vertex.  kind 0: one-hot row, the value goes to the
+// final output (a = group prefix, c = rows in group, d = row - prefix).  kind 1: regressor term, the value
+// w*v goes to partial[b][d] (d = position of the non-zero in the partial buffer, row-major order).
+struct EmitEntry {
+  int lv_kind;   // local vertex (0..31) | kind << 8
+  float w;
+  int a, c, d;
+};
+
+struct EmitTable {              // device pointers, owned by the read-out handle
+  const int* grp_ptr;           // [VP/32 + 1] entries per 32-vertex group
+  const EmitEntry* entries;
+  float* partial;               // [chunk, n_partial, 3]
+  int n_partial;
+};
+
+// Finishing pass for the rows that are not vertex one-hots: thread per (body, row).
+//   out = sum(partial[b][pk0 .. pk1))  + joint-sourced terms  - (same for the sub row)
+struct ReduceParams {
+  ReadoutParams rp;
+  const int* rows; int n_rows;
+  const int* part_ptr;                  // [R+1] range of each row in the partial buffer
+  const float* partial; int n_partial;
+};
+
+__device__ __forceinline__ void reduce_row(const ReduceParams& q, int b, int r, float& x, float& y, float& z) {
+  const ReadoutParams& p = q.rp;
+  x = y = z = 0.f;
+  const float* pp = q.partial + ((size_t)b * q.n_partial + q.part_ptr[r]) * 3;
+  const int n = q.part_ptr[r + 1] - q.part_ptr[r];
+  for (int k = 0; k < n; ++k) { x += pp[k * 3 + 0]; y += pp[k * 3 + 1]; z += pp[k * 3 + 2]; }
+  if (p.joints)   // terms whose source is a chain joint (col >= V) are not emitted by the skinning kernel
+    for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; ++k) {
+      const int col = p.col_idx[k];
+      if (col >= p.V) {
+        const float w = p.vals[k];
+        const float* s = p.joints + ((size_t)b * p.J + (col - p.V)) * 3;
+        x = fmaf(w, s[0], x); y = fmaf(w, s[1], y); z = fmaf(w, s[2], z);
+      }
+    }
+}
+
+__global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
+  const ReadoutParams& p = q.rp;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)p.B * q.n_rows) return;
+  const int b = (int)(i / q.n_rows);
+  const int r = q.rows[(int)(i % q.n_rows)];
+  float x, y, z;
+  reduce_row(q, b, r, x, y, z);
+  const int sr = p.sub_row ? p.sub_row[r] : -1;
+  if (sr >= 0) {
+    float sx, sy, sz;
+    reduce_row(q, b, sr, sx, sy, sz);
+    x -= sx; y -= sy; z -= sz;
+  }
+  float* o = readout_dst(p, b, r);
+  o[0] = x; o[1] = y; o[2] = z;
 }
 
 // verts[:, idx]

@@ -19,6 +19,7 @@
 #include <cuda/std/type_traits>
 
 #include "pose_blend_tc.cuh"
+#include "readout.cuh"
 
 namespace whmr {
 
@@ -41,11 +42,8 @@ struct SkinTcParams {
   const float* v_template_p;  // [3, VP]
   const float* transl;        // [nb,3] or null
   float* verts;               // [nb, V, 3]
-  // one-hot read-outs fused into the epilogue (vertex -> destination rows), or null
-  const int* dst_ptr;         // [VP+1]
-  const int* dst_row;         // [n_dst] row ids of the read-out table
-  const int* grp_prefix;      // [R]
-  const int* grp_rows;        // [R]
+  // read-outs fused into the epilogue: per 32-vertex group a list of EmitEntry (readout.cuh); emit.grp_ptr == null: off
+  EmitTable emit;
   float* ro_out;              // group-major read-out buffer of the WHOLE batch
   int ro_B, ro_b0;            // total batch of the read-out buffer, first body of this chunk
   int nb, V, VP, NP, n_groups, n_items;
@@ -173,15 +171,23 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     int acc = 0; uint32_t acc_phase = 0;
     int cur_vt = -1;
     float tx = 0.f, ty = 0.f, tz = 0.f;
-    int v = 0, d0 = 0, d1 = 0, nd = 0;
-    // one-hot read-out destinations of this thread's vertex: element offset for body 0 of the chunk and
-    // per-body stride (elements); 32-bit is enough (the host checks 3*B*R < 2^31)
-    int db0 = 0, db1 = 0, db2 = 0, ds0 = 0, ds1 = 0, ds2 = 0;
-    auto dest = [&](int d, int& base, int& stride) {
-      const int row = p.dst_row[d];
-      const int pre = p.grp_prefix[row], rg = p.grp_rows[row];
-      base = 3 * (p.ro_B * pre + p.ro_b0 * rg + (row - pre));
-      stride = 3 * rg;
+    int v = 0;
+    // read-out entries of this warp's 32 vertices: lane l owns entries e0+l and e0+32+l (registers); further
+    // entries (rare) are walked from memory.  Per entry: source lane, weight, destination base/stride (elements).
+    int e0 = 0, n_e = 0;
+    int lvA = 0, lvB = 0, strA = 0, strB = 0;
+    long long baseA = 0, baseB = 0;
+    float wA = 0.f, wB = 0.f;
+    float* bufA = nullptr; float* bufB = nullptr;
+    auto load_entry = [&](int e, int& lv, float& w, long long& base, int& stride, float*& buf) {
+      const EmitEntry en = p.emit.entries[e];
+      lv = (en.lv_kind & 0xff) * 3;
+      w = en.w;
+      if (en.lv_kind >> 8) {     // regressor term -> partial[b_local][d]
+        base = 3LL * en.d; stride = 3 * p.emit.n_partial; buf = p.emit.partial;
+      } else {                   // one-hot row -> final output slot
+        base = 3LL * ((long long)p.ro_B * en.a + (long long)p.ro_b0 * en.c + en.d); stride = 3 * en.c; buf = p.ro_out;
+      }
     };
     const int V3 = p.V * 3;
     const bool has_transl = p.transl != nullptr;
@@ -193,12 +199,13 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
         cur_vt = vt;
         v = vt * kTcM + q * 32 + lane;                        // < VP
         tx = p.v_template_p[v]; ty = p.v_template_p[p.VP + v]; tz = p.v_template_p[2 * p.VP + v];
-        nd = 0;
-        if (p.dst_ptr) {
-          d0 = p.dst_ptr[v]; d1 = p.dst_ptr[v + 1]; nd = d1 - d0;
-          if (nd > 0) dest(d0, db0, ds0);
-          if (nd > 1) dest(d0 + 1, db1, ds1);
-          if (nd > 2) dest(d0 + 2, db2, ds2);
+        n_e = 0;
+        if (p.emit.grp_ptr) {
+          const int g32 = vt * (kTcM / 32) + q;
+          e0 = p.emit.grp_ptr[g32];
+          n_e = p.emit.grp_ptr[g32 + 1] - e0;
+          if (lane < n_e) load_entry(e0 + lane, lvA, wA, baseA, strA, bufA);
+          if (lane + 32 < n_e) load_entry(e0 + 32 + lane, lvB, wB, baseB, strB, bufB);
         }
       }
       const int body_base = g * kSkinGB + hb * 4;
@@ -249,24 +256,23 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
             } else {
               ob[0] = sb[lane]; ob[32] = sb[32 + lane]; ob[64] = sb[64 + lane];
             }
-            // fused one-hot read-outs (vertex picks, markers, mesh down-sampling)
-            if (nd > 0) {
-              const int b = body_base + bi;
-              float* o = p.ro_out + (db0 + b * ds0);
-              o[0] = rx; o[1] = ry; o[2] = rz;
-              if (nd > 1) {
-                o = p.ro_out + (db1 + b * ds1);
-                o[0] = rx; o[1] = ry; o[2] = rz;
-                if (nd > 2) {
-                  o = p.ro_out + (db2 + b * ds2);
-                  o[0] = rx; o[1] = ry; o[2] = rz;
-                  for (int d = d0 + 3; d < d1; ++d) {   // rare: a vertex feeding more than 3 read-out rows
-                    int bb, ss;
-                    dest(d, bb, ss);
-                    o = p.ro_out + (bb + b * ss);
-                    o[0] = rx; o[1] = ry; o[2] = rz;
-                  }
-                }
+            // fused read-outs: every table entry that references one of this warp's 32 vertices takes its
+            // value from the staged tile (one-hot rows: straight to the output; regressor terms: w*v to partial)
+            if (n_e > 0) {
+              const int bl = body_base + bi;
+              if (lane < n_e) {
+                float* o = bufA + baseA + (long long)bl * strA;
+                o[0] = wA * sb[lvA]; o[1] = wA * sb[lvA + 1]; o[2] = wA * sb[lvA + 2];
+              }
+              if (lane + 32 < n_e) {
+                float* o = bufB + baseB + (long long)bl * strB;
+                o[0] = wB * sb[lvB]; o[1] = wB * sb[lvB + 1]; o[2] = wB * sb[lvB + 2];
+              }
+              for (int e = 64 + lane; e < n_e; e += 32) {
+                int lv, st; long long ba; float w; float* bf;
+                load_entry(e0 + e, lv, w, ba, st, bf);
+                float* o = bf + ba + (long long)bl * st;
+                o[0] = w * sb[lv]; o[1] = w * sb[lv + 1]; o[2] = w * sb[lv + 2];
               }
             }
           }

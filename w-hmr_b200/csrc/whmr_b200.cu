@@ -96,6 +96,13 @@ struct whmr_readout_s {
   int *grp_prefix = nullptr, *grp_rows = nullptr;
   int *dst_ptr = nullptr, *dst_row = nullptr;   // vertex -> one-hot destination rows (CSC), [VP+1] / [n_onehot]
   int4* onehot_tab = nullptr;                   // [n_onehot] {src vertex, group prefix, group rows, row - prefix}
+  // fused path (skinning epilogue emits, readout_reduce_kernel finishes)
+  int* emit_grp_ptr = nullptr;                  // [VP/32 + 1]
+  EmitEntry* emit_entries = nullptr;
+  int* part_ptr = nullptr;                      // [R+1]
+  int* rows_reduce = nullptr;                   // rows that are not vertex one-hots
+  float* partial = nullptr;                     // [partial_bodies, n_partial, 3]
+  int n_partial = 0, n_reduce = 0, partial_bodies = 0;
   int dst_VP = 0;
   float* vals = nullptr;
   bool needs_joints = false;
@@ -369,7 +376,7 @@ static int launch_readout_all(whmr_readout_t r, const float* verts, const float*
   q.rows_long = r->rows_long; q.n_long = r->n_long;
   q.rows_short = r->rows_short; q.n_short = r->n_short;
   q.n_blocks_onehot = (int)(((long long)nb * r->n_onehot + 255) / 256);
-  q.n_blocks_long = (int)(((long long)ceil_div(nb, 32) * r->n_long * 32 + 255) / 256);
+  q.n_blocks_long = (int)(((long long)ceil_div(nb, kLongBodies) * r->n_long * 32 + 255) / 256);
   const int n_blocks_short = (int)(((long long)nb * r->n_short + 255) / 256);
   const int grid = q.n_blocks_onehot + q.n_blocks_long + n_blocks_short;
   if (grid == 0) return WHMR_OK;
@@ -378,7 +385,25 @@ static int launch_readout_all(whmr_readout_t r, const float* verts, const float*
   return WHMR_OK;
 }
 
-// skinning of bodies [b0, b0+nb); with `ro` the one-hot read-out rows are written by the same kernel
+// fused path, second half: sum the partials the skinning epilogue emitted (+ joint-sourced terms, sub rows)
+static int launch_readout_reduce(whmr_readout_t r, const float* verts, const float* joints, int nb, int B_total, int b0,
+                                 float* out, cudaStream_t st) {
+  if (nb == 0 || r->n_reduce == 0) return WHMR_OK;
+  ReduceParams q{};
+  ReadoutParams& p = q.rp;
+  p.row_ptr = r->row_ptr; p.col_idx = r->col_idx; p.vals = r->vals; p.sub_row = r->sub_row;
+  p.grp_prefix = r->grp_prefix; p.grp_rows = r->grp_rows;
+  p.R = r->R; p.V = r->V; p.J = r->J; p.B = nb; p.B_total = B_total; p.b0 = b0;
+  p.verts = verts; p.joints = joints; p.out = out;
+  q.rows = r->rows_reduce; q.n_rows = r->n_reduce; q.part_ptr = r->part_ptr; q.partial = r->partial;
+  q.n_partial = r->n_partial;
+  const long long n = (long long)nb * r->n_reduce;
+  readout_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(q);
+  WHMR_LAUNCHED("readout_reduce_kernel");
+  return WHMR_OK;
+}
+
+// skinning of bodies [b0, b0+nb); with `ro` the read-out entries are emitted by the same kernel
 static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* betas, const float* transl, int B, int b0,
                        int nb, float* verts, whmr_readout_t ro, float* ro_out, cudaStream_t st) {
   const SmplDevice& d = h->d;
@@ -388,8 +413,9 @@ static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* beta
     p.v_template_p = d.v_template_p;
     p.transl = transl ? transl + (size_t)b0 * 3 : nullptr;
     p.verts = verts + (size_t)b0 * d.V * 3;
-    if (ro && ro->n_onehot) {
-      p.dst_ptr = ro->dst_ptr; p.dst_row = ro->dst_row; p.grp_prefix = ro->grp_prefix; p.grp_rows = ro->grp_rows;
+    if (ro) {   // the epilogue emits the read-out entries of each vertex (readout.cuh, path 2)
+      p.emit.grp_ptr = ro->emit_grp_ptr; p.emit.entries = ro->emit_entries; p.emit.partial = ro->partial;
+      p.emit.n_partial = ro->n_partial;
       p.ro_out = ro_out; p.ro_B = B; p.ro_b0 = b0;
     }
     p.nb = nb; p.V = d.V; p.VP = d.VP; p.NP = d.NP;
@@ -476,23 +502,22 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
   if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, st, cudaEventRecordExternal));
   // chunked so the [chunk, NP] pose-offset intermediate (and the chunk's vertices, for the read-outs)
   // stay L2-resident between the kernels
-  // measured (profiles/r01_notes.md): per-thread scattered stores in the epilogue cost more than the separate
-  // L2-resident gather kernel, so the fusion is opt-in until the epilogue scatters warp-cooperatively
-  static const bool fuse_env = getenv("WHMR_FUSE_ONEHOT") && atoi(getenv("WHMR_FUSE_ONEHOT")) == 1;
-  const bool fused_onehot = ro && h->skin_tc && fuse_env && ro->dst_VP == h->d.VP &&
-                            3LL * B * ro->R < (1LL << 31);   // 32-bit element offsets in the epilogue
+  // fused read-outs need the tensor-core skinning kernel, the handle's partial buffer to cover a chunk and
+  // 32-bit element offsets; otherwise the stand-alone gather kernel runs after the skinning kernel
+  static const bool fuse_env = !(getenv("WHMR_FUSE_READOUT") && atoi(getenv("WHMR_FUSE_READOUT")) == 0);
+  const bool fused = ro && h->skin_tc && fuse_env && ro->dst_VP == h->d.VP && ro->partial_bodies >= ws.chunk;
   for (int b0 = 0; b0 < B; b0 += ws.chunk) {
     const int nb = std::min(ws.chunk, B - b0);
     rc = launch_pose_blend(h, ws, B, b0, nb, st);
     if (rc) return rc;
     if (h->probe_blend && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_blend, st, cudaEventRecordExternal));
-    rc = launch_skin(h, ws, betas, transl, B, b0, nb, verts, fused_onehot ? ro : nullptr, ro_out, st);
+    rc = launch_skin(h, ws, betas, transl, B, b0, nb, verts, fused ? ro : nullptr, ro_out, st);
     if (rc) return rc;
     if (h->probe_skin && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_skin, st, cudaEventRecordExternal));
     if (ro) {
       const float* vch = verts + (size_t)b0 * h->d.V * 3;
       const float* jch = joints ? joints + (size_t)b0 * h->d.J * 3 : nullptr;
-      rc = launch_readout_all(ro, vch, jch, nb, B, b0, ro_out, st);
+      rc = fused ? launch_readout_reduce(ro, vch, jch, nb, B, b0, ro_out, st) : launch_readout_all(ro, vch, jch, nb, B, b0, ro_out, st);
       if (rc) return rc;
     }
   }
@@ -604,7 +629,7 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
     int len = rp[r + 1] - rp[r];
     const bool has_sub = sub_row && sr[r] >= 0;
     if (has_sub) len = std::max(len, rp[sr[r] + 1] - rp[sr[r]]);
-    const bool onehot = !has_sub && len == 1 && vv[rp[r]] == 1.0f;   // source may be a vertex or a chain joint
+    const bool onehot = !has_sub && !used_as_sub[r] && len == 1 && vv[rp[r]] == 1.0f;   // source: vertex or chain joint
     if (onehot) { ro1.push_back(r); rs_all.push_back(r); }
     else if (len <= kShortRow) { rs.push_back(r); rs_all.push_back(r); }
     else rl.push_back(r);
@@ -617,6 +642,42 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   {
     std::vector<int> fill(dptr.begin(), dptr.end() - 1);
     for (int r : ro1) if (ci[rp[r]] < n_verts) drow[fill[ci[rp[r]]]++] = r;
+  }
+  // ---- fused path tables: what the skinning epilogue emits per 32-vertex group, and the partial layout ----
+  std::vector<int> part_ptr(n_rows + 1, 0), rows_reduce;
+  std::vector<char> is_vert_onehot(n_rows, 0);
+  for (int r : ro1) if (ci[rp[r]] < n_verts) is_vert_onehot[r] = 1;
+  for (int r = 0; r < n_rows; ++r) {
+    int nv = 0;
+    if (!is_vert_onehot[r]) {
+      for (int k = rp[r]; k < rp[r + 1]; ++k) nv += ci[k] < n_verts;
+      rows_reduce.push_back(r);
+    }
+    part_ptr[r + 1] = part_ptr[r] + nv;
+  }
+  const int n_partial = part_ptr[n_rows];
+  const int n_g32 = VP / 32;
+  std::vector<std::vector<EmitEntry>> per_group(n_g32);
+  for (int r = 0; r < n_rows; ++r) {
+    if (is_vert_onehot[r]) {
+      const int v = ci[rp[r]];
+      per_group[v / 32].push_back(EmitEntry{(v % 32), 1.0f, gpre[r], grows[r], r - gpre[r]});
+    } else {
+      int d = part_ptr[r];
+      for (int k = rp[r]; k < rp[r + 1]; ++k)
+        if (ci[k] < n_verts) per_group[ci[k] / 32].push_back(EmitEntry{(ci[k] % 32) | (1 << 8), vv[k], 0, 0, d++});
+    }
+  }
+  std::vector<int> emit_ptr(n_g32 + 1, 0);
+  std::vector<EmitEntry> emit_entries;
+  for (int g = 0; g < n_g32; ++g) {
+    emit_entries.insert(emit_entries.end(), per_group[g].begin(), per_group[g].end());
+    emit_ptr[g + 1] = (int)emit_entries.size();
+  }
+  int partial_bodies = 768;
+  if (const char* ev = getenv("WHMR_CHUNK_BODIES")) {
+    const int c = atoi(ev);
+    if (c >= 8) partial_bodies = std::max(kTcBodyTile, c / kTcBodyTile * kTcBodyTile);
   }
   std::vector<int4> otab(ro1.size());
   for (size_t i = 0; i < ro1.size(); ++i) {
@@ -635,6 +696,14 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   up(rs_all, &h->rows_short_all); up(dptr, &h->dst_ptr); up(drow, &h->dst_row); up(otab, &h->onehot_tab);
   up(gpre, &h->grp_prefix); up(grows, &h->grp_rows);
   if (sub_row) up(sr, &h->sub_row);
+  up(emit_ptr, &h->emit_grp_ptr); up(emit_entries, &h->emit_entries); up(part_ptr, &h->part_ptr);
+  up(rows_reduce, &h->rows_reduce);
+  h->n_partial = n_partial; h->n_reduce = (int)rows_reduce.size(); h->partial_bodies = partial_bodies;
+  if (e == cudaSuccess) {
+    void* pb = nullptr;
+    e = h->arena.alloc((size_t)partial_bodies * std::max(n_partial, 1) * 3 * sizeof(float), &pb);
+    h->partial = static_cast<float*>(pb);
+  }
   if (e != cudaSuccess) {
     delete h;
     return set_error(WHMR_E_CUDA, "whmr_readout_create: device upload failed: %s", cudaGetErrorString(e));
