@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(256) readout_all_kernel(ReadoutAllParams q) {
 // ---------------------------------------------------------------------------------------------
 // One entry per table non-zero whose source is a vertex.  kind 0: one-hot row, the value goes to the
 // final output (a = group prefix, c = rows in group, d = row - prefix).  kind 1: regressor term, the value
-// w*v goes to partial[b][d] (d = position of the non-zero in the partial buffer, row-major order).
+// w*v goes to partial[b][d] where d is the term's slot in EMIT order (consecutive lanes -> consecutive slots,
+// so the epilogue's stores coalesce); readout_reduce_kernel finds the slots of a row through slot_of[].
 struct EmitEntry {
   int lv_kind;   // local vertex (0..31) | kind << 8
   float w;
@@ -178,48 +179,59 @@ struct EmitTable {              // device pointers, owned by the read-out handle
   int n_partial;
 };
 
-// Finishing pass for the rows that are not vertex one-hots: thread per (body, row).
-//   out = sum(partial[b][pk0 .. pk1))  + joint-sourced terms  - (same for the sub row)
+// Finishing pass for the rows that are not vertex one-hots.  One CTA per body: the body's partial array
+// (emit order, ~30 KB) is staged in shared memory with coalesced loads, then thread r sums row r's terms
+// in the row's storage order through the slot list (deterministic), adds joint-sourced terms, subtracts
+// the sub row and writes the output.
 struct ReduceParams {
   ReadoutParams rp;
-  const int* rows; int n_rows;
-  const int* part_ptr;                  // [R+1] range of each row in the partial buffer
-  const float* partial; int n_partial;
+  const int* rows; int n_rows;          // rows handled here
+  const int* part_ptr;                  // [R+1] range of each row in slot_of
+  const int* slot_of;                   // [n_vertex_terms] emit slot of each vertex-sourced term, row-major
+  const int* jt_ptr;                    // [R+1] range of each row's joint-sourced terms
+  const int* jt_col; const float* jt_val;
+  const float* partial; int n_partial;  // [chunk, n_partial, 3], n_partial % 4 == 0
 };
 
-__device__ __forceinline__ void reduce_row(const ReduceParams& q, int b, int r, float& x, float& y, float& z) {
+__device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* ps, int b, int r, float& x, float& y,
+                                           float& z) {
   const ReadoutParams& p = q.rp;
   x = y = z = 0.f;
-  const float* pp = q.partial + ((size_t)b * q.n_partial + q.part_ptr[r]) * 3;
-  const int n = q.part_ptr[r + 1] - q.part_ptr[r];
-  for (int k = 0; k < n; ++k) { x += pp[k * 3 + 0]; y += pp[k * 3 + 1]; z += pp[k * 3 + 2]; }
-  if (p.joints)   // terms whose source is a chain joint (col >= V) are not emitted by the skinning kernel
-    for (int k = p.row_ptr[r]; k < p.row_ptr[r + 1]; ++k) {
-      const int col = p.col_idx[k];
-      if (col >= p.V) {
-        const float w = p.vals[k];
-        const float* s = p.joints + ((size_t)b * p.J + (col - p.V)) * 3;
-        x = fmaf(w, s[0], x); y = fmaf(w, s[1], y); z = fmaf(w, s[2], z);
-      }
-    }
+  for (int k = q.part_ptr[r]; k < q.part_ptr[r + 1]; ++k) {
+    const float* e = ps + q.slot_of[k] * 3;
+    x += e[0]; y += e[1]; z += e[2];
+  }
+  for (int k = q.jt_ptr[r]; k < q.jt_ptr[r + 1]; ++k) {
+    const float w = q.jt_val[k];
+    const float* s = p.joints + ((size_t)b * p.J + q.jt_col[k]) * 3;
+    x = fmaf(w, s[0], x); y = fmaf(w, s[1], y); z = fmaf(w, s[2], z);
+  }
 }
 
 __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
+  extern __shared__ __align__(16) float ps[];   // [n_partial * 3]
   const ReadoutParams& p = q.rp;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)p.B * q.n_rows) return;
-  const int b = (int)(i / q.n_rows);
-  const int r = q.rows[(int)(i % q.n_rows)];
-  float x, y, z;
-  reduce_row(q, b, r, x, y, z);
-  const int sr = p.sub_row ? p.sub_row[r] : -1;
-  if (sr >= 0) {
-    float sx, sy, sz;
-    reduce_row(q, b, sr, sx, sy, sz);
-    x -= sx; y -= sy; z -= sz;
+  const int b = blockIdx.x;
+  {
+    const float4* src = reinterpret_cast<const float4*>(q.partial + (size_t)b * q.n_partial * 3);
+    float4* dst = reinterpret_cast<float4*>(ps);
+    const int n4 = q.n_partial * 3 / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
   }
-  float* o = readout_dst(p, b, r);
-  o[0] = x; o[1] = y; o[2] = z;
+  __syncthreads();
+  for (int i = threadIdx.x; i < q.n_rows; i += blockDim.x) {
+    const int r = q.rows[i];
+    float x, y, z;
+    reduce_row(q, ps, b, r, x, y, z);
+    const int sr = p.sub_row ? p.sub_row[r] : -1;
+    if (sr >= 0) {
+      float sx, sy, sz;
+      reduce_row(q, ps, b, sr, sx, sy, sz);
+      x -= sx; y -= sy; z -= sz;
+    }
+    float* o = readout_dst(p, b, r);
+    o[0] = x; o[1] = y; o[2] = z;
+  }
 }
 
 // verts[:, idx]

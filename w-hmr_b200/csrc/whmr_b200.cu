@@ -101,6 +101,8 @@ struct whmr_readout_s {
   EmitEntry* emit_entries = nullptr;
   int* part_ptr = nullptr;                      // [R+1]
   int* rows_reduce = nullptr;                   // rows that are not vertex one-hots
+  int *slot_of = nullptr, *jt_ptr = nullptr, *jt_col = nullptr;
+  float* jt_val = nullptr;
   float* partial = nullptr;                     // [partial_bodies, n_partial, 3]
   int n_partial = 0, n_reduce = 0, partial_bodies = 0;
   int dst_VP = 0;
@@ -396,9 +398,9 @@ static int launch_readout_reduce(whmr_readout_t r, const float* verts, const flo
   p.R = r->R; p.V = r->V; p.J = r->J; p.B = nb; p.B_total = B_total; p.b0 = b0;
   p.verts = verts; p.joints = joints; p.out = out;
   q.rows = r->rows_reduce; q.n_rows = r->n_reduce; q.part_ptr = r->part_ptr; q.partial = r->partial;
-  q.n_partial = r->n_partial;
-  const long long n = (long long)nb * r->n_reduce;
-  readout_reduce_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(q);
+  q.n_partial = r->n_partial; q.slot_of = r->slot_of; q.jt_ptr = r->jt_ptr; q.jt_col = r->jt_col; q.jt_val = r->jt_val;
+  const size_t smem = (size_t)r->n_partial * 3 * sizeof(float);
+  readout_reduce_kernel<<<nb, 128, smem, st>>>(q);
   WHMR_LAUNCHED("readout_reduce_kernel");
   return WHMR_OK;
 }
@@ -655,24 +657,49 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
     }
     part_ptr[r + 1] = part_ptr[r] + nv;
   }
-  const int n_partial = part_ptr[n_rows];
+  const int n_terms = part_ptr[n_rows];
+  const int n_partial = (n_terms + 3) / 4 * 4;   // rows of the partial buffer start 16-byte aligned
   const int n_g32 = VP / 32;
-  std::vector<std::vector<EmitEntry>> per_group(n_g32);
+  std::vector<std::vector<EmitEntry>> grp0(n_g32), grp1(n_g32);   // kind 0 (one-hot) / kind 1 (regressor terms)
+  std::vector<std::vector<int>> grp1_term(n_g32);                  // row-major term index of each kind-1 entry
   for (int r = 0; r < n_rows; ++r) {
     if (is_vert_onehot[r]) {
       const int v = ci[rp[r]];
-      per_group[v / 32].push_back(EmitEntry{(v % 32), 1.0f, gpre[r], grows[r], r - gpre[r]});
+      grp0[v / 32].push_back(EmitEntry{(v % 32), 1.0f, gpre[r], grows[r], r - gpre[r]});
     } else {
-      int d = part_ptr[r];
+      int t = part_ptr[r];
       for (int k = rp[r]; k < rp[r + 1]; ++k)
-        if (ci[k] < n_verts) per_group[ci[k] / 32].push_back(EmitEntry{(ci[k] % 32) | (1 << 8), vv[k], 0, 0, d++});
+        if (ci[k] < n_verts) {
+          grp1[ci[k] / 32].push_back(EmitEntry{(ci[k] % 32) | (1 << 8), vv[k], 0, 0, 0});
+          grp1_term[ci[k] / 32].push_back(t++);
+        }
     }
   }
-  std::vector<int> emit_ptr(n_g32 + 1, 0);
+  // emit order: per group the one-hot entries sorted by destination (neighbouring lanes -> neighbouring output
+  // slots), then the regressor terms, which get consecutive slots of the partial buffer
+  std::vector<int> emit_ptr(n_g32 + 1, 0), slot_of(std::max(n_terms, 1), 0);
   std::vector<EmitEntry> emit_entries;
+  int next_slot = 0;
   for (int g = 0; g < n_g32; ++g) {
-    emit_entries.insert(emit_entries.end(), per_group[g].begin(), per_group[g].end());
+    std::sort(grp0[g].begin(), grp0[g].end(), [](const EmitEntry& x, const EmitEntry& y) {
+      return x.a != y.a ? x.a < y.a : x.d < y.d;
+    });
+    emit_entries.insert(emit_entries.end(), grp0[g].begin(), grp0[g].end());
+    for (size_t i = 0; i < grp1[g].size(); ++i) {
+      EmitEntry en = grp1[g][i];
+      en.d = next_slot;
+      slot_of[grp1_term[g][i]] = next_slot++;
+      emit_entries.push_back(en);
+    }
     emit_ptr[g + 1] = (int)emit_entries.size();
+  }
+  // joint-sourced terms per row (handled by the reduce kernel: the skinning kernel only sees vertices)
+  std::vector<int> jt_ptr(n_rows + 1, 0), jt_col;
+  std::vector<float> jt_val;
+  for (int r = 0; r < n_rows; ++r) {
+    for (int k = rp[r]; k < rp[r + 1]; ++k)
+      if (ci[k] >= n_verts) { jt_col.push_back(ci[k] - n_verts); jt_val.push_back(vv[k]); }
+    jt_ptr[r + 1] = (int)jt_col.size();
   }
   int partial_bodies = 768;
   if (const char* ev = getenv("WHMR_CHUNK_BODIES")) {
@@ -697,8 +724,17 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   up(gpre, &h->grp_prefix); up(grows, &h->grp_rows);
   if (sub_row) up(sr, &h->sub_row);
   up(emit_ptr, &h->emit_grp_ptr); up(emit_entries, &h->emit_entries); up(part_ptr, &h->part_ptr);
-  up(rows_reduce, &h->rows_reduce);
+  up(rows_reduce, &h->rows_reduce); up(slot_of, &h->slot_of); up(jt_ptr, &h->jt_ptr); up(jt_col, &h->jt_col);
+  up(jt_val, &h->jt_val);
   h->n_partial = n_partial; h->n_reduce = (int)rows_reduce.size(); h->partial_bodies = partial_bodies;
+  if ((size_t)n_partial * 12 > 200 * 1024) h->partial_bodies = 0;   // partial array must fit in shared memory: else unfused path
+  else {
+    static int reduce_smem_max = 48 * 1024;   // the attribute is per function: only ever raise it
+    if (n_partial * 12 > reduce_smem_max) {
+      reduce_smem_max = n_partial * 12;
+      cudaFuncSetAttribute(readout_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, reduce_smem_max);
+    }
+  }
   if (e == cudaSuccess) {
     void* pb = nullptr;
     e = h->arena.alloc((size_t)partial_bodies * std::max(n_partial, 1) * 3 * sizeof(float), &pb);
