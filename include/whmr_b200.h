@@ -117,6 +117,15 @@ int whmr_smpl_forward_host(whmr_smpl_t h, const float* betas, const float* pose,
  * R = I + sin K + (1-cos) K K).  aa [n,3] -> R [n,3,3]. */
 int whmr_batch_rodrigues(const float* aa, int n, float* R, void* stream);
 
+/* Rotation glue around the SMPL call in Regressor.forward: one thread per rotation.
+ *   whmr_rot6d_to_rotmat       utils/geometry.py:243-257  x [n,6] (viewed [n,3,2]) -> R [n,3,3]
+ *   whmr_unbiased_gram_schmidt utils/geometry.py:260-272  x [n,3,3] -> R [n,3,3]   (models/whmr.py:129-130)
+ *   whmr_rotmat_to_axis_angle  utils/geometry.py:54-83 (kornia quaternion path, NaN -> 0)  R [n,3,3] -> aa [n,3]
+ *                              (models/whmr.py:174,632) */
+int whmr_rot6d_to_rotmat(const float* x, int n, float* R, void* stream);
+int whmr_unbiased_gram_schmidt(const float* x, int n, float* R, void* stream);
+int whmr_rotmat_to_axis_angle(const float* R, int n, float* aa, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Sparse linear read-out of the posed vertices.  Replaces every "matrix x vertices" and
  * vertex-pick on the path: J_regressor_extra + joint_map (models/smpl.py:66-76), VertexJointSelector

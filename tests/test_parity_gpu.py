@@ -261,6 +261,25 @@ def test_projection_matches_reference_golden(dev, golden):
         geo.projection(T('proj_points'), T('proj_cam'), retain_z=True)
 
 
+def test_rotation_glue_matches_reference_golden(dev, golden):
+    """rot6d_to_rotmat / unbiased_gram_schmidt / rotation_matrix_to_angle_axis vs the reference's outputs."""
+    from oracle import geometry_oracle as G
+    from whmr_b200 import geometry as geo
+    g = golden
+    T = lambda k: torch.from_numpy(g[k]).to(dev)  # noqa: E731
+    assert _maxabs(geo.rot6d_to_rotmat(T('rot6d_in')), g['rot6d_out']) <= 1e-6
+    assert _maxabs(geo.unbiased_gram_schmidt(T('ugs_in')), g['ugs_out']) <= 1e-6
+    assert _maxabs(geo.rotation_matrix_to_angle_axis(T('r2aa_in')), g['r2aa_out']) <= 2e-5
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(4096, 24, 3, 3, generator=gen) * 0.3 + torch.eye(3)
+    R = geo.unbiased_gram_schmidt(x.to(dev))
+    assert _maxabs(R, G.unbiased_gram_schmidt(x)) <= 2e-6
+    aa = geo.rotation_matrix_to_angle_axis(R.reshape(-1, 3, 3))
+    ref = G.rotation_matrix_to_angle_axis(R.reshape(-1, 3, 3).cpu())
+    assert _maxabs(aa, ref) <= 5e-5          # atan2 near pi amplifies fp32 rounding of the quaternion
+    assert torch.isfinite(aa).all()
+
+
 def test_projection_large_random(dev):
     from oracle import geometry_oracle as G
     from whmr_b200 import geometry as geo

@@ -72,6 +72,9 @@ SIGNATURES = {
     "whmr_smpl_reserve": (C.c_int, [_vp, _i]),
     "whmr_smpl_forward_host": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "whmr_batch_rodrigues": (C.c_int, [_vp, _i, _vp, _vp]),
+    "whmr_rot6d_to_rotmat": (C.c_int, [_vp, _i, _vp, _vp]),
+    "whmr_unbiased_gram_schmidt": (C.c_int, [_vp, _i, _vp, _vp]),
+    "whmr_rotmat_to_axis_angle": (C.c_int, [_vp, _i, _vp, _vp]),
     "whmr_readout_create": (C.c_int, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, C.POINTER(_vp)]),
     "whmr_readout_destroy": (C.c_int, [_vp]),
     "whmr_readout_apply": (C.c_int, [_vp, _vp, _vp, _i, _vp, _vp]),

@@ -14,6 +14,7 @@
 #include "pose_blend_tc.cuh"
 #include "projection.cuh"
 #include "readout.cuh"
+#include "rotations.cuh"
 #include "sampling.cuh"
 #include "skin_tc.cuh"
 #include "skinning.cuh"
@@ -588,6 +589,20 @@ int whmr_batch_rodrigues(const float* aa, int n, float* R, void* stream) {
   WHMR_LAUNCHED("rodrigues_kernel");
   return WHMR_OK;
 }
+
+#define WHMR_ROT_ENTRY(NAME, KERNEL)                                                              \
+  int NAME(const float* in, int n, float* out, void* stream) {                                    \
+    WHMR_CHECK_ARG(n >= 0, #NAME ": negative n");                                                 \
+    if (n == 0) return WHMR_OK;                                                                   \
+    WHMR_CHECK_ARG(in && out, #NAME ": null pointer");                                            \
+    KERNEL<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in, n, out);                       \
+    WHMR_LAUNCHED(#KERNEL);                                                                       \
+    return WHMR_OK;                                                                               \
+  }
+WHMR_ROT_ENTRY(whmr_rot6d_to_rotmat, rot6d_to_rotmat_kernel)
+WHMR_ROT_ENTRY(whmr_unbiased_gram_schmidt, unbiased_gram_schmidt_kernel)
+WHMR_ROT_ENTRY(whmr_rotmat_to_axis_angle, rotmat_to_axis_angle_kernel)
+#undef WHMR_ROT_ENTRY
 
 // =============================================================================================
 // read-out

@@ -47,3 +47,20 @@ def full_image_projection(pred_joints, pred_cam, bbox_height, center, orig_shape
 def batch_rodrigues(rot_vecs):
     """smplx.lbs.batch_rodrigues (imported at models/whmr.py:9), the variant inside SMPL.forward."""
     return ops.batch_rodrigues(rot_vecs)
+
+
+def rot6d_to_rotmat(x):
+    """utils/geometry.py:243-257."""
+    return ops.rot6d_to_rotmat(x)
+
+
+def unbiased_gram_schmidt(x):
+    """utils/geometry.py:260-272 (models/whmr.py:129-130)."""
+    return ops.unbiased_gram_schmidt(x)
+
+
+def rotation_matrix_to_angle_axis(rotation_matrix):
+    """utils/geometry.py:54-83 for [N,3,3] input (the only form the reference's hot path uses, models/whmr.py:174)."""
+    if rotation_matrix.shape[-2:] != (3, 3):
+        raise ValueError("rotation_matrix_to_angle_axis: expected [N,3,3], got %s" % (tuple(rotation_matrix.shape),))
+    return ops.rotation_matrix_to_angle_axis(rotation_matrix)

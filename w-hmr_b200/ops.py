@@ -164,6 +164,31 @@ def batch_rodrigues(aa):
     return out
 
 
+def _rot_op(fn_name, x, in_elems, out_shape):
+    x = _req(x, "x")
+    n = x.numel() // in_elems
+    out = torch.empty((n,) + out_shape, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(getattr(_lib.lib(), fn_name)(_p(x), n, _p(out), _stream()))
+    return out
+
+
+def rot6d_to_rotmat(x):
+    """utils/geometry.py:243-257: [..,6] -> [n,3,3]"""
+    return _rot_op("whmr_rot6d_to_rotmat", x, 6, (3, 3))
+
+
+def unbiased_gram_schmidt(x):
+    """utils/geometry.py:260-272: [B,k,3,3] -> [B,k,3,3]"""
+    k = x.shape[1]
+    return _rot_op("whmr_unbiased_gram_schmidt", x, 9, (3, 3)).reshape(-1, k, 3, 3)
+
+
+def rotation_matrix_to_angle_axis(R):
+    """utils/geometry.py:54-83: [N,3,3] -> [N,3]"""
+    return _rot_op("whmr_rotmat_to_axis_angle", R, 9, (3,))
+
+
 # ----------------------------------------------------------------------------------------------
 # read-out
 # ----------------------------------------------------------------------------------------------
