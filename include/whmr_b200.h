@@ -152,11 +152,22 @@ int whmr_readout_apply(whmr_readout_t r, const float* verts /*[B,V,3]*/, const f
 /* SMPL forward and its read-outs in one call (what Regressor.forward does back to back,
  * models/whmr.py:132-187): same as whmr_smpl_forward followed by whmr_readout_apply(ro, verts, joints),
  * but per 768-body chunk -- the one-hot rows (vertex picks, markers, mesh down-sampling) are written
- * by the skinning kernel's epilogue and the regressor rows read the chunk's vertices out of L2. */
+ * by the skinning kernel's epilogue and the regressor rows are summed from per-body partials it emitted.
+ * ro_workspace: whmr_readout_workspace_bytes(ro, min(B, whmr_smpl_chunk_bodies(h))) bytes of scratch for the
+ *   per-body partial sums the skinning epilogue emits (NULL: the read-outs run as a stand-alone gather).
+ * defer_finish != 0: when the whole batch is one chunk the finishing pass (regressor rows, joint copies) is NOT
+ *   enqueued; *finish_deferred is set to 1 and the caller runs whmr_readout_finish(ro, joints, B, ro_workspace,
+ *   ro_out, other_stream) whenever it likes (e.g. overlapped with the feature sampling that only needs the markers,
+ *   which the skinning kernel has already written). */
+size_t whmr_readout_workspace_bytes(whmr_readout_t ro, int n_bodies);
+int whmr_smpl_chunk_bodies(whmr_smpl_t h);
 int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
                               const float* transl, int B, float* verts, float* joints, float* rel_transforms,
-                              whmr_readout_t ro, float* ro_out /*[B*n_rows*3], group-major*/, void* workspace,
+                              whmr_readout_t ro, float* ro_out /*[B*n_rows*3], group-major*/, void* ro_workspace,
+                              size_t ro_workspace_bytes, int defer_finish, int* finish_deferred, void* workspace,
                               size_t workspace_bytes, void* stream);
+int whmr_readout_finish(whmr_readout_t ro, const float* joints /*[B,J,3] or NULL*/, int B, const void* ro_workspace,
+                        float* ro_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Projection.

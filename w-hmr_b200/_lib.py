@@ -64,7 +64,11 @@ SIGNATURES = {
     "whmr_smpl_get_info": (C.c_int, [_vp] + [C.POINTER(C.c_int32)] * 5),
     "whmr_smpl_workspace_bytes": (_sz, [_vp, _i]),
     "whmr_smpl_forward": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "whmr_smpl_forward_readout": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "whmr_smpl_forward_readout": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i,
+                                            C.POINTER(C.c_int), _vp, _sz, _vp]),
+    "whmr_readout_workspace_bytes": (_sz, [_vp, _i]),
+    "whmr_smpl_chunk_bodies": (C.c_int, [_vp]),
+    "whmr_readout_finish": (C.c_int, [_vp, _vp, _i, _vp, _vp, _vp]),
     "whmr_smpl_stage_chain": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "whmr_smpl_stage_pose_blend": (C.c_int, [_vp, _i, _vp, _sz, _vp]),
     "whmr_smpl_stage_skin": (C.c_int, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),

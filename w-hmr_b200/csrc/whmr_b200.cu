@@ -104,8 +104,8 @@ struct whmr_readout_s {
   int* rows_reduce = nullptr;                   // rows that are not vertex one-hots
   int *slot_of = nullptr, *jt_ptr = nullptr, *jt_col = nullptr;
   float* jt_val = nullptr;
-  float* partial = nullptr;                     // [partial_bodies, n_partial, 3]
-  int n_partial = 0, n_reduce = 0, partial_bodies = 0;
+  int n_partial = 0, n_reduce = 0;              // partial buffer [bodies, n_partial, 3] comes from the caller
+  bool fusable = false;                         // partial array of one body fits in shared memory
   int dst_VP = 0;
   float* vals = nullptr;
   bool needs_joints = false;
@@ -390,7 +390,7 @@ static int launch_readout_all(whmr_readout_t r, const float* verts, const float*
 
 // fused path, second half: sum the partials the skinning epilogue emitted (+ joint-sourced terms, sub rows)
 static int launch_readout_reduce(whmr_readout_t r, const float* verts, const float* joints, int nb, int B_total, int b0,
-                                 float* out, cudaStream_t st) {
+                                 const float* partial, float* out, cudaStream_t st) {
   if (nb == 0 || r->n_reduce == 0) return WHMR_OK;
   ReduceParams q{};
   ReadoutParams& p = q.rp;
@@ -398,7 +398,7 @@ static int launch_readout_reduce(whmr_readout_t r, const float* verts, const flo
   p.grp_prefix = r->grp_prefix; p.grp_rows = r->grp_rows;
   p.R = r->R; p.V = r->V; p.J = r->J; p.B = nb; p.B_total = B_total; p.b0 = b0;
   p.verts = verts; p.joints = joints; p.out = out;
-  q.rows = r->rows_reduce; q.n_rows = r->n_reduce; q.part_ptr = r->part_ptr; q.partial = r->partial;
+  q.rows = r->rows_reduce; q.n_rows = r->n_reduce; q.part_ptr = r->part_ptr; q.partial = partial;
   q.n_partial = r->n_partial; q.slot_of = r->slot_of; q.jt_ptr = r->jt_ptr; q.jt_col = r->jt_col; q.jt_val = r->jt_val;
   const size_t smem = (size_t)r->n_partial * 3 * sizeof(float);
   readout_reduce_kernel<<<nb, 128, smem, st>>>(q);
@@ -408,7 +408,7 @@ static int launch_readout_reduce(whmr_readout_t r, const float* verts, const flo
 
 // skinning of bodies [b0, b0+nb); with `ro` the read-out entries are emitted by the same kernel
 static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* betas, const float* transl, int B, int b0,
-                       int nb, float* verts, whmr_readout_t ro, float* ro_out, cudaStream_t st) {
+                       int nb, float* verts, whmr_readout_t ro, float* ro_out, float* ro_partial, cudaStream_t st) {
   const SmplDevice& d = h->d;
   if (h->skin_tc) {
     SkinTcParams p{};
@@ -417,7 +417,7 @@ static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* beta
     p.transl = transl ? transl + (size_t)b0 * 3 : nullptr;
     p.verts = verts + (size_t)b0 * d.V * 3;
     if (ro) {   // the epilogue emits the read-out entries of each vertex (readout.cuh, path 2)
-      p.emit.grp_ptr = ro->emit_grp_ptr; p.emit.entries = ro->emit_entries; p.emit.partial = ro->partial;
+      p.emit.grp_ptr = ro->emit_grp_ptr; p.emit.entries = ro->emit_entries; p.emit.partial = ro_partial;
       p.emit.n_partial = ro->n_partial;
       p.ro_out = ro_out; p.ro_B = B; p.ro_b0 = b0;
     }
@@ -481,12 +481,32 @@ int whmr_smpl_stage_skin(whmr_smpl_t h, const float* betas, int B, float* verts,
   if (B == 0) return WHMR_OK;
   WHMR_CHECK_ARG(betas && verts, "whmr_smpl_stage_skin: null betas/verts");
   WHMR_CHECK_ARG(B <= ws.chunk, "whmr_smpl_stage_skin: B=%d exceeds the chunk size %d", B, ws.chunk);
-  return launch_skin(h, ws, betas, nullptr, B, 0, B, verts, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_skin(h, ws, betas, nullptr, B, 0, B, verts, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+size_t whmr_readout_workspace_bytes(whmr_readout_t ro, int n_bodies) {
+  if (!ro || n_bodies <= 0 || !ro->fusable) return 0;
+  return (size_t)n_bodies * ro->n_partial * 3 * sizeof(float) + 256;
+}
+
+int whmr_smpl_chunk_bodies(whmr_smpl_t h) { return h ? h->chunk_bodies : 0; }
+
+int whmr_readout_finish(whmr_readout_t ro, const float* joints, int B, const void* ro_workspace, float* ro_out,
+                        void* stream) {
+  WHMR_CHECK_ARG(ro && B >= 0, "whmr_readout_finish: bad arguments");
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(ro_workspace && ro_out, "whmr_readout_finish: null buffer");
+  WHMR_CHECK_ARG(joints || !ro->needs_joints, "whmr_readout_finish: table references chain joints but joints == NULL");
+  const float* partial = reinterpret_cast<const float*>(align_up(reinterpret_cast<size_t>(ro_workspace), 256));
+  return launch_readout_reduce(ro, nullptr, joints, B, B, 0, partial, ro_out, (cudaStream_t)stream);
 }
 
 int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
                               const float* transl, int B, float* verts, float* joints, float* rel_transforms,
-                              whmr_readout_t ro, float* ro_out, void* workspace, size_t workspace_bytes, void* stream) {
+                              whmr_readout_t ro, float* ro_out, void* ro_workspace, size_t ro_workspace_bytes,
+                              int defer_finish, int* finish_deferred, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  if (finish_deferred) *finish_deferred = 0;
   SmplWorkspace ws;
   int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
   if (rc) return rc;
@@ -505,22 +525,29 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
   if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, st, cudaEventRecordExternal));
   // chunked so the [chunk, NP] pose-offset intermediate (and the chunk's vertices, for the read-outs)
   // stay L2-resident between the kernels
-  // fused read-outs need the tensor-core skinning kernel, the handle's partial buffer to cover a chunk and
-  // 32-bit element offsets; otherwise the stand-alone gather kernel runs after the skinning kernel
+  // fused read-outs need the tensor-core skinning kernel and a caller-provided partial buffer covering one
+  // chunk; otherwise the stand-alone gather kernel runs after the skinning kernel
   static const bool fuse_env = !(getenv("WHMR_FUSE_READOUT") && atoi(getenv("WHMR_FUSE_READOUT")) == 0);
-  const bool fused = ro && h->skin_tc && fuse_env && ro->dst_VP == h->d.VP && ro->partial_bodies >= ws.chunk;
+  float* partial = ro_workspace ? reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ro_workspace), 256)) : nullptr;
+  const bool fused = ro && h->skin_tc && fuse_env && ro->fusable && ro->dst_VP == h->d.VP && partial &&
+                     ro_workspace_bytes >= whmr_readout_workspace_bytes(ro, std::min(B, ws.chunk));
+  // the finishing pass may be left to the caller (another stream) when the whole batch is one chunk
+  const bool defer = fused && defer_finish && finish_deferred && B <= ws.chunk;
+  if (defer) *finish_deferred = 1;
   for (int b0 = 0; b0 < B; b0 += ws.chunk) {
     const int nb = std::min(ws.chunk, B - b0);
     rc = launch_pose_blend(h, ws, B, b0, nb, st);
     if (rc) return rc;
     if (h->probe_blend && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_blend, st, cudaEventRecordExternal));
-    rc = launch_skin(h, ws, betas, transl, B, b0, nb, verts, fused ? ro : nullptr, ro_out, st);
+    rc = launch_skin(h, ws, betas, transl, B, b0, nb, verts, fused ? ro : nullptr, ro_out, partial, st);
     if (rc) return rc;
     if (h->probe_skin && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_skin, st, cudaEventRecordExternal));
     if (ro) {
       const float* vch = verts + (size_t)b0 * h->d.V * 3;
       const float* jch = joints ? joints + (size_t)b0 * h->d.J * 3 : nullptr;
-      rc = fused ? launch_readout_reduce(ro, vch, jch, nb, B, b0, ro_out, st) : launch_readout_all(ro, vch, jch, nb, B, b0, ro_out, st);
+      if (defer) continue;
+      rc = fused ? launch_readout_reduce(ro, vch, jch, nb, B, b0, partial, ro_out, st)
+                 : launch_readout_all(ro, vch, jch, nb, B, b0, ro_out, st);
       if (rc) return rc;
     }
   }
@@ -531,7 +558,7 @@ int whmr_smpl_forward(whmr_smpl_t h, const float* betas, const float* pose, int 
                       int B, float* verts, float* joints, float* rel_transforms, void* workspace,
                       size_t workspace_bytes, void* stream) {
   return whmr_smpl_forward_readout(h, betas, pose, pose_is_rotmat, transl, B, verts, joints, rel_transforms, nullptr,
-                                   nullptr, workspace, workspace_bytes, stream);
+                                   nullptr, nullptr, 0, 0, nullptr, workspace, workspace_bytes, stream);
 }
 
 int whmr_smpl_set_probe_events(whmr_smpl_t h, void* after_chain, void* after_pose_blend, void* after_skin) {
@@ -716,11 +743,6 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
       if (ci[k] >= n_verts) { jt_col.push_back(ci[k] - n_verts); jt_val.push_back(vv[k]); }
     jt_ptr[r + 1] = (int)jt_col.size();
   }
-  int partial_bodies = 768;
-  if (const char* ev = getenv("WHMR_CHUNK_BODIES")) {
-    const int c = atoi(ev);
-    if (c >= 8) partial_bodies = std::max(kTcBodyTile, c / kTcBodyTile * kTcBodyTile);
-  }
   std::vector<int4> otab(ro1.size());
   for (size_t i = 0; i < ro1.size(); ++i) {
     const int r = ro1[i];
@@ -741,19 +763,14 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   up(emit_ptr, &h->emit_grp_ptr); up(emit_entries, &h->emit_entries); up(part_ptr, &h->part_ptr);
   up(rows_reduce, &h->rows_reduce); up(slot_of, &h->slot_of); up(jt_ptr, &h->jt_ptr); up(jt_col, &h->jt_col);
   up(jt_val, &h->jt_val);
-  h->n_partial = n_partial; h->n_reduce = (int)rows_reduce.size(); h->partial_bodies = partial_bodies;
-  if ((size_t)n_partial * 12 > 200 * 1024) h->partial_bodies = 0;   // partial array must fit in shared memory: else unfused path
-  else {
+  h->n_partial = n_partial; h->n_reduce = (int)rows_reduce.size();
+  h->fusable = (size_t)n_partial * 12 <= 200 * 1024;   // one body's partial array must fit in shared memory
+  if (h->fusable) {
     static int reduce_smem_max = 48 * 1024;   // the attribute is per function: only ever raise it
     if (n_partial * 12 > reduce_smem_max) {
       reduce_smem_max = n_partial * 12;
       cudaFuncSetAttribute(readout_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, reduce_smem_max);
     }
-  }
-  if (e == cudaSuccess) {
-    void* pb = nullptr;
-    e = h->arena.alloc((size_t)partial_bodies * std::max(n_partial, 1) * 3 * sizeof(float), &pb);
-    h->partial = static_cast<float*>(pb);
   }
   if (e != cudaSuccess) {
     delete h;

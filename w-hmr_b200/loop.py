@@ -37,6 +37,9 @@ class RegressorLoop:
         self.levels = VITPOSE_LEVELS if backbone == 'vitpose' else RES50_LEVELS
         self.layout = ops.LAYOUT_NCHW
         self._graph = None
+        # read-out finishing + joint projections of call i overlap with the sampling / SMPL kernels that follow
+        self.overlap = True
+        self._side = torch.cuda.Stream(device=self.device)
 
     def step(self, feats, params, bbox):
         """feats: 3 feature maps [B,256,H_i,W_i]; params: 5 dicts {rotmat [B,24,3,3], betas [B,10],
@@ -44,6 +47,8 @@ class RegressorLoop:
         Returns the last Regressor output dict + 'point_feats' (3 x [B,256,N]) + global outputs."""
         J = True if self.with_h36m else None
         p = params
+        main = torch.cuda.current_stream(self.device)
+        self.head.side_stream = self._side if (self.overlap and self.head.probe is None) else None
         out = self.head(p[0]['rotmat'], p[0]['betas'], p[0]['cam'], J_regressor=J)           # forward_init
         point_feats = []
         for it in range(3):
@@ -65,6 +70,8 @@ class RegressorLoop:
         gverts, gjoints24, flat = ops.smpl_lbs_readout(h.id, ro.id, g['betas'], g['rotmat'], True)  # :641-644
         r = ro.split(flat, gverts.shape[0])
         self.head._mark('skin_readout')
+        if self.head.side_stream is not None:
+            main.wait_stream(self._side)     # join: everything in the result dict is complete on the main stream
         res = dict(out)
         res['point_feats'] = point_feats
         res['global_verts'] = gverts

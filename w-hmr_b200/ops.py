@@ -108,8 +108,11 @@ class SmplHandle:
         n = int(_lib.lib().whmr_smpl_workspace_bytes(self._h, int(B)))
         return torch.empty(n, dtype=torch.uint8, device=self.device), n
 
-    def forward(self, betas, pose, pose_is_rotmat, transl=None, want_transforms=False, readout=None):
-        """-> (verts [B,V,3], chain joints [B,J,3], A [B,J,12] or None[, flat read-out buffer])"""
+    def forward(self, betas, pose, pose_is_rotmat, transl=None, want_transforms=False, readout=None,
+                defer_finish=False):
+        """-> (verts [B,V,3], chain joints [B,J,3], A [B,J,12] or None[, flat read-out buffer, read-out scratch])
+        With defer_finish the finishing pass of the read-outs may be left to the caller (`readout_finish`, any
+        stream); it was deferred iff the returned scratch tensor is non-empty."""
         betas = _req(betas, "betas", align=16)
         pose = _req(pose, "pose", align=16)
         transl = _req(transl, "transl")
@@ -128,11 +131,17 @@ class SmplHandle:
                                                    B, _p(verts), _p(joints), _p(A), _p(ws), n, _stream()))
             return verts, joints, A
         ro_flat = torch.empty(B * readout.R * 3, dtype=torch.float32, device=self.device)
+        L = _lib.lib()
+        if not hasattr(self, "_chunk"):
+            self._chunk = int(L.whmr_smpl_chunk_bodies(self._h))
+        nro = int(L.whmr_readout_workspace_bytes(readout._h, min(B, self._chunk)))
+        ro_ws = torch.empty(max(nro, 1), dtype=torch.uint8, device=self.device)
+        deferred = C.c_int(0)
         with torch.cuda.device(self.device):
-            check(_lib.lib().whmr_smpl_forward_readout(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)),
-                                                       _p(transl), B, _p(verts), _p(joints), _p(A), readout._h,
-                                                       _p(ro_flat), _p(ws), n, _stream()))
-        return verts, joints, A, ro_flat
+            check(L.whmr_smpl_forward_readout(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl), B,
+                                              _p(verts), _p(joints), _p(A), readout._h, _p(ro_flat), _p(ro_ws), nro,
+                                              int(bool(defer_finish)), C.byref(deferred), _p(ws), n, _stream()))
+        return verts, joints, A, ro_flat, (ro_ws if deferred.value else ro_ws[:0])
 
     # per-stage launches (bench.py per-kernel timing, tests)
     def stage_chain(self, betas, pose, pose_is_rotmat, ws, n, joints=None, A=None, transl=None):
@@ -465,7 +474,7 @@ def _(handle, betas, pose, pose_is_rotmat):
 def smpl_lbs_readout(handle: int, readout: int, betas: torch.Tensor, pose: torch.Tensor, pose_is_rotmat: bool) -> \
         tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """SMPL forward + all read-outs of a Readout table (flat, group-major) in one chunked pass."""
-    v, j, _, flat = _HANDLES[handle].forward(betas, pose, pose_is_rotmat, readout=_READOUTS[readout])
+    v, j, _, flat, _ws = _HANDLES[handle].forward(betas, pose, pose_is_rotmat, readout=_READOUTS[readout])
     return v, j, flat
 
 
@@ -474,6 +483,32 @@ def _(handle, readout, betas, pose, pose_is_rotmat):
     h, ro = _HANDLES[handle], _READOUTS[readout]
     B = betas.shape[0]
     return betas.new_empty(B, h.V, 3), betas.new_empty(B, h.J, 3), betas.new_empty(B * ro.R * 3)
+
+
+@torch.library.custom_op("whmr::smpl_lbs_readout_deferred", mutates_args=(), device_types="cuda")
+def smpl_lbs_readout_deferred(handle: int, readout: int, betas: torch.Tensor, pose: torch.Tensor,
+                              pose_is_rotmat: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """As smpl_lbs_readout, but the finishing pass of the read-outs (regressor rows, joint copies) is left to
+    `readout_finish` when the batch is a single chunk: then the 4th output (scratch) is non-empty.  The vertex
+    one-hot rows (markers, picks, down-sampled meshes) are complete on return either way."""
+    v, j, _, flat, ws = _HANDLES[handle].forward(betas, pose, pose_is_rotmat, readout=_READOUTS[readout],
+                                                 defer_finish=True)
+    return v, j, flat, ws
+
+
+@smpl_lbs_readout_deferred.register_fake
+def _(handle, readout, betas, pose, pose_is_rotmat):
+    h, ro = _HANDLES[handle], _READOUTS[readout]
+    B = betas.shape[0]
+    return (betas.new_empty(B, h.V, 3), betas.new_empty(B, h.J, 3), betas.new_empty(B * ro.R * 3),
+            betas.new_empty(0, dtype=torch.uint8))
+
+
+@torch.library.custom_op("whmr::readout_finish", mutates_args=("flat",), device_types="cuda")
+def readout_finish(readout: int, joints: torch.Tensor, flat: torch.Tensor, scratch: torch.Tensor) -> None:
+    ro = _READOUTS[readout]
+    with torch.cuda.device(flat.device):
+        check(_lib.lib().whmr_readout_finish(ro._h, _p(joints), joints.shape[0], _p(scratch), _p(flat), _stream()))
 
 
 @torch.library.custom_op("whmr::sample_bilinear", mutates_args=(), device_types="cuda")

@@ -30,6 +30,10 @@ class BodyModelHead(nn.Module):
         self._h36m = None if J_regressor_h36m is None else np.asarray(J_regressor_h36m, dtype=np.float64)
         self._ro = {}
         self.probe = None    # bench.py: callable(name) recording a CUDA event after each enqueued op
+        # optional torch.cuda.Stream: the read-out finishing pass and the joint projections of a call run on it,
+        # concurrently with whatever the caller enqueues next on the main stream (the feature sampling only needs
+        # the markers, which the skinning kernel itself writes).  The caller joins it (RegressorLoop.step does).
+        self.side_stream = None
 
     def _mark(self, name):
         if self.probe is not None:
@@ -93,7 +97,19 @@ class BodyModelHead(nn.Module):
         rot = pred_rotmat.reshape(B, -1, 3, 3)
         self._mark('pre_smpl')
         ro = self._readout(dev, bool(J_regressor))
-        verts, joints24, flat = ops.smpl_lbs_readout(h.id, ro.id, pred_shape, rot, True)
+        side = self.side_stream
+        main = torch.cuda.current_stream(dev)
+        if side is None:
+            verts, joints24, flat = ops.smpl_lbs_readout(h.id, ro.id, pred_shape, rot, True)
+        else:
+            verts, joints24, flat, scratch = ops.smpl_lbs_readout_deferred(h.id, ro.id, pred_shape, rot, True)
+            side.wait_stream(main)
+            torch.cuda.set_stream(side)     # finishing pass + projections below go to the side stream
+            if scratch.numel():
+                ops.readout_finish(ro.id, joints24, flat, scratch)
+            if not torch.cuda.is_current_stream_capturing():   # allocator bookkeeping for cross-stream use
+                for t in (scratch, flat, joints24, pred_cam):
+                    t.record_stream(side)
         r = ro.split(flat, B)
         self._mark('skin_readout')
         pred_joints = r['joints']
@@ -115,4 +131,10 @@ class BodyModelHead(nn.Module):
         }
         if bbox_height is not None:
             out.update(kp_2d_w=kp_w, focal_length=focal, pred_cam_t=cam_t, scale=scale)
+        if side is not None:
+            if not torch.cuda.is_current_stream_capturing():
+                for t in out.values():
+                    if torch.is_tensor(t) and t.is_cuda:
+                        t.record_stream(main)
+            torch.cuda.set_stream(main)
         return out
