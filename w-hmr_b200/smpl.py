@@ -156,8 +156,8 @@ class SMPL(nn.Module):
             full_pose = torch.cat([global_orient.reshape(-1, 1, 3, 3).expand(B, -1, -1, -1),
                                    body_pose.reshape(body_pose.shape[0], J - 1, 3, 3).expand(B, -1, -1, -1)], dim=1)
         h, ro = self._state(betas.device)
-        verts, joints24, A, flat = h.forward(betas, full_pose, not pose2rot, transl=transl,
-                                             want_transforms=return_transforms, readout=ro)
+        verts, joints24, A, flat, _ = h.forward(betas, full_pose, not pose2rot, transl=transl,
+                                                want_transforms=return_transforms, readout=ro)
         r = ro.split(flat, B)
         return ModelOutput(vertices=verts if return_verts else None, joints=r['joints'],
                            full_pose=full_pose if return_full_pose else None, betas=betas,
