@@ -375,3 +375,42 @@ def test_no_cpu_fallback():
     with pytest.raises(WhmrError):
         ops.project_weak(torch.zeros(1, 2, 3), torch.ones(1, 3), 1000., 256., 256.)
     assert os.path.exists(os.path.join(os.path.dirname(ops.__file__), "libwhmr_b200.so"))
+
+
+def test_regressor_loop_matches_oracle_and_graph_replay(dev, smpl_model):
+    """The whole hot-path loop (BASELINE configs[1] shape, small batch): eager, side-stream overlap and CUDA-graph
+    replay all match the CPU oracle loop."""
+    from oracle.loop_oracle import LoopOracle, to_cpu_inputs
+    from whmr_b200.loop import RegressorLoop, make_loop_inputs
+    B = 12
+    loop = RegressorLoop(smpl_model, dev)
+    feats, params, bbox = make_loop_inputs(B, dev, seed=4)
+    ref = LoopOracle(smpl_model).step(*to_cpu_inputs(feats, params, bbox))
+
+    def check(got):
+        assert _maxabs(got['verts'], ref['verts']) <= VERT_TOL
+        assert _maxabs(got['global_verts'], ref['global_verts']) <= VERT_TOL
+        assert _maxabs(got['kp_3d'], ref['kp_3d']) <= VERT_TOL
+        assert _maxabs(got['global_kp_3d'], ref['global_kp_3d']) <= VERT_TOL
+        assert _maxabs(got['markers'], ref['markers']) <= VERT_TOL
+        assert _maxabs(got['kp_2d'], ref['kp_2d']) * 128 <= PX_TOL
+        half = (bbox['orig_shape'].cpu()[:, [1, 0]] / 2).unsqueeze(1)
+        assert float(((got['kp_2d_w'].cpu() - ref['kp_2d_w']).abs() * half).max()) <= 4 * PX_TOL
+        for a, b in zip(got['point_feats'], ref['point_feats']):
+            assert _maxabs(a, b) <= FEAT_RTOL * float(b.abs().max())
+
+    check(loop.step(feats, params, bbox))
+    loop.overlap = True
+    check(loop.step(feats, params, bbox))
+    g, outs = loop.capture(feats, params, bbox)
+    for v in outs.values():
+        if torch.is_tensor(v):
+            v.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    check(outs)
+    loop.overlap = False
+    g2, outs2 = loop.capture(feats, params, bbox)
+    g2.replay()
+    torch.cuda.synchronize()
+    check(outs2)

@@ -37,8 +37,11 @@ class RegressorLoop:
         self.levels = VITPOSE_LEVELS if backbone == 'vitpose' else RES50_LEVELS
         self.layout = ops.LAYOUT_NCHW
         self._graph = None
-        # read-out finishing + joint projections of call i overlap with the sampling / SMPL kernels that follow
-        self.overlap = True
+        # Optional: run the read-out finishing pass + joint projections of call i on a side stream so they overlap
+        # with the sampling / SMPL kernels that follow.  Measured (tools/overlap_test.py, B=256): 0.447 -> 0.604 ms
+        # per graph replay -- the persistent 1-CTA/SM tcgen05 kernels wait for SMs still holding side-stream CTAs
+        # and lose more in their tails than the overlap gains -- so it is off by default.
+        self.overlap = False
         self._side = torch.cuda.Stream(device=self.device)
 
     def step(self, feats, params, bbox):
