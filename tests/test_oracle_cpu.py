@@ -2,6 +2,8 @@
 made by tests/golden/make_golden.py), (b) the reference's vendored known-answer tests, and
 (c) itself: the two independent SMPL restatements + analytic invariants (SMPL is parity
 unpinned -- see oracle/__init__.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -95,7 +97,41 @@ def test_procrustes_matches_reference_and_kat(golden):
     np.testing.assert_array_almost_equal(M.compute_similarity_transform(src, tgt), tgt)
 
 
-# ------------------------------------------------------------------ SMPL: unpinned, cross-checked
+# ------------------------------------------------------------------ SMPL: pinned to the reference's in-tree code
+def _smpl_golden():
+    import hashlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "smpl_webuser_outputs.npz"))
+    model = syn.make_smpl_model(seed=int(g['model_seed']), weights="random")
+    h = hashlib.sha256()
+    for k in ('v_template', 'shapedirs', 'posedirs', 'weights', 'J_regressor', 'parents'):
+        h.update(np.ascontiguousarray(model[k]).tobytes())
+    assert h.hexdigest() == str(g['model_sha256']), "synthetic model generator drifted from the one the goldens used"
+    return g, model
+
+
+def test_smpl_oracle_matches_reference_smpl_webuser_outputs():
+    """Vertices and posed joints produced by EXECUTING the reference's models/smpl_webuser code
+    (tests/golden/make_golden_smpl.py) pin both restatements: the batched smplx-style oracle (fp64 and fp32)
+    and the per-body NumPy one."""
+    g, model = _smpl_golden()
+    pose, betas = g['pose'], g['betas']
+    n = pose.shape[0]
+    o64 = smpl_oracle.SMPLOracle(model, torch.float64)
+    r = o64(betas.astype(np.float64), pose[:, 3:].astype(np.float64), pose[:, :3].astype(np.float64), pose2rot=True)
+    # 2e-7: float32 storage of the goldens (6e-8 at 1 m) + smplx's angle = ||theta + 1e-8|| vs exact cv2.Rodrigues
+    close(r['vertices'], g['verts'], 2e-7)
+    close(r['joints24'], g['Jtr'], 2e-7)
+    o32 = smpl_oracle.SMPLOracle(model, torch.float32)
+    r32 = o32(betas, pose[:, 3:], pose[:, :3], pose2rot=True)
+    close(r32['vertices'], g['verts'], 2e-6)
+    close(r32['joints24'], g['Jtr'], 2e-6)
+    for i in (0, 8, n - 1):
+        v, jtr = smpl_webuser_oracle.smpl_body(model, pose[i], betas[i])
+        close(v, g['verts'][i], 1e-7)
+        close(jtr, g['Jtr'][i], 1e-7)
+
+
+# ------------------------------------------------------------------ SMPL: the two restatements against each other
 def _bodies(n):
     b = syn.make_bodies(n, seed=1)
     return b

@@ -72,6 +72,25 @@ def test_smpl_forward_config1(dev, weights, gemm_mode):
     assert _maxabs(out.rel_transforms.view(64, 24, 3, 4), ref['A'][:, :, :3, :]) <= VERT_TOL
 
 
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+def test_smpl_matches_reference_smpl_webuser_outputs(dev, gemm_mode):
+    """The CUDA path against vertices / posed joints produced by executing the REFERENCE's own in-tree SMPL code
+    (models/smpl_webuser/{serialization,posemapper,verts,lbs}.py, see tests/golden/make_golden_smpl.py)."""
+    import hashlib
+    import whmr_b200.synthetic as syn
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "smpl_webuser_outputs.npz"))
+    model = syn.make_smpl_model(seed=int(g['model_seed']), weights="random")
+    h = hashlib.sha256()
+    for k in ('v_template', 'shapedirs', 'posedirs', 'weights', 'J_regressor', 'parents'):
+        h.update(np.ascontiguousarray(model[k]).tobytes())
+    assert h.hexdigest() == str(g['model_sha256'])
+    smpl = _smpl(model, dev, gemm_mode)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    out = smpl(betas=T(g['betas']), body_pose=T(g['pose'][:, 3:]), global_orient=T(g['pose'][:, :3]), pose2rot=True)
+    assert _maxabs(out.vertices, g['verts']) <= VERT_TOL
+    assert _maxabs(out.smpl_joints[:, :24], g["Jtr"]) <= VERT_TOL
+
+
 def test_smpl_simt_error_budget(dev, smpl_model):
     """The exact-fp32 GEMM path should sit ~1e-6 from the fp64 oracle (summation order only)."""
     b = _bodies(32)
