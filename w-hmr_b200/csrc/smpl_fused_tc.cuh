@@ -1,0 +1,427 @@
+// One kernel for the vertex half of the SMPL forward: pose+shape blend (tcgen05, bf16x3), blend of the skinning
+// transforms (tcgen05, 3xTF32) and the skinning epilogue -- the [B, 3*V] pose-offset intermediate never leaves
+// the SM: it is produced in TMEM and consumed from TMEM.
+//
+//   off_c[v, b] = sum_k P_c[v, k] * pf[b, k]          c in {x,y,z}; K = 207 pose terms + 10 betas (SURVEY K2+K4)
+//   T[v, b]     = sum_j w[v, j] * A_j[b]              3x4 per vertex and body (K6)
+//   v'[b, v]    = T[v, b] . [v_template[v] + off[v, b] ; 1] (+ transl[b])      (K7)   (+ fused read-out emits)
+//
+// Work item = (tile of 128 vertices) x (group of NBI <= 64 bodies), vertex-major.  TMEM (512 columns, lane =
+// vertex): two stages of three NBI-column accumulators (x|y|z pose offsets, one body per column) + one 96-column
+// accumulator for the blended transforms of 8 bodies.  Warp roles (640 threads, 1 CTA/SM):
+//   warp 0      TMA producer, pose blend: per 128-byte K chunk one pose-feature stage {hi,lo} (NBI rows) and per
+//               (chunk, plane) one posedirs stage {hi,lo} (128 rows) -- a 3 x 32 KB ring;
+//   warp 1      pose-blend MMA issuer (+ TMEM allocation): 3 MMAs per K step (lo.hi + hi.lo + hi.hi);
+//   warp 2      TMA producer, skinning: weight tile {hi,lo} when the vertex tile changes, A^T {hi,lo} per 8 bodies;
+//   warp 3      skinning MMA issuer: 3 K steps x 3 MMAs (M=128, N=96, tf32) per 8 bodies;
+//   warps 4-19  epilogue: TMEM lane quarter q = warp%4, two bodies per warp and 8-body group.  A warp pulls its
+//               24 T columns and 6 offset columns into registers, releases the T accumulator at once (so the next
+//               group's MMAs overlap its arithmetic and stores), applies the transform, transposes through
+//               shared memory and writes three coalesced 128-byte rows per body.
+// The two MMA issuers run independently; the tensor pipe interleaves their instructions, so the pose blend of
+// item i+1 proceeds while item i is skinned and stored.
+// Operand traffic per item (L2 -> smem): posedirs 344 KB + pose feature 0.9 KB/body + A^T 3 KB/body + weights
+// 32 KB per vertex tile; measured ingest capability 130-140 GB/s/SM (tools/microbench/l2_ingest_bench.cu).
+#pragma once
+#include <cuda/std/type_traits>
+
+#include "pose_blend_tc.cuh"
+#include "readout.cuh"
+#include "skin_tc.cuh"
+
+namespace whmr {
+
+constexpr int kFuMaxNB = 64;                  // bodies per item (runtime NBI: multiple of 16, <= 64)
+constexpr int kFuGB = 8;                      // bodies per blended-transform tile
+constexpr int kFuTN = kFuGB * 12;             // 96 accumulator columns
+constexpr int kFuAStages = 3;
+constexpr int kFuABytes = 2 * kTcM * 128;     // 32 KB: posedirs {hi,lo} of one (K chunk, plane)
+constexpr int kFuPfStages = 2;
+constexpr int kFuPfPart = kFuMaxNB * 128;     // 8 KB
+constexpr int kFuPfBytes = 2 * kFuPfPart;     // 16 KB: pose feature {hi,lo} of one K chunk
+constexpr int kFuWPart = kTcM * 128;          // 16 KB
+constexpr int kFuAtStages = 2;
+constexpr int kFuAtPart = kFuTN * 128;        // 12 KB
+constexpr int kFuAtBytes = 2 * kFuAtPart;     // 24 KB
+constexpr int kFuEpiWarps = 16;
+constexpr int kFuThreads = (4 + kFuEpiWarps) * 32;
+constexpr int kFuOffA = 0;
+constexpr int kFuOffPf = kFuOffA + kFuAStages * kFuABytes;
+constexpr int kFuOffW = kFuOffPf + kFuPfStages * kFuPfBytes;
+constexpr int kFuOffAt = kFuOffW + 2 * kFuWPart;
+constexpr int kFuOffStg = kFuOffAt + kFuAtStages * kFuAtBytes;
+constexpr int kFuOffBars = kFuOffStg + kFuEpiWarps * 192 * 4;
+constexpr int kFuSmem = kFuOffBars + 256 + 1024;
+constexpr int kFuTmemOffStage = 3 * kFuMaxNB;   // 192 columns per pose-offset stage
+constexpr int kFuTmemT = 2 * kFuTmemOffStage;   // blended transforms at column 384
+static_assert(kFuSmem <= 232448, "fused SMPL kernel exceeds the 227 KB shared-memory limit");
+static_assert(kFuTmemT + kFuTN <= 512, "TMEM budget");
+
+struct FusedParams {
+  const float* v_template_p;  // [3, VP]
+  const float* transl;        // [nb,3] or null
+  float* verts;               // [nb, V, 3]
+  EmitTable emit;             // fused read-outs (readout.cuh); grp_ptr == null: off
+  float* ro_out;
+  int ro_B, ro_b0;
+  int nb, V, VP;
+  int nbi;                    // bodies per item
+  int n_bgroups, n_items;     // ceil(nb / nbi), (VP/128) * n_bgroups
+  int kch, ksteps;            // pose blend: 128-byte K chunks, 32-byte K steps (bf16: 16 elements)
+  int jsteps;                 // skinning: ceil(J/8) tf32 K steps
+  long long* dbg;             // WHMR_FUSED_DEBUG: [grid][16] per-role wait/total cycles, or null
+};
+
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
+}
+
+// wait that adds its duration to `acc` when instrumentation is on
+#define WHMR_FU_WAIT(bar, par, acc)                       \
+  do {                                                    \
+    if (p.dbg) { const long long _w0 = clock64(); mbar_wait(bar, par); acc += clock64() - _w0; } \
+    else mbar_wait(bar, par);                             \
+  } while (0)
+
+__global__ void __launch_bounds__(kFuThreads, 1)
+smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+shapedirs bf16 [NP, 2, KP]
+                     const __grid_constant__ CUtensorMap tmapPf,   // pose feature bf16 [bodies, 2, KP], box rows = nbi
+                     const __grid_constant__ CUtensorMap tmapW,    // weights tf32 [2, VP, 32]
+                     const __grid_constant__ CUtensorMap tmapAt,   // A^T tf32 [2, bodies*12, 32], box rows = 96
+                     FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_ring = smem + kFuOffA;
+  uint8_t* pf_ring = smem + kFuOffPf;
+  uint8_t* w_smem = smem + kFuOffW;
+  uint8_t* at_ring = smem + kFuOffAt;
+  float* stage_out = reinterpret_cast<float*>(smem + kFuOffStg);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFuOffBars);
+  uint64_t* a_full = bars;                         // [3]
+  uint64_t* a_empty = a_full + kFuAStages;         // [3]
+  uint64_t* pf_full = a_empty + kFuAStages;        // [2]
+  uint64_t* pf_empty = pf_full + kFuPfStages;      // [2]
+  uint64_t* w_full = pf_empty + kFuPfStages;
+  uint64_t* w_empty = w_full + 1;
+  uint64_t* at_full = w_empty + 1;                 // [2]
+  uint64_t* at_empty = at_full + kFuAtStages;      // [2]
+  uint64_t* off_full = at_empty + kFuAtStages;     // [2]
+  uint64_t* off_empty = off_full + 2;              // [2]
+  uint64_t* t_full = off_empty + 2;
+  uint64_t* t_empty = t_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = (int)(((long long)blockIdx.x * p.n_items) / gridDim.x);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * p.n_items) / gridDim.x);
+  // 8-body groups of item t (the last body group of the batch may be ragged)
+  auto n_groups_of = [&](int bg) { return (min(p.nbi, p.nb - bg * p.nbi) + kFuGB - 1) / kFuGB; };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFuAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kFuPfStages; ++s) { mbar_init(&pf_full[s], 1); mbar_init(&pf_empty[s], 1); }
+    mbar_init(w_full, 1); mbar_init(w_empty, 1);
+    for (int s = 0; s < kFuAtStages; ++s) { mbar_init(&at_full[s], 1); mbar_init(&at_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&off_full[s], 1); mbar_init(&off_empty[s], kFuEpiWarps); }
+    mbar_init(t_full, 1); mbar_init(t_empty, kFuEpiWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ============================ TMA producer: pose-blend operands ============================
+    if (lane == 0) {
+      int as = 0; uint32_t aph = 0;
+      int ps = 0; uint32_t pph = 0;
+      const uint32_t pf_bytes = 2u * (uint32_t)p.nbi * 128u;
+      long long d_pf = 0, d_a = 0;
+      const long long k0 = p.dbg ? clock64() : 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int vt = t / p.n_bgroups, body0 = (t % p.n_bgroups) * p.nbi;
+        for (int kc = 0; kc < p.kch; ++kc) {
+          WHMR_FU_WAIT(&pf_empty[ps], pph ^ 1, d_pf);
+          uint8_t* pst = pf_ring + ps * kFuPfBytes;
+          mbar_arrive_expect_tx(&pf_full[ps], pf_bytes);
+          tma_load_3d(pst, &tmapPf, &pf_full[ps], kc * 64, 0, body0);
+          tma_load_3d(pst + kFuPfPart, &tmapPf, &pf_full[ps], kc * 64, 1, body0);
+          if (++ps == kFuPfStages) { ps = 0; pph ^= 1; }
+          for (int c = 0; c < 3; ++c) {
+            WHMR_FU_WAIT(&a_empty[as], aph ^ 1, d_a);
+            uint8_t* ast = a_ring + as * kFuABytes;
+            mbar_arrive_expect_tx(&a_full[as], kFuABytes);
+            tma_load_3d(ast, &tmapP, &a_full[as], kc * 64, 0, c * p.VP + vt * kTcM);
+            tma_load_3d(ast + kTcM * 128, &tmapP, &a_full[as], kc * 64, 1, c * p.VP + vt * kTcM);
+            if (++as == kFuAStages) { as = 0; aph ^= 1; }
+          }
+        }
+      }
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[0] = d_pf; d[1] = d_a; d[2] = clock64() - k0; }
+    }
+  } else if (warp == 1) {
+    // ============================ pose-blend MMA issuer ========================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nbi >> 3) << 17) |
+                             ((uint32_t)(kTcM >> 4) << 24);   // bf16 x bf16 -> f32, M=128, N=nbi
+      int as = 0; uint32_t aph = 0;
+      int ps = 0; uint32_t pph = 0;
+      int buf = 0; uint32_t bph = 0;
+      long long d_off = 0, d_pf = 0, d_a = 0;
+      const long long k0 = p.dbg ? clock64() : 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        WHMR_FU_WAIT(&off_empty[buf], bph ^ 1, d_off);
+        tcgen05_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * kFuTmemOffStage);
+        for (int kc = 0; kc < p.kch; ++kc) {
+          WHMR_FU_WAIT(&pf_full[ps], pph, d_pf);
+          const uint32_t b_hi = smem_u32(pf_ring + ps * kFuPfBytes), b_lo = b_hi + kFuPfPart;
+          const int nks = min(4, p.ksteps - kc * 4);
+          for (int c = 0; c < 3; ++c) {
+            WHMR_FU_WAIT(&a_full[as], aph, d_a);
+            tcgen05_fence_after();
+            const uint32_t a_hi = smem_u32(a_ring + as * kFuABytes), a_lo = a_hi + kTcM * 128;
+            const uint32_t d_tmem = d_base + (uint32_t)(c * kFuMaxNB);
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint64_t dA_hi = umma_desc_sw128(a_hi + ks * 32), dA_lo = umma_desc_sw128(a_lo + ks * 32);
+              const uint64_t dB_hi = umma_desc_sw128(b_hi + ks * 32), dB_lo = umma_desc_sw128(b_lo + ks * 32);
+              umma<0>(d_tmem, dA_lo, dB_hi, idesc, (kc | ks) != 0);   // small terms first
+              umma<0>(d_tmem, dA_hi, dB_lo, idesc, 1u);
+              umma<0>(d_tmem, dA_hi, dB_hi, idesc, 1u);
+            }
+            tcgen05_commit(&a_empty[as]);
+            if (++as == kFuAStages) { as = 0; aph ^= 1; }
+          }
+          tcgen05_commit(&pf_empty[ps]);
+          if (++ps == kFuPfStages) { ps = 0; pph ^= 1; }
+        }
+        tcgen05_commit(&off_full[buf]);
+        if (++buf == 2) { buf = 0; bph ^= 1; }
+      }
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[3] = d_off; d[4] = d_pf; d[5] = d_a; d[6] = clock64() - k0; }
+    }
+  } else if (warp == 2) {
+    // ============================ TMA producer: skinning operands ==============================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0, w_par = 1;
+      int cur_vt = -1;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int vt = t / p.n_bgroups, bg = t % p.n_bgroups;
+        if (vt != cur_vt) {
+          mbar_wait(w_empty, w_par);   // MMAs on the previous weight tile have retired
+          w_par ^= 1;
+          mbar_arrive_expect_tx(w_full, 2 * kFuWPart);
+          tma_load_3d(w_smem, &tmapW, w_full, 0, vt * kTcM, 0);
+          tma_load_3d(w_smem + kFuWPart, &tmapW, w_full, 0, vt * kTcM, 1);
+          cur_vt = vt;
+        }
+        const int ng = n_groups_of(bg);
+        for (int g = 0; g < ng; ++g) {
+          mbar_wait(&at_empty[s], ph ^ 1);
+          uint8_t* st = at_ring + s * kFuAtBytes;
+          mbar_arrive_expect_tx(&at_full[s], kFuAtBytes);
+          const int row0 = (bg * p.nbi + g * kFuGB) * 12;
+          tma_load_3d(st, &tmapAt, &at_full[s], 0, row0, 0);
+          tma_load_3d(st + kFuAtPart, &tmapAt, &at_full[s], 0, row0, 1);
+          if (++s == kFuAtStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ============================ skinning MMA issuer ==========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kFuTN >> 3) << 17) |
+                                 ((uint32_t)(kTcM >> 4) << 24);   // tf32 x tf32 -> f32, M=128, N=96
+      int s = 0; uint32_t ph = 0, w_phase = 0, t_ph = 0;
+      int cur_vt = -1;
+      const uint32_t w_hi = smem_u32(w_smem), w_lo = w_hi + kFuWPart;
+      const uint32_t d_tmem = tmem_base + (uint32_t)kFuTmemT;
+      long long d_t = 0, d_at = 0;
+      const long long k0 = p.dbg ? clock64() : 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int vt = t / p.n_bgroups, bg = t % p.n_bgroups;
+        if (vt != cur_vt) { mbar_wait(w_full, w_phase); w_phase ^= 1; cur_vt = vt; }
+        const int ng = n_groups_of(bg);
+        for (int g = 0; g < ng; ++g) {
+          WHMR_FU_WAIT(t_empty, t_ph ^ 1, d_t);
+          WHMR_FU_WAIT(&at_full[s], ph, d_at);
+          tcgen05_fence_after();
+          const uint32_t a_hi = smem_u32(at_ring + s * kFuAtBytes), a_lo = a_hi + kFuAtPart;
+          for (int ks = 0; ks < p.jsteps; ++ks) {
+            const uint64_t dW_hi = umma_desc_sw128(w_hi + ks * 32), dW_lo = umma_desc_sw128(w_lo + ks * 32);
+            const uint64_t dA_hi = umma_desc_sw128(a_hi + ks * 32), dA_lo = umma_desc_sw128(a_lo + ks * 32);
+            umma<1>(d_tmem, dW_lo, dA_hi, idesc, ks != 0);
+            umma<1>(d_tmem, dW_hi, dA_lo, idesc, 1u);
+            umma<1>(d_tmem, dW_hi, dA_hi, idesc, 1u);
+          }
+          tcgen05_commit(&at_empty[s]);
+          tcgen05_commit(t_full);
+          if (++s == kFuAtStages) { s = 0; ph ^= 1; }
+          t_ph ^= 1;
+        }
+        const int next_vt = (t + 1 < t_end) ? (t + 1) / p.n_bgroups : -1;
+        if (next_vt != vt) tcgen05_commit(w_empty);
+      }
+      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[7] = d_t; d[8] = d_at; d[9] = clock64() - k0; }
+    }
+  } else {
+    // ============================ epilogue =====================================================
+    const int q = warp & 3;             // TMEM lane quarter
+    const int w4 = (warp - 4) >> 2;     // which 2 bodies of every 8-body group
+    float* stg = stage_out + (warp - 4) * 192;   // two 96-float transpose buffers, alternated per body
+    int cur_vt = -1;
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    // read-out entries of this warp's 32 vertices (see skin_tc.cuh): lane l owns entries e0+l and e0+32+l
+    int e0 = 0, n_e = 0;
+    int lvA = 0, lvB = 0, strA = 0, strB = 0;
+    long long baseA = 0, baseB = 0;
+    float wA = 0.f, wB = 0.f;
+    float* bufA = nullptr; float* bufB = nullptr;
+    auto load_entry = [&](int e, int& lv, float& w, long long& base, int& stride, float*& buf) {
+      const EmitEntry en = p.emit.entries[e];
+      lv = (en.lv_kind & 0xff) * 3;
+      w = en.w;
+      if (en.lv_kind >> 8) {     // regressor term -> partial[b_local][d]
+        base = 3LL * en.d; stride = 3 * p.emit.n_partial; buf = p.emit.partial;
+      } else {                   // one-hot row -> final output slot
+        base = 3LL * ((long long)p.ro_B * en.a + (long long)p.ro_b0 * en.c + en.d); stride = 3 * en.c; buf = p.ro_out;
+      }
+    };
+    const int V3 = p.V * 3;
+    const bool has_transl = p.transl != nullptr;
+    int parity = 0;
+    int buf = 0; uint32_t bph = 0, t_ph = 0;
+    long long d_off = 0, d_t = 0;
+    const long long k0 = p.dbg ? clock64() : 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int vt = t / p.n_bgroups, bg = t % p.n_bgroups;
+      if (vt != cur_vt) {
+        cur_vt = vt;
+        const int v = vt * kTcM + q * 32 + lane;                  // < VP
+        tx = p.v_template_p[v]; ty = p.v_template_p[p.VP + v]; tz = p.v_template_p[2 * p.VP + v];
+        n_e = 0;
+        if (p.emit.grp_ptr) {
+          const int g32 = vt * (kTcM / 32) + q;
+          e0 = p.emit.grp_ptr[g32];
+          n_e = p.emit.grp_ptr[g32 + 1] - e0;
+          if (lane < n_e) load_entry(e0 + lane, lvA, wA, baseA, strA, bufA);
+          if (lane + 32 < n_e) load_entry(e0 + 32 + lane, lvB, wB, baseB, strB, bufB);
+        }
+      }
+      const int out_col = (vt * kTcM + q * 32) * 3 + lane;        // float index inside a body row
+      const bool full_tile = (vt + 1) * kTcM <= p.V;
+      const int ng = n_groups_of(bg);
+      WHMR_FU_WAIT(&off_full[buf], bph, d_off);
+      const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+      const uint32_t off_addr = tmem_base + lane_sel + (uint32_t)(buf * kFuTmemOffStage);
+      const uint32_t t_addr = tmem_base + lane_sel + (uint32_t)(kFuTmemT + w4 * 24);
+      for (int g = 0; g < ng; ++g) {
+        const int body_base = bg * p.nbi + g * kFuGB + w4 * 2;     // first of this warp's two bodies
+        const int n_valid = min(2, p.nb - body_base);              // may be <= 0
+        WHMR_FU_WAIT(t_full, t_ph, d_t);
+        t_ph ^= 1;
+        tcgen05_fence_after();
+        uint32_t T[24], O[6];
+        tmem_ld_32x32b_x16(t_addr, T);
+        tmem_ld_32x32b_x8(t_addr + 16, T + 16);
+        const uint32_t ocol = (uint32_t)(g * kFuGB + w4 * 2);
+        tmem_ld_32x32b_x2(off_addr + ocol, O);
+        tmem_ld_32x32b_x2(off_addr + kFuMaxNB + ocol, O + 2);
+        tmem_ld_32x32b_x2(off_addr + 2 * kFuMaxNB + ocol, O + 4);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // accumulators are in registers: hand them back before the arithmetic and the stores
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(t_empty);
+          if (g == ng - 1) mbar_arrive(&off_empty[buf]);
+        }
+        if (n_valid <= 0) continue;
+        float* outp = p.verts + (size_t)body_base * V3 + out_col;
+        auto run = [&](auto guard_tag) {
+          constexpr bool G = decltype(guard_tag)::value;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (G && i >= n_valid) continue;                      // warp-uniform
+            const float px = __uint_as_float(O[i]) + tx, py = __uint_as_float(O[2 + i]) + ty,
+                        pz = __uint_as_float(O[4 + i]) + tz;
+#define WHMR_T(k) __uint_as_float(T[i * 12 + (k)])
+            float rx = fmaf(WHMR_T(0), px, fmaf(WHMR_T(1), py, fmaf(WHMR_T(2), pz, WHMR_T(3))));
+            float ry = fmaf(WHMR_T(4), px, fmaf(WHMR_T(5), py, fmaf(WHMR_T(6), pz, WHMR_T(7))));
+            float rz = fmaf(WHMR_T(8), px, fmaf(WHMR_T(9), py, fmaf(WHMR_T(10), pz, WHMR_T(11))));
+#undef WHMR_T
+            if (G && has_transl) {
+              const float* tr = p.transl + (size_t)(body_base + i) * 3;
+              rx += tr[0]; ry += tr[1]; rz += tr[2];
+            }
+            float* sb = stg + parity * 96;
+            parity ^= 1;
+            sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz;
+            __syncwarp();
+            float* ob = outp + (size_t)i * V3;
+            if (G) {
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+                if (out_col + r * 32 < V3) ob[r * 32] = sb[r * 32 + lane];
+            } else {
+              ob[0] = sb[lane]; ob[32] = sb[32 + lane]; ob[64] = sb[64 + lane];
+            }
+            if (n_e > 0) {   // fused read-outs: entries referencing one of this warp's 32 vertices
+              const int bl = body_base + i;
+              if (lane < n_e) {
+                float* o = bufA + baseA + (long long)bl * strA;
+                o[0] = wA * sb[lvA]; o[1] = wA * sb[lvA + 1]; o[2] = wA * sb[lvA + 2];
+              }
+              if (lane + 32 < n_e) {
+                float* o = bufB + baseB + (long long)bl * strB;
+                o[0] = wB * sb[lvB]; o[1] = wB * sb[lvB + 1]; o[2] = wB * sb[lvB + 2];
+              }
+              for (int e = 64 + lane; e < n_e; e += 32) {
+                int lv, st; long long ba; float w; float* bf;
+                load_entry(e0 + e, lv, w, ba, st, bf);
+                float* o = bf + ba + (long long)bl * st;
+                o[0] = w * sb[lv]; o[1] = w * sb[lv + 1]; o[2] = w * sb[lv + 2];
+              }
+            }
+          }
+        };
+        if (n_valid == 2 && !has_transl && full_tile) run(cuda::std::false_type{}); else run(cuda::std::true_type{});
+      }
+      if (++buf == 2) { buf = 0; bph ^= 1; }
+    }
+    if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 16; d[10] = d_off; d[11] = d_t; d[12] = clock64() - k0; }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// bodies per item for a chunk of nb bodies: fewest rounds over the SMs, then the widest tile (posedirs are
+// re-streamed once per item, ~2.6 us at the measured ingest rate, against ~0.05 us of work per body)
+static inline int fused_pick_nbi(int nb, int n_vtiles, int num_sms) {
+  int best = 16;
+  double best_cost = 1e30;
+  for (int nbi = 16; nbi <= kFuMaxNB; nbi += 16) {
+    const long long items = (long long)n_vtiles * ceil_div(nb, nbi);
+    const double cost = (double)((items + num_sms - 1) / num_sms) * (2.6 + 0.05 * std::min(nbi, nb));
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = nbi; }
+  }
+  return best;
+}
+
+}  // namespace whmr

@@ -18,6 +18,7 @@
 #include "sampling.cuh"
 #include "skin_tc.cuh"
 #include "skinning.cuh"
+#include "smpl_fused_tc.cuh"
 #include "smpl_chain.cuh"
 
 namespace whmr {
@@ -79,6 +80,7 @@ struct whmr_smpl_s {
   TcPlan tc{};   // tensor maps etc. for the tcgen05 path
   cudaEvent_t probe_chain = nullptr, probe_blend = nullptr, probe_skin = nullptr;
   bool skin_tc = true;   // tensor-core skinning (WHMR_SKIN=simt selects the CUDA-core kernel)
+  bool fused = true;     // one kernel for pose blend + skinning (WHMR_FUSED=0: GEMM kernel + skinning kernel)
   // host-buffer staging (whmr_smpl_reserve)
   int reserved_B = 0;
   float *st_betas = nullptr, *st_pose = nullptr, *st_verts = nullptr, *st_joints = nullptr;
@@ -257,6 +259,9 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
     if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "cudaFuncSetAttribute(skin_tc) failed: %s", cudaGetErrorString(e)); }
   }
   if (const char* s = getenv("WHMR_SKIN")) h->skin_tc = strcmp(s, "simt") != 0;
+  if (const char* s = getenv("WHMR_FUSED")) h->fused = atoi(s) != 0;
+  e = cudaFuncSetAttribute(smpl_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem);
+  if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "cudaFuncSetAttribute(smpl_fused_tc) failed: %s", cudaGetErrorString(e)); }
   h->gemm_mode = gemm_mode;
   *out = h;
   return WHMR_OK;
@@ -463,6 +468,60 @@ static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* beta
   return WHMR_OK;
 }
 
+// pose blend + skinning of bodies [b0, b0+nb) in one kernel (smpl_fused_tc.cuh); bf16x3 pose blend only
+static bool fused_applicable(const whmr_smpl_s* h) {
+  return h->fused && h->skin_tc && h->gemm_mode == WHMR_GEMM_TC_BF16X3 && h->tc.ready && h->d.KP % 16 == 0;
+}
+
+static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* transl, int B, int b0, int nb, float* verts,
+                        whmr_readout_t ro, float* ro_out, float* ro_partial, cudaStream_t st) {
+  const SmplDevice& d = h->d;
+  FusedParams p{};
+  p.v_template_p = d.v_template_p;
+  p.transl = transl ? transl + (size_t)b0 * 3 : nullptr;
+  p.verts = verts + (size_t)b0 * d.V * 3;
+  if (ro) {
+    p.emit.grp_ptr = ro->emit_grp_ptr; p.emit.entries = ro->emit_entries; p.emit.partial = ro_partial;
+    p.emit.n_partial = ro->n_partial;
+    p.ro_out = ro_out; p.ro_B = B; p.ro_b0 = b0;
+  }
+  p.nb = nb; p.V = d.V; p.VP = d.VP;
+  const int n_vtiles = d.VP / kTcM;
+  p.nbi = fused_pick_nbi(nb, n_vtiles, h->tc.num_sms);
+  static const int nbi_env = getenv("WHMR_FUSED_NBI") ? atoi(getenv("WHMR_FUSED_NBI")) : 0;
+  if (nbi_env >= 16 && nbi_env <= kFuMaxNB && nbi_env % 16 == 0) p.nbi = nbi_env;
+  p.n_bgroups = ceil_div(nb, p.nbi);
+  p.n_items = n_vtiles * p.n_bgroups;
+  p.ksteps = d.KP * 2 / 32;
+  p.kch = ceil_div(p.ksteps, 4);
+  p.jsteps = ceil_div(d.J, 8);
+  CUtensorMap tmapPf, tmapAt;
+  char* pf_base = static_cast<char*>(ws.pf_split) + (size_t)b0 * 2 * d.KP * 2;
+  int rc = tc_encode(h->tc.encode_fn, &tmapPf, 0, pf_base, d.KP, ws.Bpad - b0, p.nbi);
+  if (rc) return rc;
+  rc = tc_encode_rows32(h->tc.encode_fn, &tmapAt, ws.At + (size_t)b0 * 12 * 32, (size_t)(ws.Bpad - b0) * 12,
+                        ws.At_part_stride * sizeof(float), kFuTN);
+  if (rc) return rc;
+  const int grid = std::min(h->tc.num_sms, p.n_items);
+  static const bool dbg_on = getenv("WHMR_FUSED_DEBUG") != nullptr;
+  if (dbg_on) { cudaMalloc(&p.dbg, sizeof(long long) * 16 * grid); cudaMemsetAsync(p.dbg, 0, sizeof(long long) * 16 * grid, st); }
+  smpl_fused_tc_kernel<<<grid, kFuThreads, kFuSmem, st>>>(h->tc.tmapA_bf16, tmapPf, h->tc.tmapW, tmapAt, p);
+  WHMR_LAUNCHED("smpl_fused_tc_kernel");
+  if (p.dbg) {   // per-role wait/total cycles averaged over CTAs (debug only: synchronises)
+    cudaStreamSynchronize(st);
+    std::vector<long long> hd((size_t)16 * grid);
+    cudaMemcpy(hd.data(), p.dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    double a[16] = {0};
+    for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)hd[(size_t)c * 16 + k] / grid;
+    fprintf(stderr, "[whmr fused dbg] nb=%d nbi=%d items=%d grid=%d | pose-producer wait pf_empty %.0f a_empty %.0f of %.0f | "
+            "pose-mma wait off_empty %.0f pf_full %.0f a_full %.0f of %.0f | skin-mma wait t_empty %.0f at_full %.0f of %.0f | "
+            "epilogue wait off_full %.0f t_full %.0f of %.0f cycles\n", nb, p.nbi, p.n_items, grid, a[0], a[1], a[2], a[3], a[4],
+            a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
+  }
+  return WHMR_OK;
+}
+
 int whmr_smpl_stage_pose_blend(whmr_smpl_t h, int B, void* workspace, size_t workspace_bytes, void* stream) {
   SmplWorkspace ws;
   int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
@@ -529,6 +588,7 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
   // chunk; otherwise the stand-alone gather kernel runs after the skinning kernel
   static const bool fuse_env = !(getenv("WHMR_FUSE_READOUT") && atoi(getenv("WHMR_FUSE_READOUT")) == 0);
   float* partial = ro_workspace ? reinterpret_cast<float*>(align_up(reinterpret_cast<size_t>(ro_workspace), 256)) : nullptr;
+  const bool one_kernel = fused_applicable(h);
   const bool fused = ro && h->skin_tc && fuse_env && ro->fusable && ro->dst_VP == h->d.VP && partial &&
                      ro_workspace_bytes >= whmr_readout_workspace_bytes(ro, std::min(B, ws.chunk));
   // the finishing pass may be left to the caller (another stream) when the whole batch is one chunk
@@ -536,10 +596,13 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
   if (defer) *finish_deferred = 1;
   for (int b0 = 0; b0 < B; b0 += ws.chunk) {
     const int nb = std::min(ws.chunk, B - b0);
-    rc = launch_pose_blend(h, ws, B, b0, nb, st);
-    if (rc) return rc;
+    if (!one_kernel) {
+      rc = launch_pose_blend(h, ws, B, b0, nb, st);
+      if (rc) return rc;
+    }
     if (h->probe_blend && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_blend, st, cudaEventRecordExternal));
-    rc = launch_skin(h, ws, betas, transl, B, b0, nb, verts, fused ? ro : nullptr, ro_out, partial, st);
+    rc = one_kernel ? launch_fused(h, ws, transl, B, b0, nb, verts, fused ? ro : nullptr, ro_out, partial, st)
+                    : launch_skin(h, ws, betas, transl, B, b0, nb, verts, fused ? ro : nullptr, ro_out, partial, st);
     if (rc) return rc;
     if (h->probe_skin && b0 + nb >= B) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_skin, st, cudaEventRecordExternal));
     if (ro) {
