@@ -138,6 +138,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) 
       : "r"(taddr));
 }
 
+// One lane of the (converged) warp, chosen by elect.sync: ptxas then knows the guarded region runs on a single
+// thread and feeds UTCHMMA / UTMALDG their uniform-register operands directly.  With `if (lane == 0)` it wraps
+// every such instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~13 extra instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 template <int NB>
 struct TcSmem {
   static constexpr int kABytes = kTcM * 128;          // one 128-row x 128-byte operand tile
@@ -191,7 +200,7 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       long long dbg_wait = 0;
       const long long k0 = dbg ? clock64() : 0;
@@ -215,7 +224,7 @@ pose_blend_tc_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_con
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    if (elect_one()) {
       // instruction descriptor: D=f32, A/B format, K-major both, N>>3 at [17,23), M>>4 at [24,29)
       constexpr uint32_t fmt = kKind == 0 ? 1u /*BF16*/ : 2u /*TF32*/;
       constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NB >> 3) << 17) |

@@ -104,7 +104,7 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0, w_par = 1;
       int ostage = 0; uint32_t ophase = 0;
       int cur_vt = -1;
@@ -133,7 +133,7 @@ skin_tc_kernel(const __grid_constant__ CUtensorMap tmapW, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kSkinN >> 3) << 17) |
                                  ((uint32_t)(kTcM >> 4) << 24);   // tf32 x tf32 -> f32, M=128, N=192
       int stage = 0; uint32_t phase = 0, w_phase = 0;

@@ -142,7 +142,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
 
   if (warp == 0) {
     // ============================ TMA producer: pose-blend operands ============================
-    if (lane == 0) {
+    if (elect_one()) {
       int as = 0; uint32_t aph = 0;
       int ps = 0; uint32_t pph = 0;
       const uint32_t pf_bytes = 2u * (uint32_t)p.nbi * 128u;
@@ -171,7 +171,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     }
   } else if (warp == 1) {
     // ============================ pose-blend MMA issuer ========================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nbi >> 3) << 17) |
                              ((uint32_t)(kTcM >> 4) << 24);   // bf16 x bf16 -> f32, M=128, N=nbi
       int as = 0; uint32_t aph = 0;
@@ -212,7 +212,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     }
   } else if (warp == 2) {
     // ============================ TMA producer: skinning operands ==============================
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0; uint32_t ph = 0, w_par = 1;
       int cur_vt = -1;
       for (int t = t_begin; t < t_end; ++t) {
@@ -239,7 +239,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     }
   } else if (warp == 3) {
     // ============================ skinning MMA issuer ==========================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kFuTN >> 3) << 17) |
                                  ((uint32_t)(kTcM >> 4) << 24);   // tf32 x tf32 -> f32, M=128, N=96
       int s = 0; uint32_t ph = 0, w_phase = 0, t_ph = 0;
@@ -278,7 +278,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     // ============================ epilogue =====================================================
     const int q = warp & 3;             // TMEM lane quarter
     const int w4 = (warp - 4) >> 2;     // which 2 bodies of every 8-body group
-    float* stg = stage_out + (warp - 4) * 192;   // two 96-float transpose buffers, alternated per body
+    float* stg = stage_out + (warp - 4) * 192;   // two 96-float transpose buffers, one per body of the group
     int cur_vt = -1;
     float tx = 0.f, ty = 0.f, tz = 0.f;
     // read-out entries of this warp's 32 vertices (see skin_tc.cuh): lane l owns entries e0+l and e0+32+l
@@ -299,9 +299,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     };
     const int V3 = p.V * 3;
     const bool has_transl = p.transl != nullptr;
-    int parity = 0;
     int buf = 0; uint32_t bph = 0, t_ph = 0;
-    long long d_off = 0, d_t = 0;
+    long long d_off = 0, d_t = 0, d_ld = 0, d_rel = 0;
     const long long k0 = p.dbg ? clock64() : 0;
     for (int t = t_begin; t < t_end; ++t) {
       const int vt = t / p.n_bgroups, bg = t % p.n_bgroups;
@@ -331,6 +330,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         WHMR_FU_WAIT(t_full, t_ph, d_t);
         t_ph ^= 1;
         tcgen05_fence_after();
+        const long long l0 = p.dbg ? clock64() : 0;
         uint32_t T[24], O[6];
         tmem_ld_32x32b_x16(t_addr, T);
         tmem_ld_32x32b_x8(t_addr + 16, T + 16);
@@ -339,6 +339,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         tmem_ld_32x32b_x2(off_addr + kFuMaxNB + ocol, O + 2);
         tmem_ld_32x32b_x2(off_addr + 2 * kFuMaxNB + ocol, O + 4);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const long long l1 = p.dbg ? clock64() : 0;
         // accumulators are in registers: hand them back before the arithmetic and the stores
         tcgen05_fence_before();
         __syncwarp();
@@ -346,10 +347,12 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           mbar_arrive(t_empty);
           if (g == ng - 1) mbar_arrive(&off_empty[buf]);
         }
+        if (p.dbg) { d_ld += l1 - l0; d_rel += clock64() - l1; }
         if (n_valid <= 0) continue;
         float* outp = p.verts + (size_t)body_base * V3 + out_col;
         auto run = [&](auto guard_tag) {
           constexpr bool G = decltype(guard_tag)::value;
+          // both bodies are staged before the single __syncwarp, so their shared-memory round trips overlap
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (G && i >= n_valid) continue;                      // warp-uniform
@@ -364,19 +367,28 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
               const float* tr = p.transl + (size_t)(body_base + i) * 3;
               rx += tr[0]; ry += tr[1]; rz += tr[2];
             }
-            float* sb = stg + parity * 96;
-            parity ^= 1;
+            float* sb = stg + i * 96;
             sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz;
-            __syncwarp();
-            float* ob = outp + (size_t)i * V3;
-            if (G) {
+          }
+          __syncwarp();
+          float v[6];
 #pragma unroll
-              for (int r = 0; r < 3; ++r)
-                if (out_col + r * 32 < V3) ob[r * 32] = sb[r * 32 + lane];
-            } else {
-              ob[0] = sb[lane]; ob[32] = sb[32 + lane]; ob[64] = sb[64 + lane];
-            }
-            if (n_e > 0) {   // fused read-outs: entries referencing one of this warp's 32 vertices
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) v[i * 3 + r] = stg[i * 96 + r * 32 + lane];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (G && i >= n_valid) continue;
+            float* ob = outp + (size_t)i * V3;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+              if (!G || out_col + r * 32 < V3) ob[r * 32] = v[i * 3 + r];
+          }
+          if (n_e > 0) {   // fused read-outs: entries referencing one of this warp's 32 vertices
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (G && i >= n_valid) continue;
+              const float* sb = stg + i * 96;
               const int bl = body_base + i;
               if (lane < n_e) {
                 float* o = bufA + baseA + (long long)bl * strA;
@@ -399,7 +411,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       }
       if (++buf == 2) { buf = 0; bph ^= 1; }
     }
-    if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 16; d[10] = d_off; d[11] = d_t; d[12] = clock64() - k0; }
+    if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 16; d[10] = d_off; d[11] = d_t; d[12] = clock64() - k0; d[13] = d_ld; d[14] = d_rel; }
   }
 
   tcgen05_fence_before();

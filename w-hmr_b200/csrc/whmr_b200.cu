@@ -516,8 +516,8 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
     for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)hd[(size_t)c * 16 + k] / grid;
     fprintf(stderr, "[whmr fused dbg] nb=%d nbi=%d items=%d grid=%d | pose-producer wait pf_empty %.0f a_empty %.0f of %.0f | "
             "pose-mma wait off_empty %.0f pf_full %.0f a_full %.0f of %.0f | skin-mma wait t_empty %.0f at_full %.0f of %.0f | "
-            "epilogue wait off_full %.0f t_full %.0f of %.0f cycles\n", nb, p.nbi, p.n_items, grid, a[0], a[1], a[2], a[3], a[4],
-            a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]);
+            "epilogue wait off_full %.0f t_full %.0f tmem-ld %.0f release %.0f of %.0f cycles\n", nb, p.nbi, p.n_items, grid, a[0], a[1], a[2], a[3], a[4],
+            a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[13], a[14], a[12]);
   }
   return WHMR_OK;
 }
