@@ -99,6 +99,8 @@ def algorithmic(kind, B, ctx):
         return {"bytes": B * (4 * (NBETA + 216) + 4 * (J * 12 + J * 3) + ctx["pf_bytes"]), "bound": "hbm"}
     if kind == "pose_blend":
         return {"flops": B * 2.0 * KPOSE * 3 * V, "bound": "tensor"}
+    if kind == "blend_skin":   # smpl_fused_tc: pose+shape blend GEMM, transform blend and skinning in one kernel
+        return {"flops": B * 2.0 * KPOSE * 3 * V, "bytes": B * (4 * 3 * V + 4 * J * 12 + 2 * 2 * 224), "bound": "tensor"}
     if kind == "skin":
         return {"bytes": B * (4 * 3 * VP + 4 * 3 * V + 4 * J * 12 + 4 * NBETA), "bound": "hbm"}
     if kind == "readout":
@@ -241,6 +243,10 @@ def run_ours(args):
                 a = acc.setdefault(name, [0.0, 0])
                 a[0] += t
                 a[1] += 1
+        if h.is_fused() and "pose_blend" in acc and "skin" in acc:
+            # one kernel: the pose_blend probe sits right after the chain kernel, the skin probe after the fused kernel
+            gap, sk = acc.pop("pose_blend"), acc.pop("skin")
+            acc["blend_skin"] = [gap[0] + sk[0], sk[1]]
         ro = loop.head._readout(dev, loop.with_h36m)
         ctx = {"pf_bytes": 2 * 208 * (2 if loop.smpl.gemm_mode == ops.GEMM_TC_BF16X3 else 4),
                "readout_nnz": int(ro.csr.nnz), "readout_rows": int(ro.R), "levels": loop.levels}
@@ -254,6 +260,9 @@ def run_ours(args):
                 mode_peak = peaks["bf16_tflops_sustained"] / 3.0 if loop.smpl.gemm_mode == ops.GEMM_TC_BF16X3 \
                     else peaks["bf16_tflops_sustained"] / 2.0 / 3.0
                 k.update(achieved=a["flops"] / (per_launch_ms * 1e-3) / 1e12, peak=mode_peak, unit="TFLOP/s")
+                if "bytes" in a:   # the same launch against the HBM roofline of its output stream
+                    k["hbm_achieved_GBs"] = a["bytes"] / (per_launch_ms * 1e-3) / 1e9
+                    k["hbm_frac"] = k["hbm_achieved_GBs"] / peaks["hbm_gbs"]
             else:
                 k.update(achieved=a["bytes"] / (per_launch_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
             k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
@@ -336,7 +345,7 @@ def run_ours(args):
         if dom:
             k = kern[dom]
             roof = {"kernel": dom, "bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"], "unit": k["unit"],
-                    "frac": k["frac"], "traffic": None, "peak_source": peaks["source"] + (
+                    "frac": k["frac"], "traffic": ncu_traffic(dom, B), "peak_source": peaks["source"] + (
                         " (sustained bf16 / 3 MMAs per product)" if k["bound"] == "tensor" else " hbm copy"),
                     "ms_per_launch": k["ms_per_launch"], "launches_per_step": k["launches_per_step"],
                     "share_of_step": k["ms_per_step"] / sum(x["ms_per_step"] for x in kern.values())}
@@ -360,6 +369,19 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` at batch B, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_traffic.py); None if not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        t = json.load(open(p)).get("B%d" % B, {}).get(kernel)
+        return None if t is None else {"dram_bytes_per_launch": t["dram_bytes"], "source": t["source"]}
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def smpl_sweep(loop, dev, peaks, sizes):

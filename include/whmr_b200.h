@@ -161,6 +161,8 @@ int whmr_readout_apply(whmr_readout_t r, const float* verts /*[B,V,3]*/, const f
  *   which the skinning kernel has already written). */
 size_t whmr_readout_workspace_bytes(whmr_readout_t ro, int n_bodies);
 int whmr_smpl_chunk_bodies(whmr_smpl_t h);
+/* 1 when pose blend + skinning run as ONE kernel (smpl_fused_tc: bf16x3 mode, tensor-core skinning), else 0 */
+int whmr_smpl_is_fused(whmr_smpl_t h);
 int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
                               const float* transl, int B, float* verts, float* joints, float* rel_transforms,
                               whmr_readout_t ro, float* ro_out /*[B*n_rows*3], group-major*/, void* ro_workspace,

@@ -522,6 +522,8 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   return WHMR_OK;
 }
 
+int whmr_smpl_is_fused(whmr_smpl_t h) { return h && fused_applicable(h) ? 1 : 0; }
+
 int whmr_smpl_stage_pose_blend(whmr_smpl_t h, int B, void* workspace, size_t workspace_bytes, void* stream) {
   SmplWorkspace ws;
   int rc = get_ws(h, B, workspace, workspace_bytes, &ws);

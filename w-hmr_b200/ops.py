@@ -99,6 +99,10 @@ class SmplHandle:
                 e.record()           # materialise the lazily created cudaEvent_t
         check(_lib.lib().whmr_smpl_set_probe_events(self._h, *[None if e is None else e.cuda_event for e in evs]))
 
+    def is_fused(self):
+        """True when pose blend + skinning run as one kernel (smpl_fused_tc)."""
+        return bool(_lib.lib().whmr_smpl_is_fused(self._h))
+
     def info(self):
         v = [C.c_int32() for _ in range(5)]
         check(_lib.lib().whmr_smpl_get_info(self._h, *[C.byref(x) for x in v]))
