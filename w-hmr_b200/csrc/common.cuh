@@ -38,6 +38,32 @@ extern std::atomic<uint64_t> g_launch_count;
                                cudaGetErrorString(_e));                                      \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the loop is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so it may become
+// resident while its predecessor in the stream is still running.  Contract inside a kernel:
+//   pdl_wait()    before the first access to global memory another kernel writes or reads (a no-op without the
+//                 attribute); everything before it may only touch constants of the handle and on-chip state;
+//   pdl_trigger() right AFTER pdl_wait(), never before: the successor can then start its own prologue, but it
+//                 cannot pass ITS pdl_wait() before this grid has completed, so at most two grids overlap.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+int pdl_mask();   // WHMR_PDL: bit mask of the kernel classes launched with the attribute (whmr_b200.cu)
+enum { kPdlChain = 1, kPdlFused = 2, kPdlReadout = 4, kPdlProject = 8, kPdlSample = 16 };
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through WHMR_LAUNCHED's cudaGetLastError
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -77,6 +103,7 @@ struct SmplWorkspace {
   float* offsets;    // [chunk,NP]   pose offsets + shape blend, planar per body
   float* At;         // [2, Bpad*12, 32] tf32 hi|lo of the skinning transforms, transposed (TC skinning)
   size_t At_part_stride;   // floats
+  void* At16;        // [Bpad*12, 64] fp16 hi|lo of the same, one 128-byte row per (body, entry) (fused kernel)
   int Bpad;
   int chunk;         // bodies per GEMM/skin chunk
 };

@@ -12,6 +12,8 @@ namespace whmr {
 __global__ void __launch_bounds__(256)
 project_weak_kernel(const float* __restrict__ points, const float* __restrict__ cam, int B, int N,
                     float focal, float img_w, float img_h, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * N) return;
   const int b = (int)(i / N);
@@ -74,6 +76,8 @@ project_full_kernel(const float* __restrict__ points, const float* __restrict__ 
                     float* __restrict__ kp_norm, float* __restrict__ kp_px,
                     float* __restrict__ focal_out, float* __restrict__ cam_t_out,
                     float* __restrict__ kp_weak, float wfocal, float wimg_w, float wimg_h) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * N) return;
   const int b = (int)(i / N);

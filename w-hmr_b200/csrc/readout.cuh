@@ -102,6 +102,8 @@ struct ReadoutAllParams {
 };
 
 __global__ void __launch_bounds__(256) readout_all_kernel(ReadoutAllParams q) {
+  pdl_wait();
+  pdl_trigger();
   ReadoutParams& p = q.rp;
   if ((int)blockIdx.x < q.n_blocks_onehot) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,6 +212,8 @@ __device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* p
 
 __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
   extern __shared__ __align__(16) float ps[];   // [n_partial * 3]
+  pdl_wait();
+  pdl_trigger();
   const ReadoutParams& p = q.rp;
   const int b = blockIdx.x;
   {

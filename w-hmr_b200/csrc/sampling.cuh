@@ -59,6 +59,8 @@ template <bool kProject>
 __global__ void __launch_bounds__(256)
 sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
                             float* __restrict__ out, int C, int H, int W, int N, SampleProj pj) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   float cs = 0.f, ctx = 0.f, cty = 0.f, ctz = 0.f;
   if (kProject) {   // utils/geometry.py:289-307
@@ -113,6 +115,8 @@ __global__ void __launch_bounds__(256)
 sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
                             float* __restrict__ out, int C, int H, int W, int N) {
   __shared__ float tile[64][33];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.z, c0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* fb = feat + (size_t)b * H * W * C;

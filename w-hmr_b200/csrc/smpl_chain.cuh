@@ -14,6 +14,7 @@
 // Traffic per body: reads 4*(NB + 216|72) B, writes 4*(J*12 + J*3 + KP) B  (~2.5 KB).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace whmr {
@@ -36,6 +37,7 @@ struct ChainParams {
   float* pf_tf32;            // [B,2,KP] hi|lo tf32-valued floats or null
   float* At;                 // [2, At_rows, 32] tf32 hi|lo of A transposed: row (b*12+e), column = joint; or null
   size_t At_part_stride;     // floats between the hi and lo parts (= At_rows*32)
+  __half* At16;              // [At_rows, 64] fp16: A transposed, hi in columns 0..31, lo in 32..63 (fused kernel); or null
 };
 
 // smplx.lbs.batch_rodrigues for one vector: angle = ||v + 1e-8||, R = I + sin*K + (1-cos)*K*K
@@ -67,6 +69,8 @@ __device__ __forceinline__ float tf32_round(float x) {
 constexpr int kChainWarpsPerBlock = 4;
 
 __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(ChainParams p) {
+  pdl_wait();      // pose / betas come from the caller's previous kernels; the scratch may still be read by them
+  pdl_trigger();
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * kChainWarpsPerBlock + (threadIdx.x >> 5);
@@ -154,6 +158,17 @@ __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(Ch
       const float hi = tf32_round(x);
       a0[(size_t)e * 32] = hi;
       a0[(size_t)e * 32 + p.At_part_stride] = tf32_round(x - hi);
+    }
+  }
+
+  if (p.At16) {   // fp16 hi|lo split: 22 mantissa bits, |lo| below the fp16 normal range only costs < 6e-8 absolute
+    __half* a0 = p.At16 + ((size_t)b * 12) * 64 + lane;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) {
+      const float x = active ? Arow[e] : 0.0f;
+      const __half hi = __float2half_rn(x);
+      a0[(size_t)e * 64] = hi;
+      a0[(size_t)e * 64 + 32] = __float2half_rn(x - __half2float(hi));
     }
   }
 

@@ -1,27 +1,27 @@
 // One kernel for the vertex half of the SMPL forward: pose+shape blend (tcgen05, bf16x3), blend of the skinning
-// transforms (tcgen05, 3xTF32) and the skinning epilogue -- the [B, 3*V] pose-offset intermediate never leaves
+// transforms (tcgen05, fp16 hi/lo split, 3 MMAs per K step: 22 mantissa bits) and the skinning epilogue -- the [B, 3*V] pose-offset intermediate never leaves
 // the SM: it is produced in TMEM and consumed from TMEM.
 //
 //   off_c[v, b] = sum_k P_c[v, k] * pf[b, k]          c in {x,y,z}; K = 207 pose terms + 10 betas (SURVEY K2+K4)
 //   T[v, b]     = sum_j w[v, j] * A_j[b]              3x4 per vertex and body (K6)
 //   v'[b, v]    = T[v, b] . [v_template[v] + off[v, b] ; 1] (+ transl[b])      (K7)   (+ fused read-out emits)
 //
-// Work item = (tile of 128 vertices) x (group of NBI <= 64 bodies), vertex-major.  TMEM (512 columns, lane =
+// Work item = (tile of 128 vertices) x (run of 16..64 bodies), vertex-major, cut so that all CTAs get equal work.  TMEM (512 columns, lane =
 // vertex): two stages of three NBI-column accumulators (x|y|z pose offsets, one body per column) + one 96-column
 // accumulator for the blended transforms of 8 bodies.  Warp roles (640 threads, 1 CTA/SM):
 //   warp 0      TMA producer, pose blend: per 128-byte K chunk one pose-feature stage {hi,lo} (NBI rows) and per
 //               (chunk, plane) one posedirs stage {hi,lo} (128 rows) -- a 3 x 32 KB ring;
 //   warp 1      pose-blend MMA issuer (+ TMEM allocation): 3 MMAs per K step (lo.hi + hi.lo + hi.hi);
 //   warp 2      TMA producer, skinning: weight tile {hi,lo} when the vertex tile changes, A^T {hi,lo} per 8 bodies;
-//   warp 3      skinning MMA issuer: 3 K steps x 3 MMAs (M=128, N=96, tf32) per 8 bodies;
+//   warp 3      skinning MMA issuer: 2 K steps x 3 MMAs (M=128, N=96, fp16 hi/lo) per 8 bodies;
 //   warps 4-19  epilogue: TMEM lane quarter q = warp%4, two bodies per warp and 8-body group.  A warp pulls its
 //               24 T columns and 6 offset columns into registers, releases the T accumulator at once (so the next
 //               group's MMAs overlap its arithmetic and stores), applies the transform, transposes through
 //               shared memory and writes three coalesced 128-byte rows per body.
 // The two MMA issuers run independently; the tensor pipe interleaves their instructions, so the pose blend of
 // item i+1 proceeds while item i is skinned and stored.
-// Operand traffic per item (L2 -> smem): posedirs 344 KB + pose feature 0.9 KB/body + A^T 3 KB/body + weights
-// 32 KB per vertex tile; measured ingest capability 130-140 GB/s/SM (tools/microbench/l2_ingest_bench.cu).
+// Operand traffic per item (L2 -> smem): posedirs 344 KB + pose feature 0.9 KB/body + A^T 1.5 KB/body + weights
+// 16 KB per vertex tile; measured ingest capability 130-140 GB/s/SM (tools/microbench/l2_ingest_bench.cu).
 #pragma once
 #include <cuda/std/type_traits>
 
@@ -31,31 +31,40 @@
 
 namespace whmr {
 
-constexpr int kFuMaxNB = 64;                  // bodies per item (runtime NBI: multiple of 16, <= 64)
+constexpr int kFuMaxNB = 64;                  // bodies per item (runtime: 16, 32, 48 or 64)
 constexpr int kFuGB = 8;                      // bodies per blended-transform tile
 constexpr int kFuTN = kFuGB * 12;             // 96 accumulator columns
-constexpr int kFuAStages = 3;
+constexpr int kFuAStages = 4;
 constexpr int kFuABytes = 2 * kTcM * 128;     // 32 KB: posedirs {hi,lo} of one (K chunk, plane)
 constexpr int kFuPfStages = 2;
 constexpr int kFuPfPart = kFuMaxNB * 128;     // 8 KB
 constexpr int kFuPfBytes = 2 * kFuPfPart;     // 16 KB: pose feature {hi,lo} of one K chunk
-constexpr int kFuWPart = kTcM * 128;          // 16 KB
+constexpr int kFuWBytes = kTcM * 128;         // 16 KB: skinning weights, fp16 hi|lo along K (64 halfs per vertex)
 constexpr int kFuAtStages = 2;
-constexpr int kFuAtPart = kFuTN * 128;        // 12 KB
-constexpr int kFuAtBytes = 2 * kFuAtPart;     // 24 KB
+constexpr int kFuAtBytes = kFuTN * 128;       // 12 KB: A^T of 8 bodies, fp16 hi|lo along K
 constexpr int kFuEpiWarps = 16;
 constexpr int kFuThreads = (4 + kFuEpiWarps) * 32;
 constexpr int kFuOffA = 0;
 constexpr int kFuOffPf = kFuOffA + kFuAStages * kFuABytes;
 constexpr int kFuOffW = kFuOffPf + kFuPfStages * kFuPfBytes;
-constexpr int kFuOffAt = kFuOffW + 2 * kFuWPart;
+constexpr int kFuOffAt = kFuOffW + kFuWBytes;
 constexpr int kFuOffStg = kFuOffAt + kFuAtStages * kFuAtBytes;
 constexpr int kFuOffBars = kFuOffStg + kFuEpiWarps * 192 * 4;
 constexpr int kFuSmem = kFuOffBars + 256 + 1024;
-constexpr int kFuTmemOffStage = 3 * kFuMaxNB;   // 192 columns per pose-offset stage
-constexpr int kFuTmemT = 2 * kFuTmemOffStage;   // blended transforms at column 384
+// TMEM plan, by the template parameter MAXM = micro-items (16 bodies) per item:
+//   MAXM = 4: 2 x 3 x 64 pose-offset columns + ONE 96-column blended-transform stage (480) -- widest items, least
+//             posedirs re-streaming: large batches;
+//   MAXM = 3: 2 x 3 x 48 pose-offset columns + TWO blended-transform stages (480) -- the skinning MMAs of the next 8
+//             bodies are already done when the epilogue asks for them: small batches, where the per-group
+//             MMA -> epilogue round trip is exposed.
+template <int MAXM> struct FuTmem {
+  static constexpr int kNB = 16 * MAXM;              // max bodies per item
+  static constexpr int kOffStage = 3 * kNB;          // columns per pose-offset stage
+  static constexpr int kT = 2 * kOffStage;           // first blended-transform column
+  static constexpr int kTStages = MAXM == 4 ? 1 : 2;
+  static_assert(kT + kTStages * kFuTN <= 512, "TMEM budget");
+};
 static_assert(kFuSmem <= 232448, "fused SMPL kernel exceeds the 227 KB shared-memory limit");
-static_assert(kFuTmemT + kFuTN <= 512, "TMEM budget");
 
 struct FusedParams {
   const float* v_template_p;  // [3, VP]
@@ -65,10 +74,11 @@ struct FusedParams {
   float* ro_out;
   int ro_B, ro_b0;
   int nb, V, VP;
-  int nbi;                    // bodies per item
-  int n_bgroups, n_items;     // ceil(nb / nbi), (VP/128) * n_bgroups
+  int npv;                    // 16-body micro-items per vertex tile = ceil(nb / 16)
+  int n_micro;                // (VP/128) * npv: the unit of work distribution
   int kch, ksteps;            // pose blend: 128-byte K chunks, 32-byte K steps (bf16: 16 elements)
-  int jsteps;                 // skinning: ceil(J/8) tf32 K steps
+  int jsteps;                 // skinning: ceil(J/16) fp16 K steps
+  int dbg_mode;               // WHMR_FUSED_DBGMODE bits (timing experiments only): 1 skip vertex stores, 2 skip read-out emits, 4 skip the transposes
   long long* dbg;             // WHMR_FUSED_DEBUG: [grid][16] per-role wait/total cycles, or null
 };
 
@@ -88,13 +98,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t* v) {
     else mbar_wait(bar, par);                             \
   } while (0)
 
+template <int MAXM>
 __global__ void __launch_bounds__(kFuThreads, 1)
 smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+shapedirs bf16 [NP, 2, KP]
                      const __grid_constant__ CUtensorMap tmapPf,   // pose feature bf16 [bodies, 2, KP], box rows = nbi
-                     const __grid_constant__ CUtensorMap tmapW,    // weights tf32 [2, VP, 32]
-                     const __grid_constant__ CUtensorMap tmapAt,   // A^T tf32 [2, bodies*12, 32], box rows = 96
+                     const __grid_constant__ CUtensorMap tmapW,    // weights fp16 hi|lo [VP, 64]
+                     const __grid_constant__ CUtensorMap tmapAt,   // A^T fp16 hi|lo [bodies*12, 64], box rows = 96
                      FusedParams p) {
+  using TM = FuTmem<MAXM>;
   extern __shared__ uint8_t smem_raw[];
+  unsigned long long gt_entry = 0;
+  if (p.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem + kFuOffA;
   uint8_t* pf_ring = smem + kFuOffPf;
@@ -112,15 +126,29 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   uint64_t* at_empty = at_full + kFuAtStages;      // [2]
   uint64_t* off_full = at_empty + kFuAtStages;     // [2]
   uint64_t* off_empty = off_full + 2;              // [2]
-  uint64_t* t_full = off_empty + 2;
-  uint64_t* t_empty = t_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 1);
+  uint64_t* t_full = off_empty + 2;                // [2]
+  uint64_t* t_empty = t_full + 2;                  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t_begin = (int)(((long long)blockIdx.x * p.n_items) / gridDim.x);
-  const int t_end = (int)(((long long)(blockIdx.x + 1) * p.n_items) / gridDim.x);
-  // 8-body groups of item t (the last body group of the batch may be ragged)
-  auto n_groups_of = [&](int bg) { return (min(p.nbi, p.nb - bg * p.nbi) + kFuGB - 1) / kFuGB; };
+  // Work distribution: the (vertex tile, 16-body micro-item) grid is cut into gridDim.x contiguous, equal ranges
+  // (vertex-major), so every CTA gets the same number of bodies +-16.  A range is walked as items = runs of <= 4
+  // micro-items (<= 64 bodies) inside one vertex tile, sized evenly (5 micro-items -> 3 + 2, not 4 + 1).
+  const int m_begin = (int)(((long long)blockIdx.x * p.n_micro) / gridDim.x);
+  const int m_end = (int)(((long long)(blockIdx.x + 1) * p.n_micro) / gridDim.x);
+  struct Item { int vt, body0, len, nbod, ng; };   // len: micro-items; nbod: valid bodies; ng: 8-body groups
+  auto item_at = [&](int m) {
+    Item it;
+    it.vt = m / p.npv;
+    const int mi = m - it.vt * p.npv;
+    const int L = min(m_end, (it.vt + 1) * p.npv) - m;
+    const int n_it = (L + MAXM - 1) / MAXM;
+    it.len = (L + n_it - 1) / n_it;
+    it.body0 = mi * 16;
+    it.nbod = min(it.len * 16, p.nb - it.body0);
+    it.ng = (it.nbod + kFuGB - 1) / kFuGB;
+    return it;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFuAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -128,7 +156,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     mbar_init(w_full, 1); mbar_init(w_empty, 1);
     for (int s = 0; s < kFuAtStages; ++s) { mbar_init(&at_full[s], 1); mbar_init(&at_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&off_full[s], 1); mbar_init(&off_empty[s], kFuEpiWarps); }
-    mbar_init(t_full, 1); mbar_init(t_empty, kFuEpiWarps);
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kFuEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -139,30 +167,58 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[blockIdx.x * 16 + 15] = (long long)(g - gt_entry);   // prologue, ns
+    p.dbg[(gridDim.x + blockIdx.x) * 16 + 0] = (long long)gt_entry;
+  }
 
   if (warp == 0) {
     // ============================ TMA producer: pose-blend operands ============================
     if (elect_one()) {
       int as = 0; uint32_t aph = 0;
       int ps = 0; uint32_t pph = 0;
-      const uint32_t pf_bytes = 2u * (uint32_t)p.nbi * 128u;
       long long d_pf = 0, d_a = 0;
       const long long k0 = p.dbg ? clock64() : 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int vt = t / p.n_bgroups, body0 = (t % p.n_bgroups) * p.nbi;
+      // PDL: posedirs are constants of the handle, so the first ring fill is issued before the predecessor (the
+      // chain kernel, which writes the pose feature) has finished; `pre` counts the stages already in flight
+      int pre = 0;
+      if (m_begin < m_end) {
+        const Item it0 = item_at(m_begin);
+        for (int i = 0; i < kFuAStages && i < 3 * p.kch; ++i) {
+          const int kc = i / 3, c = i % 3;
+          uint8_t* ast = a_ring + i * kFuABytes;
+          mbar_arrive_expect_tx(&a_full[i], kFuABytes);
+          tma_load_3d(ast, &tmapP, &a_full[i], kc * 64, 0, c * p.VP + it0.vt * kTcM);
+          tma_load_3d(ast + kTcM * 128, &tmapP, &a_full[i], kc * 64, 1, c * p.VP + it0.vt * kTcM);
+          ++pre;
+        }
+      }
+      pdl_wait();
+      for (int m = m_begin; m < m_end;) {
+        const Item it = item_at(m);
+        m += it.len;
+        const int vt = it.vt, body0 = it.body0;
+        const uint32_t pf_bytes = 2u * (uint32_t)it.len * 2048u;
         for (int kc = 0; kc < p.kch; ++kc) {
           WHMR_FU_WAIT(&pf_empty[ps], pph ^ 1, d_pf);
           uint8_t* pst = pf_ring + ps * kFuPfBytes;
           mbar_arrive_expect_tx(&pf_full[ps], pf_bytes);
-          tma_load_3d(pst, &tmapPf, &pf_full[ps], kc * 64, 0, body0);
-          tma_load_3d(pst + kFuPfPart, &tmapPf, &pf_full[ps], kc * 64, 1, body0);
+          for (int u = 0; u < it.len; ++u) {   // 16-row boxes, stacked: same image as one (16*len)-row box
+            tma_load_3d(pst + u * 2048, &tmapPf, &pf_full[ps], kc * 64, 0, body0 + u * 16);
+            tma_load_3d(pst + kFuPfPart + u * 2048, &tmapPf, &pf_full[ps], kc * 64, 1, body0 + u * 16);
+          }
           if (++ps == kFuPfStages) { ps = 0; pph ^= 1; }
           for (int c = 0; c < 3; ++c) {
-            WHMR_FU_WAIT(&a_empty[as], aph ^ 1, d_a);
-            uint8_t* ast = a_ring + as * kFuABytes;
-            mbar_arrive_expect_tx(&a_full[as], kFuABytes);
-            tma_load_3d(ast, &tmapP, &a_full[as], kc * 64, 0, c * p.VP + vt * kTcM);
-            tma_load_3d(ast + kTcM * 128, &tmapP, &a_full[as], kc * 64, 1, c * p.VP + vt * kTcM);
+            if (pre > 0) {
+              --pre;                       // this stage was filled by the prefetch above
+            } else {
+              WHMR_FU_WAIT(&a_empty[as], aph ^ 1, d_a);
+              uint8_t* ast = a_ring + as * kFuABytes;
+              mbar_arrive_expect_tx(&a_full[as], kFuABytes);
+              tma_load_3d(ast, &tmapP, &a_full[as], kc * 64, 0, c * p.VP + vt * kTcM);
+              tma_load_3d(ast + kTcM * 128, &tmapP, &a_full[as], kc * 64, 1, c * p.VP + vt * kTcM);
+            }
             if (++as == kFuAStages) { as = 0; aph ^= 1; }
           }
         }
@@ -172,17 +228,19 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   } else if (warp == 1) {
     // ============================ pose-blend MMA issuer ========================================
     if (elect_one()) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nbi >> 3) << 17) |
-                             ((uint32_t)(kTcM >> 4) << 24);   // bf16 x bf16 -> f32, M=128, N=nbi
       int as = 0; uint32_t aph = 0;
       int ps = 0; uint32_t pph = 0;
       int buf = 0; uint32_t bph = 0;
       long long d_off = 0, d_pf = 0, d_a = 0;
       const long long k0 = p.dbg ? clock64() : 0;
-      for (int t = t_begin; t < t_end; ++t) {
+      for (int m = m_begin; m < m_end;) {
+        const Item it = item_at(m);
+        m += it.len;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(it.len * 2) << 17) |
+                               ((uint32_t)(kTcM >> 4) << 24);   // bf16 x bf16 -> f32, M=128, N=16*len
         WHMR_FU_WAIT(&off_empty[buf], bph ^ 1, d_off);
         tcgen05_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)(buf * kFuTmemOffStage);
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * TM::kOffStage);
         for (int kc = 0; kc < p.kch; ++kc) {
           WHMR_FU_WAIT(&pf_full[ps], pph, d_pf);
           const uint32_t b_hi = smem_u32(pf_ring + ps * kFuPfBytes), b_lo = b_hi + kFuPfPart;
@@ -191,7 +249,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             WHMR_FU_WAIT(&a_full[as], aph, d_a);
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(a_ring + as * kFuABytes), a_lo = a_hi + kTcM * 128;
-            const uint32_t d_tmem = d_base + (uint32_t)(c * kFuMaxNB);
+            const uint32_t d_tmem = d_base + (uint32_t)(c * TM::kNB);
             for (int ks = 0; ks < nks; ++ks) {
               const uint64_t dA_hi = umma_desc_sw128(a_hi + ks * 32), dA_lo = umma_desc_sw128(a_lo + ks * 32);
               const uint64_t dB_hi = umma_desc_sw128(b_hi + ks * 32), dB_lo = umma_desc_sw128(b_lo + ks * 32);
@@ -215,24 +273,31 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     if (elect_one()) {
       int s = 0; uint32_t ph = 0, w_par = 1;
       int cur_vt = -1;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int vt = t / p.n_bgroups, bg = t % p.n_bgroups;
+      if (m_begin < m_end) {   // the first weight tile does not depend on the predecessor either
+        cur_vt = m_begin / p.npv;
+        w_par ^= 1;            // first use of w_empty passes trivially
+        mbar_arrive_expect_tx(w_full, kFuWBytes);
+        tma_load_2d(w_smem, &tmapW, w_full, 0, cur_vt * kTcM);
+      }
+      pdl_wait();
+      for (int m = m_begin; m < m_end;) {
+        const Item it = item_at(m);
+        m += it.len;
+        const int vt = it.vt;
         if (vt != cur_vt) {
           mbar_wait(w_empty, w_par);   // MMAs on the previous weight tile have retired
           w_par ^= 1;
-          mbar_arrive_expect_tx(w_full, 2 * kFuWPart);
-          tma_load_3d(w_smem, &tmapW, w_full, 0, vt * kTcM, 0);
-          tma_load_3d(w_smem + kFuWPart, &tmapW, w_full, 0, vt * kTcM, 1);
+          mbar_arrive_expect_tx(w_full, kFuWBytes);
+          tma_load_2d(w_smem, &tmapW, w_full, 0, vt * kTcM);
           cur_vt = vt;
         }
-        const int ng = n_groups_of(bg);
+        const int ng = it.ng;
         for (int g = 0; g < ng; ++g) {
           mbar_wait(&at_empty[s], ph ^ 1);
           uint8_t* st = at_ring + s * kFuAtBytes;
           mbar_arrive_expect_tx(&at_full[s], kFuAtBytes);
-          const int row0 = (bg * p.nbi + g * kFuGB) * 12;
-          tma_load_3d(st, &tmapAt, &at_full[s], 0, row0, 0);
-          tma_load_3d(st + kFuAtPart, &tmapAt, &at_full[s], 0, row0, 1);
+          const int row0 = (it.body0 + g * kFuGB) * 12;
+          tma_load_2d(st, &tmapAt, &at_full[s], 0, row0);
           if (++s == kFuAtStages) { s = 0; ph ^= 1; }
         }
       }
@@ -240,36 +305,39 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   } else if (warp == 3) {
     // ============================ skinning MMA issuer ==========================================
     if (elect_one()) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kFuTN >> 3) << 17) |
-                                 ((uint32_t)(kTcM >> 4) << 24);   // tf32 x tf32 -> f32, M=128, N=96
+      constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(kFuTN >> 3) << 17) |
+                                 ((uint32_t)(kTcM >> 4) << 24);   // fp16 x fp16 -> f32, M=128, N=96
       int s = 0; uint32_t ph = 0, w_phase = 0, t_ph = 0;
       int cur_vt = -1;
-      const uint32_t w_hi = smem_u32(w_smem), w_lo = w_hi + kFuWPart;
-      const uint32_t d_tmem = tmem_base + (uint32_t)kFuTmemT;
+      const uint32_t w_hi = smem_u32(w_smem), w_lo = w_hi + 64;   // lo half of every 128-byte row
+      int ts = 0;
       long long d_t = 0, d_at = 0;
       const long long k0 = p.dbg ? clock64() : 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int vt = t / p.n_bgroups, bg = t % p.n_bgroups;
+      for (int m = m_begin; m < m_end;) {
+        const Item it = item_at(m);
+        m += it.len;
+        const int vt = it.vt;
         if (vt != cur_vt) { mbar_wait(w_full, w_phase); w_phase ^= 1; cur_vt = vt; }
-        const int ng = n_groups_of(bg);
+        const int ng = it.ng;
         for (int g = 0; g < ng; ++g) {
-          WHMR_FU_WAIT(t_empty, t_ph ^ 1, d_t);
+          WHMR_FU_WAIT(&t_empty[ts], t_ph ^ 1, d_t);
           WHMR_FU_WAIT(&at_full[s], ph, d_at);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(TM::kT + ts * kFuTN);
           tcgen05_fence_after();
-          const uint32_t a_hi = smem_u32(at_ring + s * kFuAtBytes), a_lo = a_hi + kFuAtPart;
+          const uint32_t a_hi = smem_u32(at_ring + s * kFuAtBytes), a_lo = a_hi + 64;
           for (int ks = 0; ks < p.jsteps; ++ks) {
             const uint64_t dW_hi = umma_desc_sw128(w_hi + ks * 32), dW_lo = umma_desc_sw128(w_lo + ks * 32);
             const uint64_t dA_hi = umma_desc_sw128(a_hi + ks * 32), dA_lo = umma_desc_sw128(a_lo + ks * 32);
-            umma<1>(d_tmem, dW_lo, dA_hi, idesc, ks != 0);
-            umma<1>(d_tmem, dW_hi, dA_lo, idesc, 1u);
-            umma<1>(d_tmem, dW_hi, dA_hi, idesc, 1u);
+            umma<0>(d_tmem, dW_lo, dA_hi, idesc, ks != 0);
+            umma<0>(d_tmem, dW_hi, dA_lo, idesc, 1u);
+            umma<0>(d_tmem, dW_hi, dA_hi, idesc, 1u);
           }
           tcgen05_commit(&at_empty[s]);
-          tcgen05_commit(t_full);
+          tcgen05_commit(&t_full[ts]);
           if (++s == kFuAtStages) { s = 0; ph ^= 1; }
-          t_ph ^= 1;
+          if (++ts == TM::kTStages) { ts = 0; t_ph ^= 1; }
         }
-        const int next_vt = (t + 1 < t_end) ? (t + 1) / p.n_bgroups : -1;
+        const int next_vt = (m < m_end) ? m / p.npv : -1;
         if (next_vt != vt) tcgen05_commit(w_empty);
       }
       if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[7] = d_t; d[8] = d_at; d[9] = clock64() - k0; }
@@ -299,11 +367,15 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     };
     const int V3 = p.V * 3;
     const bool has_transl = p.transl != nullptr;
-    int buf = 0; uint32_t bph = 0, t_ph = 0;
+    int buf = 0, ts = 0; uint32_t bph = 0, t_ph = 0;
     long long d_off = 0, d_t = 0, d_ld = 0, d_rel = 0;
+    pdl_wait();      // outputs (and the read-out partial buffer) may still be in use by earlier kernels
+    pdl_trigger();
     const long long k0 = p.dbg ? clock64() : 0;
-    for (int t = t_begin; t < t_end; ++t) {
-      const int vt = t / p.n_bgroups, bg = t % p.n_bgroups;
+    for (int m = m_begin; m < m_end;) {
+      const Item it = item_at(m);
+      m += it.len;
+      const int vt = it.vt;
       if (vt != cur_vt) {
         cur_vt = vt;
         const int v = vt * kTcM + q * 32 + lane;                  // < VP
@@ -319,16 +391,17 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       }
       const int out_col = (vt * kTcM + q * 32) * 3 + lane;        // float index inside a body row
       const bool full_tile = (vt + 1) * kTcM <= p.V;
-      const int ng = n_groups_of(bg);
+      const int ng = it.ng;
       WHMR_FU_WAIT(&off_full[buf], bph, d_off);
       const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-      const uint32_t off_addr = tmem_base + lane_sel + (uint32_t)(buf * kFuTmemOffStage);
-      const uint32_t t_addr = tmem_base + lane_sel + (uint32_t)(kFuTmemT + w4 * 24);
+      const uint32_t off_addr = tmem_base + lane_sel + (uint32_t)(buf * TM::kOffStage);
       for (int g = 0; g < ng; ++g) {
-        const int body_base = bg * p.nbi + g * kFuGB + w4 * 2;     // first of this warp's two bodies
+        const int body_base = it.body0 + g * kFuGB + w4 * 2;       // first of this warp's two bodies
         const int n_valid = min(2, p.nb - body_base);              // may be <= 0
-        WHMR_FU_WAIT(t_full, t_ph, d_t);
-        t_ph ^= 1;
+        WHMR_FU_WAIT(&t_full[ts], t_ph, d_t);
+        const uint32_t t_addr = tmem_base + lane_sel + (uint32_t)(TM::kT + ts * kFuTN + w4 * 24);
+        uint64_t* const t_rel = &t_empty[ts];
+        if (++ts == TM::kTStages) { ts = 0; t_ph ^= 1; }
         tcgen05_fence_after();
         const long long l0 = p.dbg ? clock64() : 0;
         uint32_t T[24], O[6];
@@ -336,15 +409,15 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         tmem_ld_32x32b_x8(t_addr + 16, T + 16);
         const uint32_t ocol = (uint32_t)(g * kFuGB + w4 * 2);
         tmem_ld_32x32b_x2(off_addr + ocol, O);
-        tmem_ld_32x32b_x2(off_addr + kFuMaxNB + ocol, O + 2);
-        tmem_ld_32x32b_x2(off_addr + 2 * kFuMaxNB + ocol, O + 4);
+        tmem_ld_32x32b_x2(off_addr + TM::kNB + ocol, O + 2);
+        tmem_ld_32x32b_x2(off_addr + 2 * TM::kNB + ocol, O + 4);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const long long l1 = p.dbg ? clock64() : 0;
         // accumulators are in registers: hand them back before the arithmetic and the stores
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(t_empty);
+          mbar_arrive(t_rel);
           if (g == ng - 1) mbar_arrive(&off_empty[buf]);
         }
         if (p.dbg) { d_ld += l1 - l0; d_rel += clock64() - l1; }
@@ -368,23 +441,24 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
               rx += tr[0]; ry += tr[1]; rz += tr[2];
             }
             float* sb = stg + i * 96;
-            sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz;
+            if (!(p.dbg_mode & 4)) { sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz; }
+            else if (rx + ry + rz == 123.456f) sb[0] = rx;
           }
           __syncwarp();
           float v[6];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int r = 0; r < 3; ++r) v[i * 3 + r] = stg[i * 96 + r * 32 + lane];
+            for (int r = 0; r < 3; ++r) v[i * 3 + r] = (p.dbg_mode & 4) ? 0.f : stg[i * 96 + r * 32 + lane];
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (G && i >= n_valid) continue;
             float* ob = outp + (size_t)i * V3;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
-              if (!G || out_col + r * 32 < V3) ob[r * 32] = v[i * 3 + r];
+              if ((!G || out_col + r * 32 < V3) && !(p.dbg_mode & 1)) ob[r * 32] = v[i * 3 + r];
           }
-          if (n_e > 0) {   // fused read-outs: entries referencing one of this warp's 32 vertices
+          if (n_e > 0 && !(p.dbg_mode & 2)) {   // fused read-outs: entries referencing one of this warp's 32 vertices
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               if (G && i >= n_valid) continue;
@@ -421,19 +495,10 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
-}
-
-// bodies per item for a chunk of nb bodies: fewest rounds over the SMs, then the widest tile (posedirs are
-// re-streamed once per item, ~2.6 us at the measured ingest rate, against ~0.05 us of work per body)
-static inline int fused_pick_nbi(int nb, int n_vtiles, int num_sms) {
-  int best = 16;
-  double best_cost = 1e30;
-  for (int nbi = 16; nbi <= kFuMaxNB; nbi += 16) {
-    const long long items = (long long)n_vtiles * ceil_div(nb, nbi);
-    const double cost = (double)((items + num_sms - 1) / num_sms) * (2.6 + 0.05 * std::min(nbi, nb));
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = nbi; }
+  if (p.dbg && threadIdx.x == 32) {
+    unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[(gridDim.x + blockIdx.x) * 16 + 1] = (long long)g;
   }
-  return best;
 }
 
 }  // namespace whmr

@@ -1,5 +1,6 @@
 // libwhmr_b200.so -- C ABI over the sm_100a kernels (see include/whmr_b200.h).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,6 +25,12 @@
 namespace whmr {
 
 std::atomic<uint64_t> g_launch_count{0};
+
+int pdl_mask() {   // default: the fused SMPL kernel (posedirs prefetch under the chain kernel) and the projections;
+                   // the attribute on the read-out / chain / sampling launches measured as a loss (profiles/r01_notes.md)
+  static const int mask = getenv("WHMR_PDL") ? atoi(getenv("WHMR_PDL")) : (kPdlFused | kPdlProject);
+  return mask;
+}
 
 std::string& last_error_ref() {
   static thread_local std::string s;
@@ -71,6 +78,17 @@ struct DeviceArena {   // owns the cudaMalloc'ed constants of one handle
 }  // namespace whmr
 
 using namespace whmr;
+
+// dense fp32 skinning weights [V, J] -> fp16 hi|lo rows [VP, 64] (hi in 0..31, lo in 32..63), zero padded
+__global__ void split_weights_f16_kernel(const float* __restrict__ w, int V, int J, int VP, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= VP * 32) return;
+  const int v = i >> 5, j = i & 31;
+  const float x = (v < V && j < J) ? w[(size_t)v * J + j] : 0.0f;
+  const __half hi = __float2half_rn(x);
+  out[(size_t)v * 64 + j] = hi;
+  out[(size_t)v * 64 + 32 + j] = __float2half_rn(x - __half2float(hi));
+}
 
 struct whmr_smpl_s {
   SmplDevice d{};
@@ -258,9 +276,24 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
     e = cudaFuncSetAttribute(skin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSkinSmem);
     if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "cudaFuncSetAttribute(skin_tc) failed: %s", cudaGetErrorString(e)); }
   }
+  {   // fp16 hi|lo weights for the fused kernel, split on the device (exact round-to-nearest incl. subnormals)
+    std::vector<float> wdense(m->lbs_weights, m->lbs_weights + (size_t)V * J);
+    float* dwf = nullptr;
+    void* dw16 = nullptr;
+    e = h->arena.upload(wdense, &dwf);
+    if (e == cudaSuccess) e = h->arena.alloc((size_t)VP * 64 * sizeof(__half), &dw16);
+    if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "fp16 weight upload failed: %s", cudaGetErrorString(e)); }
+    split_weights_f16_kernel<<<ceil_div(VP * 32, 256), 256>>>(dwf, V, J, VP, static_cast<__half*>(dw16));
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "split_weights_f16_kernel failed: %s", cudaGetErrorString(e)); }
+    h->tc.W_f16 = dw16;
+    rc = tc_encode_rows64h(h->tc.encode_fn, &h->tc.tmapW16, dw16, (size_t)VP, kTcM);
+    if (rc != WHMR_OK) { delete h; return rc; }
+  }
   if (const char* s = getenv("WHMR_SKIN")) h->skin_tc = strcmp(s, "simt") != 0;
   if (const char* s = getenv("WHMR_FUSED")) h->fused = atoi(s) != 0;
-  e = cudaFuncSetAttribute(smpl_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem);
+  e = cudaFuncSetAttribute(smpl_fused_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem);
   if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "cudaFuncSetAttribute(smpl_fused_tc) failed: %s", cudaGetErrorString(e)); }
   h->gemm_mode = gemm_mode;
   *out = h;
@@ -293,6 +326,8 @@ int whmr_smpl_get_info(whmr_smpl_t h, int32_t* n_verts, int32_t* n_joints, int32
 }
 
 // ---- workspace carving --------------------------------------------------------------------
+static bool fused_applicable(const whmr_smpl_s* h);
+
 static size_t carve(const whmr_smpl_s* h, int B, void* base, SmplWorkspace* ws) {
   const SmplDevice& d = h->d;
   const int chunk = std::min(B, h->chunk_bodies);
@@ -304,6 +339,7 @@ static size_t carve(const whmr_smpl_s* h, int B, void* base, SmplWorkspace* ws) 
   const size_t oSplit = take((size_t)Bpad * 2 * d.KP * sizeof(float));   // sized for the tf32 variant
   const size_t oOff = take((size_t)chunk * d.NP * sizeof(float));
   const size_t oAt = take((size_t)2 * Bpad * 12 * 32 * sizeof(float));
+  const size_t oAt16 = take((size_t)Bpad * 12 * 64 * sizeof(__half));
   if (ws) {
     char* p = static_cast<char*>(base);
     ws->A = reinterpret_cast<float*>(p + oA);
@@ -311,6 +347,7 @@ static size_t carve(const whmr_smpl_s* h, int B, void* base, SmplWorkspace* ws) 
     ws->pf_split = p + oSplit;
     ws->offsets = reinterpret_cast<float*>(p + oOff);
     ws->At = reinterpret_cast<float*>(p + oAt);
+    ws->At16 = p + oAt16;
     ws->At_part_stride = (size_t)Bpad * 12 * 32;
     ws->Bpad = Bpad;
     ws->chunk = chunk;
@@ -334,9 +371,9 @@ static int get_ws(whmr_smpl_t h, int B, void* workspace, size_t bytes, SmplWorks
   return WHMR_OK;
 }
 
-int whmr_smpl_stage_chain(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
-                          const float* transl, int B, float* joints, float* rel_transforms, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+static int chain_impl(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat, const float* transl,
+                      int B, float* joints, float* rel_transforms, void* workspace, size_t workspace_bytes, void* stream,
+                      bool both_at_formats) {
   SmplWorkspace ws;
   int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
   if (rc) return rc;
@@ -351,11 +388,22 @@ int whmr_smpl_stage_chain(whmr_smpl_t h, const float* betas, const float* pose, 
   p.pf = h->gemm_mode == WHMR_GEMM_FP32_SIMT ? ws.pf : nullptr;
   p.pf_split = h->gemm_mode == WHMR_GEMM_TC_BF16X3 ? static_cast<__nv_bfloat16*>(ws.pf_split) : nullptr;
   p.pf_tf32 = h->gemm_mode == WHMR_GEMM_TC_3XTF32 ? static_cast<float*>(ws.pf_split) : nullptr;
-  p.At = h->skin_tc ? ws.At : nullptr;
+  // the fused kernel reads A^T as fp16 hi|lo rows (same scratch region), the stand-alone skinning kernel as tf32 parts
+  const bool f16 = fused_applicable(h);
+  p.At = (h->skin_tc && (!f16 || both_at_formats)) ? ws.At : nullptr;
+  p.At16 = f16 ? static_cast<__half*>(ws.At16) : nullptr;
   p.At_part_stride = ws.At_part_stride;
-  smpl_chain_kernel<<<ceil_div(B, kChainWarpsPerBlock), kChainWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p);
+  launch_pdl(kPdlChain, smpl_chain_kernel, dim3(ceil_div(B, kChainWarpsPerBlock)), dim3(kChainWarpsPerBlock * 32), 0, (cudaStream_t)stream, p);
   WHMR_LAUNCHED("smpl_chain_kernel");
   return WHMR_OK;
+}
+
+int whmr_smpl_stage_chain(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                          const float* transl, int B, float* joints, float* rel_transforms, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  // stage API: whmr_smpl_stage_skin (the stand-alone skinning kernel) may follow, so both A^T formats are written
+  return chain_impl(h, betas, pose, pose_is_rotmat, transl, B, joints, rel_transforms, workspace, workspace_bytes, stream,
+                    true);
 }
 
 // pose offsets for bodies [b0, b0+nb) -> ws.offsets[0..nb)
@@ -388,7 +436,7 @@ static int launch_readout_all(whmr_readout_t r, const float* verts, const float*
   const int n_blocks_short = (int)(((long long)nb * r->n_short + 255) / 256);
   const int grid = q.n_blocks_onehot + q.n_blocks_long + n_blocks_short;
   if (grid == 0) return WHMR_OK;
-  readout_all_kernel<<<grid, 256, 0, st>>>(q);
+  launch_pdl(kPdlReadout, readout_all_kernel, dim3(grid), dim3(256), 0, st, q);
   WHMR_LAUNCHED("readout_all_kernel");
   return WHMR_OK;
 }
@@ -406,7 +454,7 @@ static int launch_readout_reduce(whmr_readout_t r, const float* verts, const flo
   q.rows = r->rows_reduce; q.n_rows = r->n_reduce; q.part_ptr = r->part_ptr; q.partial = partial;
   q.n_partial = r->n_partial; q.slot_of = r->slot_of; q.jt_ptr = r->jt_ptr; q.jt_col = r->jt_col; q.jt_val = r->jt_val;
   const size_t smem = (size_t)r->n_partial * 3 * sizeof(float);
-  readout_reduce_kernel<<<nb, 128, smem, st>>>(q);
+  launch_pdl(kPdlReadout, readout_reduce_kernel, dim3(nb), dim3(128), smem, st, q);
   WHMR_LAUNCHED("readout_reduce_kernel");
   return WHMR_OK;
 }
@@ -470,7 +518,7 @@ static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* beta
 
 // pose blend + skinning of bodies [b0, b0+nb) in one kernel (smpl_fused_tc.cuh); bf16x3 pose blend only
 static bool fused_applicable(const whmr_smpl_s* h) {
-  return h->fused && h->skin_tc && h->gemm_mode == WHMR_GEMM_TC_BF16X3 && h->tc.ready && h->d.KP % 16 == 0;
+  return h->d.J <= 32 && h->fused && h->skin_tc && h->gemm_mode == WHMR_GEMM_TC_BF16X3 && h->tc.ready && h->d.KP % 16 == 0;
 }
 
 static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* transl, int B, int b0, int nb, float* verts,
@@ -487,36 +535,47 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   }
   p.nb = nb; p.V = d.V; p.VP = d.VP;
   const int n_vtiles = d.VP / kTcM;
-  p.nbi = fused_pick_nbi(nb, n_vtiles, h->tc.num_sms);
-  static const int nbi_env = getenv("WHMR_FUSED_NBI") ? atoi(getenv("WHMR_FUSED_NBI")) : 0;
-  if (nbi_env >= 16 && nbi_env <= kFuMaxNB && nbi_env % 16 == 0) p.nbi = nbi_env;
-  p.n_bgroups = ceil_div(nb, p.nbi);
-  p.n_items = n_vtiles * p.n_bgroups;
+  p.npv = ceil_div(nb, 16);
+  p.n_micro = n_vtiles * p.npv;
   p.ksteps = d.KP * 2 / 32;
   p.kch = ceil_div(p.ksteps, 4);
-  p.jsteps = ceil_div(d.J, 8);
+  p.jsteps = ceil_div(d.J, 16);
   CUtensorMap tmapPf, tmapAt;
   char* pf_base = static_cast<char*>(ws.pf_split) + (size_t)b0 * 2 * d.KP * 2;
-  int rc = tc_encode(h->tc.encode_fn, &tmapPf, 0, pf_base, d.KP, ws.Bpad - b0, p.nbi);
+  int rc = tc_encode(h->tc.encode_fn, &tmapPf, 0, pf_base, d.KP, ws.Bpad - b0, 16);
   if (rc) return rc;
-  rc = tc_encode_rows32(h->tc.encode_fn, &tmapAt, ws.At + (size_t)b0 * 12 * 32, (size_t)(ws.Bpad - b0) * 12,
-                        ws.At_part_stride * sizeof(float), kFuTN);
+  rc = tc_encode_rows64h(h->tc.encode_fn, &tmapAt, static_cast<__half*>(ws.At16) + (size_t)b0 * 12 * 64,
+                         (size_t)(ws.Bpad - b0) * 12, kFuTN);
   if (rc) return rc;
-  const int grid = std::min(h->tc.num_sms, p.n_items);
+  const int grid = std::min(h->tc.num_sms, p.n_micro);
   static const bool dbg_on = getenv("WHMR_FUSED_DEBUG") != nullptr;
-  if (dbg_on) { cudaMalloc(&p.dbg, sizeof(long long) * 16 * grid); cudaMemsetAsync(p.dbg, 0, sizeof(long long) * 16 * grid, st); }
-  smpl_fused_tc_kernel<<<grid, kFuThreads, kFuSmem, st>>>(h->tc.tmapA_bf16, tmapPf, h->tc.tmapW, tmapAt, p);
+  static const int dbg_mode = getenv("WHMR_FUSED_DBGMODE") ? atoi(getenv("WHMR_FUSED_DBGMODE")) : 0;
+  p.dbg_mode = dbg_mode;
+  if (dbg_on) { cudaMalloc(&p.dbg, sizeof(long long) * 32 * grid); cudaMemsetAsync(p.dbg, 0, sizeof(long long) * 32 * grid, st); }
+  // items of <= 48 bodies with two blended-transform stages while a CTA's share is small (the per-group MMA ->
+  // epilogue round trip is exposed), <= 64 bodies and one stage once posedirs re-streaming dominates
+  static const int maxm_env = getenv("WHMR_FUSED_MAXM") ? atoi(getenv("WHMR_FUSED_MAXM")) : 0;
+  const bool small = maxm_env ? maxm_env == 3 : (p.n_micro <= 8 * h->tc.num_sms);
+  if (small) launch_pdl(kPdlFused, smpl_fused_tc_kernel<3>, dim3(grid), dim3(kFuThreads), kFuSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
+  else launch_pdl(kPdlFused, smpl_fused_tc_kernel<4>, dim3(grid), dim3(kFuThreads), kFuSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
   WHMR_LAUNCHED("smpl_fused_tc_kernel");
   if (p.dbg) {   // per-role wait/total cycles averaged over CTAs (debug only: synchronises)
     cudaStreamSynchronize(st);
-    std::vector<long long> hd((size_t)16 * grid);
+    std::vector<long long> hd((size_t)32 * grid);
     cudaMemcpy(hd.data(), p.dbg, hd.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(p.dbg);
     double a[16] = {0};
     for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)hd[(size_t)c * 16 + k] / grid;
-    fprintf(stderr, "[whmr fused dbg] nb=%d nbi=%d items=%d grid=%d | pose-producer wait pf_empty %.0f a_empty %.0f of %.0f | "
+    long long t_first = hd[(size_t)grid * 16], t_last_start = t_first, t_end_min = hd[(size_t)grid * 16 + 1], t_end_max = t_end_min;
+    for (int c = 0; c < grid; ++c) {
+      t_first = std::min(t_first, hd[(size_t)(grid + c) * 16]); t_last_start = std::max(t_last_start, hd[(size_t)(grid + c) * 16]);
+      t_end_min = std::min(t_end_min, hd[(size_t)(grid + c) * 16 + 1]); t_end_max = std::max(t_end_max, hd[(size_t)(grid + c) * 16 + 1]);
+    }
+    fprintf(stderr, "[whmr fused dbg] globaltimer: CTA starts spread %lld ns, first start -> last end %lld ns, ends spread %lld ns, prologue avg %.0f ns\n",
+            t_last_start - t_first, t_end_max - t_first, t_end_max - t_end_min, a[15]);
+    fprintf(stderr, "[whmr fused dbg] nb=%d micro-items=%d grid=%d | pose-producer wait pf_empty %.0f a_empty %.0f of %.0f | "
             "pose-mma wait off_empty %.0f pf_full %.0f a_full %.0f of %.0f | skin-mma wait t_empty %.0f at_full %.0f of %.0f | "
-            "epilogue wait off_full %.0f t_full %.0f tmem-ld %.0f release %.0f of %.0f cycles\n", nb, p.nbi, p.n_items, grid, a[0], a[1], a[2], a[3], a[4],
+            "epilogue wait off_full %.0f t_full %.0f tmem-ld %.0f release %.0f of %.0f cycles\n", nb, p.n_micro, grid, a[0], a[1], a[2], a[3], a[4],
             a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[13], a[14], a[12]);
   }
   return WHMR_OK;
@@ -580,8 +639,8 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
     WHMR_CHECK_ARG(joints || !ro->needs_joints, "whmr_smpl_forward_readout: table references chain joints but joints == NULL");
   }
   cudaStream_t st = (cudaStream_t)stream;
-  rc = whmr_smpl_stage_chain(h, betas, pose, pose_is_rotmat, transl, B, joints, rel_transforms, workspace,
-                             workspace_bytes, stream);
+  rc = chain_impl(h, betas, pose, pose_is_rotmat, transl, B, joints, rel_transforms, workspace, workspace_bytes, stream,
+                  false);
   if (rc) return rc;
   if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, st, cudaEventRecordExternal));
   // chunked so the [chunk, NP] pose-offset intermediate (and the chunk's vertices, for the read-outs)
@@ -875,7 +934,7 @@ int whmr_project_weak(const float* points, const float* cam, int B, int N, float
   WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_weak: negative size");
   if (B == 0 || N == 0) return WHMR_OK;
   WHMR_CHECK_ARG(points && cam && out, "whmr_project_weak: null pointer");
-  project_weak_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(points, cam, B, N, focal, img_w, img_h, out);
+  launch_pdl(kPdlProject, project_weak_kernel, dim3(WHMR_BN_GRID(B, N)), dim3(256), 0, (cudaStream_t)stream, points, cam, B, N, focal, img_w, img_h, out);
   WHMR_LAUNCHED("project_weak_kernel");
   return WHMR_OK;
 }
@@ -901,9 +960,8 @@ int whmr_project_full(const float* points, const float* cam, const float* bbox_h
   WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_full: negative size");
   if (B == 0 || N == 0) return WHMR_OK;
   WHMR_CHECK_ARG(points && cam && bbox_height && center && orig_shape && Tz, "whmr_project_full: null input");
-  project_full_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(points, cam, bbox_height, center, orig_shape,
-                                                                           Tz, B, N, kp_norm, kp_px, focal_out, cam_t_out,
-                                                                           nullptr, 0.f, 0.f, 0.f);
+  launch_pdl(kPdlProject, project_full_kernel, dim3(WHMR_BN_GRID(B, N)), dim3(256), 0, (cudaStream_t)stream, points, cam, bbox_height, center,
+             orig_shape, Tz, B, N, kp_norm, kp_px, focal_out, cam_t_out, (float*)nullptr, 0.f, 0.f, 0.f);
   WHMR_LAUNCHED("project_full_kernel");
   return WHMR_OK;
 }
@@ -915,9 +973,8 @@ int whmr_project_weak_full(const float* points, const float* cam, const float* b
   WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_weak_full: negative size");
   if (B == 0 || N == 0) return WHMR_OK;
   WHMR_CHECK_ARG(points && cam && bbox_height && center && orig_shape && Tz && kp_weak, "whmr_project_weak_full: null input");
-  project_full_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(points, cam, bbox_height, center, orig_shape,
-                                                                           Tz, B, N, kp_norm, kp_px, focal_out, cam_t_out,
-                                                                           kp_weak, weak_focal, weak_img_w, weak_img_h);
+  launch_pdl(kPdlProject, project_full_kernel, dim3(WHMR_BN_GRID(B, N)), dim3(256), 0, (cudaStream_t)stream, points, cam, bbox_height, center,
+             orig_shape, Tz, B, N, kp_norm, kp_px, focal_out, cam_t_out, kp_weak, weak_focal, weak_img_w, weak_img_h);
   WHMR_LAUNCHED("project_full_kernel");
   return WHMR_OK;
 }
@@ -949,11 +1006,11 @@ int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int
   cudaStream_t st = (cudaStream_t)stream;
   if (layout == WHMR_LAYOUT_NCHW) {
     dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
-    sample_bilinear_nchw_kernel<false><<<grid, 256, 0, st>>>(feat, points, pts_bstride, out, C, H, W, N, SampleProj{});
+    launch_pdl(kPdlSample, sample_bilinear_nchw_kernel<false>, grid, dim3(256), 0, st, feat, points, pts_bstride, out, C, H, W, N, SampleProj{});
     WHMR_LAUNCHED("sample_bilinear_nchw_kernel");
   } else {
     dim3 grid(ceil_div(N, 32), ceil_div(C, 64), B);
-    sample_bilinear_nhwc_kernel<<<grid, 256, 0, st>>>(feat, points, pts_bstride, out, C, H, W, N);
+    launch_pdl(kPdlSample, sample_bilinear_nhwc_kernel, grid, dim3(256), 0, st, feat, points, pts_bstride, out, C, H, W, N);
     WHMR_LAUNCHED("sample_bilinear_nhwc_kernel");
   }
   return WHMR_OK;
@@ -969,7 +1026,7 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
     WHMR_CHECK_ARG(!points2d_out || (reinterpret_cast<size_t>(points2d_out) & 7) == 0, "whmr_project_sample: points2d_out must be 8-byte aligned");
     dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
     SampleProj pj{cam, focal, img_w, img_h, points2d_out};
-    sample_bilinear_nchw_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, p, N * 3, out, C, H, W, N, pj);
+    launch_pdl(kPdlSample, sample_bilinear_nchw_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, feat, p, N * 3, out, C, H, W, N, pj);
     WHMR_LAUNCHED("sample_bilinear_nchw_kernel<project>");
     return WHMR_OK;
   }
