@@ -236,6 +236,8 @@ int whmr_gather_vertices(const float* verts, const int32_t* idx, int B, int V, i
  * ------------------------------------------------------------------------------------------ */
 int whmr_joint_errors(const float* pred, const float* gt, int n, int J, float* mpjpe /*or NULL*/,
                       float* pa_mpjpe /*or NULL*/, void* stream);
+/* PVE, evaluate/eval.py:208-209: pve[n] = mean_v ||pred[n,v,:] - gt[n,v,:]||;  pred, gt [n,V,3] */
+int whmr_vertex_errors(const float* pred, const float* gt, int n, int V, float* pve, void* stream);
 
 #ifdef __cplusplus
 }

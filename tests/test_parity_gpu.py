@@ -387,6 +387,41 @@ def test_joint_errors_match_reference_golden(dev, golden):
     assert float(pa[:5].max()) <= 1e-6
 
 
+def test_eval_pass_matches_oracle(dev, smpl_model):
+    """BASELINE config 5 (evaluate/eval.py:157-223): GT SMPL (axis-angle) + predicted SMPL (rotmat) + H36M 17 -> 14
+    pelvis-centred + MPJPE / PA-MPJPE / PVE, against the CPU oracle; then size-independent properties on a
+    3DPW-sized shard walked in chunks."""
+    from oracle import metrics_oracle as M
+    from whmr_b200.evaluate import EvalPass
+    import whmr_b200.synthetic as syn
+    smpl = _smpl(smpl_model, dev, None)
+    ev = EvalPass(smpl, smpl_model['J_regressor_h36m'])
+    n = 24
+    gt, pr = syn.make_bodies(n, seed=21), syn.make_bodies(n, seed=22)
+    pr_rot = pr['rotmat'].copy(); pr_betas = pr['betas'].copy()
+    pr_rot[:4] = gt['rotmat'][:4]; pr_betas[:4] = gt['betas'][:4]        # exact predictions -> (near) zero errors
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    got = ev(T(gt['pose_aa']), T(gt['betas']), T(pr_rot), T(pr_betas))
+    ref = M.eval_pass(smpl_model, gt['pose_aa'], gt['betas'], pr_rot, pr_betas)
+    for k in ('mpjpe', 'pa_mpjpe', 'pve'):
+        assert _maxabs(got[k], ref[k]) <= 2e-5, k          # joints/vertices carry <= 1e-5 m each side
+    assert float(got['mpjpe'][:4].max()) <= 2e-5 and float(got['pve'][:4].max()) <= 2e-5
+    # predicted vertices handed in directly (the model's global_verts, eval.py:181)
+    pv, _ = ev.joints(T(pr_betas), T(pr_rot), True)
+    got2 = ev(T(gt['pose_aa']), T(gt['betas']), pred_vertices=pv)
+    for k in ('mpjpe', 'pa_mpjpe', 'pve'):
+        assert _maxabs(got2[k], got[k].cpu()) <= 2e-6, k
+    # chunked pass over a larger shard: chunk size must be invisible, frames independent of position
+    N = 3000
+    g2, p2 = syn.make_bodies(N, seed=23), syn.make_bodies(N, seed=24)
+    a = ev.run_sharded(g2['pose_aa'], g2['betas'], p2['rotmat'], p2['betas'], chunk=1024)
+    b = ev.run_sharded(g2['pose_aa'], g2['betas'], p2['rotmat'], p2['betas'], chunk=777)
+    for k in a:
+        assert a[k].shape == (N,) and torch.equal(a[k], b[k]), k
+        assert bool(torch.isfinite(a[k]).all()) and float(a[k].min()) >= 0
+    assert bool((a['pa_mpjpe'] <= a['mpjpe'] + 1e-6).all())            # alignment never increases the error
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly on CPU tensors instead of routing anywhere else."""
     from whmr_b200 import ops

@@ -132,4 +132,26 @@ joint_errors_kernel(const float* __restrict__ pred, const float* __restrict__ gt
   pa_mpjpe[i] = (float)(acc / J);
 }
 
+// Per-vertex error (evaluate/eval.py:208-209): pve[i] = mean_v ||pred[i,v] - gt[i,v]||.  One CTA per frame; the
+// vertex distances are summed in a fixed order (per-thread strided partial sums, then a shared-memory tree), so the
+// result is deterministic.  HBM: 2 * 12 B per vertex.
+__global__ void __launch_bounds__(256)
+vertex_errors_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int V, float* __restrict__ pve) {
+  __shared__ float red[256];
+  const size_t base = (size_t)blockIdx.x * V * 3;
+  float acc = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    const float dx = pred[base + v * 3] - gt[base + v * 3], dy = pred[base + v * 3 + 1] - gt[base + v * 3 + 1],
+                dz = pred[base + v * 3 + 2] - gt[base + v * 3 + 2];
+    acc += sqrtf(dx * dx + dy * dy + dz * dz);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) pve[blockIdx.x] = red[0] / (float)V;
+}
+
 }  // namespace whmr

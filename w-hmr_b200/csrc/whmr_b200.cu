@@ -94,7 +94,9 @@ struct whmr_smpl_s {
   SmplDevice d{};
   DeviceArena arena;
   int gemm_mode = WHMR_GEMM_FP32_SIMT;
-  int chunk_bodies = 768;
+  int chunk_bodies = 768;         // two-kernel path: keeps the [chunk, 3*VP] pose-offset intermediate inside the L2
+  int chunk_bodies_fused = 4096;  // fused kernel: no intermediate; the chunk only bounds the read-out partial buffer
+  bool chunk_from_env = false;
   TcPlan tc{};   // tensor maps etc. for the tcgen05 path
   cudaEvent_t probe_chain = nullptr, probe_blend = nullptr, probe_skin = nullptr;
   bool skin_tc = true;   // tensor-core skinning (WHMR_SKIN=simt selects the CUDA-core kernel)
@@ -167,7 +169,7 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
   d.KP = std::max(16, ceil_div(nfeat + NB, 16) * 16);   // pose terms, then the NB shape coefficients, zero padded
   if (const char* e = getenv("WHMR_CHUNK_BODIES")) {
     const int c = atoi(e);
-    if (c >= 8) h->chunk_bodies = std::max(kTcBodyTile, c / kTcBodyTile * kTcBodyTile);   // whole 256-body tiles
+    if (c >= 8) { h->chunk_bodies = std::max(kTcBodyTile, c / kTcBodyTile * kTcBodyTile); h->chunk_from_env = true; }   // whole 256-body tiles
   }
 
   // kinematic tree depth
@@ -327,17 +329,20 @@ int whmr_smpl_get_info(whmr_smpl_t h, int32_t* n_verts, int32_t* n_joints, int32
 
 // ---- workspace carving --------------------------------------------------------------------
 static bool fused_applicable(const whmr_smpl_s* h);
+static int effective_chunk(const whmr_smpl_s* h) {
+  return (fused_applicable(h) && !h->chunk_from_env) ? h->chunk_bodies_fused : h->chunk_bodies;
+}
 
 static size_t carve(const whmr_smpl_s* h, int B, void* base, SmplWorkspace* ws) {
   const SmplDevice& d = h->d;
-  const int chunk = std::min(B, h->chunk_bodies);
+  const int chunk = std::min(B, effective_chunk(h));
   const int Bpad = ceil_div(std::max(B, 1), kTcBodyTile) * kTcBodyTile;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   const size_t oA = take((size_t)B * d.J * 12 * sizeof(float));
   const size_t oPf = take((size_t)B * d.KP * sizeof(float));
   const size_t oSplit = take((size_t)Bpad * 2 * d.KP * sizeof(float));   // sized for the tf32 variant
-  const size_t oOff = take((size_t)chunk * d.NP * sizeof(float));
+  const size_t oOff = take(fused_applicable(h) ? 16 : (size_t)chunk * d.NP * sizeof(float));   // unused by the fused kernel
   const size_t oAt = take((size_t)2 * Bpad * 12 * 32 * sizeof(float));
   const size_t oAt16 = take((size_t)Bpad * 12 * 64 * sizeof(__half));
   if (ws) {
@@ -588,6 +593,8 @@ int whmr_smpl_stage_pose_blend(whmr_smpl_t h, int B, void* workspace, size_t wor
   int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
   if (rc) return rc;
   if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(!fused_applicable(h), "whmr_smpl_stage_pose_blend: the handle runs pose blend + skinning as one kernel "
+                 "(no pose-offset intermediate); use whmr_smpl_forward, or WHMR_FUSED=0 / another gemm_mode for the stage API");
   WHMR_CHECK_ARG(B <= ws.chunk, "whmr_smpl_stage_pose_blend: B=%d exceeds the chunk size %d (stage calls are per chunk)", B,
                  ws.chunk);
   return launch_pose_blend(h, ws, B, 0, B, (cudaStream_t)stream);
@@ -600,6 +607,8 @@ int whmr_smpl_stage_skin(whmr_smpl_t h, const float* betas, int B, float* verts,
   if (rc) return rc;
   if (B == 0) return WHMR_OK;
   WHMR_CHECK_ARG(betas && verts, "whmr_smpl_stage_skin: null betas/verts");
+  WHMR_CHECK_ARG(!fused_applicable(h), "whmr_smpl_stage_skin: the handle runs pose blend + skinning as one kernel; use "
+                 "whmr_smpl_forward, or WHMR_FUSED=0 / another gemm_mode for the stage API");
   WHMR_CHECK_ARG(B <= ws.chunk, "whmr_smpl_stage_skin: B=%d exceeds the chunk size %d", B, ws.chunk);
   return launch_skin(h, ws, betas, nullptr, B, 0, B, verts, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -609,7 +618,7 @@ size_t whmr_readout_workspace_bytes(whmr_readout_t ro, int n_bodies) {
   return (size_t)n_bodies * ro->n_partial * 3 * sizeof(float) + 256;
 }
 
-int whmr_smpl_chunk_bodies(whmr_smpl_t h) { return h ? h->chunk_bodies : 0; }
+int whmr_smpl_chunk_bodies(whmr_smpl_t h) { return h ? effective_chunk(h) : 0; }
 
 int whmr_readout_finish(whmr_readout_t ro, const float* joints, int B, const void* ro_workspace, float* ro_out,
                         void* stream) {
@@ -1045,6 +1054,15 @@ int whmr_joint_errors(const float* pred, const float* gt, int n, int J, float* m
   WHMR_CHECK_ARG(pred && gt, "whmr_joint_errors: null pointer");
   joint_errors_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(pred, gt, n, J, mpjpe, pa_mpjpe);
   WHMR_LAUNCHED("joint_errors_kernel");
+  return WHMR_OK;
+}
+
+int whmr_vertex_errors(const float* pred, const float* gt, int n, int V, float* pve, void* stream) {
+  WHMR_CHECK_ARG(n >= 0 && V > 0, "whmr_vertex_errors: bad sizes n=%d V=%d", n, V);
+  if (n == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(pred && gt && pve, "whmr_vertex_errors: null pointer");
+  vertex_errors_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(pred, gt, V, pve);
+  WHMR_LAUNCHED("vertex_errors_kernel");
   return WHMR_OK;
 }
 

@@ -136,9 +136,7 @@ class SmplHandle:
             return verts, joints, A
         ro_flat = torch.empty(B * readout.R * 3, dtype=torch.float32, device=self.device)
         L = _lib.lib()
-        if not hasattr(self, "_chunk"):
-            self._chunk = int(L.whmr_smpl_chunk_bodies(self._h))
-        nro = int(L.whmr_readout_workspace_bytes(readout._h, min(B, self._chunk)))
+        nro = int(L.whmr_readout_workspace_bytes(readout._h, min(B, int(L.whmr_smpl_chunk_bodies(self._h)))))
         ro_ws = torch.empty(max(nro, 1), dtype=torch.uint8, device=self.device)
         deferred = C.c_int(0)
         with torch.cuda.device(self.device):
@@ -453,6 +451,18 @@ def joint_errors(pred, gt, want_pa=True):
     with torch.cuda.device(pred.device):
         check(_lib.lib().whmr_joint_errors(_p(pred), _p(gt), n, J, _p(mp), _p(pa), _stream()))
     return mp, pa
+
+
+def vertex_errors(pred, gt):
+    """PVE per frame (evaluate/eval.py:208-209): mean_v ||pred - gt||, pred/gt [n,V,3] -> [n]."""
+    pred, gt = _req(pred, "pred"), _req(gt, "gt")
+    if pred.shape != gt.shape:
+        raise ValueError("vertex_errors: shapes differ %s vs %s" % (tuple(pred.shape), tuple(gt.shape)))
+    n, V = pred.shape[0], pred.shape[1]
+    out = torch.empty(n, dtype=torch.float32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        check(_lib.lib().whmr_vertex_errors(_p(pred), _p(gt), n, V, _p(out), _stream()))
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
