@@ -195,12 +195,12 @@ struct ReduceParams {
   const float* partial; int n_partial;  // [chunk, n_partial, 3], n_partial % 4 == 0
 };
 
-__device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* ps, int b, int r, float& x, float& y,
-                                           float& z) {
+__device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* ps, const int* slots, int b, int r,
+                                           float& x, float& y, float& z) {
   const ReadoutParams& p = q.rp;
   x = y = z = 0.f;
   for (int k = q.part_ptr[r]; k < q.part_ptr[r + 1]; ++k) {
-    const float* e = ps + q.slot_of[k] * 3;
+    const float* e = ps + slots[k] * 3;      // slot list staged in shared memory: no dependent global load per term
     x += e[0]; y += e[1]; z += e[2];
   }
   for (int k = q.jt_ptr[r]; k < q.jt_ptr[r + 1]; ++k) {
@@ -216,21 +216,25 @@ __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
   pdl_trigger();
   const ReadoutParams& p = q.rp;
   const int b = blockIdx.x;
+  int* slots = reinterpret_cast<int*>(ps + q.n_partial * 3);   // [n_partial] emit slot of every vertex-sourced term
   {
     const float4* src = reinterpret_cast<const float4*>(q.partial + (size_t)b * q.n_partial * 3);
     float4* dst = reinterpret_cast<float4*>(ps);
     const int n4 = q.n_partial * 3 / 4;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+    const int4* ssrc = reinterpret_cast<const int4*>(q.slot_of);   // padded to n_partial entries by the host
+    int4* sdst = reinterpret_cast<int4*>(slots);
+    for (int i = threadIdx.x; i < q.n_partial / 4; i += blockDim.x) sdst[i] = ssrc[i];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < q.n_rows; i += blockDim.x) {
     const int r = q.rows[i];
     float x, y, z;
-    reduce_row(q, ps, b, r, x, y, z);
+    reduce_row(q, ps, slots, b, r, x, y, z);
     const int sr = p.sub_row ? p.sub_row[r] : -1;
     if (sr >= 0) {
       float sx, sy, sz;
-      reduce_row(q, ps, b, sr, sx, sy, sz);
+      reduce_row(q, ps, slots, b, sr, sx, sy, sz);
       x -= sx; y -= sy; z -= sz;
     }
     float* o = readout_dst(p, b, r);

@@ -458,7 +458,7 @@ static int launch_readout_reduce(whmr_readout_t r, const float* verts, const flo
   p.verts = verts; p.joints = joints; p.out = out;
   q.rows = r->rows_reduce; q.n_rows = r->n_reduce; q.part_ptr = r->part_ptr; q.partial = partial;
   q.n_partial = r->n_partial; q.slot_of = r->slot_of; q.jt_ptr = r->jt_ptr; q.jt_col = r->jt_col; q.jt_val = r->jt_val;
-  const size_t smem = (size_t)r->n_partial * 3 * sizeof(float);
+  const size_t smem = (size_t)r->n_partial * 4 * sizeof(float);   // partials [n_partial,3] + slot list [n_partial]
   launch_pdl(kPdlReadout, readout_reduce_kernel, dim3(nb), dim3(128), smem, st, q);
   WHMR_LAUNCHED("readout_reduce_kernel");
   return WHMR_OK;
@@ -852,7 +852,7 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   }
   // emit order: per group the one-hot entries sorted by destination (neighbouring lanes -> neighbouring output
   // slots), then the regressor terms, which get consecutive slots of the partial buffer
-  std::vector<int> emit_ptr(n_g32 + 1, 0), slot_of(std::max(n_terms, 1), 0);
+  std::vector<int> emit_ptr(n_g32 + 1, 0), slot_of(std::max(n_partial, 4), 0);   // padded: staged with 16-byte loads
   std::vector<EmitEntry> emit_entries;
   int next_slot = 0;
   for (int g = 0; g < n_g32; ++g) {
@@ -897,11 +897,11 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   up(rows_reduce, &h->rows_reduce); up(slot_of, &h->slot_of); up(jt_ptr, &h->jt_ptr); up(jt_col, &h->jt_col);
   up(jt_val, &h->jt_val);
   h->n_partial = n_partial; h->n_reduce = (int)rows_reduce.size();
-  h->fusable = (size_t)n_partial * 12 <= 200 * 1024;   // one body's partial array must fit in shared memory
+  h->fusable = (size_t)n_partial * 16 <= 200 * 1024;   // one body's partial array + slot list must fit in shared memory
   if (h->fusable) {
     static int reduce_smem_max = 48 * 1024;   // the attribute is per function: only ever raise it
-    if (n_partial * 12 > reduce_smem_max) {
-      reduce_smem_max = n_partial * 12;
+    if (n_partial * 16 > reduce_smem_max) {
+      reduce_smem_max = n_partial * 16;
       cudaFuncSetAttribute(readout_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, reduce_smem_max);
     }
   }
