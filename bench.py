@@ -417,8 +417,17 @@ def smpl_sweep(loop, dev, peaks, sizes):
     return res
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it may run on."""
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_loop_baseline(backbone, n_bodies, reps=3):
     import torch
+    use_all_host_threads()
     import whmr_b200.synthetic as syn
     from oracle.loop_oracle import LoopOracle, make_cpu_inputs
     model = syn.make_smpl_model(seed=0, weights="random")
@@ -446,6 +455,7 @@ def run_reference(args):
     import torch
     import whmr_b200.synthetic as syn
     from oracle.loop_oracle import LoopOracle, make_cpu_inputs
+    use_all_host_threads()
     n = args.cpu_sample
     K, W = args.steps if args.steps_given else 10, max(1, min(args.warmup, 3))
     K = min(K, 40)
