@@ -446,6 +446,108 @@ def cpu_loop_baseline(backbone, n_bodies, reps=3):
                       "torch %s CPU kernels, os.cpu_count()=%d" % (n_bodies, reps, t, torch.__version__, os.cpu_count())}
 
 
+def run_extra(args):
+    """Non-default workloads = the other BASELINE.json configs (parity-test cases; measured here for the record):
+      smpl_sweep   configs[2]: SMPL + H36M joint regression, 1k..64k bodies in total, sharded over the ranks
+      maf_sampling configs[3]: MAF_Extractor sampling of 431 points, 14/28/56 maps, 1024 bodies per rank, NCHW and NHWC
+      eval_pass    configs[4]: 35,515 frames GT SMPL + predicted SMPL + H36M 17->14 + MPJPE/PA-MPJPE/PVE, gathered."""
+    import torch
+    import torch.distributed as dist
+    import whmr_b200.synthetic as syn
+    from whmr_b200 import ops
+    from whmr_b200.dist import shard_bounds
+    from whmr_b200.evaluate import EvalPass
+    from whmr_b200.smpl import SMPL
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    model = syn.make_smpl_model(seed=0, weights="random")
+    smpl = SMPL(model=model).to(dev)
+    res = {"workload": args.workload, "n_gpus": world, "data": "synthetic", "dtype": "f32"}
+    if args.workload == "smpl_sweep":
+        ev = EvalPass(smpl, model["J_regressor_h36m"])
+        rows = {}
+        for total in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+            lo, hi = shard_bounds(total, rank, world)
+            b = syn.make_bodies(hi - lo, seed=5, rank=rank)
+            betas, rot = torch.from_numpy(b["betas"]).to(dev), torch.from_numpy(b["rotmat"]).to(dev)
+            ms = timed(lambda: ev.joints(betas, rot, True), 10)
+            bps = total / (ms * 1e-3)
+            rows[str(total)] = {"ms": ms, "bodies_per_s": bps, "per_gpu_bodies": hi - lo,
+                                "hbm_frac_algorithmic": bps / world * 84172 / 1e9 / peaks["hbm_gbs"],
+                                "tensor_frac_bf16x3": bps / world * 2.0 * KPOSE * 3 * V / 1e12 / (peaks["bf16_tflops_sustained"] / 3)}
+            del betas, rot
+        res.update(metric="smpl_h36m_bodies_per_sec", unit="bodies/s", sweep=rows)
+    elif args.workload == "maf_sampling":
+        B, N, C = 1024, 431, 256
+        pts = torch.from_numpy(syn.make_sample_points(B, N, seed=2, rank=rank)).to(dev)
+        rows = {}
+        for (H, W) in ((14, 14), (28, 28), (56, 56)):
+            feat = torch.randn(B, C, H, W, device=dev)
+            alg = B * (4 * C * (min(4 * N, H * W) + N) + 8 * N)
+            ms = timed(lambda: ops.sample_bilinear(feat, pts, ops.LAYOUT_NCHW), 20)
+            fl = feat.contiguous(memory_format=torch.channels_last)
+            ms2 = timed(lambda: ops.sample_bilinear(fl, pts, ops.LAYOUT_NCHW), 20)   # channels_last -> NHWC kernel, no copy
+            rows["%dx%d" % (H, W)] = {"nchw_ms": ms, "nchw_GBs_algorithmic": alg / ms / 1e6, "nchw_frac": alg / ms / 1e6 / peaks["hbm_gbs"],
+                                      "channels_last_ms": ms2, "channels_last_GBs_algorithmic": alg / ms2 / 1e6,
+                                      "channels_last_frac": alg / ms2 / 1e6 / peaks["hbm_gbs"],
+                                      "bodies_per_s_nchw": world * B / (ms * 1e-3)}
+            del feat, fl
+        res.update(metric="maf_sampling_431pts", unit="ms per level (1024 bodies per GPU)", levels=rows)
+    elif args.workload == "eval_pass":
+        Nf = 35515
+        ev = EvalPass(smpl, model["J_regressor_h36m"])
+        lo, hi = shard_bounds(Nf, rank, world)
+        gt, pr = syn.make_bodies(hi - lo, seed=31, rank=rank), syn.make_bodies(hi - lo, seed=32, rank=rank)
+        # per-rank shard resident on the device (the reference's loader feeds batches of 32, evaluate/eval.py:155)
+        T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        import numpy as np
+        g_pose, g_betas, p_rot, p_betas = T(gt["pose_aa"]), T(gt["betas"]), T(pr["rotmat"]), T(pr["betas"])
+        from whmr_b200.dist import all_gather_rows
+
+        def one_pass():
+            parts = []
+            for a in range(0, hi - lo, 4096):
+                r = ev(g_pose[a:a + 4096], g_betas[a:a + 4096], p_rot[a:a + 4096], p_betas[a:a + 4096])
+                parts.append(torch.stack([r["mpjpe"], r["pa_mpjpe"], r["pve"]], dim=1))
+            return all_gather_rows(torch.cat(parts), Nf)
+        ms = timed(one_pass, 5)
+        full = one_pass()
+        res.update(metric="eval_frames_per_sec", unit="frames/s", value=Nf / (ms * 1e-3), ms_per_pass=ms, frames=Nf,
+                   gathered_shape=list(full.shape),
+                   mean_mm={"mpjpe": float(full[:, 0].mean()) * 1e3, "pa_mpjpe": float(full[:, 1].mean()) * 1e3,
+                            "pve": float(full[:, 2].mean()) * 1e3},
+                   note="2 SMPL forwards + H36M read-outs + MPJPE/PA-MPJPE/PVE per frame, NCCL all_gather of [n,3] errors")
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path = the oracle port (smplx / pare / the SMPL
     weights are not installable offline, so the reference itself cannot run)."""
@@ -497,6 +599,8 @@ def main():
     ap.add_argument("--skip-sweep", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--workload", default="regressor_loop", choices=["regressor_loop", "smpl_sweep", "maf_sampling", "eval_pass"],
+                    help="regressor_loop = BASELINE configs[1] (the bench contract); the others are the remaining configs")
     ap.add_argument("--channels-last", action="store_true",
                     help="feature maps in torch.channels_last memory format (reported separately; the contract layout is NCHW)")
     args = ap.parse_args()
@@ -505,6 +609,8 @@ def main():
         args.steps = 1000
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "regressor_loop":
+        run_extra(args)
     else:
         run_ours(args)
 

@@ -11,6 +11,10 @@
 //  * NHWC: lanes run over channels so every tap is a coalesced 128 B read; the [points x channels]
 //    tile is transposed through shared memory so the [B,C,N] store is coalesced too.
 #pragma once
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace whmr {
@@ -110,6 +114,65 @@ sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restr
   }
 }
 
+// Dense regime (4N >= H*W: the 431 down-sampled vertices on 14x14 / 28x28 maps, BASELINE configs[3]): nearly every
+// pixel of a plane is a tap of some point, and the direct gather is bound by L1 wavefronts (32 lanes hit ~7 cache
+// lines of one small plane per load), not by memory.  Here a CTA stages CG whole channel planes of one body in shared
+// memory -- consecutive channels are contiguous in NCHW, so this is one coalesced 16-byte-vector stream and every byte
+// of the map is read exactly once -- and gathers the taps from shared memory.  A thread keeps the taps of its point(s)
+// in registers across the CG channels; for a fixed channel consecutive threads write consecutive n (coalesced).
+// Same arithmetic order as the gather kernel: results are bit-identical.
+// grid = (ceil(C / CG), B), block 256, dynamic smem = CG*H*W*4.
+template <bool kProject>
+__global__ void __launch_bounds__(256)
+sample_bilinear_nchw_staged_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
+                                   float* __restrict__ out, int C, int H, int W, int N, int CG, SampleProj pj) {
+  extern __shared__ __align__(16) float planes[];   // [CG][H*W]
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y, c0 = blockIdx.x * CG;
+  const int cg = min(CG, C - c0);
+  const int HW = H * W;
+  const float* src = feat + ((size_t)b * C + c0) * HW;
+  const int total = cg * HW;
+  if ((reinterpret_cast<size_t>(src) & 15) == 0 && (total & 3) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(planes);
+    for (int i = threadIdx.x; i < (total >> 2); i += 256) d4[i] = __ldg(s4 + i);
+  } else {
+    for (int i = threadIdx.x; i < total; i += 256) planes[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  float cs = 0.f, ctx = 0.f, cty = 0.f, ctz = 0.f;
+  if (kProject) {   // utils/geometry.py:289-307
+    cs = pj.cam[b * 3 + 0]; ctx = pj.cam[b * 3 + 1]; cty = pj.cam[b * 3 + 2];
+    ctz = 2.0f * pj.focal / (pj.img_h * cs + 1e-9f);
+  }
+  const float* pb = points + (size_t)b * pts_bstride;
+  for (int n = threadIdx.x; n < N; n += 256) {
+    float2 g;
+    if (kProject) {
+      const float* q = pb + (size_t)n * 3;
+      const float px = q[0] + ctx, py = q[1] + cty, pz = q[2] + ctz;
+      g.x = (pj.focal * (px / pz)) / (pj.img_w * 0.5f);
+      g.y = (pj.focal * (py / pz)) / (pj.img_h * 0.5f);
+      if (pj.pts2d_out && blockIdx.x == 0) *reinterpret_cast<float2*>(pj.pts2d_out + ((size_t)b * N + n) * 2) = g;
+    } else {
+      g = *reinterpret_cast<const float2*>(pb + (size_t)n * 2);
+    }
+    const Taps tp = make_taps(g.x, g.y, H, W);
+    float* ob = out + ((size_t)b * C + c0) * N + n;
+#pragma unroll 4
+    for (int c = 0; c < cg; ++c) {
+      const float* pl = planes + c * HW;
+      float acc = pl[tp.o00] * tp.w00;
+      acc = fmaf(pl[tp.o01], tp.w01, acc);
+      acc = fmaf(pl[tp.o10], tp.w10, acc);
+      acc = fmaf(pl[tp.o11], tp.w11, acc);
+      ob[(size_t)c * N] = acc;
+    }
+  }
+}
+
 // NHWC input: grid = (ceil(N/32), ceil(C/64), B), block 256 (8 warps x 4 points each)
 __global__ void __launch_bounds__(256)
 sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
@@ -149,6 +212,30 @@ sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restr
     const int c = c0 + cl, n = n0 + lane;
     if (c < C && n < N) out[((size_t)b * C + c) * N + n] = tile[cl][lane];
   }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+// Dense regime of the NCHW sampler (sampling.cuh): channels per CTA for the shared-memory-staged kernel, or 0 when
+// the direct gather is the better kernel (sparse sampling, or planes too large to stage a useful number of).
+static int staged_channels(int C, int H, int W, int N) {
+  static const int mode = getenv("WHMR_SAMPLE_STAGED") ? atoi(getenv("WHMR_SAMPLE_STAGED")) : -1;   // 0 never, 1 whenever it fits
+  if (mode == 0) return 0;
+  const long long HW = (long long)H * W;
+  if (mode != 1 && 4LL * N < HW) return 0;
+  const int cg = (int)std::min<long long>(C, (64 * 1024) / (HW * 4));
+  return cg >= 4 ? cg : 0;
+}
+
+template <bool kProject>
+static void launch_staged(const float* feat, const float* points, int pts_bstride, float* out, int B, int C, int H, int W,
+                          int N, int cg, SampleProj pj, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(sample_bilinear_nchw_staged_kernel<kProject>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr_set = true;
+  }
+  launch_pdl(kPdlSample, sample_bilinear_nchw_staged_kernel<kProject>, dim3(ceil_div(C, cg), B), dim3(256),
+             (size_t)cg * H * W * sizeof(float), st, feat, points, pts_bstride, out, C, H, W, N, cg, pj);
 }
 
 }  // namespace whmr

@@ -1014,6 +1014,11 @@ int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int
   WHMR_CHECK_ARG((long long)C * N < (1ll << 31) && B < 65536, "whmr_sample_bilinear: C*N or B too large");
   cudaStream_t st = (cudaStream_t)stream;
   if (layout == WHMR_LAYOUT_NCHW) {
+    if (const int cg = staged_channels(C, H, W, N)) {
+      launch_staged<false>(feat, points, pts_bstride, out, B, C, H, W, N, cg, SampleProj{}, st);
+      WHMR_LAUNCHED("sample_bilinear_nchw_staged_kernel");
+      return WHMR_OK;
+    }
     dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
     launch_pdl(kPdlSample, sample_bilinear_nchw_kernel<false>, grid, dim3(256), 0, st, feat, points, pts_bstride, out, C, H, W, N, SampleProj{});
     WHMR_LAUNCHED("sample_bilinear_nchw_kernel");
@@ -1033,8 +1038,13 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
     WHMR_CHECK_ARG(feat && p && cam && out, "whmr_project_sample: null pointer");
     WHMR_CHECK_ARG((long long)C * N < (1ll << 31) && B < 65536, "whmr_project_sample: C*N or B too large");
     WHMR_CHECK_ARG(!points2d_out || (reinterpret_cast<size_t>(points2d_out) & 7) == 0, "whmr_project_sample: points2d_out must be 8-byte aligned");
-    dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
     SampleProj pj{cam, focal, img_w, img_h, points2d_out};
+    if (const int cg = staged_channels(C, H, W, N)) {
+      launch_staged<true>(feat, p, N * 3, out, B, C, H, W, N, cg, pj, (cudaStream_t)stream);
+      WHMR_LAUNCHED("sample_bilinear_nchw_staged_kernel<project>");
+      return WHMR_OK;
+    }
+    dim3 grid(ceil_div(C * N, 256 * kSampleItems), B);
     launch_pdl(kPdlSample, sample_bilinear_nchw_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, feat, p, N * 3, out, C, H, W, N, pj);
     WHMR_LAUNCHED("sample_bilinear_nchw_kernel<project>");
     return WHMR_OK;
