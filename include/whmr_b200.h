@@ -239,6 +239,26 @@ int whmr_joint_errors(const float* pred, const float* gt, int n, int J, float* m
 /* PVE, evaluate/eval.py:208-209: pve[n] = mean_v ||pred[n,v,:] - gt[n,v,:]||;  pred, gt [n,V,3] */
 int whmr_vertex_errors(const float* pred, const float* gt, int n, int V, float* pve, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Backward entry points (what core/trainer.py:380-636 needs to train through the drop-ins).
+ * Reference graph (models/whmr.py:145-173, 586-591): projections see detached joints (gradient -> pred_cam, Tz),
+ * sampling points are detached (gradient -> feature maps), SMPL vertices/joints -> betas / rotation matrices.
+ * ------------------------------------------------------------------------------------------ */
+/* utils/geometry.py:289-307.  g_out [B,N,2] -> g_points [B,N,3] (or NULL), g_cam [B,3] */
+int whmr_project_weak_backward(const float* points, const float* cam, const float* g_out, int B, int N, float focal,
+                               float img_w, float img_h, float* g_points, float* g_cam, void* stream);
+/* models/whmr.py:142-173 (whmr_project_weak_full / whmr_project_full).  Upstream gradients may be NULL.
+ * -> g_points [B,N,3] (or NULL), g_cam [B,3], g_Tz [B] */
+int whmr_project_full_backward(const float* points, const float* cam, const float* bbox_height, const float* center,
+                               const float* orig_shape, const float* Tz, int B, int N, float weak_focal,
+                               float weak_img_w, float weak_img_h, const float* g_kp_weak, const float* g_kp_norm,
+                               const float* g_focal, const float* g_cam_t, float* g_points, float* g_cam, float* g_Tz,
+                               void* stream);
+/* models/maf_extractor.py:119 w.r.t. the feature maps.  g_out [B,C,N]; g_feat (layout as the forward's feat) must be
+ * zero-filled by the caller; fp32 atomics (summation order over points sharing a pixel is not fixed). */
+int whmr_sample_bilinear_backward(const float* g_out, int layout, int B, int C, int H, int W, const float* points,
+                                  int points_shared, int N, float* g_feat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -422,6 +422,82 @@ def test_eval_pass_matches_oracle(dev, smpl_model):
     assert bool((a['pa_mpjpe'] <= a['mpjpe'] + 1e-6).all())            # alignment never increases the error
 
 
+# ------------------------------------------------------------------------------------------ backward
+def test_projection_backward_matches_autograd_of_oracle(dev):
+    """d(weak projection)/d(points, cam) and d(weak + predicted-focal block)/d(points, cam, Tz) against torch autograd
+    through the float64 oracle (utils/geometry.py:289-307, models/whmr.py:147-173 restated)."""
+    from oracle import geometry_oracle as G
+    from whmr_b200 import constants, ops
+    import whmr_b200.synthetic as syn
+    B, N = 7, 49
+    b = syn.make_bodies(B, seed=41)
+    rng = np.random.default_rng(5)
+    pts = rng.normal(0, 0.4, size=(B, N, 3)).astype(np.float32)
+    T = lambda a, g=False: torch.from_numpy(np.ascontiguousarray(a)).to(dev).requires_grad_(g)  # noqa: E731
+    # (the geometry oracle builds float32 constants, as the reference does: autograd reference in float32)
+    D = lambda a, g=False: torch.from_numpy(np.ascontiguousarray(a)).float().requires_grad_(g)  # noqa: E731
+    gk = rng.normal(size=(B, N, 2)).astype(np.float32)
+    gw = rng.normal(size=(B, N, 2)).astype(np.float32)
+    gf = rng.normal(size=(B,)).astype(np.float32)
+    gt = rng.normal(size=(B, 3)).astype(np.float32)
+    # weak projection
+    p, c = T(pts, True), T(b['cam'], True)
+    out = ops.project_weak_op(p, c, constants.FOCAL_LENGTH, 256., 256.)
+    out.backward(T(gk))
+    p64, c64 = D(pts, True), D(b['cam'], True)
+    G.projection(p64, c64).backward(D(gk))
+    rel = lambda a, r: float((a.detach().cpu().double() - r).abs().max() / (r.abs().max() + 1e-30))  # noqa: E731
+    assert rel(p.grad, p64.grad) <= 1e-4 and rel(c.grad, c64.grad) <= 1e-4
+    # weak + full block, all four outputs feeding the loss
+    p, c, tz = T(pts, True), T(b['cam'], True), T(b['Tz'], True)
+    kp, kpw, fl, cam_t = ops.project_weak_full_op(p, c, T(b['bbox_height']), T(b['center']), T(b['orig_shape']), tz,
+                                                  constants.FOCAL_LENGTH, 256., 256.)
+    ((kp * T(gk)).sum() + (kpw * T(gw)).sum() + (fl * T(gf)).sum() + (cam_t * T(gt)).sum()).backward()
+    p64, c64, tz64 = D(pts, True), D(b['cam'], True), D(b['Tz'], True)
+    kn, f64, ct64, _ = G.full_projection(p64, c64, D(b['bbox_height']), D(b['center']), D(b['orig_shape']), tz64)
+    ((G.projection(p64, c64) * D(gk)).sum() + (kn * D(gw)).sum() + (f64 * D(gf)).sum() + (ct64 * D(gt)).sum()).backward()
+    assert rel(p.grad, p64.grad) <= 1e-4
+    assert rel(c.grad, c64.grad) <= 1e-4
+    assert rel(tz.grad, tz64.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("layout", ["nchw", "channels_last", "shared_grid"])
+def test_sampling_backward_matches_grid_sample_autograd(dev, layout):
+    """d(sample_bilinear)/d(feature map) against autograd through F.grid_sample (the reference's call,
+    models/maf_extractor.py:119); points are detached in the reference (models/whmr.py:586-591)."""
+    from oracle.sampling_oracle import grid_sample_points
+    from whmr_b200 import constants, ops
+    import whmr_b200.synthetic as syn
+    B, C, H, W, N = 3, 32, 16, 12, 67
+    g = torch.Generator().manual_seed(9)
+    feat = torch.randn(B, C, H, W, generator=g)
+    pts = torch.from_numpy(syn.make_sample_points(B, N, seed=7))
+    if layout == "shared_grid":
+        pts = pts[:1].expand(B, -1, -1).contiguous()
+    go = torch.randn(B, C, N, generator=g)
+    f64 = feat.double().requires_grad_(True)
+    grid_sample_points(f64, pts.double()).backward(go.double())
+    fd = feat.to(dev)
+    if layout == "channels_last":
+        fd = fd.contiguous(memory_format=torch.channels_last)
+    fd.requires_grad_(True)
+    pd = pts[0].to(dev) if layout == "shared_grid" else pts.to(dev)
+    out = ops.sample_bilinear_op(fd, pd, ops.LAYOUT_NCHW)
+    out.backward(go.to(dev))
+    assert fd.grad.shape == feat.shape
+    assert _maxabs(fd.grad, f64.grad) <= 1e-5 * float(f64.grad.abs().max())
+    # MAF_Extractor.forward path: projection fused into the sampling launch
+    b = syn.make_bodies(B, seed=43)
+    p3 = torch.from_numpy(np.random.default_rng(2).normal(0, 0.35, size=(B, N, 3)).astype(np.float32))
+    fd2 = feat.to(dev).requires_grad_(True)
+    pf, p2d = ops.project_sample_op(fd2, p3.to(dev), torch.from_numpy(b['cam']).to(dev), constants.FOCAL_LENGTH, 256., 256.,
+                                    ops.LAYOUT_NCHW)
+    pf.backward(go.to(dev))
+    f64b = feat.double().requires_grad_(True)
+    grid_sample_points(f64b, p2d.detach().cpu().double()).backward(go.double())
+    assert _maxabs(fd2.grad, f64b.grad) <= 1e-5 * float(f64b.grad.abs().max())
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly on CPU tensors instead of routing anywhere else."""
     from whmr_b200 import ops

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "backward.cuh"
 #include "metrics.cuh"
 #include "pose_blend_simt.cuh"
 #include "pose_blend_tc.cuh"
@@ -1073,6 +1074,59 @@ int whmr_vertex_errors(const float* pred, const float* gt, int n, int V, float* 
   WHMR_CHECK_ARG(pred && gt && pve, "whmr_vertex_errors: null pointer");
   vertex_errors_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(pred, gt, V, pve);
   WHMR_LAUNCHED("vertex_errors_kernel");
+  return WHMR_OK;
+}
+
+// =============================================================================================
+// backward
+// =============================================================================================
+int whmr_project_weak_backward(const float* points, const float* cam, const float* g_out, int B, int N, float focal,
+                               float img_w, float img_h, float* g_points, float* g_cam, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_weak_backward: negative size");
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(points && cam && g_out && g_cam, "whmr_project_weak_backward: null pointer");
+  project_weak_bwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(points, cam, g_out, N, focal, img_w, img_h, g_points, g_cam);
+  WHMR_LAUNCHED("project_weak_bwd_kernel");
+  return WHMR_OK;
+}
+
+int whmr_project_full_backward(const float* points, const float* cam, const float* bbox_height, const float* center,
+                               const float* orig_shape, const float* Tz, int B, int N, float weak_focal,
+                               float weak_img_w, float weak_img_h, const float* g_kp_weak, const float* g_kp_norm,
+                               const float* g_focal, const float* g_cam_t, float* g_points, float* g_cam, float* g_Tz,
+                               void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_full_backward: negative size");
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(points && cam && bbox_height && center && orig_shape && Tz && g_cam && g_Tz,
+                 "whmr_project_full_backward: null pointer");
+  project_full_bwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(points, cam, bbox_height, center, orig_shape, Tz, N, weak_focal,
+                                                              weak_img_w, weak_img_h, g_kp_weak, g_kp_norm, g_focal, g_cam_t,
+                                                              g_points, g_cam, g_Tz);
+  WHMR_LAUNCHED("project_full_bwd_kernel");
+  return WHMR_OK;
+}
+
+int whmr_sample_bilinear_backward(const float* g_out, int layout, int B, int C, int H, int W, const float* points,
+                                  int points_shared, int N, float* g_feat, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && H > 0 && W > 0, "whmr_sample_bilinear_backward: bad sizes");
+  WHMR_CHECK_ARG(layout == WHMR_LAYOUT_NCHW || layout == WHMR_LAYOUT_NHWC, "whmr_sample_bilinear_backward: bad layout %d", layout);
+  if (B == 0 || C == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(g_out && points && g_feat, "whmr_sample_bilinear_backward: null pointer");
+  WHMR_CHECK_ARG((reinterpret_cast<size_t>(points) & 7) == 0, "whmr_sample_bilinear_backward: points must be 8-byte aligned");
+  WHMR_CHECK_ARG(B < 65536, "whmr_sample_bilinear_backward: B too large");
+  const int pts_bstride = points_shared ? 0 : N * 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layout == WHMR_LAYOUT_NCHW) {
+    const long long total = (long long)C * N;
+    dim3 grid((unsigned)std::min<long long>((total + 255) / 256, 1024), B);
+    sample_bilinear_bwd_nchw_kernel<<<grid, 256, 0, st>>>(g_out, points, pts_bstride, g_feat, C, H, W, N);
+    WHMR_LAUNCHED("sample_bilinear_bwd_nchw_kernel");
+  } else {
+    const long long warps = (long long)B * N;
+    sample_bilinear_bwd_nhwc_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(g_out, points, pts_bstride, g_feat, B, C,
+                                                                                       H, W, N);
+    WHMR_LAUNCHED("sample_bilinear_bwd_nhwc_kernel");
+  }
   return WHMR_OK;
 }
 

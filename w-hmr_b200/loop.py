@@ -58,7 +58,7 @@ class RegressorLoop:
             if it == 0:
                 pf = ops.sample_bilinear_op(feats[0], self.grid, self.layout)                # :596-597
             else:                                                                            # :606
-                pf, _ = ops.project_sample(feats[it], out['markers'], p[it]['cam'], constants.FOCAL_LENGTH,
+                pf, _ = ops.project_sample_op(feats[it], out['markers'], p[it]['cam'], constants.FOCAL_LENGTH,
                                            float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT),
                                            self.layout)   # projection fused into the sampling launch
             self.head._mark('sample_l%d' % it)

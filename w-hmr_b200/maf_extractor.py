@@ -70,7 +70,7 @@ class MAF_Extractor(nn.Module):
         if cam is None:
             cam = self.cam
         im_feat = self.im_feat if s_feat is None else s_feat
-        point_feat, _ = ops.project_sample(im_feat, p, cam, constants.FOCAL_LENGTH,
+        point_feat, _ = ops.project_sample_op(im_feat, p, cam, constants.FOCAL_LENGTH,
                                            float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT),
                                            self.layout)
         return self.reduce_dim(point_feat), point_feat

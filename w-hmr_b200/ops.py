@@ -536,6 +536,62 @@ def _(feat, points, layout):
     return feat.new_empty(feat.shape[0], Cc, points.shape[-2])
 
 
+def _sample_backward(g_out, feat, points, layout):
+    """gradient of sample_bilinear w.r.t. feat (same shape and memory layout as feat); points [B,N,2] or shared [N,2]"""
+    feat_k, lay, B, Cc, H, W = _feat_layout(feat, layout)
+    g_feat = torch.zeros_like(feat_k)            # preserves channels_last strides
+    g_out = _req(g_out, "grad_out")
+    points = _req(points, "points", align=8)
+    shared = points.dim() == 2 or (points.shape[0] == 1 and B != 1)
+    N = points.shape[-2]
+    with torch.cuda.device(feat.device):
+        check(_lib.lib().whmr_sample_bilinear_backward(_p(g_out), int(lay), B, Cc, H, W, _p(points), int(shared), N,
+                                                       _p(g_feat), _stream()))
+    return g_feat
+
+
+def _sample_setup(ctx, inputs, output):
+    feat, points, layout = inputs
+    ctx.save_for_backward(feat, points)
+    ctx.layout = layout
+
+
+def _sample_bwd(ctx, g):
+    feat, points = ctx.saved_tensors
+    return _sample_backward(g, feat, points.detach(), ctx.layout), None, None
+
+
+# the reference detaches the sampling points (models/whmr.py:586-591): the gradient goes to the feature maps only
+sample_bilinear_op.register_autograd(_sample_bwd, setup_context=_sample_setup)
+
+
+@torch.library.custom_op("whmr::project_sample", mutates_args=(), device_types="cuda")
+def project_sample_op(feat: torch.Tensor, p: torch.Tensor, cam: torch.Tensor, focal: float, img_w: float, img_h: float,
+                      layout: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """MAF_Extractor.forward: weak projection of the mesh points + sampling -> (point_feat [B,C,N], points2d [B,N,2])"""
+    return project_sample(feat, p, cam, focal, img_w, img_h, layout)
+
+
+@project_sample_op.register_fake
+def _(feat, p, cam, focal, img_w, img_h, layout):
+    Cc = feat.shape[1] if layout == LAYOUT_NCHW else feat.shape[3]
+    return feat.new_empty(feat.shape[0], Cc, p.shape[1]), feat.new_empty(feat.shape[0], p.shape[1], 2)
+
+
+def _psample_setup(ctx, inputs, output):
+    feat, p, cam, focal, img_w, img_h, layout = inputs
+    ctx.save_for_backward(feat, output[1])
+    ctx.layout = layout
+
+
+def _psample_bwd(ctx, g_feat_out, g_pts):
+    feat, pts2d = ctx.saved_tensors
+    return _sample_backward(g_feat_out, feat, pts2d.detach(), ctx.layout), None, None, None, None, None, None
+
+
+project_sample_op.register_autograd(_psample_bwd, setup_context=_psample_setup)
+
+
 @torch.library.custom_op("whmr::project_weak", mutates_args=(), device_types="cuda")
 def project_weak_op(points: torch.Tensor, cam: torch.Tensor, focal: float, img_w: float, img_h: float) -> torch.Tensor:
     return project_weak(points, cam, focal, img_w, img_h)
@@ -544,3 +600,95 @@ def project_weak_op(points: torch.Tensor, cam: torch.Tensor, focal: float, img_w
 @project_weak_op.register_fake
 def _(points, cam, focal, img_w, img_h):
     return points.new_empty(points.shape[0], points.shape[1], 2)
+
+
+@torch.library.custom_op("whmr::project_weak_backward", mutates_args=(), device_types="cuda")
+def project_weak_backward(points: torch.Tensor, cam: torch.Tensor, g_out: torch.Tensor, focal: float, img_w: float,
+                          img_h: float) -> tuple[torch.Tensor, torch.Tensor]:
+    points, cam, g_out = _req(points, "points"), _req(cam, "cam"), _req(g_out, "grad_out")
+    B, N = points.shape[0], points.shape[1]
+    g_points = torch.empty_like(points)
+    g_cam = torch.empty(B, 3, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().whmr_project_weak_backward(_p(points), _p(cam), _p(g_out), B, N, float(focal), float(img_w),
+                                                    float(img_h), _p(g_points), _p(g_cam), _stream()))
+    return g_points, g_cam
+
+
+@project_weak_backward.register_fake
+def _(points, cam, g_out, focal, img_w, img_h):
+    return torch.empty_like(points), cam.new_empty(points.shape[0], 3)
+
+
+def _pw_setup(ctx, inputs, output):
+    points, cam, focal, img_w, img_h = inputs
+    ctx.save_for_backward(points, cam)
+    ctx.consts = (focal, img_w, img_h)
+
+
+def _pw_bwd(ctx, g):
+    points, cam = ctx.saved_tensors
+    g_points, g_cam = project_weak_backward(points, cam, g.contiguous(), *ctx.consts)
+    return g_points, g_cam, None, None, None
+
+
+project_weak_op.register_autograd(_pw_bwd, setup_context=_pw_setup)
+
+
+@torch.library.custom_op("whmr::project_weak_full", mutates_args=(), device_types="cuda")
+def project_weak_full_op(points: torch.Tensor, cam: torch.Tensor, bbox_height: torch.Tensor, center: torch.Tensor,
+                         orig_shape: torch.Tensor, Tz: torch.Tensor, focal: float, img_w: float, img_h: float) -> \
+        tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """weak projection + predicted-focal block (models/whmr.py:142-173) -> (kp_2d, kp_2d_w, focal_length, cam_t)"""
+    return project_weak_full(points, cam, bbox_height, center, orig_shape, Tz, focal, img_w, img_h)
+
+
+@project_weak_full_op.register_fake
+def _(points, cam, bbox_height, center, orig_shape, Tz, focal, img_w, img_h):
+    B, N = points.shape[0], points.shape[1]
+    return points.new_empty(B, N, 2), points.new_empty(B, N, 2), points.new_empty(B), points.new_empty(B, 3)
+
+
+@torch.library.custom_op("whmr::project_full_backward", mutates_args=(), device_types="cuda")
+def project_full_backward(points: torch.Tensor, cam: torch.Tensor, bbox_height: torch.Tensor, center: torch.Tensor,
+                          orig_shape: torch.Tensor, Tz: torch.Tensor, focal: float, img_w: float, img_h: float,
+                          g_kp_weak: torch.Tensor, g_kp_norm: torch.Tensor, g_focal: torch.Tensor,
+                          g_cam_t: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    points = _req(points, "points")
+    B, N = points.shape[0], points.shape[1]
+    args = [_req(x, n) for x, n in ((cam, "cam"), (bbox_height, "bbox_height"), (center, "center"),
+                                    (orig_shape, "orig_shape"), (Tz, "Tz"))]
+    gs = [_req(x, n) for x, n in ((g_kp_weak, "g_kp_weak"), (g_kp_norm, "g_kp_norm"), (g_focal, "g_focal"),
+                                  (g_cam_t, "g_cam_t"))]
+    g_points = torch.empty_like(points)
+    g_cam = torch.empty(B, 3, dtype=torch.float32, device=points.device)
+    g_Tz = torch.empty(B, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(_lib.lib().whmr_project_full_backward(_p(points), *[_p(a) for a in args], B, N, float(focal), float(img_w),
+                                                    float(img_h), *[_p(g) for g in gs], _p(g_points), _p(g_cam), _p(g_Tz),
+                                                    _stream()))
+    return g_points, g_cam, g_Tz
+
+
+@project_full_backward.register_fake
+def _(points, cam, bbox_height, center, orig_shape, Tz, focal, img_w, img_h, g_kp_weak, g_kp_norm, g_focal, g_cam_t):
+    return torch.empty_like(points), cam.new_empty(points.shape[0], 3), cam.new_empty(points.shape[0])
+
+
+def _pwf_setup(ctx, inputs, output):
+    points, cam, bbox_height, center, orig_shape, Tz, focal, img_w, img_h = inputs
+    ctx.save_for_backward(points, cam, bbox_height, center, orig_shape, Tz)
+    ctx.consts = (focal, img_w, img_h)
+
+
+def _pwf_bwd(ctx, g_kp, g_kpw, g_focal, g_cam_t):
+    points, cam, bbox_height, center, orig_shape, Tz = ctx.saved_tensors
+    B, N = points.shape[0], points.shape[1]
+    z = lambda g, shape: g.contiguous() if g is not None else points.new_zeros(shape)  # noqa: E731
+    g_points, g_cam, g_Tz = project_full_backward(points, cam, bbox_height, center, orig_shape, Tz, *ctx.consts,
+                                                  z(g_kp, (B, N, 2)), z(g_kpw, (B, N, 2)), z(g_focal, (B,)),
+                                                  z(g_cam_t, (B, 3)))
+    return g_points, g_cam, None, None, None, g_Tz, None, None, None
+
+
+project_weak_full_op.register_autograd(_pwf_bwd, setup_context=_pwf_setup)

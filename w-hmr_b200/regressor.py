@@ -114,7 +114,7 @@ class BodyModelHead(nn.Module):
         self._mark('skin_readout')
         pred_joints = r['joints']
         if bbox_height is not None:   # Regressor.forward: weak + predicted-focal projection, one launch
-            kp_2d, kp_w, focal, cam_t = ops.project_weak_full(
+            kp_2d, kp_w, focal, cam_t = ops.project_weak_full_op(
                 pred_joints, pred_cam, bbox_height, center, orig_shape, Tz, constants.FOCAL_LENGTH,
                 float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
             self._mark('project_weak_full')
