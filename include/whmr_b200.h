@@ -244,6 +244,18 @@ int whmr_vertex_errors(const float* pred, const float* gt, int n, int V, float* 
  * Reference graph (models/whmr.py:145-173, 586-591): projections see detached joints (gradient -> pred_cam, Tz),
  * sampling points are detached (gradient -> feature maps), SMPL vertices/joints -> betas / rotation matrices.
  * ------------------------------------------------------------------------------------------ */
+/* SMPL.forward in rotation-matrix mode (models/whmr.py:132-137): gradients of the vertices and of the posed chain
+ * joints w.r.t. betas and the rotation matrices.  g_verts [B,V,3] and/or g_joints [B,J,3] may be NULL (= zero).
+ * -> g_betas [B,n_betas], g_pose [B,J,9].  Scratch: whmr_smpl_backward_workspace_bytes(h, B). */
+size_t whmr_smpl_backward_workspace_bytes(whmr_smpl_t h, int B);
+int whmr_smpl_backward(whmr_smpl_t h, const float* betas, const float* pose, int B, const float* g_verts,
+                       const float* g_joints, float* g_betas, float* g_pose, void* workspace, size_t workspace_bytes,
+                       void* stream);
+/* Transposed read-out: accumulates (atomics) the gradient of every read-out row into g_verts [B,V,3] and
+ * g_joints [B,J,3] (may be NULL if no row references a chain joint); both must be initialised by the caller
+ * (zeros, or the direct gradients of vertices / chain joints).  g_out: flat group-major buffer as produced by
+ * whmr_readout_apply / whmr_smpl_forward_readout. */
+int whmr_readout_backward(whmr_readout_t ro, const float* g_out, int B, float* g_verts, float* g_joints, void* stream);
 /* utils/geometry.py:289-307.  g_out [B,N,2] -> g_points [B,N,3] (or NULL), g_cam [B,3] */
 int whmr_project_weak_backward(const float* points, const float* cam, const float* g_out, int B, int N, float focal,
                                float img_w, float img_h, float* g_points, float* g_cam, void* stream);

@@ -498,6 +498,110 @@ def test_sampling_backward_matches_grid_sample_autograd(dev, layout):
     assert _maxabs(fd2.grad, f64b.grad) <= 1e-5 * float(f64b.grad.abs().max())
 
 
+class _default_f64:
+    """the geometry oracle creates its constants (eye, camera centre) in the default dtype, as the reference does"""
+
+    def __enter__(self):
+        self.old = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+
+    def __exit__(self, *a):
+        torch.set_default_dtype(self.old)
+
+
+def _relmax(a, r):
+    r = r.detach().double().cpu()
+    return float((a.detach().double().cpu() - r).abs().max() / (r.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+@pytest.mark.parametrize("weights", ["random", "dense"])
+def test_smpl_backward_matches_autograd_of_oracle(dev, weights, gemm_mode):
+    """d(vertices, 49 joints, 45 smpl joints)/d(betas, rotation matrices) of SMPL.forward in the model's mode
+    (pose2rot=False, models/whmr.py:132-137) against torch autograd through the float64 oracle (smplx lbs restated)."""
+    import whmr_b200.synthetic as syn
+    model = syn.make_smpl_model(seed={"random": 0, "dense": 5}[weights], weights=weights)
+    B = 11
+    b = _bodies(B, seed=51)
+    rng = np.random.default_rng(8)
+    gv = rng.normal(size=(B, 6890, 3)).astype(np.float32)
+    gj = rng.normal(size=(B, 49, 3)).astype(np.float32) * 30
+    gs = rng.normal(size=(B, 45, 3)).astype(np.float32) * 30
+    smpl = _smpl(model, dev, gemm_mode)
+    T = lambda a, g=False: torch.from_numpy(np.ascontiguousarray(a)).to(dev).requires_grad_(g)  # noqa: E731
+    D = lambda a, g=False: torch.from_numpy(np.ascontiguousarray(a)).double().requires_grad_(g)  # noqa: E731
+    o64 = _oracle(model, torch.float64)
+
+    def ref_grads(use_v, use_j):
+        be, rm = D(b['betas'], True), D(b['rotmat'], True)
+        ref = o64(be, rm[:, 1:], rm[:, :1], pose2rot=False)
+        loss = 0
+        if use_v:
+            loss = loss + (ref['vertices'] * D(gv)).sum()
+        if use_j:
+            loss = loss + (ref['joints'] * D(gj)).sum() + (ref['joints45'] * D(gs)).sum()
+        loss.backward()
+        return be.grad, rm.grad
+
+    for use_v, use_j in ((True, True), (True, False), (False, True)):
+        be, rm = T(b['betas'], True), T(b['rotmat'], True)
+        out = smpl(betas=be, body_pose=rm[:, 1:], global_orient=rm[:, :1], pose2rot=False)
+        loss = 0
+        if use_v:
+            loss = loss + (out.vertices * T(gv)).sum()
+        if use_j:
+            loss = loss + (out.joints * T(gj)).sum() + (out.smpl_joints * T(gs)).sum()
+        loss.backward()
+        gb_ref, gr_ref = ref_grads(use_v, use_j)
+        assert be.grad.shape == (B, 10) and rm.grad.shape == (B, 24, 3, 3)
+        assert _relmax(be.grad, gb_ref) <= 1e-4, (use_v, use_j)
+        assert _relmax(rm.grad, gr_ref) <= 1e-4, (use_v, use_j)
+
+
+def test_body_model_head_backward(dev, smpl_model):
+    """Training losses of core/trainer.py:380-636 sit on verts, kp_3d (H36M 17->14, pelvis-centred), smpl_kp_3d,
+    the down-sampled meshes and the projected keypoints: gradients through every read-out of BodyModelHead and both
+    projections down to (pred_rotmat, pred_shape, pred_cam, Tz) against autograd through the float64 oracle."""
+    from oracle import geometry_oracle as G
+    from oracle.smpl_oracle import regressor_readouts
+    from whmr_b200.regressor import BodyModelHead
+    B = 9
+    b = _bodies(B, seed=53)
+    rng = np.random.default_rng(9)
+    smpl = _smpl(smpl_model, dev, "bf16x3")
+    head = BodyModelHead(smpl, smpl_model['Dmap0'], smpl_model['Dmap1'], smpl_model['ssm'], smpl_model['J_regressor_h36m'])
+    T = lambda a, g=False: torch.from_numpy(np.ascontiguousarray(a)).to(dev).requires_grad_(g)  # noqa: E731
+    D = lambda a, g=False: torch.from_numpy(np.ascontiguousarray(a)).double().requires_grad_(g)  # noqa: E731
+    keys = {'verts': (6890, 3), 'kp_3d': (14, 3), 'smpl_kp_3d': (45, 3), 'sub_verts': (1723, 3), 'temp_verts': (431, 3),
+            'markers': (67, 3), 'kp_2d': (49, 2), 'kp_2d_w': (49, 2)}
+    gs = {k: rng.normal(size=(B,) + s).astype(np.float32) * (1.0 if s[0] > 1000 else 20.0) for k, s in keys.items()}
+    for stage in (None, 1, 2):
+        head.train_stage = stage
+        rm, be, cam, tz = T(b['rotmat'], True), T(b['betas'], True), T(b['cam'], True), T(b['Tz'], True)
+        out = head(rm, be, cam, T(b['bbox_height']), T(b['center']), T(b['orig_shape']), tz, J_regressor=True)
+        sum((out[k] * T(g)).sum() for k, g in gs.items()).backward()
+        rm64, be64, cam64, tz64 = D(b['rotmat'], True), D(b['betas'], True), D(b['cam'], True), D(b['Tz'], True)
+        ref = _oracle(smpl_model, torch.float64)(be64, rm64[:, 1:], rm64[:, :1], pose2rot=False)
+        rr = regressor_readouts(smpl_model, ref['vertices'], torch.float64)
+        j = ref['joints']
+        # models/whmr.py:142-165: which projection sees the joints depends on cfg.TRAIN.STAGE; pred_cam is detached
+        # inside the predicted-focal block.  stage None: no detach anywhere (the op's full gradient)
+        jw = j if stage in (None, 1) else j.detach()
+        jf = j if stage in (None, 2) else j.detach()
+        camf = cam64 if stage is None else cam64.detach()
+        with _default_f64():
+            kp = G.projection(jw, cam64)
+            kpn = G.full_projection(jf, camf, D(b['bbox_height']), D(b['center']), D(b['orig_shape']), tz64)[0]
+        refs = {'verts': ref['vertices'], 'kp_3d': rr['kp_3d_h36m'], 'smpl_kp_3d': rr['smpl_kp_3d'],
+                'sub_verts': rr['sub_verts'], 'temp_verts': rr['temp_verts'], 'markers': rr['markers'], 'kp_2d': kp,
+                'kp_2d_w': kpn}
+        sum((refs[k] * D(g)).sum() for k, g in gs.items()).backward()
+        assert _relmax(rm.grad, rm64.grad) <= 2e-4, stage
+        assert _relmax(be.grad, be64.grad) <= 2e-4, stage
+        assert _relmax(cam.grad, cam64.grad) <= 2e-4, stage
+        assert _relmax(tz.grad, tz64.grad) <= 2e-4, stage
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly on CPU tensors instead of routing anywhere else."""
     from whmr_b200 import ops

@@ -25,3 +25,14 @@ for hw in ((14, 14), (56, 56)):
     o = ops.sample_bilinear(f, pts, ops.LAYOUT_NCHW)
     torch.cuda.synchronize()
     print("sample", hw, float(o.abs().max()))
+# backward: SMPL (skin, pose-blend transpose, chain), transposed read-out
+from whmr_b200.smpl import SMPL  # noqa: E402
+smpl = SMPL(model=model).to(dev)
+for B in (1, 13):
+    b = syn.make_bodies(B, seed=5)
+    rm = torch.from_numpy(b['rotmat']).to(dev).requires_grad_(True)
+    be = torch.from_numpy(b['betas']).to(dev).requires_grad_(True)
+    o = smpl(betas=be, body_pose=rm[:, 1:], global_orient=rm[:, :1], pose2rot=False)
+    (o.vertices.sum() + o.joints.pow(2).sum()).backward()
+    torch.cuda.synchronize()
+    print("smpl backward B=%d" % B, float(rm.grad.abs().max()), float(be.grad.abs().max()))

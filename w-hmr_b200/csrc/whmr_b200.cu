@@ -22,6 +22,7 @@
 #include "skinning.cuh"
 #include "smpl_fused_tc.cuh"
 #include "smpl_chain.cuh"
+#include "smpl_backward.cuh"
 
 namespace whmr {
 
@@ -1080,6 +1081,116 @@ int whmr_vertex_errors(const float* pred, const float* gt, int n, int V, float* 
 // =============================================================================================
 // backward
 // =============================================================================================
+namespace {
+struct BwdCarve {
+  float *A, *pf, *offsets, *g_off, *g_A, *g_pf;
+  void* pf_split;
+  int Bpad, chunk;
+};
+size_t carve_backward(const whmr_smpl_s* h, int B, void* base, BwdCarve* c) {
+  const SmplDevice& d = h->d;
+  const int chunk = std::min(B, h->chunk_bodies);
+  const int Bpad = ceil_div(std::max(B, 1), kTcBodyTile) * kTcBodyTile;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  const size_t oA = take((size_t)B * d.J * 12 * sizeof(float));
+  const size_t oPf = take((size_t)B * d.KP * sizeof(float));
+  const size_t oSplit = take((size_t)Bpad * 2 * d.KP * sizeof(float));
+  const size_t oOff = take((size_t)chunk * d.NP * sizeof(float));
+  const size_t oGoff = take((size_t)chunk * d.NP * sizeof(float));
+  const size_t oGA = take((size_t)B * d.J * 12 * sizeof(float));
+  const size_t oGpf = take((size_t)B * d.KP * sizeof(float));
+  if (c) {
+    char* p = static_cast<char*>(base);
+    c->A = reinterpret_cast<float*>(p + oA); c->pf = reinterpret_cast<float*>(p + oPf); c->pf_split = p + oSplit;
+    c->offsets = reinterpret_cast<float*>(p + oOff); c->g_off = reinterpret_cast<float*>(p + oGoff);
+    c->g_A = reinterpret_cast<float*>(p + oGA); c->g_pf = reinterpret_cast<float*>(p + oGpf);
+    c->Bpad = Bpad; c->chunk = chunk;
+  }
+  return off;
+}
+}  // namespace
+
+size_t whmr_smpl_backward_workspace_bytes(whmr_smpl_t h, int B) {
+  if (!h || B < 0) return 0;
+  return carve_backward(h, B, nullptr, nullptr) + 1024;
+}
+
+int whmr_smpl_backward(whmr_smpl_t h, const float* betas, const float* pose, int B, const float* g_verts,
+                       const float* g_joints, float* g_betas, float* g_pose, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  WHMR_CHECK_ARG(h && B >= 0, "whmr_smpl_backward: bad arguments");
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(betas && pose && g_betas && g_pose && workspace, "whmr_smpl_backward: null pointer");
+  const size_t need = whmr_smpl_backward_workspace_bytes(h, B);
+  if (workspace_bytes < need) return set_error(WHMR_E_WORKSPACE, "backward workspace too small: %zu < %zu bytes for B=%d", workspace_bytes, need, B);
+  const SmplDevice& d = h->d;
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdCarve c;
+  carve_backward(h, B, reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 1024)), &c);
+  WHMR_CUDA(cudaMemsetAsync(c.g_A, 0, (size_t)B * d.J * 12 * sizeof(float), st));
+  WHMR_CUDA(cudaMemsetAsync(c.g_pf, 0, (size_t)B * d.KP * sizeof(float), st));
+  if (g_verts) {
+    // forward recompute: chain (A, pose feature), then per chunk the pose offsets with the handle's GEMM mode
+    ChainParams p{};
+    p.betas = betas; p.pose = pose; p.pose_is_rotmat = 1;
+    p.B = B; p.J = d.J; p.NB = d.NB; p.KP = d.KP; p.max_depth = d.max_depth;
+    p.J_template = d.J_template; p.J_shapedirs = d.J_shapedirs; p.parents = d.parents; p.depth = d.depth;
+    p.A = c.A;
+    p.pf = h->gemm_mode == WHMR_GEMM_FP32_SIMT ? c.pf : nullptr;
+    p.pf_split = h->gemm_mode == WHMR_GEMM_TC_BF16X3 ? static_cast<__nv_bfloat16*>(c.pf_split) : nullptr;
+    p.pf_tf32 = h->gemm_mode == WHMR_GEMM_TC_3XTF32 ? static_cast<float*>(c.pf_split) : nullptr;
+    launch_pdl(0, smpl_chain_kernel, dim3(ceil_div(B, kChainWarpsPerBlock)), dim3(kChainWarpsPerBlock * 32), 0, st, p);
+    WHMR_LAUNCHED("smpl_chain_kernel");
+    SmplWorkspace ws{};
+    ws.A = c.A; ws.pf = c.pf; ws.pf_split = c.pf_split; ws.offsets = c.offsets; ws.Bpad = c.Bpad; ws.chunk = c.chunk;
+    int ksplit = 1;
+    for (int s2 = 24; s2 >= 1; --s2) if ((d.NP / 32) % s2 == 0) { ksplit = s2; break; }
+    for (int b0 = 0; b0 < B; b0 += c.chunk) {
+      const int nb = std::min(c.chunk, B - b0);
+      int rc = launch_pose_blend(h, ws, B, b0, nb, st);
+      if (rc) return rc;
+      SkinBwdParams q{};
+      q.g_verts = g_verts + (size_t)b0 * d.V * 3;
+      q.offsets = c.offsets; q.A = c.A + (size_t)b0 * d.J * 12;
+      q.v_template_p = d.v_template_p; q.ell_idx = d.ell_idx; q.ell_w = d.ell_w;
+      q.g_offsets = c.g_off; q.g_A = c.g_A + (size_t)b0 * d.J * 12;
+      q.B = nb; q.V = d.V; q.VP = d.VP; q.NP = d.NP; q.J = d.J; q.ell_k = d.ell_k;
+      const size_t smem = (size_t)2 * kBwdBodies * d.J * 12 * sizeof(float);
+      skin_backward_kernel<<<dim3(d.VP / kVertTile, ceil_div(nb, kBwdBodies)), kVertTile, smem, st>>>(q);
+      WHMR_LAUNCHED("skin_backward_kernel");
+      pose_blend_backward_kernel<<<dim3(ceil_div(d.KP, 32), ceil_div(nb, 32), ksplit), dim3(32, 8), 0, st>>>(
+          c.g_off, d.posedirs_p, c.g_pf + (size_t)b0 * d.KP, nb, d.KP, d.NP);
+      WHMR_LAUNCHED("pose_blend_backward_kernel");
+    }
+  }
+  ChainBwdParams cb{};
+  cb.betas = betas; cb.pose = pose; cb.B = B; cb.J = d.J; cb.NB = d.NB; cb.KP = d.KP; cb.max_depth = d.max_depth;
+  cb.J_template = d.J_template; cb.J_shapedirs = d.J_shapedirs; cb.parents = d.parents; cb.depth = d.depth;
+  cb.g_A = c.g_A; cb.g_joints = g_joints; cb.g_pf = c.g_pf; cb.g_pose = g_pose; cb.g_betas = g_betas;
+  chain_backward_kernel<<<ceil_div(B, kChainWarpsPerBlock), kChainWarpsPerBlock * 32, 0, st>>>(cb);
+  WHMR_LAUNCHED("chain_backward_kernel");
+  return WHMR_OK;
+}
+
+int whmr_readout_backward(whmr_readout_t r, const float* g_out, int B, float* g_verts, float* g_joints, void* stream) {
+  WHMR_CHECK_ARG(r && B >= 0, "whmr_readout_backward: bad arguments");
+  if (B == 0 || r->R == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(g_out && g_verts, "whmr_readout_backward: null pointer");
+  WHMR_CHECK_ARG(g_joints || !r->needs_joints, "whmr_readout_backward: table references chain joints but g_joints == NULL");
+  ReadoutBwdParams q{};
+  ReadoutParams& p = q.rp;
+  p.row_ptr = r->row_ptr; p.col_idx = r->col_idx; p.vals = r->vals; p.sub_row = r->sub_row;
+  p.grp_prefix = r->grp_prefix; p.grp_rows = r->grp_rows;
+  p.R = r->R; p.V = r->V; p.J = r->J; p.B = B; p.B_total = B; p.b0 = 0;
+  p.out = const_cast<float*>(g_out);
+  q.g_verts = g_verts; q.g_joints = g_joints;
+  const long long n = (long long)B * r->R;
+  readout_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(q);
+  WHMR_LAUNCHED("readout_backward_kernel");
+  return WHMR_OK;
+}
+
 int whmr_project_weak_backward(const float* points, const float* cam, const float* g_out, int B, int N, float focal,
                                float img_w, float img_h, float* g_points, float* g_cam, void* stream) {
   WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_project_weak_backward: negative size");

@@ -146,6 +146,24 @@ class SmplHandle:
         return verts, joints, A, ro_flat, (ro_ws if deferred.value else ro_ws[:0])
 
     # per-stage launches (bench.py per-kernel timing, tests)
+    def backward(self, betas, pose, g_verts=None, g_joints=None):
+        """Rotation-matrix mode: (g_verts [B,V,3] | None, g_joints [B,J,3] | None) -> (g_betas [B,NB], g_pose [B,J,9])."""
+        betas = _req(betas, "betas", align=16)
+        pose = _req(pose, "pose", align=16)
+        g_verts, g_joints = _req(g_verts, "g_verts"), _req(g_joints, "g_joints")
+        B = betas.shape[0]
+        if pose.numel() != B * self.J * 9:
+            raise ValueError("smpl backward needs rotation matrices [B,%d,3,3], got %s" % (self.J, tuple(pose.shape)))
+        g_betas = torch.empty(B, self.NB, dtype=torch.float32, device=self.device)
+        g_pose = torch.empty(B, self.J, 3, 3, dtype=torch.float32, device=self.device)
+        L = _lib.lib()
+        n = int(L.whmr_smpl_backward_workspace_bytes(self._h, B))
+        ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(L.whmr_smpl_backward(self._h, _p(betas), _p(pose), B, _p(g_verts), _p(g_joints), _p(g_betas), _p(g_pose),
+                                       _p(ws), n, _stream()))
+        return g_betas, g_pose
+
     def stage_chain(self, betas, pose, pose_is_rotmat, ws, n, joints=None, A=None, transl=None):
         check(_lib.lib().whmr_smpl_stage_chain(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl),
                                                betas.shape[0], _p(joints), _p(A), _p(ws), n, _stream()))
@@ -274,6 +292,13 @@ class Readout:
             res[name] = flat[off:off + B * r * 3].view(B, r, 3)
             off += B * r * 3
         return res
+
+    def backward(self, g_flat, g_verts, g_joints=None):
+        """Accumulate the gradient of every read-out row (flat group-major g_flat) into g_verts [B,V,3] / g_joints."""
+        g_flat = _req(g_flat, "g_flat")
+        B = g_verts.shape[0]
+        with torch.cuda.device(g_verts.device):
+            check(_lib.lib().whmr_readout_backward(self._h, _p(g_flat), B, _p(g_verts), _p(g_joints), _stream()))
 
     def apply(self, verts, joints=None):
         """-> dict name -> contiguous [B, R_g, 3] tensor (all from one launch pair)."""
@@ -497,6 +522,50 @@ def _(handle, readout, betas, pose, pose_is_rotmat):
     h, ro = _HANDLES[handle], _READOUTS[readout]
     B = betas.shape[0]
     return betas.new_empty(B, h.V, 3), betas.new_empty(B, h.J, 3), betas.new_empty(B * ro.R * 3)
+
+
+def _smpl_need_rotmat(pose_is_rotmat):
+    if not pose_is_rotmat:
+        raise NotImplementedError("whmr SMPL backward is implemented for rotation-matrix input (pose2rot=False, the "
+                                  "model path models/whmr.py:132-137); axis-angle input is used for ground truth only")
+
+
+def _smpl_setup(ctx, inputs, output):
+    handle, betas, pose, pose_is_rotmat = inputs
+    ctx.save_for_backward(betas, pose)
+    ctx.handle, ctx.rotmat = handle, pose_is_rotmat
+
+
+def _smpl_bwd(ctx, g_v, g_j):
+    _smpl_need_rotmat(ctx.rotmat)
+    betas, pose = ctx.saved_tensors
+    g_betas, g_pose = _HANDLES[ctx.handle].backward(betas, pose, g_v, g_j)
+    return None, g_betas, g_pose.view_as(pose), None
+
+
+smpl_lbs.register_autograd(_smpl_bwd, setup_context=_smpl_setup)
+
+
+def _smpl_ro_setup(ctx, inputs, output):
+    handle, readout, betas, pose, pose_is_rotmat = inputs
+    ctx.save_for_backward(betas, pose)
+    ctx.handle, ctx.readout, ctx.rotmat = handle, readout, pose_is_rotmat
+
+
+def _smpl_ro_bwd(ctx, g_v, g_j, g_flat):
+    _smpl_need_rotmat(ctx.rotmat)
+    betas, pose = ctx.saved_tensors
+    h, ro = _HANDLES[ctx.handle], _READOUTS[ctx.readout]
+    B = betas.shape[0]
+    if g_flat is not None:   # fold the read-out gradients into those of the vertices / chain joints
+        g_v = g_v.contiguous().clone() if g_v is not None else torch.zeros(B, h.V, 3, dtype=torch.float32, device=betas.device)
+        g_j = g_j.contiguous().clone() if g_j is not None else torch.zeros(B, h.J, 3, dtype=torch.float32, device=betas.device)
+        ro.backward(g_flat.contiguous(), g_v, g_j)
+    g_betas, g_pose = h.backward(betas, pose, g_v, g_j)
+    return None, None, g_betas, g_pose.view_as(pose), None
+
+
+smpl_lbs_readout.register_autograd(_smpl_ro_bwd, setup_context=_smpl_ro_setup)
 
 
 @torch.library.custom_op("whmr::smpl_lbs_readout_deferred", mutates_args=(), device_types="cuda")

@@ -34,6 +34,11 @@ class BodyModelHead(nn.Module):
         # concurrently with whatever the caller enqueues next on the main stream (the feature sampling only needs
         # the markers, which the skinning kernel itself writes).  The caller joins it (RegressorLoop.step does).
         self.side_stream = None
+        # Gradient routing of the reference's training graph (models/whmr.py:142-165): cfg.TRAIN.STAGE == 1 -> `projection`
+        # sees the joints, the predicted-focal block sees joints.detach(); any other stage the opposite; pred_cam is
+        # always detached inside the predicted-focal block (s and pred_cam_t).  None = no detach (forward-only use:
+        # one fused launch for both projections).
+        self.train_stage = None
 
     def _mark(self, name):
         if self.probe is not None:
@@ -113,7 +118,14 @@ class BodyModelHead(nn.Module):
         r = ro.split(flat, B)
         self._mark('skin_readout')
         pred_joints = r['joints']
-        if bbox_height is not None:   # Regressor.forward: weak + predicted-focal projection, one launch
+        if bbox_height is not None and self.train_stage is not None and torch.is_grad_enabled():
+            f, w, hgt = constants.FOCAL_LENGTH, float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT)
+            st1 = self.train_stage == 1
+            kp_2d = ops.project_weak_op(pred_joints if st1 else pred_joints.detach(), pred_cam, f, w, hgt)
+            _, kp_w, focal, cam_t = ops.project_weak_full_op(pred_joints.detach() if st1 else pred_joints, pred_cam.detach(),
+                                                             bbox_height, center, orig_shape, Tz, f, w, hgt)
+            self._mark('project_weak_full')
+        elif bbox_height is not None:   # Regressor.forward: weak + predicted-focal projection, one launch
             kp_2d, kp_w, focal, cam_t = ops.project_weak_full_op(
                 pred_joints, pred_cam, bbox_height, center, orig_shape, Tz, constants.FOCAL_LENGTH,
                 float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))

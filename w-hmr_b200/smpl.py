@@ -156,8 +156,14 @@ class SMPL(nn.Module):
             full_pose = torch.cat([global_orient.reshape(-1, 1, 3, 3).expand(B, -1, -1, -1),
                                    body_pose.reshape(body_pose.shape[0], J - 1, 3, 3).expand(B, -1, -1, -1)], dim=1)
         h, ro = self._state(betas.device)
-        verts, joints24, A, flat, _ = h.forward(betas, full_pose, not pose2rot, transl=transl,
-                                                want_transforms=return_transforms, readout=ro)
+        A = None
+        if transl is None and not return_transforms:
+            # torch.library op: differentiable w.r.t. betas / rotation matrices (core/trainer.py:380-636 back-propagates
+            # through pred_vertices and pred_keypoints_3d)
+            verts, joints24, flat = ops.smpl_lbs_readout(h.id, ro.id, betas, full_pose.contiguous(), not pose2rot)
+        else:
+            verts, joints24, A, flat, _ = h.forward(betas, full_pose, not pose2rot, transl=transl,
+                                                    want_transforms=return_transforms, readout=ro)
         r = ro.split(flat, B)
         return ModelOutput(vertices=verts if return_verts else None, joints=r['joints'],
                            full_pose=full_pose if return_full_pose else None, betas=betas,
