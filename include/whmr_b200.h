@@ -189,6 +189,13 @@ int whmr_perspective_projection(const float* points, const float* rotation, int 
                                 const float* camera_center, const float* distortion, int B, int N,
                                 int retain_z, float* out, void* stream);
 
+/* utils/geometry.py:386-408 estimate_translation (+ estimate_translation_np :344-383; called core/trainer.py:435):
+ * confidence-weighted least-squares camera translation per sample, normal equations accumulated and solved in
+ * float64 on the device.  S [B,N,3] 3-D joints, joints_2d [B,N,3] = (x, y, confidence); joints [j0, N) take part
+ * (the reference uses 25: of 49).  -> out [B,3]. */
+int whmr_estimate_translation(const float* S, const float* joints_2d, int B, int N, int j0, float focal, float img_w,
+                              float img_h, float* out, void* stream);
+
 /* The predicted-focal block of Regressor.forward, models/whmr.py:147-173, fused:
  * focal = s*bbox_h*Tz/2; cam_t = convert_pare_to_full_img_cam(...) (utils/geometry.py:139-157);
  * kp = perspective_projection(...); kp_norm = kp/center - 1.

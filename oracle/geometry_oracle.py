@@ -204,3 +204,32 @@ def maf_project(points, pred_cam, center, scale, img_focal, img_center, crop_siz
     p2 = p2 * (crop_size / b)[:, None, None]
     half = torch.tensor([IMG_W, IMG_H]) / 2.
     return full, (p2 - half) / half
+
+
+def estimate_translation_np(S, joints_2d, joints_conf, focal_length=5000, img_size=(224., 224.)):
+    """utils/geometry.py:344-383: weighted least squares for one sample; S [n,3], joints_2d [n,2], conf [n]."""
+    import numpy as np
+    n = S.shape[0]
+    f = np.array([focal_length, focal_length], dtype=np.float64)
+    center = np.array(img_size, dtype=np.float64) / 2.
+    Z = np.repeat(S[:, 2], 2)                                   # :360
+    XY = S[:, 0:2].reshape(-1)                                  # :361
+    O = np.tile(center, n)                                      # :362
+    F = np.tile(f, n)                                           # :363
+    w2 = np.repeat(np.sqrt(joints_conf), 2)                     # :364
+    Q = np.stack([F * np.tile([1., 0.], n), F * np.tile([0., 1.], n), O - joints_2d.reshape(-1)], axis=1)  # :367-368
+    c = (joints_2d.reshape(-1) - O) * Z - F * XY                # :369
+    Q = w2[:, None] * Q                                         # :372-374 (diagflat product)
+    c = w2 * c
+    return np.linalg.solve(Q.T @ Q, Q.T @ c)                    # :377-381
+
+
+def estimate_translation(S, joints_2d, focal_length=5000., img_size=(224., 224.)):
+    """utils/geometry.py:386-408: joints 25: only, one solve per sample, float32 result."""
+    import numpy as np
+    S = np.asarray(S)[:, 25:, :]
+    j2 = np.asarray(joints_2d)[:, 25:, :]
+    out = np.zeros((S.shape[0], 3), dtype=np.float32)
+    for i in range(S.shape[0]):
+        out[i] = estimate_translation_np(S[i], j2[i, :, :2], j2[i, :, 2], focal_length, img_size)
+    return out

@@ -207,6 +207,19 @@ def main():
     re, _ = pu.reconstruction_error(S1.astype(np.float32), S2.astype(np.float32), reduction=None)
     out['pa_err'] = re
 
+    # ---- estimate_translation (utils/geometry.py:344-408; host NumPy in the reference) ----
+    Be = 9
+    S3 = f32(rng.normal(0, 0.35, size=(Be, 49, 3)))
+    true_t = f32(np.stack([rng.uniform(-0.4, 0.4, Be), rng.uniform(-0.4, 0.4, Be), rng.uniform(2.5, 12.0, Be)], axis=1))
+    pe = S3 + true_t[:, None, :]
+    kp = 5000. * pe[..., :2] / pe[..., 2:] + 112. + f32(rng.normal(0, 1.5, size=(Be, 49, 2)))   # noisy pixels
+    conf = f32(rng.uniform(0, 1, size=(Be, 49, 1)))
+    conf[1, 30:40] = 0.0                                      # undetected joints
+    j2 = torch.cat([kp, conf], dim=-1)
+    out['et_S'] = S3.numpy(); out['et_joints_2d'] = j2.numpy()
+    out['et_out'] = geo.estimate_translation(S3, j2, focal_length=5000., img_size=[224., 224.]).numpy()
+    out['et_out_f1000'] = geo.estimate_translation(S3, j2, focal_length=1000., img_size=[256., 192.]).numpy()
+
     np.savez_compressed(os.path.join(HERE, 'reference_outputs.npz'), **out)
     print('wrote reference_outputs.npz with', len(out), 'arrays,',
           os.path.getsize(os.path.join(HERE, 'reference_outputs.npz')) // 1024, 'KiB')

@@ -109,6 +109,15 @@ def _smpl_golden():
     return g, model
 
 
+def test_estimate_translation_matches_reference(golden):
+    """utils/geometry.py:344-408 restated vs outputs of the reference's own function."""
+    from oracle import geometry_oracle as G
+    S, j2 = golden['et_S'], golden['et_joints_2d']
+    np.testing.assert_allclose(G.estimate_translation(S, j2, 5000., (224., 224.)), golden['et_out'], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(G.estimate_translation(S, j2, 1000., (256., 192.)), golden['et_out_f1000'], rtol=2e-6,
+                               atol=2e-6)
+
+
 def test_smpl_oracle_matches_reference_smpl_webuser_outputs():
     """Vertices and posed joints produced by EXECUTING the reference's models/smpl_webuser code
     (tests/golden/make_golden_smpl.py) pin both restatements: the batched smplx-style oracle (fp64 and fp32)

@@ -602,6 +602,30 @@ def test_body_model_head_backward(dev, smpl_model):
         assert _relmax(tz.grad, tz64.grad) <= 2e-4, stage
 
 
+def test_estimate_translation_matches_reference_golden(dev, golden):
+    """utils/geometry.py:386-408 (host NumPy + np.linalg.solve per sample in the reference) on the device."""
+    from whmr_b200 import geometry as geo
+    from oracle import geometry_oracle as G
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    S, j2 = golden['et_S'], golden['et_joints_2d']
+    out = geo.estimate_translation(T(S), T(j2), focal_length=5000., img_size=[224., 224.])
+    np.testing.assert_allclose(out.cpu().numpy(), golden['et_out'], rtol=2e-6, atol=2e-6)
+    out = geo.estimate_translation(T(S), T(j2), focal_length=1000., img_size=[256., 192.])
+    np.testing.assert_allclose(out.cpu().numpy(), golden['et_out_f1000'], rtol=2e-6, atol=2e-6)
+    # a training-sized batch against the oracle
+    rng = np.random.default_rng(3)
+    B = 300
+    S = rng.normal(0, 0.35, size=(B, 49, 3)).astype(np.float32)
+    t = np.stack([rng.uniform(-.4, .4, B), rng.uniform(-.4, .4, B), rng.uniform(2.5, 12, B)], 1).astype(np.float32)
+    pe = S + t[:, None]
+    kp = (5000. * pe[..., :2] / pe[..., 2:] + 112.).astype(np.float32)
+    j2 = np.concatenate([kp, rng.uniform(0.1, 1, size=(B, 49, 1)).astype(np.float32)], -1)
+    out = geo.estimate_translation(T(S), T(j2)).cpu().numpy()
+    np.testing.assert_allclose(out, G.estimate_translation(S, j2), rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(out, t, rtol=2e-3, atol=2e-3)      # noise-free key points: recovers the translation
+    assert geo.estimate_translation(T(S[:0]), T(j2[:0])).shape == (0, 3)
+
+
 def test_no_cpu_fallback():
     """The product path must fail loudly on CPU tensors instead of routing anywhere else."""
     from whmr_b200 import ops

@@ -92,6 +92,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   printf("whmr pose_blend_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
   __trap();
 }
+// Same with a sleep between polls: for single-thread roles that wait long (an idle poller still takes issue slots
+// and mbarrier-unit bandwidth from the epilogue warps of its scheduler).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (clock64() - t0 < 4000000000LL) {
+    if (ns) __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  printf("whmr: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
                                             int c2) {
   asm volatile(
@@ -121,19 +133,28 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
   return d;
 }
-template <int kKind>   // 0: kind::f16 (bf16 in), 1: kind::tf32
+// kColl: collector usage of the A operand (PTX tcgen05.mma .collector::a::{fill,use,lastuse}).  Two consecutive MMAs on
+// the SAME A tile (the hi part of a split operand meets the lo and the hi part of the other one): the first keeps the
+// tile in the collector buffer (fill), the second takes it from there (lastuse) instead of reading 4 KB of shared
+// memory again.  0: default (discard).
+template <int kKind, int kColl = 0>   // kind 0: kind::f16 (bf16/fp16 in), 1: kind::tf32
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+#define WHMR_UMMA_ASM(KIND, COLL)                                                            \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                           \
+               "tcgen05.mma.cta_group::1.kind::" KIND COLL " [%0], %1, %2, %3, p;\n\t}"      \
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory")
   if (kKind == 0) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    if (kColl == 1) WHMR_UMMA_ASM("f16", ".collector::a::fill");
+    else if (kColl == 2) WHMR_UMMA_ASM("f16", ".collector::a::use");
+    else if (kColl == 3) WHMR_UMMA_ASM("f16", ".collector::a::lastuse");
+    else WHMR_UMMA_ASM("f16", "");
   } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    if (kColl == 1) WHMR_UMMA_ASM("tf32", ".collector::a::fill");
+    else if (kColl == 2) WHMR_UMMA_ASM("tf32", ".collector::a::use");
+    else if (kColl == 3) WHMR_UMMA_ASM("tf32", ".collector::a::lastuse");
+    else WHMR_UMMA_ASM("tf32", "");
   }
+#undef WHMR_UMMA_ASM
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
   asm volatile(

@@ -149,4 +149,40 @@ project_crop_kernel(const float* __restrict__ points, const float* __restrict__ 
   }
 }
 
+// utils/geometry.py:344-408 estimate_translation: per sample, the camera translation that best re-projects the 3-D
+// joints onto the 2-D key points, a confidence-weighted least-squares problem with the 3x3 normal equations
+//   rows (per joint i):  [F 0 (cx - x_i)] t = (x_i - cx) Z_i - F X_i ,   [0 F (cy - y_i)] t = (y_i - cy) Z_i - F Y_i
+// weighted by sqrt(conf_i) (so conf_i in the normal equations).  The reference does this on the host, one
+// np.linalg.solve per sample in float64, with a device->host->device round trip every training step
+// (core/trainer.py:435); here one thread per sample accumulates and solves in float64 on the device.
+// Joints [j0, N) take part (the reference slices 25: of 49 -- the ground-truth joints).  A singular system (all
+// confidences zero) makes np.linalg.solve raise; here it yields non-finite values.
+__global__ void __launch_bounds__(128)
+estimate_translation_kernel(const float* __restrict__ S, const float* __restrict__ joints_2d, int B, int N, int j0,
+                            float focal, float img_w, float img_h, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double F = (double)focal, cx = (double)img_w * 0.5, cy = (double)img_h * 0.5;
+  double a00 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0, b0 = 0, b1 = 0, b2 = 0;
+  for (int i = j0; i < N; ++i) {
+    const float* s = S + ((size_t)b * N + i) * 3;
+    const float* k = joints_2d + ((size_t)b * N + i) * 3;
+    const double X = s[0], Y = s[1], Z = s[2], x = k[0], y = k[1];
+    const double w = sqrt((double)k[2]);     // weight2; the normal equations see w*w
+    const double qx = w * (cx - x), qy = w * (cy - y), wf = w * F;
+    const double c0 = w * ((x - cx) * Z - F * X), c1 = w * ((y - cy) * Z - F * Y);
+    a00 += wf * wf; a02 += wf * qx; a11 += wf * wf; a12 += wf * qy; a22 += qx * qx + qy * qy;
+    b0 += wf * c0; b1 += wf * c1; b2 += qx * c0 + qy * c1;
+  }
+  // A = [[a00 0 a02] [0 a11 a12] [a02 a12 a22]]: eliminate the two leading unknowns
+  const double m0 = a02 / a00, m1 = a12 / a11;
+  const double d = a22 - m0 * a02 - m1 * a12;
+  const double tz = (b2 - m0 * b0 - m1 * b1) / d;
+  out[b * 3 + 0] = (float)((b0 - a02 * tz) / a00);
+  out[b * 3 + 1] = (float)((b1 - a12 * tz) / a11);
+  out[b * 3 + 2] = (float)tz;
+}
+
 }  // namespace whmr

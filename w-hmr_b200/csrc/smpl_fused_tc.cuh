@@ -31,40 +31,54 @@
 
 namespace whmr {
 
-constexpr int kFuMaxNB = 64;                  // bodies per item (runtime: 16, 32, 48 or 64)
+// A-operand collector reuse (.collector::a::fill / ::lastuse) between the two MMAs that share a hi tile.  Alone in the
+// tensor pipe it saves ~12 % per MMA triplet (tools/microbench/umma_rate_bench.cu: 78.7 -> 69.1 cycles); inside this
+// kernel, where two issuing threads interleave their MMAs, it measured no gain (and as a run-time switch the extra
+// predicated UTCHMMAs cost 2.7 us per B=256 launch), so it is a compile-time option, off by default.
+#ifdef WHMR_FUSED_COLLECTOR
+constexpr bool kFuCollector = true;
+#else
+constexpr bool kFuCollector = false;
+#endif
 constexpr int kFuGB = 8;                      // bodies per blended-transform tile
 constexpr int kFuTN = kFuGB * 12;             // 96 accumulator columns
-constexpr int kFuAStages = 4;
+constexpr int kFuMaxAStages = 4;
 constexpr int kFuABytes = 2 * kTcM * 128;     // 32 KB: posedirs {hi,lo} of one (K chunk, plane)
 constexpr int kFuPfStages = 2;
-constexpr int kFuPfPart = kFuMaxNB * 128;     // 8 KB
-constexpr int kFuPfBytes = 2 * kFuPfPart;     // 16 KB: pose feature {hi,lo} of one K chunk
 constexpr int kFuWBytes = kTcM * 128;         // 16 KB: skinning weights, fp16 hi|lo along K (64 halfs per vertex)
 constexpr int kFuAtStages = 2;
 constexpr int kFuAtBytes = kFuTN * 128;       // 12 KB: A^T of 8 bodies, fp16 hi|lo along K
 constexpr int kFuEpiWarps = 16;
 constexpr int kFuThreads = (4 + kFuEpiWarps) * 32;
-constexpr int kFuOffA = 0;
-constexpr int kFuOffPf = kFuOffA + kFuAStages * kFuABytes;
-constexpr int kFuOffW = kFuOffPf + kFuPfStages * kFuPfBytes;
-constexpr int kFuOffAt = kFuOffW + kFuWBytes;
-constexpr int kFuOffStg = kFuOffAt + kFuAtStages * kFuAtBytes;
-constexpr int kFuOffBars = kFuOffStg + kFuEpiWarps * 192 * 4;
-constexpr int kFuSmem = kFuOffBars + 256 + 1024;
-// TMEM plan, by the template parameter MAXM = micro-items (16 bodies) per item:
-//   MAXM = 4: 2 x 3 x 64 pose-offset columns + ONE 96-column blended-transform stage (480) -- widest items, least
-//             posedirs re-streaming: large batches;
-//   MAXM = 3: 2 x 3 x 48 pose-offset columns + TWO blended-transform stages (480) -- the skinning MMAs of the next 8
-//             bodies are already done when the epilogue asks for them: small batches, where the per-group
-//             MMA -> epilogue round trip is exposed.
+// TMEM / shared-memory plan, by the template parameter MAXM = micro-items (16 bodies) per item.
+// Measured (tools/microbench/umma_rate_bench.cu): a tcgen05.mma with M=128, K=16 costs max(~70, N/2) cycles -- the
+// 4 KB A tile enters at 64 B/clk -- so below N=128 the cost of a pose-blend MMA does not depend on the number of
+// bodies it covers.  The plan therefore packs as many bodies as TMEM allows behind every posedirs tile:
+//   MAXM = 8: ONE stage of 3 x 128 pose-offset columns + one 96-column blended-transform stage (480): half the
+//             pose-blend MMAs per body; the pose blend of item i+1 cannot overlap the epilogue of item i, but both
+//             sides are bound by the same tensor pipe, which stays busy with the skinning MMAs meanwhile;
+//   MAXM = 4: 2 x 3 x 64 pose-offset columns + one blended-transform stage (480);
+//   MAXM = 3: 2 x 3 x 48 pose-offset columns + TWO blended-transform stages (480): tiny batches.
 template <int MAXM> struct FuTmem {
   static constexpr int kNB = 16 * MAXM;              // max bodies per item
+  static constexpr int kOffStages = MAXM <= 4 ? 2 : 1;
   static constexpr int kOffStage = 3 * kNB;          // columns per pose-offset stage
-  static constexpr int kT = 2 * kOffStage;           // first blended-transform column
-  static constexpr int kTStages = MAXM == 4 ? 1 : 2;
+  static constexpr int kT = kOffStages * kOffStage;  // first blended-transform column
+  static constexpr int kTStages = (512 - kT) / kFuTN >= 2 ? 2 : 1;
   static_assert(kT + kTStages * kFuTN <= 512, "TMEM budget");
+  // shared memory
+  static constexpr int kAStages = MAXM <= 4 ? 4 : 3;
+  static constexpr int kPfPart = (kNB < 64 ? 64 : kNB) * 128;   // pose feature, one of {hi,lo}, one K chunk
+  static constexpr int kPfBytes = 2 * kPfPart;
+  static constexpr int kOffA = 0;
+  static constexpr int kOffPf = kOffA + kAStages * kFuABytes;
+  static constexpr int kOffW = kOffPf + kFuPfStages * kPfBytes;
+  static constexpr int kOffAt = kOffW + kFuWBytes;
+  static constexpr int kOffStg = kOffAt + kFuAtStages * kFuAtBytes;
+  static constexpr int kOffBars = kOffStg + kFuEpiWarps * 192 * 4;
+  static constexpr int kSmem = kOffBars + 256 + 1024;
+  static_assert(kSmem <= 232448, "fused SMPL kernel exceeds the 227 KB shared-memory limit");
 };
-static_assert(kFuSmem <= 232448, "fused SMPL kernel exceeds the 227 KB shared-memory limit");
 
 struct FusedParams {
   const float* v_template_p;  // [3, VP]
@@ -74,10 +88,12 @@ struct FusedParams {
   float* ro_out;
   int ro_B, ro_b0;
   int nb, V, VP;
+  int split;                  // > 0: CTA c takes part c % split of vertex tile c / split (grid = tiles * split): one item per CTA
   int npv;                    // 16-body micro-items per vertex tile = ceil(nb / 16)
   int n_micro;                // (VP/128) * npv: the unit of work distribution
   int kch, ksteps;            // pose blend: 128-byte K chunks, 32-byte K steps (bf16: 16 elements)
   int jsteps;                 // skinning: ceil(J/16) fp16 K steps
+  unsigned backoff;           // WHMR_FUSED_BACKOFF: ns between mbarrier polls of the single-thread roles
   int dbg_mode;               // WHMR_FUSED_DBGMODE bits (timing experiments only): 1 skip vertex stores, 2 skip read-out emits, 4 skip the transposes
   long long* dbg;             // WHMR_FUSED_DEBUG: [grid][16] per-role wait/total cycles, or null
 };
@@ -97,6 +113,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t* v) {
     if (p.dbg) { const long long _w0 = clock64(); mbar_wait(bar, par); acc += clock64() - _w0; } \
     else mbar_wait(bar, par);                             \
   } while (0)
+// single-thread roles (producers, MMA issuers): polls spaced by p.backoff ns
+#define WHMR_FU_WAIT_R(bar, par, acc)                     \
+  do {                                                    \
+    if (p.dbg) { const long long _w0 = clock64(); mbar_wait_backoff(bar, par, p.backoff); acc += clock64() - _w0; } \
+    else mbar_wait_backoff(bar, par, p.backoff);          \
+  } while (0)
 
 template <int MAXM>
 __global__ void __launch_bounds__(kFuThreads, 1)
@@ -110,15 +132,17 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   unsigned long long gt_entry = 0;
   if (p.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* a_ring = smem + kFuOffA;
-  uint8_t* pf_ring = smem + kFuOffPf;
-  uint8_t* w_smem = smem + kFuOffW;
-  uint8_t* at_ring = smem + kFuOffAt;
-  float* stage_out = reinterpret_cast<float*>(smem + kFuOffStg);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFuOffBars);
-  uint64_t* a_full = bars;                         // [3]
-  uint64_t* a_empty = a_full + kFuAStages;         // [3]
-  uint64_t* pf_full = a_empty + kFuAStages;        // [2]
+  uint8_t* a_ring = smem + TM::kOffA;
+  uint8_t* pf_ring = smem + TM::kOffPf;
+  uint8_t* w_smem = smem + TM::kOffW;
+  uint8_t* at_ring = smem + TM::kOffAt;
+  float* stage_out = reinterpret_cast<float*>(smem + TM::kOffStg);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TM::kOffBars);
+  constexpr int kFuAStages = TM::kAStages;
+  constexpr int kFuPfBytes = TM::kPfBytes, kFuPfPart = TM::kPfPart;
+  uint64_t* a_full = bars;                         // [4]
+  uint64_t* a_empty = a_full + kFuMaxAStages;      // [4]
+  uint64_t* pf_full = a_empty + kFuMaxAStages;     // [2]
   uint64_t* pf_empty = pf_full + kFuPfStages;      // [2]
   uint64_t* w_full = pf_empty + kFuPfStages;
   uint64_t* w_empty = w_full + 1;
@@ -134,8 +158,15 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   // Work distribution: the (vertex tile, 16-body micro-item) grid is cut into gridDim.x contiguous, equal ranges
   // (vertex-major), so every CTA gets the same number of bodies +-16.  A range is walked as items = runs of <= 4
   // micro-items (<= 64 bodies) inside one vertex tile, sized evenly (5 micro-items -> 3 + 2, not 4 + 1).
-  const int m_begin = (int)(((long long)blockIdx.x * p.n_micro) / gridDim.x);
-  const int m_end = (int)(((long long)(blockIdx.x + 1) * p.n_micro) / gridDim.x);
+  int m_begin, m_end;
+  if (p.split > 0) {   // small batches: tile-aligned parts, so that no CTA streams a posedirs tile for a sliver of bodies
+    const int vt = blockIdx.x / p.split, part = blockIdx.x - vt * p.split;
+    m_begin = vt * p.npv + (part * p.npv) / p.split;
+    m_end = vt * p.npv + ((part + 1) * p.npv) / p.split;
+  } else {
+    m_begin = (int)(((long long)blockIdx.x * p.n_micro) / gridDim.x);
+    m_end = (int)(((long long)(blockIdx.x + 1) * p.n_micro) / gridDim.x);
+  }
   struct Item { int vt, body0, len, nbod, ng; };   // len: micro-items; nbod: valid bodies; ng: 8-body groups
   auto item_at = [&](int m) {
     Item it;
@@ -201,7 +232,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         const int vt = it.vt, body0 = it.body0;
         const uint32_t pf_bytes = 2u * (uint32_t)it.len * 2048u;
         for (int kc = 0; kc < p.kch; ++kc) {
-          WHMR_FU_WAIT(&pf_empty[ps], pph ^ 1, d_pf);
+          WHMR_FU_WAIT_R(&pf_empty[ps], pph ^ 1, d_pf);
           uint8_t* pst = pf_ring + ps * kFuPfBytes;
           mbar_arrive_expect_tx(&pf_full[ps], pf_bytes);
           for (int u = 0; u < it.len; ++u) {   // 16-row boxes, stacked: same image as one (16*len)-row box
@@ -213,7 +244,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             if (pre > 0) {
               --pre;                       // this stage was filled by the prefetch above
             } else {
-              WHMR_FU_WAIT(&a_empty[as], aph ^ 1, d_a);
+              WHMR_FU_WAIT_R(&a_empty[as], aph ^ 1, d_a);
               uint8_t* ast = a_ring + as * kFuABytes;
               mbar_arrive_expect_tx(&a_full[as], kFuABytes);
               tma_load_3d(ast, &tmapP, &a_full[as], kc * 64, 0, c * p.VP + vt * kTcM);
@@ -238,15 +269,15 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         m += it.len;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(it.len * 2) << 17) |
                                ((uint32_t)(kTcM >> 4) << 24);   // bf16 x bf16 -> f32, M=128, N=16*len
-        WHMR_FU_WAIT(&off_empty[buf], bph ^ 1, d_off);
+        WHMR_FU_WAIT_R(&off_empty[buf], bph ^ 1, d_off);
         tcgen05_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(buf * TM::kOffStage);
         for (int kc = 0; kc < p.kch; ++kc) {
-          WHMR_FU_WAIT(&pf_full[ps], pph, d_pf);
+          WHMR_FU_WAIT_R(&pf_full[ps], pph, d_pf);
           const uint32_t b_hi = smem_u32(pf_ring + ps * kFuPfBytes), b_lo = b_hi + kFuPfPart;
           const int nks = min(4, p.ksteps - kc * 4);
           for (int c = 0; c < 3; ++c) {
-            WHMR_FU_WAIT(&a_full[as], aph, d_a);
+            WHMR_FU_WAIT_R(&a_full[as], aph, d_a);
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(a_ring + as * kFuABytes), a_lo = a_hi + kTcM * 128;
             const uint32_t d_tmem = d_base + (uint32_t)(c * TM::kNB);
@@ -254,8 +285,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
               const uint64_t dA_hi = umma_desc_sw128(a_hi + ks * 32), dA_lo = umma_desc_sw128(a_lo + ks * 32);
               const uint64_t dB_hi = umma_desc_sw128(b_hi + ks * 32), dB_lo = umma_desc_sw128(b_lo + ks * 32);
               umma<0>(d_tmem, dA_lo, dB_hi, idesc, (kc | ks) != 0);   // small terms first
-              umma<0>(d_tmem, dA_hi, dB_lo, idesc, 1u);
-              umma<0>(d_tmem, dA_hi, dB_hi, idesc, 1u);
+              umma<0, kFuCollector ? 1 : 0>(d_tmem, dA_hi, dB_lo, idesc, 1u);   // (collector: hi tile kept ...
+              umma<0, kFuCollector ? 3 : 0>(d_tmem, dA_hi, dB_hi, idesc, 1u);   //  ... and reused, see kFuCollector)
             }
             tcgen05_commit(&a_empty[as]);
             if (++as == kFuAStages) { as = 0; aph ^= 1; }
@@ -264,7 +295,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           if (++ps == kFuPfStages) { ps = 0; pph ^= 1; }
         }
         tcgen05_commit(&off_full[buf]);
-        if (++buf == 2) { buf = 0; bph ^= 1; }
+        if (++buf == TM::kOffStages) { buf = 0; bph ^= 1; }
       }
       if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[3] = d_off; d[4] = d_pf; d[5] = d_a; d[6] = clock64() - k0; }
     }
@@ -285,7 +316,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         m += it.len;
         const int vt = it.vt;
         if (vt != cur_vt) {
-          mbar_wait(w_empty, w_par);   // MMAs on the previous weight tile have retired
+          mbar_wait_backoff(w_empty, w_par, p.backoff);   // MMAs on the previous weight tile have retired
           w_par ^= 1;
           mbar_arrive_expect_tx(w_full, kFuWBytes);
           tma_load_2d(w_smem, &tmapW, w_full, 0, vt * kTcM);
@@ -293,7 +324,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         }
         const int ng = it.ng;
         for (int g = 0; g < ng; ++g) {
-          mbar_wait(&at_empty[s], ph ^ 1);
+          mbar_wait_backoff(&at_empty[s], ph ^ 1, p.backoff);
           uint8_t* st = at_ring + s * kFuAtBytes;
           mbar_arrive_expect_tx(&at_full[s], kFuAtBytes);
           const int row0 = (it.body0 + g * kFuGB) * 12;
@@ -317,11 +348,11 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         const Item it = item_at(m);
         m += it.len;
         const int vt = it.vt;
-        if (vt != cur_vt) { mbar_wait(w_full, w_phase); w_phase ^= 1; cur_vt = vt; }
+        if (vt != cur_vt) { mbar_wait_backoff(w_full, w_phase, p.backoff); w_phase ^= 1; cur_vt = vt; }
         const int ng = it.ng;
         for (int g = 0; g < ng; ++g) {
-          WHMR_FU_WAIT(&t_empty[ts], t_ph ^ 1, d_t);
-          WHMR_FU_WAIT(&at_full[s], ph, d_at);
+          WHMR_FU_WAIT_R(&t_empty[ts], t_ph ^ 1, d_t);
+          WHMR_FU_WAIT_R(&at_full[s], ph, d_at);
           const uint32_t d_tmem = tmem_base + (uint32_t)(TM::kT + ts * kFuTN);
           tcgen05_fence_after();
           const uint32_t a_hi = smem_u32(at_ring + s * kFuAtBytes), a_lo = a_hi + 64;
@@ -329,8 +360,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             const uint64_t dW_hi = umma_desc_sw128(w_hi + ks * 32), dW_lo = umma_desc_sw128(w_lo + ks * 32);
             const uint64_t dA_hi = umma_desc_sw128(a_hi + ks * 32), dA_lo = umma_desc_sw128(a_lo + ks * 32);
             umma<0>(d_tmem, dW_lo, dA_hi, idesc, ks != 0);
-            umma<0>(d_tmem, dW_hi, dA_lo, idesc, 1u);
-            umma<0>(d_tmem, dW_hi, dA_hi, idesc, 1u);
+            umma<0, kFuCollector ? 1 : 0>(d_tmem, dW_hi, dA_lo, idesc, 1u);
+            umma<0, kFuCollector ? 3 : 0>(d_tmem, dW_hi, dA_hi, idesc, 1u);
           }
           tcgen05_commit(&at_empty[s]);
           tcgen05_commit(&t_full[ts]);
@@ -369,6 +400,9 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     const bool has_transl = p.transl != nullptr;
     int buf = 0, ts = 0; uint32_t bph = 0, t_ph = 0;
     long long d_off = 0, d_t = 0, d_ld = 0, d_rel = 0;
+#ifdef WHMR_FUSED_FINE_PROBES   // per-section cycles of one epilogue warp (math+stage | vertex stores | read-out emits)
+    long long d_math = 0, d_st = 0, d_emit = 0;
+#endif
     pdl_wait();      // outputs (and the read-out partial buffer) may still be in use by earlier kernels
     pdl_trigger();
     const long long k0 = p.dbg ? clock64() : 0;
@@ -423,6 +457,9 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         if (p.dbg) { d_ld += l1 - l0; d_rel += clock64() - l1; }
         if (n_valid <= 0) continue;
         float* outp = p.verts + (size_t)body_base * V3 + out_col;
+#ifdef WHMR_FUSED_FINE_PROBES
+        const long long e0c = p.dbg ? clock64() : 0;
+#endif
         auto run = [&](auto guard_tag) {
           constexpr bool G = decltype(guard_tag)::value;
           // both bodies are staged before the single __syncwarp, so their shared-memory round trips overlap
@@ -445,6 +482,9 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             else if (rx + ry + rz == 123.456f) sb[0] = rx;
           }
           __syncwarp();
+#ifdef WHMR_FUSED_FINE_PROBES
+          const long long e1c = p.dbg ? clock64() : 0;
+#endif
           float v[6];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
@@ -458,6 +498,9 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             for (int r = 0; r < 3; ++r)
               if ((!G || out_col + r * 32 < V3) && !(p.dbg_mode & 1)) ob[r * 32] = v[i * 3 + r];
           }
+#ifdef WHMR_FUSED_FINE_PROBES
+          const long long e2c = p.dbg ? clock64() : 0;
+#endif
           if (n_e > 0 && !(p.dbg_mode & 2)) {   // fused read-outs: entries referencing one of this warp's 32 vertices
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -480,12 +523,19 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
               }
             }
           }
+#ifdef WHMR_FUSED_FINE_PROBES
+          if (p.dbg) { const long long e3c = clock64(); d_math += e1c - e0c; d_st += e2c - e1c; d_emit += e3c - e2c; }
+#endif
         };
         if (n_valid == 2 && !has_transl && full_tile) run(cuda::std::false_type{}); else run(cuda::std::true_type{});
       }
-      if (++buf == 2) { buf = 0; bph ^= 1; }
+      if (++buf == TM::kOffStages) { buf = 0; bph ^= 1; }
     }
-    if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 16; d[10] = d_off; d[11] = d_t; d[12] = clock64() - k0; d[13] = d_ld; d[14] = d_rel; }
+    if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 16; d[10] = d_off; d[11] = d_t; d[12] = clock64() - k0; d[13] = d_ld; d[14] = d_rel;
+#ifdef WHMR_FUSED_FINE_PROBES
+      long long* d2 = p.dbg + (gridDim.x + blockIdx.x) * 16; d2[2] = d_math; d2[3] = d_st; d2[4] = d_emit;
+#endif
+    }
   }
 
   tcgen05_fence_before();

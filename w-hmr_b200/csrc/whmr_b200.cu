@@ -296,8 +296,10 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
   }
   if (const char* s = getenv("WHMR_SKIN")) h->skin_tc = strcmp(s, "simt") != 0;
   if (const char* s = getenv("WHMR_FUSED")) h->fused = atoi(s) != 0;
-  e = cudaFuncSetAttribute(smpl_fused_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem);
+  e = cudaFuncSetAttribute(smpl_fused_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<3>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<8>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<6>::kSmem);
   if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "cudaFuncSetAttribute(smpl_fused_tc) failed: %s", cudaGetErrorString(e)); }
   h->gemm_mode = gemm_mode;
   *out = h;
@@ -554,17 +556,36 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   rc = tc_encode_rows64h(h->tc.encode_fn, &tmapAt, static_cast<__half*>(ws.At16) + (size_t)b0 * 12 * 64,
                          (size_t)(ws.Bpad - b0) * 12, kFuTN);
   if (rc) return rc;
-  const int grid = std::min(h->tc.num_sms, p.n_micro);
+  // Item width (MAXM x 16 bodies behind one pass over a posedirs tile) -- measured, profiles/r01_notes.md section 5.
+  // A pose-blend MMA costs the same ~70-100 cycles for 16 or 128 bodies (the 4 KB A tile enters the tensor core at
+  // 64 B/clk: tools/microbench/umma_rate_bench.cu), which argues for wide items; but the wide plans (MAXM = 6, 8) have
+  // a single pose-offset stage in TMEM, so pose blend and epilogue serialise, and the epilogue (issue-bound: ~170
+  // instructions per warp and 8-body group) is the longer phase.  Measured: B=256 loop step 0.4075 ms (MAXM 8, aligned
+  // halves, 108 CTAs) vs 0.3977 ms (MAXM 3); 16 k bodies 12.1 M bodies/s (MAXM 8) / 12.2 M (MAXM 6) vs 14.6 M (MAXM 4).
+  // Default therefore: 48-body items with two blended-transform stages while a CTA's share is small, 64-body items
+  // once posedirs re-streaming dominates; WHMR_FUSED_MAXM / WHMR_FUSED_SPLIT select the other plans.
+  static const int maxm_env = getenv("WHMR_FUSED_MAXM") ? atoi(getenv("WHMR_FUSED_MAXM")) : 0;
+  static const int split_env = getenv("WHMR_FUSED_SPLIT") ? atoi(getenv("WHMR_FUSED_SPLIT")) : -1;
+  int maxm = p.n_micro <= 8 * h->tc.num_sms ? 3 : 4;
+  if (maxm_env == 3 || maxm_env == 4 || maxm_env == 6 || maxm_env == 8) maxm = maxm_env;
+  p.split = 0;
+  if (split_env >= 0) {
+    p.split = split_env;
+  } else if (maxm >= 6 && p.npv <= 2 * maxm) {
+    p.split = std::max(1, std::min(p.npv, h->tc.num_sms / n_vtiles));
+  }
+  if (p.split > 0 && (ceil_div(p.npv, p.split) > maxm || n_vtiles * p.split > h->tc.num_sms)) p.split = 0;
+  const int grid = p.split > 0 ? n_vtiles * p.split : std::min(h->tc.num_sms, p.n_micro);
   static const bool dbg_on = getenv("WHMR_FUSED_DEBUG") != nullptr;
   static const int dbg_mode = getenv("WHMR_FUSED_DBGMODE") ? atoi(getenv("WHMR_FUSED_DBGMODE")) : 0;
   p.dbg_mode = dbg_mode;
+  static const int backoff = getenv("WHMR_FUSED_BACKOFF") ? atoi(getenv("WHMR_FUSED_BACKOFF")) : 0;
+  p.backoff = (unsigned)backoff;
   if (dbg_on) { cudaMalloc(&p.dbg, sizeof(long long) * 32 * grid); cudaMemsetAsync(p.dbg, 0, sizeof(long long) * 32 * grid, st); }
-  // items of <= 48 bodies with two blended-transform stages while a CTA's share is small (the per-group MMA ->
-  // epilogue round trip is exposed), <= 64 bodies and one stage once posedirs re-streaming dominates
-  static const int maxm_env = getenv("WHMR_FUSED_MAXM") ? atoi(getenv("WHMR_FUSED_MAXM")) : 0;
-  const bool small = maxm_env ? maxm_env == 3 : (p.n_micro <= 8 * h->tc.num_sms);
-  if (small) launch_pdl(kPdlFused, smpl_fused_tc_kernel<3>, dim3(grid), dim3(kFuThreads), kFuSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
-  else launch_pdl(kPdlFused, smpl_fused_tc_kernel<4>, dim3(grid), dim3(kFuThreads), kFuSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
+  if (maxm == 3) launch_pdl(kPdlFused, smpl_fused_tc_kernel<3>, dim3(grid), dim3(kFuThreads), FuTmem<3>::kSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
+  else if (maxm == 6) launch_pdl(kPdlFused, smpl_fused_tc_kernel<6>, dim3(grid), dim3(kFuThreads), FuTmem<6>::kSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
+  else if (maxm == 4) launch_pdl(kPdlFused, smpl_fused_tc_kernel<4>, dim3(grid), dim3(kFuThreads), FuTmem<4>::kSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
+  else launch_pdl(kPdlFused, smpl_fused_tc_kernel<8>, dim3(grid), dim3(kFuThreads), FuTmem<8>::kSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
   WHMR_LAUNCHED("smpl_fused_tc_kernel");
   if (p.dbg) {   // per-role wait/total cycles averaged over CTAs (debug only: synchronises)
     cudaStreamSynchronize(st);
@@ -578,6 +599,13 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
       t_first = std::min(t_first, hd[(size_t)(grid + c) * 16]); t_last_start = std::max(t_last_start, hd[(size_t)(grid + c) * 16]);
       t_end_min = std::min(t_end_min, hd[(size_t)(grid + c) * 16 + 1]); t_end_max = std::max(t_end_max, hd[(size_t)(grid + c) * 16 + 1]);
     }
+#ifdef WHMR_FUSED_FINE_PROBES
+    {
+      double m = 0, s2 = 0, e = 0;
+      for (int c = 0; c < grid; ++c) { m += (double)hd[(size_t)(grid + c) * 16 + 2] / grid; s2 += (double)hd[(size_t)(grid + c) * 16 + 3] / grid; e += (double)hd[(size_t)(grid + c) * 16 + 4] / grid; }
+      fprintf(stderr, "[whmr fused dbg] epilogue warp 4: math+stage %.0f | vertex stores %.0f | read-out emits %.0f cycles\n", m, s2, e);
+    }
+#endif
     fprintf(stderr, "[whmr fused dbg] globaltimer: CTA starts spread %lld ns, first start -> last end %lld ns, ends spread %lld ns, prologue avg %.0f ns\n",
             t_last_start - t_first, t_end_max - t_first, t_end_max - t_end_min, a[15]);
     fprintf(stderr, "[whmr fused dbg] nb=%d micro-items=%d grid=%d | pose-producer wait pf_empty %.0f a_empty %.0f of %.0f | "
@@ -962,6 +990,17 @@ int whmr_perspective_projection(const float* points, const float* rotation, int 
   perspective_projection_kernel<<<WHMR_BN_GRID(B, N), 256, 0, (cudaStream_t)stream>>>(
       points, rotation, rot_batch, translation, focal_dev, focal_scalar, camera_center, distortion, B, N, retain_z, out);
   WHMR_LAUNCHED("perspective_projection_kernel");
+  return WHMR_OK;
+}
+
+int whmr_estimate_translation(const float* S, const float* joints_2d, int B, int N, int j0, float focal, float img_w,
+                              float img_h, float* out, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0 && j0 >= 0 && j0 <= N, "whmr_estimate_translation: bad sizes");
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(S && joints_2d && out, "whmr_estimate_translation: null pointer");
+  launch_pdl(0, estimate_translation_kernel, dim3(ceil_div(B, 128)), dim3(128), 0, (cudaStream_t)stream, S, joints_2d, B, N,
+             j0, focal, img_w, img_h, out);
+  WHMR_LAUNCHED("estimate_translation_kernel");
   return WHMR_OK;
 }
 

@@ -64,3 +64,10 @@ def rotation_matrix_to_angle_axis(rotation_matrix):
     if rotation_matrix.shape[-2:] != (3, 3):
         raise ValueError("rotation_matrix_to_angle_axis: expected [N,3,3], got %s" % (tuple(rotation_matrix.shape),))
     return ops.rotation_matrix_to_angle_axis(rotation_matrix)
+
+
+def estimate_translation(S, joints_2d, focal_length=5000., img_size=[224., 224.]):
+    """utils/geometry.py:386-408 (core/trainer.py:435): S [B,49,3], joints_2d [B,49,3] = (x, y, conf); joints 25:
+    (the ground-truth set) take part.  The reference round-trips through NumPy on the host with one
+    np.linalg.solve per sample; this stays on the device and on the current stream."""
+    return ops.estimate_translation(S, joints_2d, focal_length, img_size, first_joint=25)

@@ -365,6 +365,20 @@ def perspective_projection(points, rotation, translation, focal_length, camera_c
     return out
 
 
+def estimate_translation(S, joints_2d, focal_length=5000., img_size=(224., 224.), first_joint=25):
+    """utils/geometry.py:386-408 on the device (no host round trip): S [B,N,3], joints_2d [B,N,3] = (x, y, conf);
+    joints [first_joint, N) take part.  -> [B,3]."""
+    S, joints_2d = _req(S, "S"), _req(joints_2d, "joints_2d")
+    B, N = S.shape[0], S.shape[1]
+    if joints_2d.shape != (B, N, 3) or S.shape[2] != 3:
+        raise ValueError("estimate_translation: S %s / joints_2d %s" % (tuple(S.shape), tuple(joints_2d.shape)))
+    out = torch.empty(B, 3, dtype=torch.float32, device=S.device)
+    with torch.cuda.device(S.device):
+        check(_lib.lib().whmr_estimate_translation(_p(S), _p(joints_2d), B, N, min(int(first_joint), N), float(focal_length),
+                                                   float(img_size[0]), float(img_size[1]), _p(out), _stream()))
+    return out
+
+
 def project_full(points, cam, bbox_height, center, orig_shape, Tz, want_px=False):
     """models/whmr.py:147-173 fused.  -> (kp_norm [B,N,2], focal [B], cam_t [B,3], kp_px or None)"""
     points = _req(points, "points")
