@@ -199,8 +199,20 @@ __device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* p
                                            float& x, float& y, float& z) {
   const ReadoutParams& p = q.rp;
   x = y = z = 0.f;
-  for (int k = q.part_ptr[r]; k < q.part_ptr[r + 1]; ++k) {
-    const float* e = ps + slots[k] * 3;      // slot list staged in shared memory: no dependent global load per term
+  int k = q.part_ptr[r];
+  const int k1 = q.part_ptr[r + 1];
+  for (; k + 4 <= k1; k += 4) {   // four terms' loads in flight; the additions keep the row's storage order
+    const float* e0 = ps + slots[k] * 3;     // slot list staged in shared memory: no dependent global load per term
+    const float* e1 = ps + slots[k + 1] * 3;
+    const float* e2 = ps + slots[k + 2] * 3;
+    const float* e3 = ps + slots[k + 3] * 3;
+    const float a0 = e0[0], a1 = e0[1], a2 = e0[2], b0 = e1[0], b1 = e1[1], b2 = e1[2];
+    const float c0 = e2[0], c1 = e2[1], c2 = e2[2], d0 = e3[0], d1 = e3[1], d2 = e3[2];
+    x += a0; y += a1; z += a2; x += b0; y += b1; z += b2;
+    x += c0; y += c1; z += c2; x += d0; y += d1; z += d2;
+  }
+  for (; k < k1; ++k) {
+    const float* e = ps + slots[k] * 3;
     x += e[0]; y += e[1]; z += e[2];
   }
   for (int k = q.jt_ptr[r]; k < q.jt_ptr[r + 1]; ++k) {

@@ -110,17 +110,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t* v) {
 // wait that adds its duration to `acc` when instrumentation is on
 #define WHMR_FU_WAIT(bar, par, acc)                       \
   do {                                                    \
-    if (p.dbg) { const long long _w0 = clock64(); mbar_wait(bar, par); acc += clock64() - _w0; } \
+    if (dbgp) { const long long _w0 = clock64(); mbar_wait(bar, par); acc += clock64() - _w0; } \
     else mbar_wait(bar, par);                             \
   } while (0)
 // single-thread roles (producers, MMA issuers): polls spaced by p.backoff ns
 #define WHMR_FU_WAIT_R(bar, par, acc)                     \
   do {                                                    \
-    if (p.dbg) { const long long _w0 = clock64(); mbar_wait_backoff(bar, par, p.backoff); acc += clock64() - _w0; } \
+    if (dbgp) { const long long _w0 = clock64(); mbar_wait_backoff(bar, par, p.backoff); acc += clock64() - _w0; } \
     else mbar_wait_backoff(bar, par, p.backoff);          \
   } while (0)
 
-template <int MAXM>
+// kDbg: instrumented instantiation (WHMR_FUSED_DEBUG / WHMR_FUSED_DBGMODE); the production instantiation carries
+// none of the probes' predicates or branches (the epilogue is instruction-issue bound).
+template <int MAXM, bool kDbg>
 __global__ void __launch_bounds__(kFuThreads, 1)
 smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+shapedirs bf16 [NP, 2, KP]
                      const __grid_constant__ CUtensorMap tmapPf,   // pose feature bf16 [bodies, 2, KP], box rows = nbi
@@ -128,9 +130,11 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
                      const __grid_constant__ CUtensorMap tmapAt,   // A^T fp16 hi|lo [bodies*12, 64], box rows = 96
                      FusedParams p) {
   using TM = FuTmem<MAXM>;
+  long long* const dbgp = kDbg ? p.dbg : nullptr;
+  const int dbg_mode = kDbg ? p.dbg_mode : 0;
   extern __shared__ uint8_t smem_raw[];
   unsigned long long gt_entry = 0;
-  if (p.dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
+  if (dbgp && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_entry));
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem + TM::kOffA;
   uint8_t* pf_ring = smem + TM::kOffPf;
@@ -198,10 +202,10 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  if (p.dbg && threadIdx.x == 0) {
+  if (dbgp && threadIdx.x == 0) {
     unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-    p.dbg[blockIdx.x * 16 + 15] = (long long)(g - gt_entry);   // prologue, ns
-    p.dbg[(gridDim.x + blockIdx.x) * 16 + 0] = (long long)gt_entry;
+    dbgp[blockIdx.x * 16 + 15] = (long long)(g - gt_entry);   // prologue, ns
+    dbgp[(gridDim.x + blockIdx.x) * 16 + 0] = (long long)gt_entry;
   }
 
   if (warp == 0) {
@@ -210,7 +214,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       int as = 0; uint32_t aph = 0;
       int ps = 0; uint32_t pph = 0;
       long long d_pf = 0, d_a = 0;
-      const long long k0 = p.dbg ? clock64() : 0;
+      const long long k0 = dbgp ? clock64() : 0;
       // PDL: posedirs are constants of the handle, so the first ring fill is issued before the predecessor (the
       // chain kernel, which writes the pose feature) has finished; `pre` counts the stages already in flight
       int pre = 0;
@@ -254,7 +258,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           }
         }
       }
-      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[0] = d_pf; d[1] = d_a; d[2] = clock64() - k0; }
+      if (dbgp) { long long* d = dbgp + blockIdx.x * 16; d[0] = d_pf; d[1] = d_a; d[2] = clock64() - k0; }
     }
   } else if (warp == 1) {
     // ============================ pose-blend MMA issuer ========================================
@@ -263,7 +267,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       int ps = 0; uint32_t pph = 0;
       int buf = 0; uint32_t bph = 0;
       long long d_off = 0, d_pf = 0, d_a = 0;
-      const long long k0 = p.dbg ? clock64() : 0;
+      const long long k0 = dbgp ? clock64() : 0;
       for (int m = m_begin; m < m_end;) {
         const Item it = item_at(m);
         m += it.len;
@@ -297,7 +301,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         tcgen05_commit(&off_full[buf]);
         if (++buf == TM::kOffStages) { buf = 0; bph ^= 1; }
       }
-      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[3] = d_off; d[4] = d_pf; d[5] = d_a; d[6] = clock64() - k0; }
+      if (dbgp) { long long* d = dbgp + blockIdx.x * 16; d[3] = d_off; d[4] = d_pf; d[5] = d_a; d[6] = clock64() - k0; }
     }
   } else if (warp == 2) {
     // ============================ TMA producer: skinning operands ==============================
@@ -343,7 +347,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       const uint32_t w_hi = smem_u32(w_smem), w_lo = w_hi + 64;   // lo half of every 128-byte row
       int ts = 0;
       long long d_t = 0, d_at = 0;
-      const long long k0 = p.dbg ? clock64() : 0;
+      const long long k0 = dbgp ? clock64() : 0;
       for (int m = m_begin; m < m_end;) {
         const Item it = item_at(m);
         m += it.len;
@@ -371,7 +375,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         const int next_vt = (m < m_end) ? m / p.npv : -1;
         if (next_vt != vt) tcgen05_commit(w_empty);
       }
-      if (p.dbg) { long long* d = p.dbg + blockIdx.x * 16; d[7] = d_t; d[8] = d_at; d[9] = clock64() - k0; }
+      if (dbgp) { long long* d = dbgp + blockIdx.x * 16; d[7] = d_t; d[8] = d_at; d[9] = clock64() - k0; }
     }
   } else {
     // ============================ epilogue =====================================================
@@ -405,7 +409,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
 #endif
     pdl_wait();      // outputs (and the read-out partial buffer) may still be in use by earlier kernels
     pdl_trigger();
-    const long long k0 = p.dbg ? clock64() : 0;
+    const long long k0 = dbgp ? clock64() : 0;
     for (int m = m_begin; m < m_end;) {
       const Item it = item_at(m);
       m += it.len;
@@ -437,7 +441,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         uint64_t* const t_rel = &t_empty[ts];
         if (++ts == TM::kTStages) { ts = 0; t_ph ^= 1; }
         tcgen05_fence_after();
-        const long long l0 = p.dbg ? clock64() : 0;
+        const long long l0 = dbgp ? clock64() : 0;
         uint32_t T[24], O[6];
         tmem_ld_32x32b_x16(t_addr, T);
         tmem_ld_32x32b_x8(t_addr + 16, T + 16);
@@ -446,7 +450,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         tmem_ld_32x32b_x2(off_addr + TM::kNB + ocol, O + 2);
         tmem_ld_32x32b_x2(off_addr + 2 * TM::kNB + ocol, O + 4);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const long long l1 = p.dbg ? clock64() : 0;
+        const long long l1 = dbgp ? clock64() : 0;
         // accumulators are in registers: hand them back before the arithmetic and the stores
         tcgen05_fence_before();
         __syncwarp();
@@ -454,11 +458,11 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           mbar_arrive(t_rel);
           if (g == ng - 1) mbar_arrive(&off_empty[buf]);
         }
-        if (p.dbg) { d_ld += l1 - l0; d_rel += clock64() - l1; }
+        if (dbgp) { d_ld += l1 - l0; d_rel += clock64() - l1; }
         if (n_valid <= 0) continue;
         float* outp = p.verts + (size_t)body_base * V3 + out_col;
 #ifdef WHMR_FUSED_FINE_PROBES
-        const long long e0c = p.dbg ? clock64() : 0;
+        const long long e0c = dbgp ? clock64() : 0;
 #endif
         auto run = [&](auto guard_tag) {
           constexpr bool G = decltype(guard_tag)::value;
@@ -478,30 +482,30 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
               rx += tr[0]; ry += tr[1]; rz += tr[2];
             }
             float* sb = stg + i * 96;
-            if (!(p.dbg_mode & 4)) { sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz; }
+            if (!(dbg_mode & 4)) { sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz; }
             else if (rx + ry + rz == 123.456f) sb[0] = rx;
           }
           __syncwarp();
 #ifdef WHMR_FUSED_FINE_PROBES
-          const long long e1c = p.dbg ? clock64() : 0;
+          const long long e1c = dbgp ? clock64() : 0;
 #endif
           float v[6];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int r = 0; r < 3; ++r) v[i * 3 + r] = (p.dbg_mode & 4) ? 0.f : stg[i * 96 + r * 32 + lane];
+            for (int r = 0; r < 3; ++r) v[i * 3 + r] = (dbg_mode & 4) ? 0.f : stg[i * 96 + r * 32 + lane];
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (G && i >= n_valid) continue;
             float* ob = outp + (size_t)i * V3;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
-              if ((!G || out_col + r * 32 < V3) && !(p.dbg_mode & 1)) ob[r * 32] = v[i * 3 + r];
+              if ((!G || out_col + r * 32 < V3) && !(dbg_mode & 1)) ob[r * 32] = v[i * 3 + r];
           }
 #ifdef WHMR_FUSED_FINE_PROBES
-          const long long e2c = p.dbg ? clock64() : 0;
+          const long long e2c = dbgp ? clock64() : 0;
 #endif
-          if (n_e > 0 && !(p.dbg_mode & 2)) {   // fused read-outs: entries referencing one of this warp's 32 vertices
+          if (n_e > 0 && !(dbg_mode & 2)) {   // fused read-outs: entries referencing one of this warp's 32 vertices
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               if (G && i >= n_valid) continue;
@@ -524,16 +528,16 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             }
           }
 #ifdef WHMR_FUSED_FINE_PROBES
-          if (p.dbg) { const long long e3c = clock64(); d_math += e1c - e0c; d_st += e2c - e1c; d_emit += e3c - e2c; }
+          if (dbgp) { const long long e3c = clock64(); d_math += e1c - e0c; d_st += e2c - e1c; d_emit += e3c - e2c; }
 #endif
         };
         if (n_valid == 2 && !has_transl && full_tile) run(cuda::std::false_type{}); else run(cuda::std::true_type{});
       }
       if (++buf == TM::kOffStages) { buf = 0; bph ^= 1; }
     }
-    if (p.dbg && warp == 4 && lane == 0) { long long* d = p.dbg + blockIdx.x * 16; d[10] = d_off; d[11] = d_t; d[12] = clock64() - k0; d[13] = d_ld; d[14] = d_rel;
+    if (dbgp && warp == 4 && lane == 0) { long long* d = dbgp + blockIdx.x * 16; d[10] = d_off; d[11] = d_t; d[12] = clock64() - k0; d[13] = d_ld; d[14] = d_rel;
 #ifdef WHMR_FUSED_FINE_PROBES
-      long long* d2 = p.dbg + (gridDim.x + blockIdx.x) * 16; d2[2] = d_math; d2[3] = d_st; d2[4] = d_emit;
+      long long* d2 = dbgp + (gridDim.x + blockIdx.x) * 16; d2[2] = d_math; d2[3] = d_st; d2[4] = d_emit;
 #endif
     }
   }
@@ -545,9 +549,9 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
-  if (p.dbg && threadIdx.x == 32) {
+  if (dbgp && threadIdx.x == 32) {
     unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-    p.dbg[(gridDim.x + blockIdx.x) * 16 + 1] = (long long)g;
+    dbgp[(gridDim.x + blockIdx.x) * 16 + 1] = (long long)g;
   }
 }
 

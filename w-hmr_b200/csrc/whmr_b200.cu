@@ -296,10 +296,10 @@ int whmr_smpl_create(const whmr_smpl_model_desc* m, int gemm_mode, whmr_smpl_t* 
   }
   if (const char* s = getenv("WHMR_SKIN")) h->skin_tc = strcmp(s, "simt") != 0;
   if (const char* s = getenv("WHMR_FUSED")) h->fused = atoi(s) != 0;
-  e = cudaFuncSetAttribute(smpl_fused_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<4>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<3>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<8>::kSmem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<6>::kSmem);
+  e = cudaFuncSetAttribute(smpl_fused_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<4>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<3>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<8>::kSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(smpl_fused_tc_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<6>::kSmem);
   if (e != cudaSuccess) { delete h; return set_error(WHMR_E_CUDA, "cudaFuncSetAttribute(smpl_fused_tc) failed: %s", cudaGetErrorString(e)); }
   h->gemm_mode = gemm_mode;
   *out = h;
@@ -582,10 +582,26 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   static const int backoff = getenv("WHMR_FUSED_BACKOFF") ? atoi(getenv("WHMR_FUSED_BACKOFF")) : 0;
   p.backoff = (unsigned)backoff;
   if (dbg_on) { cudaMalloc(&p.dbg, sizeof(long long) * 32 * grid); cudaMemsetAsync(p.dbg, 0, sizeof(long long) * 32 * grid, st); }
-  if (maxm == 3) launch_pdl(kPdlFused, smpl_fused_tc_kernel<3>, dim3(grid), dim3(kFuThreads), FuTmem<3>::kSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
-  else if (maxm == 6) launch_pdl(kPdlFused, smpl_fused_tc_kernel<6>, dim3(grid), dim3(kFuThreads), FuTmem<6>::kSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
-  else if (maxm == 4) launch_pdl(kPdlFused, smpl_fused_tc_kernel<4>, dim3(grid), dim3(kFuThreads), FuTmem<4>::kSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
-  else launch_pdl(kPdlFused, smpl_fused_tc_kernel<8>, dim3(grid), dim3(kFuThreads), FuTmem<8>::kSmem, st, h->tc.tmapA_bf16, tmapPf, h->tc.tmapW16, tmapAt, p);
+  const bool instrumented = dbg_on || dbg_mode != 0;
+#define WHMR_FUSED_LAUNCH(M, D)                                                                                         \
+  launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, D>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st, h->tc.tmapA_bf16, \
+             tmapPf, h->tc.tmapW16, tmapAt, p)
+  if (instrumented) {
+    static bool attr_done = false;
+    if (!attr_done) {   // the instrumented instantiations are only ever launched from here
+      cudaFuncSetAttribute(smpl_fused_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<3>::kSmem);
+      cudaFuncSetAttribute(smpl_fused_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<4>::kSmem);
+      cudaFuncSetAttribute(smpl_fused_tc_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<6>::kSmem);
+      cudaFuncSetAttribute(smpl_fused_tc_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<8>::kSmem);
+      attr_done = true;
+    }
+    if (maxm == 3) WHMR_FUSED_LAUNCH(3, true); else if (maxm == 4) WHMR_FUSED_LAUNCH(4, true);
+    else if (maxm == 6) WHMR_FUSED_LAUNCH(6, true); else WHMR_FUSED_LAUNCH(8, true);
+  } else {
+    if (maxm == 3) WHMR_FUSED_LAUNCH(3, false); else if (maxm == 4) WHMR_FUSED_LAUNCH(4, false);
+    else if (maxm == 6) WHMR_FUSED_LAUNCH(6, false); else WHMR_FUSED_LAUNCH(8, false);
+  }
+#undef WHMR_FUSED_LAUNCH
   WHMR_LAUNCHED("smpl_fused_tc_kernel");
   if (p.dbg) {   // per-role wait/total cycles averaged over CTAs (debug only: synchronises)
     cudaStreamSynchronize(st);
