@@ -37,7 +37,7 @@ struct ChainParams {
   float* pf_tf32;            // [B,2,KP] hi|lo tf32-valued floats or null
   float* At;                 // [2, At_rows, 32] tf32 hi|lo of A transposed: row (b*12+e), column = joint; or null
   size_t At_part_stride;     // floats between the hi and lo parts (= At_rows*32)
-  __half* At16;              // [At_rows, 64] fp16: A transposed, hi in columns 0..31, lo in 32..63 (fused kernel); or null
+  __half* At16;              // [At_rows, 64] fp16: A transposed, hi in columns 0..31, lo in 32..63, row = (b/2)*24 + e*2 + b%2 (fused kernel); or null
 };
 
 // smplx.lbs.batch_rodrigues for one vector: angle = ||v + 1e-8||, R = I + sin*K + (1-cos)*K*K
@@ -162,13 +162,15 @@ __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(Ch
   }
 
   if (p.At16) {   // fp16 hi|lo split: 22 mantissa bits, |lo| below the fp16 normal range only costs < 6e-8 absolute
-    __half* a0 = p.At16 + ((size_t)b * 12) * 64 + lane;
+    // rows of a body PAIR interleaved, (pair, element, body-in-pair): the blended transforms of two bodies then land
+    // in adjacent TMEM columns = adjacent registers of the skinning epilogue, which applies them with packed f32x2 FMAs
+    __half* a0 = p.At16 + ((size_t)(b >> 1) * 24 + (b & 1)) * 64 + lane;
 #pragma unroll
     for (int e = 0; e < 12; ++e) {
       const float x = active ? Arow[e] : 0.0f;
       const __half hi = __float2half_rn(x);
-      a0[(size_t)e * 64] = hi;
-      a0[(size_t)e * 64 + 32] = __float2half_rn(x - __half2float(hi));
+      a0[(size_t)e * 128] = hi;
+      a0[(size_t)e * 128 + 32] = __float2half_rn(x - __half2float(hi));
     }
   }
 

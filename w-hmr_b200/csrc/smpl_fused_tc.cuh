@@ -107,6 +107,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
 }
 
+// packed fp32 pairs (Blackwell FFMA2 / FADD2): one instruction for the two bodies a warp handles per group
+__device__ __forceinline__ uint64_t u32x2_pack(uint32_t lo, uint32_t hi) {
+  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
+}
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
 // wait that adds its duration to `acc` when instrumentation is on
 #define WHMR_FU_WAIT(bar, par, acc)                       \
   do {                                                    \
@@ -467,12 +484,29 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         auto run = [&](auto guard_tag) {
           constexpr bool G = decltype(guard_tag)::value;
           // both bodies are staged before the single __syncwarp, so their shared-memory round trips overlap
+          // T holds the two bodies' transforms interleaved (element k of body i in T[2k + i], see smpl_chain.cuh)
+          if (!G) {   // both bodies valid: packed f32x2 arithmetic, same operation order as the scalar path
+            const uint64_t t2x = f32x2_pack(tx, tx), t2y = f32x2_pack(ty, ty), t2z = f32x2_pack(tz, tz);
+            const uint64_t px = f32x2_add(u32x2_pack(O[0], O[1]), t2x), py = f32x2_add(u32x2_pack(O[2], O[3]), t2y),
+                           pz = f32x2_add(u32x2_pack(O[4], O[5]), t2z);
+#define WHMR_T2(k) u32x2_pack(T[2 * (k)], T[2 * (k) + 1])
+            const uint64_t rx = f32x2_fma(WHMR_T2(0), px, f32x2_fma(WHMR_T2(1), py, f32x2_fma(WHMR_T2(2), pz, WHMR_T2(3))));
+            const uint64_t ry = f32x2_fma(WHMR_T2(4), px, f32x2_fma(WHMR_T2(5), py, f32x2_fma(WHMR_T2(6), pz, WHMR_T2(7))));
+            const uint64_t rz = f32x2_fma(WHMR_T2(8), px, f32x2_fma(WHMR_T2(9), py, f32x2_fma(WHMR_T2(10), pz, WHMR_T2(11))));
+#undef WHMR_T2
+            float x0, x1, y0, y1, z0, z1;
+            f32x2_unpack(rx, x0, x1); f32x2_unpack(ry, y0, y1); f32x2_unpack(rz, z0, z1);
+            if (!(dbg_mode & 4)) {
+              stg[lane * 3 + 0] = x0; stg[lane * 3 + 1] = y0; stg[lane * 3 + 2] = z0;
+              stg[96 + lane * 3 + 0] = x1; stg[96 + lane * 3 + 1] = y1; stg[96 + lane * 3 + 2] = z1;
+            } else if (x0 + y0 + z0 + x1 + y1 + z1 == 123.456f) stg[0] = x0;
+          } else {
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (G && i >= n_valid) continue;                      // warp-uniform
             const float px = __uint_as_float(O[i]) + tx, py = __uint_as_float(O[2 + i]) + ty,
                         pz = __uint_as_float(O[4 + i]) + tz;
-#define WHMR_T(k) __uint_as_float(T[i * 12 + (k)])
+#define WHMR_T(k) __uint_as_float(T[(k) * 2 + i])
             float rx = fmaf(WHMR_T(0), px, fmaf(WHMR_T(1), py, fmaf(WHMR_T(2), pz, WHMR_T(3))));
             float ry = fmaf(WHMR_T(4), px, fmaf(WHMR_T(5), py, fmaf(WHMR_T(6), pz, WHMR_T(7))));
             float rz = fmaf(WHMR_T(8), px, fmaf(WHMR_T(9), py, fmaf(WHMR_T(10), pz, WHMR_T(11))));
@@ -484,6 +518,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             float* sb = stg + i * 96;
             if (!(dbg_mode & 4)) { sb[lane * 3 + 0] = rx; sb[lane * 3 + 1] = ry; sb[lane * 3 + 2] = rz; }
             else if (rx + ry + rz == 123.456f) sb[0] = rx;
+          }
           }
           __syncwarp();
 #ifdef WHMR_FUSED_FINE_PROBES
