@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
         if os.path.getmtime(LIB_PATH) >= newest:
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("WHMR_NVCC_EXTRA", "").split()   # e.g. -DWHMR_FUSED_COLLECTOR (experiments)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", LIB_PATH, os.path.join(CSRC, "whmr_b200.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
