@@ -425,7 +425,7 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
-def cpu_loop_baseline(backbone, n_bodies, reps=3):
+def cpu_loop_baseline(backbone, n_bodies, reps=3, min_seconds=10.0, max_seconds=30.0):
     import torch
     use_all_host_threads()
     import whmr_b200.synthetic as syn
@@ -435,10 +435,16 @@ def cpu_loop_baseline(backbone, n_bodies, reps=3):
     f, p, bb = make_cpu_inputs(n_bodies, backbone)
     orc.step(f, p, bb)
     ts = []
-    for _ in range(reps):
+    t_begin = time.perf_counter()
+    while True:   # a bounded sample: >= `reps` passes and ~min_seconds of CPU work, never more than max_seconds
         t0 = time.perf_counter()
         orc.step(f, p, bb)
-        ts.append(time.perf_counter() - t0)
+        t1 = time.perf_counter()
+        ts.append(t1 - t0)
+        spent = t1 - t_begin
+        if (len(ts) >= reps and spent >= min_seconds) or spent >= max_seconds:
+            break
+    reps = len(ts)
     t = sorted(ts)[len(ts) // 2]
     return {"value": n_bodies / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d bodies of the same loop workload (same generators), median of %d passes, %.2f s/pass; "
@@ -558,9 +564,9 @@ def run_reference(args):
     import whmr_b200.synthetic as syn
     from oracle.loop_oracle import LoopOracle, make_cpu_inputs
     use_all_host_threads()
-    n = args.cpu_sample
-    K, W = args.steps if args.steps_given else 10, max(1, min(args.warmup, 3))
-    K = min(K, 40)
+    K, W = args.steps if args.steps_given else 20, max(1, min(args.warmup, 3))
+    # exactly K timed steps; the per-step sample shrinks so that K steps stay within ~2 minutes (~450 bodies/s on 16 threads)
+    n = max(8, min(args.cpu_sample, int(120.0 * 450.0 / max(K, 1))))
     model = syn.make_smpl_model(seed=0, weights="random")
     orc = LoopOracle(model, args.backbone)
     f, p, bb = make_cpu_inputs(n, args.backbone)
