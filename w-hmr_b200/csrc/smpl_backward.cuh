@@ -8,9 +8,10 @@
 //   A_j = [Rg_j | tg_j - Rg_j J_j],  Rg_j = Rg_p R_j,  tg_j = Rg_p (J_j - J_p) + tg_p,  J = Jt + Jd beta,
 //   pf = [(R_j - I)_{j>=1} ; beta]                                                chain_backward_kernel
 //
-// First version: correctness first (tests: autograd through the float64 oracle).  The skinning backward accumulates
-// g_A with shared-memory atomics and the P^T contraction is a plain FFMA kernel with a split K; moving both onto the
-// tensor cores is a later step.  fp32 atomics => the last bits of the gradients depend on the execution order.
+// CUDA-core kernels (tests: autograd through the float64 oracle).  The per-joint transform gradients are a small dense
+// contraction per CTA (no shared-memory atomics), the P^T contraction is a register-tiled FFMA kernel with a split K;
+// moving both onto the tensor cores is a later step.  Global fp32 atomics across CTAs => the last bits of the
+// gradients depend on the execution order.
 #pragma once
 #include "common.cuh"
 #include "readout.cuh"
@@ -32,92 +33,175 @@ struct SkinBwdParams {
   int B, V, VP, NP, J, ell_k;
 };
 
-// CTA = 128 consecutive vertices x kBwdBodies bodies; thread = vertex.
-__global__ void __launch_bounds__(kVertTile) skin_backward_kernel(SkinBwdParams p) {
+// CTA = 128 consecutive vertices x kBwdBodies bodies, 256 threads.
+//  phase A (thread = vertex x body half): blended rotation from the ELL weights, g_p = Trot^T g_v -> g_offsets, and the
+//           outer products gT[v] = g_v (x) [p_v ; 1] staged in shared memory, element-major;
+//  phase B (warp = body, lane = 3 joints x 3 elements): g_A[j][e] += sum_v W[v][j] gT[v][e] as a small dense
+//           contraction over the tile's 128 vertices against a dense [128, J] weight tile rebuilt from the ELL form --
+//           every shared-memory load is a broadcast, no atomics; one global atomicAdd per (body, joint, element) and CTA.
+//  (First version: 48 shared-memory atomicAdds per vertex and body, 316 us at B=256; this one: see profiles/r01_notes.md.)
+constexpr int kBwdThreads = 256;
+constexpr int kGtLd = kVertTile + 1;   // element stride of the staged outer products (odd: the 4 element groups of a warp hit 4 banks)
+__host__ __device__ inline size_t skin_backward_smem_bytes(int J) {
+  // A_s [bodies][J*12] + W_s [128][JP] + gT_s [bodies][12][128], JP = J rounded up to a multiple of 3
+  const int JP = (J + 2) / 3 * 3;
+  return ((size_t)kBwdBodies * J * 12 + (size_t)kVertTile * JP + (size_t)kBwdBodies * 12 * kGtLd) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(kBwdThreads) skin_backward_kernel(SkinBwdParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* A_s = smem;                                // [kBwdBodies][J*12]
-  float* gA_s = A_s + kBwdBodies * p.J * 12;         // [kBwdBodies][J*12]
+  const int JP = (p.J + 2) / 3 * 3;
+  float* A_s = smem;                                         // [kBwdBodies][J*12]
+  float* W_s = A_s + kBwdBodies * p.J * 12;                   // [128][JP]
+  float* gT_s = W_s + kVertTile * JP;                         // [kBwdBodies][12][kGtLd]
   const int tid = threadIdx.x;
-  const int v = blockIdx.x * kVertTile + tid;        // < VP
+  const int v0 = blockIdx.x * kVertTile;
   const int b0 = blockIdx.y * kBwdBodies;
   const int nb_here = min(kBwdBodies, p.B - b0);
   const int nA = nb_here * p.J * 12;
-  for (int i = tid; i < nA; i += kVertTile) { A_s[i] = p.A[(size_t)b0 * p.J * 12 + i]; gA_s[i] = 0.f; }
-  const bool real = v < p.V;
-  const float tx = p.v_template_p[v], ty = p.v_template_p[p.VP + v], tz = p.v_template_p[2 * p.VP + v];
+  for (int i = tid; i < nA; i += kBwdThreads) A_s[i] = p.A[(size_t)b0 * p.J * 12 + i];
+  for (int i = tid; i < kVertTile * JP; i += kBwdThreads) W_s[i] = 0.f;
   __syncthreads();
-  for (int bi = 0; bi < nb_here; ++bi) {
-    const int b = b0 + bi;
-    float gx = 0.f, gy = 0.f, gz = 0.f;
-    if (real) {
-      const float* g = p.g_verts + ((size_t)b * p.V + v) * 3;
-      gx = g[0]; gy = g[1]; gz = g[2];
-    }
-    const float* o = p.offsets + (size_t)b * p.NP + v;
-    const float px = o[0] + tx, py = o[p.VP] + ty, pz = o[2 * p.VP] + tz;
-    const float* Ab = A_s + bi * p.J * 12;
-    float* gAb = gA_s + bi * p.J * 12;
-    float r[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // blended rotation part of T
-    const float gT[12] = {gx * px, gx * py, gx * pz, gx, gy * px, gy * py, gy * pz, gy, gz * px, gz * py, gz * pz, gz};
+  if (tid < kVertTile) {   // dense weight tile from the ELL rows (a vertex's joints are distinct: no write conflicts)
+    const int v = v0 + tid;
     for (int k = 0; k < p.ell_k; ++k) {
-      const int j = p.ell_idx[(size_t)k * p.VP + v] * 12;
       const float w = p.ell_w[(size_t)k * p.VP + v];
-      if (w == 0.f) continue;
-#pragma unroll
-      for (int rr = 0; rr < 3; ++rr)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) r[rr * 3 + c] = fmaf(w, Ab[j + rr * 4 + c], r[rr * 3 + c]);
-      if (real) {
-#pragma unroll
-        for (int e = 0; e < 12; ++e) atomicAdd(gAb + j + e, w * gT[e]);
-      }
+      if (w != 0.f) W_s[tid * JP + p.ell_idx[(size_t)k * p.VP + v]] += w;
     }
-    // g_p = Trot^T g_v
-    float* go = p.g_offsets + (size_t)b * p.NP + v;
-    go[0] = r[0] * gx + r[3] * gy + r[6] * gz;
-    go[p.VP] = r[1] * gx + r[4] * gy + r[7] * gz;
-    go[2 * p.VP] = r[2] * gx + r[5] * gy + r[8] * gz;
+  }
+  // ---- phase A ----
+  {
+    const int lv = tid & (kVertTile - 1), half = tid >> 7;     // bodies [half*4, half*4+4)
+    const int v = v0 + lv;
+    const bool real = v < p.V;
+    const float tx = p.v_template_p[v], ty = p.v_template_p[p.VP + v], tz = p.v_template_p[2 * p.VP + v];
+    int jidx[4]; float jw[4];                                  // first four ELL entries in registers (the SMPL case)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      jidx[k] = k < p.ell_k ? p.ell_idx[(size_t)k * p.VP + v] * 12 : 0;
+      jw[k] = k < p.ell_k ? p.ell_w[(size_t)k * p.VP + v] : 0.f;
+    }
+    for (int bi = half * (kBwdBodies / 2); bi < min(nb_here, (half + 1) * (kBwdBodies / 2)); ++bi) {
+      const int b = b0 + bi;
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      if (real) {
+        const float* g = p.g_verts + ((size_t)b * p.V + v) * 3;
+        gx = g[0]; gy = g[1]; gz = g[2];
+      }
+      const float* o = p.offsets + (size_t)b * p.NP + v;
+      const float px = o[0] + tx, py = o[p.VP] + ty, pz = o[2 * p.VP] + tz;
+      const float* Ab = A_s + bi * p.J * 12;
+      float r[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // blended rotation part of T
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = jw[k];
+        const float* a = Ab + jidx[k];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) r[rr * 3 + c] = fmaf(w, a[rr * 4 + c], r[rr * 3 + c]);
+      }
+      for (int k = 4; k < p.ell_k; ++k) {   // models with more than four influences per vertex
+        const float w = p.ell_w[(size_t)k * p.VP + v];
+        if (w == 0.f) continue;
+        const float* a = Ab + p.ell_idx[(size_t)k * p.VP + v] * 12;
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) r[rr * 3 + c] = fmaf(w, a[rr * 4 + c], r[rr * 3 + c]);
+      }
+      // g_p = Trot^T g_v
+      float* go = p.g_offsets + (size_t)b * p.NP + v;
+      go[0] = r[0] * gx + r[3] * gy + r[6] * gz;
+      go[p.VP] = r[1] * gx + r[4] * gy + r[7] * gz;
+      go[2 * p.VP] = r[2] * gx + r[5] * gy + r[8] * gz;
+      float* gt = gT_s + (size_t)bi * 12 * kGtLd + lv;            // [e][v]
+      gt[0 * kGtLd] = gx * px; gt[1 * kGtLd] = gx * py; gt[2 * kGtLd] = gx * pz; gt[3 * kGtLd] = gx;
+      gt[4 * kGtLd] = gy * px; gt[5 * kGtLd] = gy * py; gt[6 * kGtLd] = gy * pz; gt[7 * kGtLd] = gy;
+      gt[8 * kGtLd] = gz * px; gt[9 * kGtLd] = gz * py; gt[10 * kGtLd] = gz * pz; gt[11 * kGtLd] = gz;
+    }
   }
   __syncthreads();
-  for (int i = tid; i < nA; i += kVertTile) {
-    const float x = gA_s[i];
-    if (x != 0.f) atomicAdd(p.g_A + (size_t)b0 * p.J * 12 + i, x);
+  // ---- phase B ----
+  {
+    const int bi = tid >> 5, lane = tid & 31;
+    if (bi >= nb_here) return;                                  // warp-uniform
+    const int eg = (lane & 3) * 3;                              // elements eg .. eg+2
+    const float* gt = gT_s + (size_t)bi * 12 * kGtLd + eg * kGtLd;
+    for (int jg = (lane >> 2) * 3; jg < JP; jg += 24) {         // joints jg .. jg+2 (one pass for J <= 24)
+      float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float* wv = W_s + jg;
+#pragma unroll 8
+      for (int v = 0; v < kVertTile; ++v) {
+        const float w0 = wv[v * JP], w1 = wv[v * JP + 1], w2 = wv[v * JP + 2];
+        const float t0 = gt[v], t1 = gt[kGtLd + v], t2 = gt[2 * kGtLd + v];
+        acc[0] = fmaf(w0, t0, acc[0]); acc[1] = fmaf(w0, t1, acc[1]); acc[2] = fmaf(w0, t2, acc[2]);
+        acc[3] = fmaf(w1, t0, acc[3]); acc[4] = fmaf(w1, t1, acc[4]); acc[5] = fmaf(w1, t2, acc[5]);
+        acc[6] = fmaf(w2, t0, acc[6]); acc[7] = fmaf(w2, t1, acc[7]); acc[8] = fmaf(w2, t2, acc[8]);
+      }
+      float* dst = p.g_A + ((size_t)(b0 + bi) * p.J) * 12;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (jg + a >= p.J) continue;
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+          if (acc[a * 3 + e] != 0.f) atomicAdd(dst + (jg + a) * 12 + eg + e, acc[a * 3 + e]);
+      }
+    }
   }
 }
 
 // g_pf[b, k] = sum_n g_off[b, n] * P[k, n]   (P = posedirs_p [KP, NP] fp32 planar; K of this product = NP = 20736)
-// grid = (KP/32, ceil(B/32), kBwdKSplit), block (32, 8): a 32x32 output tile per CTA over one slice of n,
-// accumulated into g_pf (zero-initialised) with atomics.
-constexpr int kBwdKSplit = 18;   // 20736 / 18 = 1152 = 36 tiles of 32
+// grid = (ceil(KP/64), ceil(B/64), split), 256 threads: a 64 x 64 output tile per CTA over one slice of n, 4 x 4 outputs
+// per thread; both operands are staged transposed ([n][row], 32 n at a time) so that the inner loop is two 16-byte
+// shared-memory loads per 16 FMAs.  Slices are accumulated into g_pf (zero-initialised) with atomics.
+constexpr int kPbTile = 64, kPbN = 32, kPbLd = kPbTile + 4;
 __global__ void __launch_bounds__(256)
 pose_blend_backward_kernel(const float* __restrict__ g_off, const float* __restrict__ P, float* __restrict__ g_pf, int B,
                            int KP, int NP) {
-  __shared__ float Gs[32][33], Ps[32][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;          // 32 x 8
-  const int k0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
-  const int n_per = NP / gridDim.z;
+  __shared__ __align__(16) float Gs[kPbN][kPbLd], Ps[kPbN][kPbLd];
+  const int tid = threadIdx.x;
+  const int tb = tid >> 4, tk = tid & 15;                 // bodies tb*4.., pose-feature columns tk*4..
+  const int k0 = blockIdx.x * kPbTile, b0 = blockIdx.y * kPbTile;
+  const int n_per = NP / gridDim.z;                       // a multiple of kPbN (the host picks the split)
   const int n_begin = blockIdx.z * n_per, n_end = n_begin + n_per;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};                   // outputs (b0 + ty + 8*i, k0 + tx)
-  for (int n0 = n_begin; n0 < n_end; n0 += 32) {
+  float acc[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = ty + 8 * i;
-      Gs[r][tx] = (b0 + r < B) ? g_off[(size_t)(b0 + r) * NP + n0 + tx] : 0.f;
-      Ps[r][tx] = (k0 + r < KP) ? P[(size_t)(k0 + r) * NP + n0 + tx] : 0.f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int n0 = n_begin; n0 < n_end; n0 += kPbN) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256, row = idx >> 3, q = (idx & 7) * 4;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f), w = g;
+      if (b0 + row < B) g = __ldg(reinterpret_cast<const float4*>(g_off + (size_t)(b0 + row) * NP + n0 + q));
+      if (k0 + row < KP) w = __ldg(reinterpret_cast<const float4*>(P + (size_t)(k0 + row) * NP + n0 + q));
+      Gs[q + 0][row] = g.x; Gs[q + 1][row] = g.y; Gs[q + 2][row] = g.z; Gs[q + 3][row] = g.w;
+      Ps[q + 0][row] = w.x; Ps[q + 1][row] = w.y; Ps[q + 2][row] = w.z; Ps[q + 3][row] = w.w;
     }
     __syncthreads();
 #pragma unroll 8
-    for (int n = 0; n < 32; ++n) {
-      const float pv = Ps[tx][n];
+    for (int n = 0; n < kPbN; ++n) {
+      const float4 a = *reinterpret_cast<const float4*>(&Gs[n][tb * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ps[n][tk * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(Gs[ty + 8 * i][n], pv, acc[i]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int b = b0 + ty + 8 * i;
-    if (b < B && k0 + tx < KP) atomicAdd(g_pf + (size_t)b * KP + k0 + tx, acc[i]);
+    const int b = b0 + tb * 4 + i;
+    if (b >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk * 4 + j;
+      if (k < KP) atomicAdd(g_pf + (size_t)b * KP + k, acc[i][j]);
+    }
   }
 }
 

@@ -1199,8 +1199,13 @@ int whmr_smpl_backward(whmr_smpl_t h, const float* betas, const float* pose, int
     WHMR_LAUNCHED("smpl_chain_kernel");
     SmplWorkspace ws{};
     ws.A = c.A; ws.pf = c.pf; ws.pf_split = c.pf_split; ws.offsets = c.offsets; ws.Bpad = c.Bpad; ws.chunk = c.chunk;
+    // split of the n = 3*VP reduction: enough CTAs to fill the machine, slices a multiple of the 32-wide staging step
     int ksplit = 1;
-    for (int s2 = 24; s2 >= 1; --s2) if ((d.NP / 32) % s2 == 0) { ksplit = s2; break; }
+    {
+      const int tiles = ceil_div(d.KP, kPbTile) * ceil_div(std::min(B, c.chunk), kPbTile);
+      const int want = std::max(1, ceil_div(3 * h->tc.num_sms, tiles));
+      for (int s2 = std::min(want, d.NP / kPbN); s2 >= 1; --s2) if ((d.NP / kPbN) % s2 == 0) { ksplit = s2; break; }
+    }
     for (int b0 = 0; b0 < B; b0 += c.chunk) {
       const int nb = std::min(c.chunk, B - b0);
       int rc = launch_pose_blend(h, ws, B, b0, nb, st);
@@ -1211,10 +1216,15 @@ int whmr_smpl_backward(whmr_smpl_t h, const float* betas, const float* pose, int
       q.v_template_p = d.v_template_p; q.ell_idx = d.ell_idx; q.ell_w = d.ell_w;
       q.g_offsets = c.g_off; q.g_A = c.g_A + (size_t)b0 * d.J * 12;
       q.B = nb; q.V = d.V; q.VP = d.VP; q.NP = d.NP; q.J = d.J; q.ell_k = d.ell_k;
-      const size_t smem = (size_t)2 * kBwdBodies * d.J * 12 * sizeof(float);
-      skin_backward_kernel<<<dim3(d.VP / kVertTile, ceil_div(nb, kBwdBodies)), kVertTile, smem, st>>>(q);
+      const size_t smem = skin_backward_smem_bytes(d.J);
+      static size_t smem_set = 0;
+      if (smem > smem_set) {
+        WHMR_CUDA(cudaFuncSetAttribute(skin_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+      }
+      skin_backward_kernel<<<dim3(d.VP / kVertTile, ceil_div(nb, kBwdBodies)), kBwdThreads, smem, st>>>(q);
       WHMR_LAUNCHED("skin_backward_kernel");
-      pose_blend_backward_kernel<<<dim3(ceil_div(d.KP, 32), ceil_div(nb, 32), ksplit), dim3(32, 8), 0, st>>>(
+      pose_blend_backward_kernel<<<dim3(ceil_div(d.KP, kPbTile), ceil_div(nb, kPbTile), ksplit), 256, 0, st>>>(
           c.g_off, d.posedirs_p, c.g_pf + (size_t)b0 * d.KP, nb, d.KP, d.NP);
       WHMR_LAUNCHED("pose_blend_backward_kernel");
     }
