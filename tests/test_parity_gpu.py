@@ -149,6 +149,31 @@ def test_smpl_chunked_large_batch_properties(dev, smpl_model, gemm_mode):
     assert ops is not None
 
 
+def test_smpl_fused_chunk_boundary_and_readouts(dev, smpl_model):
+    """The fused kernel runs in 4096-body chunks (the chunk bounds the read-out partial buffer): bodies on either side of
+    the boundary, with the full BodyModelHead read-out table, are bitwise independent of their batch position and match
+    the oracle; the flat group-major read-out buffer is laid out for the WHOLE batch, not per chunk."""
+    from oracle.smpl_oracle import regressor_readouts
+    from whmr_b200.regressor import BodyModelHead
+    B = 4096 + 53
+    b = _bodies(B, seed=13)
+    smpl = _smpl(smpl_model, dev, "bf16x3")
+    head = BodyModelHead(smpl, smpl_model['Dmap0'], smpl_model['Dmap1'], smpl_model['ssm'], smpl_model['J_regressor_h36m'])
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    rot, betas, cam = T(b['rotmat']), T(b['betas']), T(b['cam'])
+    big = head(rot, betas, cam, J_regressor=True)
+    idx = [0, 1, 4094, 4095, 4096, 4097, B - 1]
+    sel = torch.tensor(idx, device=dev)
+    small = head(rot[sel], betas[sel], cam[sel], J_regressor=True)
+    for k in ('verts', 'kp_3d', 'smpl_kp_3d', 'sub_verts', 'temp_verts', 'markers', 'joints49', 'kp_2d'):
+        assert torch.equal(big[k][sel], small[k]), k
+    ref = _oracle(smpl_model)(b['betas'][idx], b['rotmat'][idx, 1:], b['rotmat'][idx, :1], pose2rot=False)
+    rr = regressor_readouts(smpl_model, ref['vertices'])
+    assert _maxabs(big['verts'][sel], ref['vertices']) <= VERT_TOL
+    assert _maxabs(big['kp_3d'][sel], rr['kp_3d_h36m']) <= VERT_TOL
+    assert _maxabs(big['temp_verts'][sel], rr['temp_verts']) <= VERT_TOL
+
+
 def test_smpl_transl_and_default_params(dev, smpl_model):
     from whmr_b200.smpl import SMPL
     smpl = SMPL(model=smpl_model, batch_size=4, create_transl=True, gemm_mode="fp32_simt").to(dev)
@@ -352,6 +377,24 @@ def test_sampling_vs_grid_sample(dev, layout, H, W, N, C):
         out = ops.sample_bilinear(feat.permute(0, 2, 3, 1).contiguous().to(dev), pts.to(dev), ops.LAYOUT_NHWC)
     assert out.shape == (B, C, N)
     assert _maxabs(out, ref) <= FEAT_RTOL * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (1, 9), (9, 1), (2, 2)])
+def test_sampling_degenerate_maps(dev, H, W):
+    """align_corners=True with a size-1 axis maps every coordinate to pixel 0 (grid_sample semantics); empty point sets
+    and empty batches return empty tensors."""
+    from oracle.sampling_oracle import grid_sample_points
+    from whmr_b200 import ops
+    B, C, N = 2, 5, 33
+    g = torch.Generator().manual_seed(H * 10 + W)
+    feat = torch.randn(B, C, H, W, generator=g)
+    pts = torch.rand(B, N, 2, generator=g) * 2.4 - 1.2
+    ref = grid_sample_points(feat, pts)
+    for layout, f in ((ops.LAYOUT_NCHW, feat), (ops.LAYOUT_NHWC, feat.permute(0, 2, 3, 1).contiguous())):
+        out = ops.sample_bilinear(f.to(dev), pts.to(dev), layout)
+        assert _maxabs(out, ref) <= FEAT_RTOL * max(float(ref.abs().max()), 1e-6)
+    assert ops.sample_bilinear(feat.to(dev), pts[:, :0].to(dev), ops.LAYOUT_NCHW).shape == (B, C, 0)
+    assert ops.sample_bilinear(feat[:0].to(dev), pts[:0].to(dev), ops.LAYOUT_NCHW).shape == (0, C, N)
 
 
 def test_maf_project_matches_reference_golden(dev, golden):
