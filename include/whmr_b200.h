@@ -170,6 +170,11 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
                               size_t workspace_bytes, void* stream);
 int whmr_readout_finish(whmr_readout_t ro, const float* joints /*[B,J,3] or NULL*/, int B, const void* ro_workspace,
                         float* ro_out, void* stream);
+/* The deferred finishing passes of up to 8 whmr_smpl_forward_readout calls (same table, same B, each with its own
+ * workspace / output / chain joints) in ONE launch: host arrays of n_calls device pointers.  Inside the regressor loop
+ * (models/whmr.py:550-651) nothing but the caller reads the finished rows, so the loop defers them to its end. */
+int whmr_readout_finish_multi(whmr_readout_t ro, int n_calls, const float* const* joints, const void* const* ro_workspaces,
+                              float* const* ro_outs, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Projection.

@@ -71,6 +71,7 @@ SIGNATURES = {
     "whmr_smpl_chunk_bodies": (C.c_int, [_vp]),
     "whmr_smpl_is_fused": (C.c_int, [_vp]),
     "whmr_readout_finish": (C.c_int, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "whmr_readout_finish_multi": (C.c_int, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _vp]),
     "whmr_smpl_stage_chain": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "whmr_smpl_stage_pose_blend": (C.c_int, [_vp, _i, _vp, _sz, _vp]),
     "whmr_smpl_stage_skin": (C.c_int, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),

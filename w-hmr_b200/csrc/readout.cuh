@@ -193,10 +193,16 @@ struct ReduceParams {
   const int* jt_ptr;                    // [R+1] range of each row's joint-sourced terms
   const int* jt_col; const float* jt_val;
   const float* partial; int n_partial;  // [chunk, n_partial, 3], n_partial % 4 == 0
+  // batched finish (whmr_readout_finish_multi): blockIdx.y selects one of n_multi independent (joints, partial, out)
+  // triples of the same table and batch size -- the finishing passes of several SMPL calls in ONE launch
+  int n_multi;
+  const float* joints_m[8];
+  const float* partial_m[8];
+  float* out_m[8];
 };
 
-__device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* ps, const int* slots, int b, int r,
-                                           float& x, float& y, float& z) {
+__device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* joints, const float* ps, const int* slots,
+                                           int b, int r, float& x, float& y, float& z) {
   const ReadoutParams& p = q.rp;
   x = y = z = 0.f;
   int k = q.part_ptr[r];
@@ -217,7 +223,7 @@ __device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* p
   }
   for (int k = q.jt_ptr[r]; k < q.jt_ptr[r + 1]; ++k) {
     const float w = q.jt_val[k];
-    const float* s = p.joints + ((size_t)b * p.J + q.jt_col[k]) * 3;
+    const float* s = joints + ((size_t)b * p.J + q.jt_col[k]) * 3;
     x = fmaf(w, s[0], x); y = fmaf(w, s[1], y); z = fmaf(w, s[2], z);
   }
 }
@@ -226,11 +232,13 @@ __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
   extern __shared__ __align__(16) float ps[];   // [n_partial * 3]
   pdl_wait();
   pdl_trigger();
-  const ReadoutParams& p = q.rp;
+  ReadoutParams p = q.rp;
   const int b = blockIdx.x;
+  const float* partial = q.partial;
+  if (q.n_multi > 0) { p.joints = q.joints_m[blockIdx.y]; p.out = q.out_m[blockIdx.y]; partial = q.partial_m[blockIdx.y]; }
   int* slots = reinterpret_cast<int*>(ps + q.n_partial * 3);   // [n_partial] emit slot of every vertex-sourced term
   {
-    const float4* src = reinterpret_cast<const float4*>(q.partial + (size_t)b * q.n_partial * 3);
+    const float4* src = reinterpret_cast<const float4*>(partial + (size_t)b * q.n_partial * 3);
     float4* dst = reinterpret_cast<float4*>(ps);
     const int n4 = q.n_partial * 3 / 4;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
@@ -242,11 +250,11 @@ __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
   for (int i = threadIdx.x; i < q.n_rows; i += blockDim.x) {
     const int r = q.rows[i];
     float x, y, z;
-    reduce_row(q, ps, slots, b, r, x, y, z);
+    reduce_row(q, p.joints, ps, slots, b, r, x, y, z);
     const int sr = p.sub_row ? p.sub_row[r] : -1;
     if (sr >= 0) {
       float sx, sy, sz;
-      reduce_row(q, ps, slots, b, sr, sx, sy, sz);
+      reduce_row(q, p.joints, ps, slots, b, sr, sx, sy, sz);
       x -= sx; y -= sy; z -= sz;
     }
     float* o = readout_dst(p, b, r);

@@ -676,6 +676,31 @@ int whmr_readout_finish(whmr_readout_t ro, const float* joints, int B, const voi
   return launch_readout_reduce(ro, nullptr, joints, B, B, 0, partial, ro_out, (cudaStream_t)stream);
 }
 
+int whmr_readout_finish_multi(whmr_readout_t ro, int n_calls, const float* const* joints, const void* const* ro_workspaces,
+                              float* const* ro_outs, int B, void* stream) {
+  WHMR_CHECK_ARG(ro && B >= 0 && n_calls >= 0 && n_calls <= 8, "whmr_readout_finish_multi: bad arguments (at most 8 calls)");
+  if (B == 0 || n_calls == 0 || ro->n_reduce == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(joints && ro_workspaces && ro_outs, "whmr_readout_finish_multi: null pointer array");
+  ReduceParams q{};
+  ReadoutParams& p = q.rp;
+  p.row_ptr = ro->row_ptr; p.col_idx = ro->col_idx; p.vals = ro->vals; p.sub_row = ro->sub_row;
+  p.grp_prefix = ro->grp_prefix; p.grp_rows = ro->grp_rows;
+  p.R = ro->R; p.V = ro->V; p.J = ro->J; p.B = B; p.B_total = B; p.b0 = 0;
+  q.rows = ro->rows_reduce; q.n_rows = ro->n_reduce; q.part_ptr = ro->part_ptr;
+  q.n_partial = ro->n_partial; q.slot_of = ro->slot_of; q.jt_ptr = ro->jt_ptr; q.jt_col = ro->jt_col; q.jt_val = ro->jt_val;
+  q.n_multi = n_calls;
+  for (int i = 0; i < n_calls; ++i) {
+    WHMR_CHECK_ARG(ro_workspaces[i] && ro_outs[i] && (joints[i] || !ro->needs_joints), "whmr_readout_finish_multi: null buffer");
+    q.joints_m[i] = joints[i];
+    q.partial_m[i] = reinterpret_cast<const float*>(align_up(reinterpret_cast<size_t>(ro_workspaces[i]), 256));
+    q.out_m[i] = ro_outs[i];
+  }
+  const size_t smem = (size_t)ro->n_partial * 4 * sizeof(float);
+  launch_pdl(kPdlReadout, readout_reduce_kernel, dim3(B, n_calls), dim3(128), smem, (cudaStream_t)stream, q);
+  WHMR_LAUNCHED("readout_reduce_kernel");
+  return WHMR_OK;
+}
+
 int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
                               const float* transl, int B, float* verts, float* joints, float* rel_transforms,
                               whmr_readout_t ro, float* ro_out, void* ro_workspace, size_t ro_workspace_bytes,

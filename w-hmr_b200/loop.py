@@ -43,6 +43,9 @@ class RegressorLoop:
         # and lose more in their tails than the overlap gains -- so it is off by default.
         self.overlap = False
         self._side = torch.cuda.Stream(device=self.device)
+        # finishing passes of the five read-outs + the joint projections after the loop, in one + four launches
+        # (inference only: under autograd the immediate schedule is used); 0.389 -> see profiles/r01_notes.md
+        self.defer = True
 
     def step(self, feats, params, bbox):
         """feats: 3 feature maps [B,256,H_i,W_i]; params: 5 dicts {rotmat [B,24,3,3], betas [B,10],
@@ -51,16 +54,14 @@ class RegressorLoop:
         J = True if self.with_h36m else None
         p = params
         main = torch.cuda.current_stream(self.device)
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for q in p for t in q.values())
+        if self.defer and self.head.probe is None and not self.overlap and not needs_grad:
+            return self._step_deferred(feats, params, bbox, J)
         self.head.side_stream = self._side if (self.overlap and self.head.probe is None) else None
         out = self.head(p[0]['rotmat'], p[0]['betas'], p[0]['cam'], J_regressor=J)           # forward_init
         point_feats = []
         for it in range(3):
-            if it == 0:
-                pf = ops.sample_bilinear_op(feats[0], self.grid, self.layout)                # :596-597
-            else:                                                                            # :606
-                pf, _ = ops.project_sample_op(feats[it], out['markers'], p[it]['cam'], constants.FOCAL_LENGTH,
-                                           float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT),
-                                           self.layout)   # projection fused into the sampling launch
+            pf = self._sample(it, feats, out['markers'], p[it]['cam'])
             self.head._mark('sample_l%d' % it)
             point_feats.append(pf)
             q = p[it + 1]
@@ -79,6 +80,35 @@ class RegressorLoop:
         res['point_feats'] = point_feats
         res['global_verts'] = gverts
         res['global_kp_3d'] = r['kp_3d_h36m'] if self.with_h36m else r['joints']            # :646-651
+        return res
+
+    def _sample(self, it, feats, markers, cam):
+        if it == 0:
+            return ops.sample_bilinear_op(feats[0], self.grid, self.layout)                  # :596-597
+        pf, _ = ops.project_sample_op(feats[it], markers, cam, constants.FOCAL_LENGTH,       # :606
+                                      float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT),
+                                      self.layout)   # projection fused into the sampling launch
+        return pf
+
+    def _step_deferred(self, feats, params, bbox, J):
+        """Same results, 18 launches instead of 22: the next iteration needs only the markers (written by the SMPL
+        kernel itself) and the camera, so the five finishing passes of the read-outs run as ONE launch after the loop,
+        followed by the four joint projections (models/whmr.py:550-651 returns everything at the end as well)."""
+        p = params
+        states = [self.head.begin(p[0]['rotmat'], p[0]['betas'], J)]
+        point_feats = []
+        for it in range(3):
+            point_feats.append(self._sample(it, feats, states[-1]['markers'], p[it]['cam']))
+            q = p[it + 1]
+            states.append(self.head.begin(q['rotmat'], q['betas'], J))
+        states.append(self.head.begin(p[4]['rotmat'], p[4]['betas'], J))                     # global call, :641-644
+        outs = self.head.complete_all(states, [p[0]['cam'], p[1]['cam'], p[2]['cam'], p[3]['cam'], None],
+                                      bbox['bbox_height'], bbox['center'], bbox['orig_shape'], bbox['Tz'],
+                                      full=[False, True, True, True, False])
+        res = dict(outs[3])
+        res['point_feats'] = point_feats
+        res['global_verts'] = outs[4]['verts']
+        res['global_kp_3d'] = outs[4]['r']['kp_3d_h36m'] if self.with_h36m else outs[4]['r']['joints']
         return res
 
     # ---- CUDA-graph replay ------------------------------------------------------------------------

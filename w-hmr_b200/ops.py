@@ -608,6 +608,19 @@ def readout_finish(readout: int, joints: torch.Tensor, flat: torch.Tensor, scrat
         check(_lib.lib().whmr_readout_finish(ro._h, _p(joints), joints.shape[0], _p(scratch), _p(flat), _stream()))
 
 
+def readout_finish_multi(readout, joints, flats, scratches):
+    """The deferred finishing passes of several smpl_lbs_readout_deferred calls (same table, same batch) in one launch;
+    writes the regressor rows into each `flat` in place.  (Plain function: inference-side scheduling, no autograd.)"""
+    ro = _READOUTS[readout]
+    n = len(flats)
+    if n == 0:
+        return
+    B = joints[0].shape[0]
+    arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+    with torch.cuda.device(flats[0].device):
+        check(_lib.lib().whmr_readout_finish_multi(ro._h, n, arr(joints), arr(scratches), arr(flats), B, _stream()))
+
+
 @torch.library.custom_op("whmr::sample_bilinear", mutates_args=(), device_types="cuda")
 def sample_bilinear_op(feat: torch.Tensor, points: torch.Tensor, layout: int) -> torch.Tensor:
     return sample_bilinear(feat, points, layout)

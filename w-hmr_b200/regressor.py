@@ -86,6 +86,79 @@ class BodyModelHead(nn.Module):
             self._ro[key] = ro
         return ro
 
+    def _assemble(self, r, verts, rot, pred_rotmat, pred_shape, pred_cam, bbox_height, center, orig_shape, Tz, J_regressor,
+                  scale):
+        """projections of the 49 joints + the result dict of Regressor.forward / forward_init (models/whmr.py:142-208)"""
+        B = rot.shape[0]
+        pred_joints = r['joints']
+        if bbox_height is not None and self.train_stage is not None and torch.is_grad_enabled():
+            f, w, hgt = constants.FOCAL_LENGTH, float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT)
+            st1 = self.train_stage == 1
+            kp_2d = ops.project_weak_op(pred_joints if st1 else pred_joints.detach(), pred_cam, f, w, hgt)
+            _, kp_w, focal, cam_t = ops.project_weak_full_op(pred_joints.detach() if st1 else pred_joints, pred_cam.detach(),
+                                                             bbox_height, center, orig_shape, Tz, f, w, hgt)
+            self._mark('project_weak_full')
+        elif bbox_height is not None:   # Regressor.forward: weak + predicted-focal projection, one launch
+            kp_2d, kp_w, focal, cam_t = ops.project_weak_full_op(
+                pred_joints, pred_cam, bbox_height, center, orig_shape, Tz, constants.FOCAL_LENGTH,
+                float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
+            self._mark('project_weak_full')
+        else:                         # forward_init: weak projection only
+            kp_2d = ops.project_weak_op(pred_joints, pred_cam, constants.FOCAL_LENGTH,
+                                        float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
+            self._mark('project_weak')
+        out = {
+            'verts': verts, 'sub_verts': r['sub_verts'], 'temp_verts': r['temp_verts'], 'kp_2d': kp_2d,
+            'kp_3d': r['kp_3d_h36m'] if J_regressor else pred_joints,
+            'smpl_kp_3d': r['smpl_kp_3d'], 'rotmat': rot, 'pred_cam': pred_cam, 'pred_shape': pred_shape,
+            'pred_pose': pred_rotmat.reshape(B, -1), 'pelvis': r['smpl_kp_3d'][:, :1, :], 'markers': r['markers'],
+            'joints49': pred_joints,
+        }
+        if bbox_height is not None:
+            out.update(kp_2d_w=kp_w, focal_length=focal, pred_cam_t=cam_t, scale=scale)
+        return out
+
+    # -- deferred schedule (RegressorLoop): inside WHMR.forward's loop (models/whmr.py:550-651) the next iteration reads
+    #    only the markers / camera / shape / pose of a Regressor result; the regressor-row read-outs and the joint
+    #    projections are read by the caller after the loop.  `begin` runs the SMPL kernels (vertices, one-hot read-outs
+    #    such as the markers are complete on return), `complete_all` finishes every pending call in one launch.
+    def begin(self, pred_rotmat, pred_shape, J_regressor=None):
+        if torch.is_tensor(J_regressor):
+            if self._h36m is None:
+                self.set_h36m_regressor(J_regressor)
+            J_regressor = True
+        B = pred_rotmat.shape[0]
+        dev = pred_rotmat.device
+        h, _ = self.smpl._state(dev)
+        rot = pred_rotmat.reshape(B, -1, 3, 3)
+        ro = self._readout(dev, bool(J_regressor))
+        verts, joints24, flat, scratch = ops.smpl_lbs_readout_deferred(h.id, ro.id, pred_shape, rot, True)
+        r = ro.split(flat, B)
+        return {'ro': ro, 'verts': verts, 'joints24': joints24, 'flat': flat, 'scratch': scratch, 'r': r, 'rot': rot,
+                'pred_rotmat': pred_rotmat, 'pred_shape': pred_shape, 'J': bool(J_regressor), 'markers': r['markers']}
+
+    def complete_all(self, states, cams, bbox_height=None, center=None, orig_shape=None, Tz=None, full=None, scale=None):
+        """states: list from `begin`; cams: pred_cam per state; full[i]: evaluate the predicted-focal block for state i
+        (Regressor.forward) or only the weak projection (forward_init); None entries in cams: no projection (the global
+        SMPL call, models/whmr.py:641-651).  -> list of result dicts."""
+        pend = [s for s in states if s['scratch'].numel()]
+        by_ro = {}
+        for s in pend:
+            by_ro.setdefault(s['ro'].id, []).append(s)
+        for rid, group in by_ro.items():
+            for i in range(0, len(group), 8):
+                g = group[i:i + 8]
+                ops.readout_finish_multi(rid, [s['joints24'] for s in g], [s['flat'] for s in g], [s['scratch'] for s in g])
+        outs = []
+        for i, s in enumerate(states):
+            if cams[i] is None:
+                outs.append({'verts': s['verts'], 'r': s['r']})
+                continue
+            use_full = bool(full[i]) if full is not None else bbox_height is not None
+            outs.append(self._assemble(s['r'], s['verts'], s['rot'], s['pred_rotmat'], s['pred_shape'], cams[i],
+                                       bbox_height if use_full else None, center, orig_shape, Tz, s['J'], scale))
+        return outs
+
     def forward(self, pred_rotmat, pred_shape, pred_cam, bbox_height=None, center=None, orig_shape=None,
                 Tz=None, J_regressor=None, scale=None):
         """pred_rotmat [B,24,3,3]; pred_shape [B,10]; pred_cam [B,3].  With bbox_height/center/
@@ -117,32 +190,8 @@ class BodyModelHead(nn.Module):
                     t.record_stream(side)
         r = ro.split(flat, B)
         self._mark('skin_readout')
-        pred_joints = r['joints']
-        if bbox_height is not None and self.train_stage is not None and torch.is_grad_enabled():
-            f, w, hgt = constants.FOCAL_LENGTH, float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT)
-            st1 = self.train_stage == 1
-            kp_2d = ops.project_weak_op(pred_joints if st1 else pred_joints.detach(), pred_cam, f, w, hgt)
-            _, kp_w, focal, cam_t = ops.project_weak_full_op(pred_joints.detach() if st1 else pred_joints, pred_cam.detach(),
-                                                             bbox_height, center, orig_shape, Tz, f, w, hgt)
-            self._mark('project_weak_full')
-        elif bbox_height is not None:   # Regressor.forward: weak + predicted-focal projection, one launch
-            kp_2d, kp_w, focal, cam_t = ops.project_weak_full_op(
-                pred_joints, pred_cam, bbox_height, center, orig_shape, Tz, constants.FOCAL_LENGTH,
-                float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
-            self._mark('project_weak_full')
-        else:                         # forward_init: weak projection only
-            kp_2d = ops.project_weak_op(pred_joints, pred_cam, constants.FOCAL_LENGTH,
-                                        float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT))
-            self._mark('project_weak')
-        out = {
-            'verts': verts, 'sub_verts': r['sub_verts'], 'temp_verts': r['temp_verts'], 'kp_2d': kp_2d,
-            'kp_3d': r['kp_3d_h36m'] if J_regressor else pred_joints,
-            'smpl_kp_3d': r['smpl_kp_3d'], 'rotmat': rot, 'pred_cam': pred_cam, 'pred_shape': pred_shape,
-            'pred_pose': pred_rotmat.reshape(B, -1), 'pelvis': r['smpl_kp_3d'][:, :1, :], 'markers': r['markers'],
-            'joints49': pred_joints,
-        }
-        if bbox_height is not None:
-            out.update(kp_2d_w=kp_w, focal_length=focal, pred_cam_t=cam_t, scale=scale)
+        out = self._assemble(r, verts, rot, pred_rotmat, pred_shape, pred_cam, bbox_height, center, orig_shape, Tz,
+                             J_regressor, scale)
         if side is not None:
             if not torch.cuda.is_current_stream_capturing():
                 for t in out.values():
