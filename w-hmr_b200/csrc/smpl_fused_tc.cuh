@@ -88,6 +88,7 @@ struct FusedParams {
   float* ro_out;
   int ro_B, ro_b0;
   int nb, V, VP;
+  int pieces;                 // > 0: balanced pieces per vertex tile, CTA c takes pieces c and c + grid (small batches)
   int split;                  // > 0: CTA c takes part c % split of vertex tile c / split (grid = tiles * split): one item per CTA
   int npv;                    // 16-body micro-items per vertex tile = ceil(nb / 16)
   int n_micro;                // (VP/128) * npv: the unit of work distribution
@@ -179,17 +180,33 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   // Work distribution: the (vertex tile, 16-body micro-item) grid is cut into gridDim.x contiguous, equal ranges
   // (vertex-major), so every CTA gets the same number of bodies +-16.  A range is walked as items = runs of <= 4
   // micro-items (<= 64 bodies) inside one vertex tile, sized evenly (5 micro-items -> 3 + 2, not 4 + 1).
-  int m_begin, m_end;
-  if (p.split > 0) {   // small batches: tile-aligned parts, so that no CTA streams a posedirs tile for a sliver of bodies
+  // A CTA's work is up to two ranges of micro-items.  Small batches (p.pieces > 0): the kernel time is the CTA with the
+  // most ITEMS (every item streams a whole posedirs tile, ~9 k cycles whatever its width), and equal ranges that straddle
+  // a tile boundary give some CTAs three items.  So every vertex tile is cut into p.pieces balanced pieces of <= MAXM
+  // micro-items, and CTA c takes piece c and piece c + gridDim.x (if it exists): never more than two items per CTA.
+  int seg_b[2], seg_e[2];
+  seg_b[1] = seg_e[1] = 0;
+  if (p.pieces > 0) {
+    const int base = p.npv / p.pieces, rem = p.npv - base * p.pieces, total = (p.n_micro / p.npv) * p.pieces;
+    auto piece = [&](int q, int& b, int& e) {
+      const int t = q / p.pieces, j = q - t * p.pieces;
+      b = t * p.npv + j * base + min(j, rem);
+      e = b + base + (j < rem ? 1 : 0);
+    };
+    piece(blockIdx.x, seg_b[0], seg_e[0]);
+    if ((int)(blockIdx.x + gridDim.x) < total) piece(blockIdx.x + gridDim.x, seg_b[1], seg_e[1]);
+  } else if (p.split > 0) {   // tile-aligned parts
     const int vt = blockIdx.x / p.split, part = blockIdx.x - vt * p.split;
-    m_begin = vt * p.npv + (part * p.npv) / p.split;
-    m_end = vt * p.npv + ((part + 1) * p.npv) / p.split;
+    seg_b[0] = vt * p.npv + (part * p.npv) / p.split;
+    seg_e[0] = vt * p.npv + ((part + 1) * p.npv) / p.split;
   } else {
-    m_begin = (int)(((long long)blockIdx.x * p.n_micro) / gridDim.x);
-    m_end = (int)(((long long)(blockIdx.x + 1) * p.n_micro) / gridDim.x);
+    seg_b[0] = (int)(((long long)blockIdx.x * p.n_micro) / gridDim.x);
+    seg_e[0] = (int)(((long long)(blockIdx.x + 1) * p.n_micro) / gridDim.x);
   }
+  const int m_begin = seg_b[0];
+  const bool any_work = seg_b[0] < seg_e[0];
   struct Item { int vt, body0, len, nbod, ng; };   // len: micro-items; nbod: valid bodies; ng: 8-body groups
-  auto item_at = [&](int m) {
+  auto item_at = [&](int m, int m_end) {
     Item it;
     it.vt = m / p.npv;
     const int mi = m - it.vt * p.npv;
@@ -201,6 +218,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     it.ng = (it.nbod + kFuGB - 1) / kFuGB;
     return it;
   };
+#define WHMR_FU_FOR_ITEMS for (int sg = 0; sg < 2; ++sg) for (int m = seg_b[sg]; m < seg_e[sg];)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFuAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -235,8 +253,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       // PDL: posedirs are constants of the handle, so the first ring fill is issued before the predecessor (the
       // chain kernel, which writes the pose feature) has finished; `pre` counts the stages already in flight
       int pre = 0;
-      if (m_begin < m_end) {
-        const Item it0 = item_at(m_begin);
+      if (any_work) {
+        const Item it0 = item_at(m_begin, seg_e[0]);
         for (int i = 0; i < kFuAStages && i < 3 * p.kch; ++i) {
           const int kc = i / 3, c = i % 3;
           uint8_t* ast = a_ring + i * kFuABytes;
@@ -247,8 +265,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         }
       }
       pdl_wait();
-      for (int m = m_begin; m < m_end;) {
-        const Item it = item_at(m);
+      WHMR_FU_FOR_ITEMS {
+        const Item it = item_at(m, seg_e[sg]);
         m += it.len;
         const int vt = it.vt, body0 = it.body0;
         const uint32_t pf_bytes = 2u * (uint32_t)it.len * 2048u;
@@ -285,8 +303,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       int buf = 0; uint32_t bph = 0;
       long long d_off = 0, d_pf = 0, d_a = 0;
       const long long k0 = dbgp ? clock64() : 0;
-      for (int m = m_begin; m < m_end;) {
-        const Item it = item_at(m);
+      WHMR_FU_FOR_ITEMS {
+        const Item it = item_at(m, seg_e[sg]);
         m += it.len;
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(it.len * 2) << 17) |
                                ((uint32_t)(kTcM >> 4) << 24);   // bf16 x bf16 -> f32, M=128, N=16*len
@@ -325,15 +343,15 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     if (elect_one()) {
       int s = 0; uint32_t ph = 0, w_par = 1;
       int cur_vt = -1;
-      if (m_begin < m_end) {   // the first weight tile does not depend on the predecessor either
+      if (any_work) {   // the first weight tile does not depend on the predecessor either
         cur_vt = m_begin / p.npv;
         w_par ^= 1;            // first use of w_empty passes trivially
         mbar_arrive_expect_tx(w_full, kFuWBytes);
         tma_load_2d(w_smem, &tmapW, w_full, 0, cur_vt * kTcM);
       }
       pdl_wait();
-      for (int m = m_begin; m < m_end;) {
-        const Item it = item_at(m);
+      WHMR_FU_FOR_ITEMS {
+        const Item it = item_at(m, seg_e[sg]);
         m += it.len;
         const int vt = it.vt;
         if (vt != cur_vt) {
@@ -365,8 +383,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       int ts = 0;
       long long d_t = 0, d_at = 0;
       const long long k0 = dbgp ? clock64() : 0;
-      for (int m = m_begin; m < m_end;) {
-        const Item it = item_at(m);
+      WHMR_FU_FOR_ITEMS {
+        const Item it = item_at(m, seg_e[sg]);
         m += it.len;
         const int vt = it.vt;
         if (vt != cur_vt) { mbar_wait_backoff(w_full, w_phase, p.backoff); w_phase ^= 1; cur_vt = vt; }
@@ -389,7 +407,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           if (++s == kFuAtStages) { s = 0; ph ^= 1; }
           if (++ts == TM::kTStages) { ts = 0; t_ph ^= 1; }
         }
-        const int next_vt = (m < m_end) ? m / p.npv : -1;
+        const int next_vt = (m < seg_e[sg]) ? m / p.npv : ((sg == 0 && seg_b[1] < seg_e[1]) ? seg_b[1] / p.npv : -1);
         if (next_vt != vt) tcgen05_commit(w_empty);
       }
       if (dbgp) { long long* d = dbgp + blockIdx.x * 16; d[7] = d_t; d[8] = d_at; d[9] = clock64() - k0; }
@@ -427,8 +445,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     pdl_wait();      // outputs (and the read-out partial buffer) may still be in use by earlier kernels
     pdl_trigger();
     const long long k0 = dbgp ? clock64() : 0;
-    for (int m = m_begin; m < m_end;) {
-      const Item it = item_at(m);
+    WHMR_FU_FOR_ITEMS {
+      const Item it = item_at(m, seg_e[sg]);
       m += it.len;
       const int vt = it.vt;
       if (vt != cur_vt) {
@@ -577,6 +595,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     }
   }
 
+#undef WHMR_FU_FOR_ITEMS
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {

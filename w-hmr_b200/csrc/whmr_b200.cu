@@ -569,13 +569,28 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   int maxm = p.n_micro <= 8 * h->tc.num_sms ? 3 : 4;
   if (maxm_env == 3 || maxm_env == 4 || maxm_env == 6 || maxm_env == 8) maxm = maxm_env;
   p.split = 0;
+  p.pieces = 0;
+  // Small batches, optional (WHMR_FUSED_PIECES=-1 automatic, k > 0 forced): at most two items per CTA (see the kernel).
+  // Pieces of <= 4 micro-items (the 64-body plan), as many pieces per tile as two per CTA allow.  Measured neutral at
+  // B=256 (382.6 vs 384.2 us per step): the epilogue, not the number of posedirs passes, sets a CTA's time; off by default.
+  static const int pieces_env = getenv("WHMR_FUSED_PIECES") ? atoi(getenv("WHMR_FUSED_PIECES")) : 0;
+  if (pieces_env != 0 && !maxm_env && split_env < 0) {
+    const int k_min = ceil_div(p.npv, 4);
+    const int k_one = h->tc.num_sms / n_vtiles, k_two = 2 * h->tc.num_sms / n_vtiles;
+    int k = 0;
+    if (k_min <= k_one) k = std::min(k_one, p.npv);
+    else if (k_min <= k_two) k = std::min(k_two, p.npv);
+    if (pieces_env > 0) k = pieces_env;
+    if (k > 0 && ceil_div(p.npv, k) <= 4 && n_vtiles * k <= 2 * h->tc.num_sms) { p.pieces = k; maxm = 4; }
+  }
   if (split_env >= 0) {
     p.split = split_env;
-  } else if (maxm >= 6 && p.npv <= 2 * maxm) {
+  } else if (!p.pieces && maxm >= 6 && p.npv <= 2 * maxm) {
     p.split = std::max(1, std::min(p.npv, h->tc.num_sms / n_vtiles));
   }
   if (p.split > 0 && (ceil_div(p.npv, p.split) > maxm || n_vtiles * p.split > h->tc.num_sms)) p.split = 0;
-  const int grid = p.split > 0 ? n_vtiles * p.split : std::min(h->tc.num_sms, p.n_micro);
+  const int grid = p.pieces > 0 ? std::min(h->tc.num_sms, n_vtiles * p.pieces)
+                                : (p.split > 0 ? n_vtiles * p.split : std::min(h->tc.num_sms, p.n_micro));
   static const bool dbg_on = getenv("WHMR_FUSED_DEBUG") != nullptr;
   static const int dbg_mode = getenv("WHMR_FUSED_DBGMODE") ? atoi(getenv("WHMR_FUSED_DBGMODE")) : 0;
   p.dbg_mode = dbg_mode;
