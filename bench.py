@@ -266,6 +266,11 @@ def run_ours(args):
             else:
                 k.update(achieved=a["bytes"] / (per_launch_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
             k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
+            tr = ncu_traffic(name, B)   # bytes the kernel actually moved (committed ncu capture), against the live time
+            if tr is not None and a["bound"] == "hbm":
+                k["dram_bytes_per_launch_ncu"] = tr["dram_bytes_per_launch"]
+                k["dram_GBs_moved"] = tr["dram_bytes_per_launch"] / (per_launch_ms * 1e-3) / 1e9
+                k["dram_frac_moved"] = k["dram_GBs_moved"] / peaks["hbm_gbs"]
             kern[name] = k
 
     # ---- end to end through host buffers ------------------------------------------------------------
