@@ -397,6 +397,30 @@ def test_sampling_degenerate_maps(dev, H, W):
     assert ops.sample_bilinear(feat[:0].to(dev), pts[:0].to(dev), ops.LAYOUT_NCHW).shape == (0, C, N)
 
 
+def test_project_sample_channels_last_matches_nchw(dev):
+    """MAF_Extractor.forward (weak projection + sampling in one launch) on channels_last maps goes through the NHWC kernel
+    with the projection fused in: same 2-D points, same features as the NCHW kernel and as the oracle."""
+    from oracle import geometry_oracle as G
+    from oracle.sampling_oracle import grid_sample_points
+    from whmr_b200 import constants, ops
+    import whmr_b200.synthetic as syn
+    B, C, H, W, N = 4, 70, 24, 20, 67
+    g = torch.Generator().manual_seed(77)
+    feat = torch.randn(B, C, H, W, generator=g)
+    p3 = torch.randn(B, N, 3, generator=g) * 0.35
+    cam = torch.from_numpy(syn.make_bodies(B, seed=9)['cam'])
+    a_feat, a_pts = ops.project_sample_op(feat.to(dev), p3.to(dev), cam.to(dev), constants.FOCAL_LENGTH, 256., 256.,
+                                          ops.LAYOUT_NCHW)
+    fcl = feat.to(dev).contiguous(memory_format=torch.channels_last)
+    b_feat, b_pts = ops.project_sample_op(fcl, p3.to(dev), cam.to(dev), constants.FOCAL_LENGTH, 256., 256., ops.LAYOUT_NCHW)
+    assert torch.equal(a_pts, b_pts)
+    ref_pts = G.projection(p3, cam)
+    assert _maxabs(b_pts, ref_pts) * 128 <= PX_TOL
+    ref = grid_sample_points(feat, b_pts.cpu())
+    assert _maxabs(b_feat, ref) <= FEAT_RTOL * float(ref.abs().max())
+    assert _maxabs(a_feat, ref) <= FEAT_RTOL * float(ref.abs().max())
+
+
 def test_maf_project_matches_reference_golden(dev, golden):
     from whmr_b200.maf_extractor import MAF_Extractor
     g = golden

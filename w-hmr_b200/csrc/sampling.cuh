@@ -173,22 +173,40 @@ sample_bilinear_nchw_staged_kernel(const float* __restrict__ feat, const float* 
   }
 }
 
-// NHWC input: grid = (ceil(N/32), ceil(C/64), B), block 256 (8 warps x 4 points each)
+// NHWC input: grid = (ceil(N/32), ceil(C/64), B), block 256 (8 warps x 4 points each).  kProject: `points` are the
+// [B,N,3] mesh points and the weak projection (utils/geometry.py:289-307) is evaluated here (MAF_Extractor.forward).
+template <bool kProject>
 __global__ void __launch_bounds__(256)
 sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
-                            float* __restrict__ out, int C, int H, int W, int N) {
+                            float* __restrict__ out, int C, int H, int W, int N, SampleProj pj) {
   __shared__ float tile[64][33];
   pdl_wait();
   pdl_trigger();
   const int b = blockIdx.z, c0 = blockIdx.y * 64, n0 = blockIdx.x * 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* fb = feat + (size_t)b * H * W * C;
+  float ctx = 0.f, cty = 0.f, ctz = 0.f;
+  if (kProject) {
+    const float cs = pj.cam[b * 3 + 0];
+    ctx = pj.cam[b * 3 + 1]; cty = pj.cam[b * 3 + 2];
+    ctz = 2.0f * pj.focal / (pj.img_h * cs + 1e-9f);
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int pt = warp * 4 + q;
     const int n = n0 + pt;
     if (n < N) {
-      const float2 g = *reinterpret_cast<const float2*>(points + (size_t)b * pts_bstride + (size_t)n * 2);
+      float2 g;
+      if (kProject) {
+        const float* qp = points + (size_t)b * pts_bstride + (size_t)n * 3;
+        const float px = qp[0] + ctx, py = qp[1] + cty, pz = qp[2] + ctz;
+        g.x = (pj.focal * (px / pz)) / (pj.img_w * 0.5f);
+        g.y = (pj.focal * (py / pz)) / (pj.img_h * 0.5f);
+        if (pj.pts2d_out && blockIdx.y == 0 && lane == 0)
+          *reinterpret_cast<float2*>(pj.pts2d_out + ((size_t)b * N + n) * 2) = g;
+      } else {
+        g = *reinterpret_cast<const float2*>(points + (size_t)b * pts_bstride + (size_t)n * 2);
+      }
       const Taps t = make_taps(g.x, g.y, H, W);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {

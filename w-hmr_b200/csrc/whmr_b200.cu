@@ -1121,7 +1121,7 @@ int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int
     WHMR_LAUNCHED("sample_bilinear_nchw_kernel");
   } else {
     dim3 grid(ceil_div(N, 32), ceil_div(C, 64), B);
-    launch_pdl(kPdlSample, sample_bilinear_nhwc_kernel, grid, dim3(256), 0, st, feat, points, pts_bstride, out, C, H, W, N);
+    launch_pdl(kPdlSample, sample_bilinear_nhwc_kernel<false>, grid, dim3(256), 0, st, feat, points, pts_bstride, out, C, H, W, N, SampleProj{});
     WHMR_LAUNCHED("sample_bilinear_nhwc_kernel");
   }
   return WHMR_OK;
@@ -1146,10 +1146,17 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
     WHMR_LAUNCHED("sample_bilinear_nchw_kernel<project>");
     return WHMR_OK;
   }
-  WHMR_CHECK_ARG(points2d_out, "whmr_project_sample: points2d_out scratch [B,N,2] is required for NHWC");
-  int rc = whmr_project_weak(p, cam, B, N, focal, img_w, img_h, points2d_out, stream);
-  if (rc) return rc;
-  return whmr_sample_bilinear(feat, layout, B, C, H, W, points2d_out, 0, N, out, stream);
+  WHMR_CHECK_ARG(layout == WHMR_LAYOUT_NHWC, "whmr_project_sample: bad layout %d", layout);
+  WHMR_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && H > 0 && W > 0 && B < 65536, "whmr_project_sample: bad sizes");
+  if (B == 0 || C == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(feat && p && cam && out, "whmr_project_sample: null pointer");
+  WHMR_CHECK_ARG(!points2d_out || (reinterpret_cast<size_t>(points2d_out) & 7) == 0, "whmr_project_sample: points2d_out must be 8-byte aligned");
+  SampleProj pj{cam, focal, img_w, img_h, points2d_out};
+  dim3 grid(ceil_div(N, 32), ceil_div(C, 64), B);
+  launch_pdl(kPdlSample, sample_bilinear_nhwc_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, feat, p, N * 3, out, C, H, W,
+             N, pj);
+  WHMR_LAUNCHED("sample_bilinear_nhwc_kernel<project>");
+  return WHMR_OK;
 }
 
 // =============================================================================================
