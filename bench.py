@@ -267,7 +267,9 @@ def run_ours(args):
                 k.update(achieved=a["bytes"] / (per_launch_ms * 1e-3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
             k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
             tr = ncu_traffic(name, B)   # bytes the kernel actually moved (committed ncu capture), against the live time
-            if tr is not None and a["bound"] == "hbm":
+            # (only when the capture has the same launch count per pass as this probed schedule: the deferred schedule
+            #  batches the five read-out finishes into one launch)
+            if tr is not None and a["bound"] == "hbm" and tr.get("launches") in (None, launches):
                 k["dram_bytes_per_launch_ncu"] = tr["dram_bytes_per_launch"]
                 k["dram_GBs_moved"] = tr["dram_bytes_per_launch"] / (per_launch_ms * 1e-3) / 1e9
                 k["dram_frac_moved"] = k["dram_GBs_moved"] / peaks["hbm_gbs"]
@@ -384,7 +386,8 @@ def ncu_traffic(kernel, B):
         return None
     try:
         t = json.load(open(p)).get("B%d" % B, {}).get(kernel)
-        return None if t is None else {"dram_bytes_per_launch": t["dram_bytes"], "source": t["source"]}
+        return None if t is None else {"dram_bytes_per_launch": t["dram_bytes"], "source": t["source"],
+                                       "launches": t.get("launches")}
     except Exception:  # noqa: BLE001
         return None
 
