@@ -40,6 +40,18 @@ constexpr bool kFuCollector = true;
 #else
 constexpr bool kFuCollector = false;
 #endif
+// Skinning weights as the TMEM-resident A operand of the transform blend (tcgen05.mma [d], [a_tmem], b_desc): the four
+// warps w4 == 0 of the epilogue write the tile's weight rows (64 halfs = 32 columns per vertex/lane: hi K-steps 0,1 then
+// lo K-steps 0,1) into TMEM columns 480..511 with tcgen05.st when the vertex tile changes; the transform MMAs then fetch
+// no A tile from shared memory (4 KB per MMA at 64 B/clk = the per-instruction floor of section 5.2 of the notes).
+// Measured (B200): B=256 loop step 384.5 -> 377.3 us, 16 k bodies + H36M read-outs 15.2 -> 15.9 M bodies/s, SMPL alone
+// 19.4 -> 20.8 M bodies/s.  -DWHMR_FUSED_WSMEM restores the shared-memory operand (TMA weight tile).
+#ifdef WHMR_FUSED_WSMEM
+constexpr bool kFuWTmem = false;
+#else
+constexpr bool kFuWTmem = true;
+#endif
+constexpr int kFuWCol = 480;                  // TMEM column of the weight operand (all plans end at 480)
 constexpr int kFuGB = 8;                      // bodies per blended-transform tile
 constexpr int kFuTN = kFuGB * 12;             // 96 accumulator columns
 constexpr int kFuMaxAStages = 4;
@@ -88,6 +100,7 @@ struct FusedParams {
   float* ro_out;
   int ro_B, ro_b0;
   int nb, V, VP;
+  const uint4* W16;           // weights fp16 hi|lo [VP, 64] in global memory (kFuWTmem: read by the epilogue warps)
   int pieces;                 // > 0: balanced pieces per vertex tile, CTA c takes pieces c and c + grid (small batches)
   int split;                  // > 0: CTA c takes part c % split of vertex tile c / split (grid = tiles * split): one item per CTA
   int npv;                    // 16-body micro-items per vertex tile = ceil(nb / 16)
@@ -103,6 +116,23 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr));
@@ -223,7 +253,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFuAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kFuPfStages; ++s) { mbar_init(&pf_full[s], 1); mbar_init(&pf_empty[s], 1); }
-    mbar_init(w_full, 1); mbar_init(w_empty, 1);
+    mbar_init(w_full, kFuWTmem ? 4 : 1); mbar_init(w_empty, 1);
     for (int s = 0; s < kFuAtStages; ++s) { mbar_init(&at_full[s], 1); mbar_init(&at_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&off_full[s], 1); mbar_init(&off_empty[s], kFuEpiWarps); }
     for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kFuEpiWarps); }
@@ -343,7 +373,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     if (elect_one()) {
       int s = 0; uint32_t ph = 0, w_par = 1;
       int cur_vt = -1;
-      if (any_work) {   // the first weight tile does not depend on the predecessor either
+      if (any_work && !kFuWTmem) {   // the first weight tile does not depend on the predecessor either
         cur_vt = m_begin / p.npv;
         w_par ^= 1;            // first use of w_empty passes trivially
         mbar_arrive_expect_tx(w_full, kFuWBytes);
@@ -354,7 +384,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         const Item it = item_at(m, seg_e[sg]);
         m += it.len;
         const int vt = it.vt;
-        if (vt != cur_vt) {
+        if (!kFuWTmem && vt != cur_vt) {
           mbar_wait_backoff(w_empty, w_par, p.backoff);   // MMAs on the previous weight tile have retired
           w_par ^= 1;
           mbar_arrive_expect_tx(w_full, kFuWBytes);
@@ -398,9 +428,16 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           for (int ks = 0; ks < p.jsteps; ++ks) {
             const uint64_t dW_hi = umma_desc_sw128(w_hi + ks * 32), dW_lo = umma_desc_sw128(w_lo + ks * 32);
             const uint64_t dA_hi = umma_desc_sw128(a_hi + ks * 32), dA_lo = umma_desc_sw128(a_lo + ks * 32);
-            umma<0>(d_tmem, dW_lo, dA_hi, idesc, ks != 0);
-            umma<0, kFuCollector ? 1 : 0>(d_tmem, dW_hi, dA_lo, idesc, 1u);
-            umma<0, kFuCollector ? 3 : 0>(d_tmem, dW_hi, dA_hi, idesc, 1u);
+            if (kFuWTmem) {
+              const uint32_t tw_hi = tmem_base + (uint32_t)(kFuWCol + ks * 8), tw_lo = tw_hi + 16;
+              umma_ta(d_tmem, tw_lo, dA_hi, idesc, ks != 0);
+              umma_ta(d_tmem, tw_hi, dA_lo, idesc, 1u);
+              umma_ta(d_tmem, tw_hi, dA_hi, idesc, 1u);
+            } else {
+              umma<0>(d_tmem, dW_lo, dA_hi, idesc, ks != 0);
+              umma<0, kFuCollector ? 1 : 0>(d_tmem, dW_hi, dA_lo, idesc, 1u);
+              umma<0, kFuCollector ? 3 : 0>(d_tmem, dW_hi, dA_hi, idesc, 1u);
+            }
           }
           tcgen05_commit(&at_empty[s]);
           tcgen05_commit(&t_full[ts]);
@@ -437,7 +474,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     };
     const int V3 = p.V * 3;
     const bool has_transl = p.transl != nullptr;
-    int buf = 0, ts = 0; uint32_t bph = 0, t_ph = 0;
+    int buf = 0, ts = 0; uint32_t bph = 0, t_ph = 0, w_par_e = 0;
     long long d_off = 0, d_t = 0, d_ld = 0, d_rel = 0;
 #ifdef WHMR_FUSED_FINE_PROBES   // per-section cycles of one epilogue warp (math+stage | vertex stores | read-out emits)
     long long d_math = 0, d_st = 0, d_emit = 0;
@@ -450,8 +487,25 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       m += it.len;
       const int vt = it.vt;
       if (vt != cur_vt) {
+        const bool first_tile = cur_vt < 0;
         cur_vt = vt;
         const int v = vt * kTcM + q * 32 + lane;                  // < VP
+        if (kFuWTmem && w4 == 0) {   // this lane-quarter's 32 weight rows -> TMEM columns kFuWCol .. kFuWCol+31
+          uint32_t wr[32];
+          const uint4* src = p.W16 + (size_t)v * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 t = __ldg(src + i);
+            wr[i * 4 + 0] = t.x; wr[i * 4 + 1] = t.y; wr[i * 4 + 2] = t.z; wr[i * 4 + 3] = t.w;
+          }
+          if (!first_tile) { mbar_wait(w_empty, w_par_e); w_par_e ^= 1; }   // MMAs on the previous tile have retired
+          tcgen05_fence_after();
+          tmem_st_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kFuWCol, wr);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(w_full);
+        }
         tx = p.v_template_p[v]; ty = p.v_template_p[p.VP + v]; tz = p.v_template_p[2 * p.VP + v];
         n_e = 0;
         if (p.emit.grp_ptr) {

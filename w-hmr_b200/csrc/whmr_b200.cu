@@ -543,6 +543,7 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
     p.ro_out = ro_out; p.ro_B = B; p.ro_b0 = b0;
   }
   p.nb = nb; p.V = d.V; p.VP = d.VP;
+  p.W16 = static_cast<const uint4*>(h->tc.W_f16);
   const int n_vtiles = d.VP / kTcM;
   p.npv = ceil_div(nb, 16);
   p.n_micro = n_vtiles * p.npv;
