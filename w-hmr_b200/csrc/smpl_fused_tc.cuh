@@ -56,7 +56,7 @@ constexpr int kFuGB = 8;                      // bodies per blended-transform ti
 constexpr int kFuTN = kFuGB * 12;             // 96 accumulator columns
 constexpr int kFuMaxAStages = 4;
 constexpr int kFuABytes = 2 * kTcM * 128;     // 32 KB: posedirs {hi,lo} of one (K chunk, plane)
-constexpr int kFuPfStages = 2;
+constexpr int kFuMaxPfStages = 3;
 constexpr int kFuWBytes = kTcM * 128;         // 16 KB: skinning weights, fp16 hi|lo along K (64 halfs per vertex)
 constexpr int kFuAtStages = 2;
 constexpr int kFuAtBytes = kFuTN * 128;       // 12 KB: A^T of 8 bodies, fp16 hi|lo along K
@@ -84,8 +84,10 @@ template <int MAXM> struct FuTmem {
   static constexpr int kPfBytes = 2 * kPfPart;
   static constexpr int kOffA = 0;
   static constexpr int kOffPf = kOffA + kAStages * kFuABytes;
-  static constexpr int kOffW = kOffPf + kFuPfStages * kPfBytes;
-  static constexpr int kOffAt = kOffW + kFuWBytes;
+  // pose-feature ring: a third stage in the room the weight tile left when it moved to TMEM (64-body and smaller plans)
+  static constexpr int kPfStages = (kFuWTmem && MAXM <= 4) ? 3 : 2;
+  static constexpr int kOffW = kOffPf + kPfStages * kPfBytes;
+  static constexpr int kOffAt = kOffW + (kFuWTmem ? 0 : kFuWBytes);
   static constexpr int kOffStg = kOffAt + kFuAtStages * kFuAtBytes;
   static constexpr int kOffBars = kOffStg + kFuEpiWarps * 192 * 4;
   static constexpr int kSmem = kOffBars + 256 + 1024;
@@ -195,8 +197,9 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   uint64_t* a_full = bars;                         // [4]
   uint64_t* a_empty = a_full + kFuMaxAStages;      // [4]
   uint64_t* pf_full = a_empty + kFuMaxAStages;     // [2]
-  uint64_t* pf_empty = pf_full + kFuPfStages;      // [2]
-  uint64_t* w_full = pf_empty + kFuPfStages;
+  constexpr int kFuPfStages = TM::kPfStages;
+  uint64_t* pf_empty = pf_full + kFuMaxPfStages;   // [3]
+  uint64_t* w_full = pf_empty + kFuMaxPfStages;
   uint64_t* w_empty = w_full + 1;
   uint64_t* at_full = w_empty + 1;                 // [2]
   uint64_t* at_empty = at_full + kFuAtStages;      // [2]
