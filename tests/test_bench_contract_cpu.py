@@ -1,0 +1,35 @@
+"""The reference arm of bench.py runs on the host only (the oracle port on CPU): its JSON line must carry the keys the
+driver's contract names.  (The GPU arm's line is produced on the B200 box; profiles/r01_bench_v*.json are its records.)"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--cpu-sample", "8"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "smpl_bodies_per_sec" and line["unit"] == "bodies/s"
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["sample"]
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_committed_gpu_bench_line_has_the_contract_keys():
+    """the last GPU bench line recorded under profiles/ (written on the B200 box)"""
+    recs = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("r01_bench_v") and f.endswith(".json")
+                  and "reference" not in f and "gpu" not in f and "channels" not in f)
+    assert recs
+    line = json.loads(open(os.path.join(ROOT, "profiles", recs[-1])).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["vs_baseline"] is None and line["gpu_launches"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
