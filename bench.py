@@ -342,6 +342,14 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_loop_baseline(args.backbone, args.cpu_sample, reps=3)
 
+    # ---- the same dense PyTorch path, eager, on THIS GPU ("the real bar"), rank 0, N == 1 ---------------
+    eager = None
+    if rank == 0 and world == 1 and not args.skip_eager:
+        try:
+            eager = torch_gpu_eager_baseline(model, args.backbone, feats, params, bbox, B)
+        except Exception as e:  # noqa: BLE001  (a baseline leg must never take the bench line down)
+            eager = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     clocks = sampler.summary()
@@ -371,7 +379,7 @@ def run_ours(args):
                        "feature_layout": "channels_last (NHWC memory)" if args.channels_last else "NCHW contiguous (reference layout)"},
             "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident,
             "gpu_launches": int(launches_per_step) * K, "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "smpl_at_scale": scale, "parity": parity,
+            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "torch_gpu_eager": eager, "smpl_at_scale": scale, "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
@@ -458,6 +466,28 @@ def cpu_loop_baseline(backbone, n_bodies, reps=3, min_seconds=10.0, max_seconds=
             "sample": "%d bodies of the same loop workload (same generators), median of %d passes, %.2f s/pass; "
                       "oracle = CPU restatement of the reference path (dense SMPL + dense Dmap matmuls + grid_sample), "
                       "torch %s CPU kernels, os.cpu_count()=%d" % (n_bodies, reps, t, torch.__version__, os.cpu_count())}
+
+
+def torch_gpu_eager_baseline(model, backbone, feats, params, bbox, B, reps=10):
+    """The reference's way of computing the path -- dense smplx-style SMPL, dense Dmap / regressor matmuls, F.grid_sample,
+    ~100+ ATen launches per SMPL call -- as eager PyTorch on the same GPU and the same device-resident inputs (the oracle
+    restatement with its tensors on the device; fp32 matmuls, torch defaults).  A reported baseline like cpu_baseline."""
+    import torch
+    from oracle.loop_oracle import LoopOracle
+    orc = LoopOracle(model, backbone, device="cuda")
+    for _ in range(2):
+        orc.step(feats, params, bbox)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        orc.step(feats, params, bbox)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": reps,
+            "sample": "the full B=%d loop step, eager PyTorch %s on cuda:0 (oracle restatement of the reference path, "
+                      "dense matmuls, allow_tf32=%s)" % (B, torch.__version__, torch.backends.cuda.matmul.allow_tf32)}
 
 
 def run_extra(args):
@@ -610,6 +640,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg")
     ap.add_argument("--skip-sweep", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--quick", action="store_true")

@@ -14,12 +14,12 @@ from .smpl_oracle import SMPLOracle, regressor_readouts
 
 
 class LoopOracle:
-    def __init__(self, model, backbone='vitpose', with_h36m=True):
+    def __init__(self, model, backbone='vitpose', with_h36m=True, device='cpu'):
         import importlib
         syn = importlib.import_module('whmr_b200.synthetic')
         self.model = model
-        self.smpl = SMPLOracle(model, torch.float32)
-        self.grid = torch.from_numpy(syn.grid_points(backbone))
+        self.smpl = SMPLOracle(model, torch.float32, device=device)
+        self.grid = torch.from_numpy(syn.grid_points(backbone)).to(device)
         self.with_h36m = with_h36m
 
     def regressor_outputs(self, p, bbox=None):

@@ -27,9 +27,9 @@ def batch_rodrigues(rot_vecs):
     cos = torch.unsqueeze(torch.cos(angle), dim=1)
     sin = torch.unsqueeze(torch.sin(angle), dim=1)
     rx, ry, rz = torch.split(rot_dir, 1, dim=1)
-    zeros = torch.zeros((n, 1), dtype=dtype)
+    zeros = torch.zeros((n, 1), dtype=dtype, device=rot_vecs.device)
     K = torch.cat([zeros, -rz, ry, rz, zeros, -rx, -ry, rx, zeros], dim=1).view(n, 3, 3)
-    ident = torch.eye(3, dtype=dtype).unsqueeze(0)
+    ident = torch.eye(3, dtype=dtype, device=rot_vecs.device).unsqueeze(0)
     return ident + sin * K + (1 - cos) * torch.bmm(K, K)
 
 
@@ -51,7 +51,7 @@ def batch_rigid_transform(rot_mats, joints, parents):
     joints = joints.unsqueeze(-1)
     rel = joints.clone()
     rel[:, 1:] = rel[:, 1:] - joints[:, parents[1:]]
-    tm = torch.zeros(B, nj, 4, 4, dtype=joints.dtype)
+    tm = torch.zeros(B, nj, 4, 4, dtype=joints.dtype, device=joints.device)
     tm[:, :, :3, :3] = rot_mats
     tm[:, :, :3, 3:] = rel
     tm[:, :, 3, 3] = 1.0
@@ -75,7 +75,7 @@ def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_
     dtype = betas.dtype
     v_shaped = v_template + blend_shapes(betas, shapedirs)
     J = vertices2joints(J_regressor, v_shaped)
-    ident = torch.eye(3, dtype=dtype)
+    ident = torch.eye(3, dtype=dtype, device=betas.device)
     if pose2rot:
         rot_mats = batch_rodrigues(pose.reshape(-1, 3)).view(B, -1, 3, 3)
     else:
@@ -87,7 +87,7 @@ def lbs(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_
     nj = J_regressor.shape[0]
     W = lbs_weights.unsqueeze(0).expand(B, -1, -1)
     T = torch.matmul(W, A.view(B, nj, 16)).view(B, -1, 4, 4)
-    homo = torch.ones(B, v_posed.shape[1], 1, dtype=dtype)
+    homo = torch.ones(B, v_posed.shape[1], 1, dtype=dtype, device=v_posed.device)
     v_posed_homo = torch.cat([v_posed, homo], dim=2)
     v_homo = torch.matmul(T, v_posed_homo.unsqueeze(-1))
     verts = v_homo[:, :, :3, 0]
@@ -102,26 +102,29 @@ class SMPLOracle:
        joints   = joints54[:, joint_map]  -> 49
     """
 
-    def __init__(self, model, dtype=torch.float32):
-        from_np = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dtype)  # noqa: E731
+    def __init__(self, model, dtype=torch.float32, device='cpu'):
+        """device: where the model tensors live ('cpu' for the oracle proper; bench.py's torch-GPU-eager leg passes
+        'cuda' to time the same dense PyTorch path on the GPU)."""
+        from_np = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype)  # noqa: E731
         self.dtype = dtype
+        self.device = torch.device(device)
         self.v_template = from_np(model['v_template'])
         self.shapedirs = from_np(model['shapedirs'])
         self.posedirs = from_np(model['posedirs'])
         self.J_regressor = from_np(model['J_regressor'])
         self.lbs_weights = from_np(model['weights'])
-        self.parents = torch.as_tensor(np.asarray(model['parents']), dtype=torch.long)
+        self.parents = torch.as_tensor(np.asarray(model['parents']), dtype=torch.long)   # host indices
         self.J_regressor_extra = from_np(model['J_regressor_extra'])
-        self.vertex_ids = torch.as_tensor(np.asarray(model['vertex_ids']), dtype=torch.long)
+        self.vertex_ids = torch.as_tensor(np.asarray(model['vertex_ids']), dtype=torch.long).to(device)
         import importlib
         c = importlib.import_module('whmr_b200.constants')
-        self.joint_map = torch.tensor(c.JOINT_MAP_49, dtype=torch.long)
+        self.joint_map = torch.tensor(c.JOINT_MAP_49, dtype=torch.long).to(device)
         self.faces = model.get('f')
 
     def forward(self, betas, body_pose, global_orient, pose2rot=True, transl=None):
-        betas = torch.as_tensor(betas).to(self.dtype)
-        body_pose = torch.as_tensor(body_pose).to(self.dtype)
-        global_orient = torch.as_tensor(global_orient).to(self.dtype)
+        betas = torch.as_tensor(betas).to(device=self.device, dtype=self.dtype)
+        body_pose = torch.as_tensor(body_pose).to(device=self.device, dtype=self.dtype)
+        global_orient = torch.as_tensor(global_orient).to(device=self.device, dtype=self.dtype)
         B = betas.shape[0]
         if pose2rot:
             full_pose = torch.cat([global_orient.reshape(B, 3), body_pose.reshape(B, -1)], dim=1)
@@ -134,7 +137,7 @@ class SMPLOracle:
         # smplx VertexJointSelector.forward: index_select + cat
         joints45 = torch.cat([joints24, torch.index_select(verts, 1, self.vertex_ids)], dim=1)
         if transl is not None:
-            transl = torch.as_tensor(transl).to(self.dtype)
+            transl = torch.as_tensor(transl).to(device=self.device, dtype=self.dtype)
             joints45 = joints45 + transl.unsqueeze(1)
             verts = verts + transl.unsqueeze(1)
         # wrapper, models/smpl.py:71-83
@@ -150,6 +153,9 @@ class SMPLOracle:
     __call__ = forward
 
 
+_DEVICE_CACHE = {}
+
+
 def regressor_readouts(model, verts, dtype=None):
     """Everything Regressor.forward derives linearly from the posed vertices
     (models/whmr.py:176-187, 240-251): H36M joints (17 -> pelvis-centred 14), the dense
@@ -160,7 +166,15 @@ def regressor_readouts(model, verts, dtype=None):
     verts = torch.as_tensor(verts)
     dt = dtype or verts.dtype
     verts = verts.to(dt)
-    t = lambda k: torch.from_numpy(np.ascontiguousarray(model[k])).to(dt)  # noqa: E731
+    dev = verts.device
+
+    def t(k):   # on an accelerator the dense matrices are uploaded once (the reference keeps them as module buffers)
+        if dev.type == 'cpu':
+            return torch.from_numpy(np.ascontiguousarray(model[k])).to(dt)
+        key = (id(model), k, str(dev), dt)
+        if key not in _DEVICE_CACHE:
+            _DEVICE_CACHE[key] = torch.from_numpy(np.ascontiguousarray(model[k])).to(device=dev, dtype=dt)
+        return _DEVICE_CACHE[key]
     out = {}
     j17 = torch.matmul(t('J_regressor_h36m'), verts)               # whmr.py:177
     pelvis = j17[:, [0], :].clone()                                # :178
@@ -168,8 +182,8 @@ def regressor_readouts(model, verts, dtype=None):
     out['kp_3d_h36m'] = j17[:, list(c.H36M_TO_J14), :] - pelvis    # :179-180
     out['sub_verts'] = torch.matmul(t('Dmap0'), verts)             # :182
     out['temp_verts'] = torch.matmul(t('Dmap1'), out['sub_verts'])  # :183
-    out['markers'] = verts[:, torch.as_tensor(np.asarray(model['ssm']), dtype=torch.long)]  # :184
+    out['markers'] = verts[:, torch.as_tensor(np.asarray(model['ssm']), dtype=torch.long).to(dev)]  # :184
     sj = vertices2joints(t('J_regressor'), verts)                  # :186
-    vid = torch.as_tensor(np.asarray(model['vertex_ids']), dtype=torch.long)
+    vid = torch.as_tensor(np.asarray(model['vertex_ids']), dtype=torch.long).to(dev)
     out['smpl_kp_3d'] = torch.cat([sj, torch.index_select(verts, 1, vid)], dim=1)  # :187
     return out
