@@ -48,6 +48,10 @@ const char* whmr_last_error(void);
  * `gpu_launches`); whmr_launch_count_reset() zeroes it. */
 uint64_t whmr_launch_count(void);
 void whmr_launch_count_reset(void);
+/* Diagnostics: `host_mapped` = 16 ints of PINNED host memory (device-accessible through UVA), or NULL to clear.  A bounded
+ * mbarrier wait that times out inside a kernel (a protocol bug) records {1, blockIdx.x, threadIdx.x, barrier offset in
+ * shared memory, parity, line tag} there before it traps, so the host can read it although the context is lost. */
+void whmr_debug_set_trap_buffer(int* host_mapped);
 
 /* ------------------------------------------------------------------------------------------
  * SMPL body model.  Replaces pare.models.SMPL / smplx.SMPL as constructed at

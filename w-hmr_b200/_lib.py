@@ -59,6 +59,7 @@ SIGNATURES = {
     "whmr_last_error": (C.c_char_p, []),
     "whmr_launch_count": (C.c_uint64, []),
     "whmr_launch_count_reset": (None, []),
+    "whmr_debug_set_trap_buffer": (None, [_vp]),
     "whmr_smpl_create": (C.c_int, [C.POINTER(SmplModelDesc), _i, C.POINTER(_vp)]),
     "whmr_smpl_destroy": (C.c_int, [_vp]),
     "whmr_smpl_set_gemm_mode": (C.c_int, [_vp, _i]),

@@ -83,14 +83,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ int* g_trap_buf = nullptr;   // whmr_debug_set_trap_buffer: pinned host memory or null (single translation unit)
+__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+  int* t = g_trap_buf;
+  if (t && atomicCAS(t, 0, 1) == 0) {
+    t[1] = (int)blockIdx.x; t[2] = (int)threadIdx.x; t[3] = (int)(smem_u32(bar)); t[4] = (int)parity;
+    __threadfence_system();
+  }
+  printf("whmr: mbarrier wait timed out (block %d thread %d barrier@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+         smem_u32(bar), parity);
+  __trap();
+}
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (clock64() - t0 < 4000000000LL)   // ~2 s at 1.9 GHz
     if (mbar_try_wait(bar, parity)) return;
-  printf("whmr pose_blend_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-  __trap();
+  mbar_timeout(bar, parity);
 }
 // Same with a sleep between polls: for single-thread roles that wait long (an idle poller still takes issue slots
 // and mbarrier-unit bandwidth from the epilogue warps of its scheduler).
@@ -101,8 +111,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     if (ns) __nanosleep(ns);
     if (mbar_try_wait(bar, parity)) return;
   }
-  printf("whmr: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-  __trap();
+  mbar_timeout(bar, parity);
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
                                             int c2) {

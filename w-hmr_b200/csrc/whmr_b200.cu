@@ -141,6 +141,7 @@ int whmr_abi_version(void) { return WHMR_ABI_VERSION; }
 const char* whmr_last_error(void) { return last_error_ref().c_str(); }
 uint64_t whmr_launch_count(void) { return g_launch_count.load(); }
 void whmr_launch_count_reset(void) { g_launch_count.store(0); }
+void whmr_debug_set_trap_buffer(int* host_mapped) { cudaMemcpyToSymbol(whmr::g_trap_buf, &host_mapped, sizeof(int*)); }
 
 // =============================================================================================
 // SMPL
