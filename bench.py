@@ -9,9 +9,14 @@ metric = SMPL bodies/s (batch rows through the whole loop), whole job over all N
   value     : inputs resident in HBM, the step replayed as one CUDA graph, CUDA-event timed.
   e2e       : through the host-buffer path -- every step copies ALL step inputs (feature maps 4.2 GB
               + parameters) from pinned host memory, runs the step, and copies the results the
-              reference's caller reads (demo/tester.py:164-165) back to pinned host memory.
-  roofline  : dominant kernel of the step, timed inside the timed region with external CUDA events
-              recorded as graph nodes; algorithmic bytes/flops per DESIGN.md.
+              reference's caller reads (demo/tester.py:164-165) back to pinned host memory; H2D, compute
+              and D2H run on three streams over two buffer sets (step k+1's copies under step k's kernels).
+  roofline  : dominant kernel CLASS of the step (the three sampling launches are one class), timed inside
+              the timed region with external CUDA events recorded as graph nodes; algorithmic bytes/flops
+              per DESIGN.md, DRAM bytes actually moved from the committed ncu capture.
+  channels_last / other_configs : the same step with channels_last feature maps (NHWC kernel); BASELINE
+              configs[2] (65,536-body SMPL + H36M sweep point, strong scaling over the ranks) and configs[4]
+              (35,515-frame evaluation pass + NCCL gather) -- so the multi-GPU record has a collective in it.
   cpu_baseline : the oracle (CPU restatement of the reference's path, torch CPU kernels, all host
               threads) on a bounded sample of the same workload (rank 0, N=1 only).
 `--impl reference` times that CPU path alone, same metric/config.
@@ -90,6 +95,29 @@ class ClockSampler(threading.Thread):
                 "samples_under_load": len(load), "samples_timed": len([s for s in load if s[0] == "timed"])}
 
 
+def bind_to_gpu_numa_node(dev_index):
+    """Pin this process (and so its first-touch pinned allocations) to the CPUs of the NUMA node the GPU hangs off:
+    eight ranks pulling GBs per step through pinned buffers on the wrong socket halve their H2D rate.  Best effort."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return {"node": None, "note": "no NUMA affinity reported for %s" % bus}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return {"node": node, "note": "node CPUs not in this process's affinity mask"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed), "pci": bus}
+    except Exception as e:  # noqa: BLE001
+        return {"node": None, "note": "%s: %s" % (type(e).__name__, str(e)[:80])}
+
+
 # ------------------------------------------------------------------------------------------------
 # algorithmic bytes / flops per launch (DESIGN.md section "Kernels"; SURVEY 8d)
 # ------------------------------------------------------------------------------------------------
@@ -139,6 +167,7 @@ def run_ours(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -170,7 +199,7 @@ def run_ours(args):
         e_k = float(((got["kp_2d_w"].cpu() - ref["kp_2d_w"]).abs() * (sub[2]["orig_shape"].cpu()[:, [1, 0]] / 2).unsqueeze(1)).max())
         e_f = max(float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(got["point_feats"], ref["point_feats"]))
         parity = {"verts_m": max(e_v, e_g), "kp2d_px": e_k, "sampled_rel": e_f, "bodies": n}
-        if not (parity["verts_m"] <= 1e-5 and e_f <= 1e-4 and e_k <= 4e-3):
+        if not (parity["verts_m"] <= 1e-5 and e_f <= 1e-4 and e_k <= 1e-3):   # north-star tolerances
             raise SystemExit("bench.py: parity gate failed: %s" % parity)
 
     # ---- device-resident timing: the step as one CUDA graph ----------------------------------------
@@ -274,6 +303,54 @@ def run_ours(args):
                 k["dram_GBs_moved"] = tr["dram_bytes_per_launch"] / (per_launch_ms * 1e-3) / 1e9
                 k["dram_frac_moved"] = k["dram_GBs_moved"] / peaks["hbm_gbs"]
             kern[name] = k
+        lv = [kern[n] for n in ("sample_l0", "sample_l1", "sample_l2") if n in kern]
+        if len(lv) == 3:   # the three sampling launches of a step as ONE kernel class
+            alg = sum(algorithmic(n, B, ctx)["bytes"] for n in ("sample_l0", "sample_l1", "sample_l2"))
+            ms = sum(k["ms_per_step"] for k in lv)
+            agg = {"launches_per_step": 3, "ms_per_launch": ms / 3, "ms_per_step": ms, "bound": "hbm",
+                   "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "algorithmic_bytes_per_step": alg}
+            agg["frac"] = agg["achieved"] / agg["peak"]
+            if all("dram_bytes_per_launch_ncu" in k for k in lv):
+                moved = sum(k["dram_bytes_per_launch_ncu"] for k in lv)
+                agg.update(dram_bytes_per_step_ncu=moved, dram_GBs_moved=moved / (ms * 1e-3) / 1e9,
+                           dram_frac_moved=moved / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], wasted_traffic_factor=moved / alg)
+            kern["sampling"] = agg
+
+    # ---- the same step with channels_last feature maps (NHWC sampling kernel; no copy: a backbone run in channels_last
+    #      hands over exactly this memory) -----------------------------------------------------------------------------
+    cl = None
+    if not args.skip_channels_last and not args.channels_last:
+        feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+        g_cl, outs_cl = loop.capture(feats_cl, params, bbox)
+        for _ in range(W):
+            g_cl.replay()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        e_pf = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(outs_cl["point_feats"], outs["point_feats"]))
+        same_verts = bool(torch.equal(outs_cl["verts"], outs["verts"]))
+        if world > 1:
+            dist.barrier()
+        ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kc = min(K, 300)
+        ca.record()
+        for _ in range(kc):
+            g_cl.replay()
+        cb.record()
+        torch.cuda.synchronize()
+        t_cl = torch.tensor([ca.elapsed_time(cb)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_cl, op=dist.ReduceOp.MAX)
+        ms_cl = float(t_cl) / kc
+        cl = {"ms_per_step": ms_cl, "value": world * B / (ms_cl * 1e-3), "unit": UNIT, "steps": kc,
+              "parity_vs_nchw": {"sampled_rel": e_pf, "verts_identical": same_verts},
+              "note": "feature maps in torch.channels_last memory format: the NHWC sampling kernel reads 128 contiguous bytes "
+                      "per tap instead of one DRAM atom per (tap row, channel)"}
+        if not (e_pf <= 1e-4 and same_verts):
+            raise SystemExit("bench.py: channels_last leg differs from the NCHW step: %s" % cl["parity_vs_nchw"])
+        del g_cl, outs_cl, feats_cl
+        torch.cuda.empty_cache()
 
     # ---- end to end through host buffers ------------------------------------------------------------
     e2e = None
@@ -283,52 +360,97 @@ def run_ours(args):
         h_feats = [pin(f) for f in feats]
         h_params = [{k: pin(v) for k, v in q.items()} for q in params]
         h_bbox = {k: pin(v) for k, v in bbox.items()}
-        out_keys = ["verts", "global_verts", "pred_cam_t", "focal_length", "kp_2d_w", "global_kp_3d"]
-        h_out = {k: torch.empty(outs[k].shape, dtype=outs[k].dtype, pin_memory=True) for k in out_keys}
+        out_keys = ["verts", "global_verts", "pred_cam_t", "focal_length", "kp_2d_w", "global_kp_3d", "theta"]
         h2d_small = sum(v.numel() * 4 for q in h_params for v in q.values()) + sum(v.numel() * 4 for v in h_bbox.values())
         h2d_feat = sum(f.numel() * 4 for f in h_feats)
-        d2h = sum(v.numel() * 4 for v in h_out.values())
+        s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        s_cmp = torch.cuda.current_stream(dev)
 
-        def e2e_step(with_feats):
-            if with_feats:
-                for d, s in zip(feats, h_feats):
-                    d.copy_(s, non_blocking=True)
-            for dq, sq in zip(params, h_params):
-                for k in dq:
-                    dq[k].copy_(sq[k], non_blocking=True)
-            for k in bbox:
-                bbox[k].copy_(h_bbox[k], non_blocking=True)
-            graph.replay()
-            for k in out_keys:
-                h_out[k].copy_(outs[k], non_blocking=True)
+        def make_sets(own_feats):
+            """two independent buffer sets (inputs, captured graph, outputs, pinned result buffers)"""
+            sets = []
+            for i in range(2):
+                f_i = [torch.empty_like(f) for f in feats] if own_feats else feats
+                p_i = [{k: v.clone() for k, v in q.items()} for q in params]
+                b_i = {k: v.clone() for k, v in bbox.items()}
+                if own_feats:
+                    for d_, s_ in zip(f_i, feats):
+                        d_.copy_(s_)
+                g_i, o_i = loop.capture(f_i, p_i, b_i)
+                h_o = {k: torch.empty(o_i[k].shape, dtype=o_i[k].dtype, pin_memory=True) for k in out_keys}
+                sets.append({"feats": f_i, "params": p_i, "bbox": b_i, "graph": g_i, "outs": o_i, "h_out": h_o,
+                             "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event()})
+            return sets
 
-        def time_e2e(with_feats, steps):
-            for _ in range(2):
-                e2e_step(with_feats)
+        def run_pipeline(sets, with_feats, steps):
+            """step k: H2D of its inputs (stream 1) -> graph replay (stream 2) -> D2H of its results (stream 3); buffer set
+            k % 2, so the copies of step k+1 run under the kernels of step k and the read-back of step k-1.  The host
+            waits for the results of step k-1 before it enqueues step k+1 (a caller that consumes every result)."""
+            for st in sets:
+                st["ev_cmp"].record(s_cmp)
+                st["ev_out"].record(s_d2h)
+            for k in range(steps):
+                st = sets[k % 2]
+                with torch.cuda.stream(s_h2d):
+                    s_h2d.wait_event(st["ev_cmp"])          # the previous replay on this set has consumed its inputs
+                    if with_feats:
+                        for d_, s_ in zip(st["feats"], h_feats):
+                            d_.copy_(s_, non_blocking=True)
+                    for dq, sq in zip(st["params"], h_params):
+                        for kk in dq:
+                            dq[kk].copy_(sq[kk], non_blocking=True)
+                    for kk in st["bbox"]:
+                        st["bbox"][kk].copy_(h_bbox[kk], non_blocking=True)
+                    st["ev_in"].record(s_h2d)
+                s_cmp.wait_event(st["ev_in"])
+                s_cmp.wait_event(st["ev_out"])              # the previous results of this set have left the device
+                st["graph"].replay()
+                st["ev_cmp"].record(s_cmp)
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(st["ev_cmp"])
+                    for kk in out_keys:
+                        st["h_out"][kk].copy_(st["outs"][kk], non_blocking=True)
+                    st["ev_out"].record(s_d2h)
+                if k >= 1:
+                    sets[(k - 1) % 2]["ev_out"].synchronize()   # the caller reads step k-1's results now
+            sets[(steps - 1) % 2]["ev_out"].synchronize()
+
+        def time_e2e(sets, with_feats, steps):
+            run_pipeline(sets, with_feats, 3)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(steps):
-                e2e_step(with_feats)
-                torch.cuda.current_stream().synchronize()    # the caller reads the result every step
-            b.record()
+            t0 = time.perf_counter()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(s_cmp)
+            run_pipeline(sets, with_feats, steps)
             torch.cuda.synchronize()
-            t = torch.tensor([a.elapsed_time(b)], device=dev)
+            b_.record(s_cmp)
+            torch.cuda.synchronize()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            t = torch.tensor([max(a_.elapsed_time(b_), wall_ms)], device=dev)   # the slower of device and host clocks
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t) / steps
 
-        ke = max(3, min(K, args.e2e_steps))
-        ms_e2e = time_e2e(True, ke)
-        ms_e2e_res = time_e2e(False, max(ke, min(K, 200)))
+        ke = max(4, min(K, args.e2e_steps))
+        sets = make_sets(True)
+        d2h = sum(v.numel() * 4 for v in sets[0]["h_out"].values())
+        ms_e2e = time_e2e(sets, True, ke)
+        del sets
+        torch.cuda.empty_cache()
+        sets = make_sets(False)
+        ms_e2e_res = time_e2e(sets, False, max(ke, min(K, 200)))
+        del sets
+        torch.cuda.empty_cache()
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_small + h2d_feat,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": ke,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": ke, "pipeline": "3 streams x 2 buffer sets",
+               "h2d_GBs_per_rank": (h2d_small + h2d_feat) / (ms_e2e * 1e-3) / 1e9, "numa": numa,
                "note": "ALL step inputs from pinned host memory, incl. the 3 feature-map levels (in the reference "
                        "these are produced on the device by the backbone and never cross PCIe)"}
         e2e_resident = {"value": world * B / (ms_e2e_res * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_small,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_res,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_res, "pipeline": "3 streams x 2 buffer sets",
+                        "d2h_GBs_per_rank": d2h / (ms_e2e_res * 1e-3) / 1e9,
                         "note": "same, feature maps device-resident as in the reference (backbone output)"}
     sampler.region = "idle"
 
@@ -337,10 +459,15 @@ def run_ours(args):
     if rank == 0 and not args.skip_sweep:
         scale = smpl_sweep(loop, dev, peaks, [4096, 16384] if not args.quick else [4096])
 
+    # ---- BASELINE configs[2] and configs[4] on all ranks: a strong-scaling point and a pass that ends in a collective ----
+    other = None
+    if not args.skip_other:
+        other = other_configs(loop, model, dev, rank, world, peaks)
+
     # ---- CPU baseline (oracle on host cores), rank 0, N == 1 ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        cpu = cpu_loop_baseline(args.backbone, args.cpu_sample, reps=3)
+        cpu = cpu_loop_baseline(args.backbone, args.cpu_sample or 64, reps=3)
 
     # ---- the same dense PyTorch path, eager, on THIS GPU ("the real bar"), rank 0, N == 1 ---------------
     eager = None
@@ -355,15 +482,24 @@ def run_ours(args):
     clocks = sampler.summary()
 
     if rank == 0:
-        dom = max(kern.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if kern else None
+        classes = {n: k for n, k in kern.items() if not n.startswith("sample_l")} if "sampling" in kern else kern
+        dom = max(classes.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if classes else None
         roof = None
         if dom:
             k = kern[dom]
+            total_ms = sum(x["ms_per_step"] for x in classes.values())
+            if dom == "sampling":
+                traffic = ({"dram_bytes_per_launch": k["dram_bytes_per_step_ncu"] / 3, "source": "profiles/traffic.json (ncu --set full), mean of the 3 launches"}
+                           if "dram_bytes_per_step_ncu" in k else None)
+            else:
+                traffic = ncu_traffic(dom, B)
             roof = {"kernel": dom, "bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"], "unit": k["unit"],
-                    "frac": k["frac"], "traffic": ncu_traffic(dom, B), "peak_source": peaks["source"] + (
+                    "frac": k["frac"], "traffic": traffic, "peak_source": peaks["source"] + (
                         " (sustained bf16 / 3 MMAs per product)" if k["bound"] == "tensor" else " hbm copy"),
                     "ms_per_launch": k["ms_per_launch"], "launches_per_step": k["launches_per_step"],
-                    "share_of_step": k["ms_per_step"] / sum(x["ms_per_step"] for x in kern.values())}
+                    "share_of_step": k["ms_per_step"] / total_ms}
+            if "dram_frac_moved" in k:
+                roof.update(frac_of_bytes_moved=k["dram_frac_moved"], wasted_traffic_factor=k.get("wasted_traffic_factor"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -376,8 +512,9 @@ def run_ours(args):
                        "parallelism": "dp%d (bodies sharded by rank, no data-path collective)" % world,
                        "l2": "inputs larger than L2: feature maps 4.2 GB/step/GPU + ~0.2 GB of outputs vs 126 MB L2",
                        "launch": "one CUDA graph replay per step; schedule: finishing passes of the 5 read-outs + the 4 joint projections after the loop (1 + 4 launches), per-kernel probes taken on the immediate 22-launch schedule",
-                       "feature_layout": "channels_last (NHWC memory)" if args.channels_last else "NCHW contiguous (reference layout)"},
-            "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident,
+                       "feature_layout": "channels_last (NHWC memory)" if args.channels_last else "NCHW contiguous (reference layout)",
+                       "rotation_glue": "unbiased_gram_schmidt (eval mode) + rotation_matrix_to_angle_axis + theta inside the chain kernel, every SMPL call"},
+            "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident, "channels_last": cl, "other_configs": other,
             "gpu_launches": int(launches_per_step) * K, "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "torch_gpu_eager": eager, "smpl_at_scale": scale, "parity": parity,
         }
@@ -430,6 +567,74 @@ def smpl_sweep(loop, dev, peaks, sizes):
         res[str(Bs)] = {"ms": ms, "bodies_per_s": Bs / (ms * 1e-3), "hbm_GBs_algorithmic": gb,
                         "hbm_frac": gb / peaks["hbm_gbs"], "pose_blend_TFLOPs_algorithmic_if_alone": tf,
                         "tensor_frac_lower_bound": tf / tpeak}
+    return res
+
+
+def other_configs(loop, model, dev, rank, world, peaks):
+    """BASELINE configs[2] at its largest point (65,536 bodies in total: SMPL + H36M joint regression, sharded over the
+    ranks = strong scaling) and configs[4] (35,515 frames: GT SMPL + predicted SMPL + H36M 17->14 + MPJPE / PA-MPJPE / PVE,
+    sharded, then ONE all_gather_into_tensor of the [n,3] errors).  Timed on the device, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import whmr_b200.synthetic as syn
+    from whmr_b200.dist import all_gather_rows, shard_bounds
+    from whmr_b200.evaluate import EvalPass
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    ev = EvalPass(loop.smpl, model["J_regressor_h36m"])
+    res = {}
+    total = 65536
+    lo, hi = shard_bounds(total, rank, world)
+    b = syn.make_bodies(hi - lo, seed=5, rank=rank)
+    betas, rot = torch.from_numpy(b["betas"]).to(dev), torch.from_numpy(b["rotmat"]).to(dev)
+    ms = timed(lambda: ev.joints(betas, rot, True), 5)
+    bps = total / (ms * 1e-3)
+    res["smpl_sweep_65536"] = {"workload": "configs[2]: SMPL + H36M joint regression, 65,536 bodies in total, %d per GPU" % (hi - lo),
+                               "ms": ms, "bodies_per_s": bps, "scaling": "strong",
+                               "hbm_frac_algorithmic_per_gpu": bps / world * 84172 / 1e9 / peaks["hbm_gbs"],
+                               "tensor_frac_bf16x3_per_gpu": bps / world * 2.0 * KPOSE * 3 * V / 1e12 / (peaks["bf16_tflops_sustained"] / 3)}
+    del betas, rot
+    torch.cuda.empty_cache()
+    Nf = 35515
+    lo, hi = shard_bounds(Nf, rank, world)
+    gt, pr = syn.make_bodies(hi - lo, seed=31, rank=rank), syn.make_bodies(hi - lo, seed=32, rank=rank)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    g_pose, g_betas, p_rot, p_betas = T(gt["pose_aa"]), T(gt["betas"]), T(pr["rotmat"]), T(pr["betas"])
+
+    def shard_pass():
+        parts = []
+        for a in range(0, hi - lo, 4096):
+            r = ev(g_pose[a:a + 4096], g_betas[a:a + 4096], p_rot[a:a + 4096], p_betas[a:a + 4096])
+            parts.append(torch.stack([r["mpjpe"], r["pa_mpjpe"], r["pve"]], dim=1))
+        return torch.cat(parts) if parts else torch.empty(0, 3, device=dev)
+
+    ms_full = timed(lambda: all_gather_rows(shard_pass(), Nf), 5)
+    local = shard_pass()
+    ms_gather = timed(lambda: all_gather_rows(local, Nf), 20) if world > 1 else 0.0
+    full = all_gather_rows(local, Nf)
+    res["eval_pass_35515"] = {"workload": "configs[4]: 35,515 frames, 2 SMPL forwards + H36M read-outs + MPJPE/PA-MPJPE/PVE per frame, "
+                                          "%d frames per GPU, all_gather_into_tensor of the [n,3] errors" % (hi - lo),
+                              "ms_per_pass": ms_full, "frames_per_s": Nf / (ms_full * 1e-3), "ms_gather_alone": ms_gather,
+                              "gathered_shape": list(full.shape), "scaling": "strong",
+                              "mean_mm": {"mpjpe": float(full[:, 0].mean()) * 1e3, "pa_mpjpe": float(full[:, 1].mean()) * 1e3,
+                                          "pve": float(full[:, 2].mean()) * 1e3}}
     return res
 
 
@@ -602,9 +807,10 @@ def run_reference(args):
     import whmr_b200.synthetic as syn
     from oracle.loop_oracle import LoopOracle, make_cpu_inputs
     use_all_host_threads()
-    K, W = args.steps if args.steps_given else 20, max(1, min(args.warmup, 3))
-    # exactly K timed steps; the per-step sample shrinks so that K steps stay within ~2 minutes (~450 bodies/s on 16 threads)
-    n = max(8, min(args.cpu_sample, int(120.0 * 450.0 / max(K, 1))))
+    K, W = args.steps if args.steps_given else 20, max(1, min(args.warmup, 10))
+    # exactly K timed steps of the SAME batch as the GPU arm (256 bodies) while K steps stay within ~3 minutes
+    # (~450 bodies/s on 16 threads: K <= ~300); beyond that the per-step sample shrinks
+    n = max(8, min(args.batch, args.cpu_sample or args.batch, int(180.0 * 450.0 / max(K, 1))))
     model = syn.make_smpl_model(seed=0, weights="random")
     orc = LoopOracle(model, args.backbone)
     f, p, bb = make_cpu_inputs(n, args.backbone)
@@ -620,7 +826,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
             "steps": K, "warmup": W, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "whmr_regressor_loop_B256 (BASELINE configs[1]), CPU arm on a %d-body sample" % n,
+            "config": {"workload": "whmr_regressor_loop_B256 (BASELINE configs[1]), CPU arm, %d bodies per step" % n,
                        "batch_per_gpu": args.batch, "parallelism": "cpu"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -636,12 +842,15 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--backbone", default="vitpose", choices=["vitpose", "res50"])
     ap.add_argument("--gemm-mode", default=None, choices=[None, "fp32_simt", "bf16x3", "3xtf32"])
-    ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="bodies per CPU pass (default: 64 for the cpu_baseline leg, the full batch for --impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg")
     ap.add_argument("--skip-sweep", action="store_true")
+    ap.add_argument("--skip-other", action="store_true", help="skip the configs[2] / configs[4] legs")
+    ap.add_argument("--skip-channels-last", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--workload", default="regressor_loop", choices=["regressor_loop", "smpl_sweep", "maf_sampling", "eval_pass"],

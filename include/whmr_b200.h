@@ -172,6 +172,23 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
                               whmr_readout_t ro, float* ro_out /*[B*n_rows*3], group-major*/, void* ro_workspace,
                               size_t ro_workspace_bytes, int defer_finish, int* finish_deferred, void* workspace,
                               size_t workspace_bytes, void* stream);
+/* Regressor.forward's rotation glue around the SMPL call, folded into the chain kernel (no extra launch, no extra
+ * pass over HBM).  Replaces utils/geometry.py:260-272 unbiased_gram_schmidt (models/whmr.py:129-130, eval mode) on the
+ * way in and utils/geometry.py:54-83 rotation_matrix_to_angle_axis (models/whmr.py:174) + the `theta` concatenation
+ * (:190) on the way out. */
+typedef struct whmr_smpl_glue {
+  int32_t gram_schmidt;   /* != 0 (rotation-matrix mode only): R <- unbiased_gram_schmidt(R) before it is used */
+  float* rotmat_out;      /* [B,J,9] the rotations actually used, or NULL */
+  float* pose_aa_out;     /* [B,J*3] axis-angle of them ('pose'), or NULL */
+  float* theta_out;       /* [B, 3+n_betas+J*3] = cat(cam, betas, pose) ('theta'), or NULL */
+  const float* cam;       /* [B,3] (theta's head), or NULL (zeros) */
+} whmr_smpl_glue;
+/* whmr_smpl_forward_readout + the glue above (glue == NULL: identical to whmr_smpl_forward_readout; ro may be NULL). */
+int whmr_smpl_forward_regressor(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                                const float* transl, int B, float* verts, float* joints, float* rel_transforms,
+                                whmr_readout_t ro, float* ro_out, void* ro_workspace, size_t ro_workspace_bytes,
+                                int defer_finish, int* finish_deferred, const whmr_smpl_glue* glue, void* workspace,
+                                size_t workspace_bytes, void* stream);
 int whmr_readout_finish(whmr_readout_t ro, const float* joints /*[B,J,3] or NULL*/, int B, const void* ro_workspace,
                         float* ro_out, void* stream);
 /* The deferred finishing passes of up to 8 whmr_smpl_forward_readout calls (same table, same B, each with its own
@@ -275,6 +292,13 @@ int whmr_readout_backward(whmr_readout_t ro, const float* g_out, int B, float* g
 /* utils/geometry.py:289-307.  g_out [B,N,2] -> g_points [B,N,3] (or NULL), g_cam [B,3] */
 int whmr_project_weak_backward(const float* points, const float* cam, const float* g_out, int B, int N, float focal,
                                float img_w, float img_h, float* g_points, float* g_cam, void* stream);
+/* utils/geometry.py:310-341 perspective_projection (no distortion): g_out [B,N,2|3] (the retained z column has zero
+ * gradient) -> g_points [B,N,3] (or NULL), g_translation [B,3] (or NULL), g_focal [B] (or NULL), g_center [B,2] (or NULL).
+ * rotation: NULL, one [3,3] (rot_batch 1) or [B,3,3]; it receives no gradient (the reference passes an identity). */
+int whmr_perspective_projection_backward(const float* points, const float* rotation, int rot_batch,
+                                         const float* translation, const float* focal_dev, float focal_scalar,
+                                         const float* g_out, int B, int N, int retain_z, float* g_points,
+                                         float* g_translation, float* g_focal, float* g_center, void* stream);
 /* models/whmr.py:142-173 (whmr_project_weak_full / whmr_project_full).  Upstream gradients may be NULL.
  * -> g_points [B,N,3] (or NULL), g_cam [B,3], g_Tz [B] */
 int whmr_project_full_backward(const float* points, const float* cam, const float* bbox_height, const float* center,

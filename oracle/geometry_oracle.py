@@ -17,14 +17,14 @@ def perspective_projection(points, rotation, translation, focal_length, camera_c
     """utils/geometry.py:310-341.  points [B,N,3]; rotation [B or 1,3,3]; translation [B,3];
     focal_length scalar or [B]; camera_center [B,2].  -> [B,N,2] (or [B,N,3])."""
     B = points.shape[0]
-    p = torch.einsum('bij,bkj->bki', rotation, points)          # :329
+    p = torch.einsum('bij,bkj->bki', rotation.to(points.dtype), points)          # :329
     p = p + translation.unsqueeze(1)                            # :330
     q = p / p[:, :, -1].unsqueeze(-1)                           # :333
-    f = torch.as_tensor(focal_length, dtype=torch.float32, device=points.device)
+    dt = points.dtype        # fp32 like the reference; float64 when a test apportions rounding error / takes gradients
+    f = torch.as_tensor(focal_length, dtype=dt, device=points.device)
     f = f.expand(B) if f.dim() == 0 else f
-    cc = torch.as_tensor(camera_center, dtype=torch.float32, device=points.device)
+    cc = torch.as_tensor(camera_center, dtype=dt, device=points.device)
     # K = [[f,0,cx],[0,f,cy],[0,0,1]]  (:322-326) applied as einsum (:336)
-    q = q.to(torch.float32)
     u = f.view(B, 1) * q[:, :, 0] + cc[:, 0].view(B, 1) * q[:, :, 2]
     v = f.view(B, 1) * q[:, :, 1] + cc[:, 1].view(B, 1) * q[:, :, 2]
     out = torch.stack([u, v, q[:, :, 2]], dim=-1)
@@ -37,12 +37,12 @@ def projection(pred_joints, pred_camera, retain_z=False):
     B = pred_joints.shape[0]
     t = torch.stack([pred_camera[:, 1], pred_camera[:, 2],
                      2 * FOCAL_LENGTH / (IMG_H * pred_camera[:, 0] + 1e-9)], dim=-1)
-    eye = torch.eye(3, device=pred_joints.device).unsqueeze(0).expand(B, -1, -1)
-    kp = perspective_projection(pred_joints, eye, t, FOCAL_LENGTH, torch.zeros(B, 2, device=pred_joints.device),
-                                retain_z=retain_z)
+    eye = torch.eye(3, device=pred_joints.device, dtype=pred_joints.dtype).unsqueeze(0).expand(B, -1, -1)
+    kp = perspective_projection(pred_joints, eye, t, FOCAL_LENGTH,
+                                torch.zeros(B, 2, device=pred_joints.device, dtype=pred_joints.dtype), retain_z=retain_z)
     if retain_z:
         _retain_z_div(kp)
-    return kp / (torch.tensor([IMG_W, IMG_H], device=pred_joints.device) / 2.)
+    return kp / (torch.tensor([IMG_W, IMG_H], device=pred_joints.device, dtype=pred_joints.dtype) / 2.)
 
 
 def _retain_z_div(kp):
@@ -73,7 +73,7 @@ def full_projection(pred_joints, pred_cam, bbox_height, center, orig_shape, Tz):
     camera_center = img_shape / 2.                                # :153
     pred_cam_t = convert_pare_to_full_img_cam(pred_cam, bbox_height, center,
                                               orig_shape[:, 1], orig_shape[:, 0], Tz=Tz)  # :154
-    eye = torch.eye(3, device=pred_joints.device).unsqueeze(0).expand(1, -1, -1)
+    eye = torch.eye(3, device=pred_joints.device, dtype=pred_joints.dtype).unsqueeze(0).expand(1, -1, -1)
     kp_px = perspective_projection(pred_joints, eye.expand(pred_joints.shape[0], -1, -1),
                                    pred_cam_t, focal_length, camera_center)  # :165-171
     kp_norm = kp_px / camera_center.unsqueeze(1) - 1              # :173

@@ -22,12 +22,18 @@ class LoopOracle:
         self.grid = torch.from_numpy(syn.grid_points(backbone)).to(device)
         self.with_h36m = with_h36m
 
-    def regressor_outputs(self, p, bbox=None):
-        """Regressor.forward / forward_init after the MLP (models/whmr.py:128-209, 225-269)."""
-        o = self.smpl(p['betas'], p['rotmat'][:, 1:], p['rotmat'][:, :1], pose2rot=False)
+    def regressor_outputs(self, p, bbox=None, is_train=False):
+        """Regressor.forward / forward_init after the MLP (models/whmr.py:128-209, 225-269).  Regressor.forward (bbox
+        given) orthonormalises the predicted rotations in eval mode (:129-130); both compute `pose` / `theta` (:174,190)."""
+        rotmat = p['rotmat']
+        if bbox is not None and not is_train:
+            rotmat = G.unbiased_gram_schmidt(rotmat)
+        o = self.smpl(p['betas'], rotmat[:, 1:], rotmat[:, :1], pose2rot=False)
         verts, joints = o['vertices'], o['joints']
         r = regressor_readouts(self.model, verts)
-        out = {'verts': verts, 'joints49': joints, 'kp_2d': G.projection(joints, p['cam']),
+        pose = G.rotation_matrix_to_angle_axis(rotmat.reshape(-1, 3, 3)).reshape(-1, 72)
+        out = {'verts': verts, 'joints49': joints, 'kp_2d': G.projection(joints, p['cam']), 'rotmat': rotmat, 'pose': pose,
+               'theta': torch.cat([p['cam'], p['betas'], pose], dim=1),
                'sub_verts': r['sub_verts'], 'temp_verts': r['temp_verts'], 'markers': r['markers'],
                'smpl_kp_3d': r['smpl_kp_3d'], 'kp_3d': r['kp_3d_h36m'] if self.with_h36m else joints}
         if bbox is not None:
@@ -49,6 +55,8 @@ class LoopOracle:
             out = self.regressor_outputs(params[it + 1], bbox)
         g = self.smpl(params[4]['betas'], params[4]['rotmat'][:, 1:], params[4]['rotmat'][:, :1], pose2rot=False)
         res = dict(out)
+        # models/whmr.py:632-633: global_pose = cat(axis-angle of the re-estimated global rotation, pose[:, 3:])
+        res['global_pose'] = G.rotation_matrix_to_angle_axis(params[4]['rotmat'].reshape(-1, 3, 3)).reshape(-1, 72)
         res['point_feats'] = point_feats
         res['global_verts'] = g['vertices']
         if self.with_h36m:

@@ -116,9 +116,7 @@ class SMPLOracle:
         self.parents = torch.as_tensor(np.asarray(model['parents']), dtype=torch.long)   # host indices
         self.J_regressor_extra = from_np(model['J_regressor_extra'])
         self.vertex_ids = torch.as_tensor(np.asarray(model['vertex_ids']), dtype=torch.long).to(device)
-        import importlib
-        c = importlib.import_module('whmr_b200.constants')
-        self.joint_map = torch.tensor(c.JOINT_MAP_49, dtype=torch.long).to(device)
+        self.joint_map = torch.tensor(reference_tables()['joint_map_49'], dtype=torch.long).to(device)
         self.faces = model.get('f')
 
     def forward(self, betas, body_pose, global_orient, pose2rot=True, transl=None):
@@ -154,6 +152,19 @@ class SMPLOracle:
 
 
 _DEVICE_CACHE = {}
+_TABLES = None
+
+
+def reference_tables():
+    """Index tables extracted from the reference's own module (models/smpl.py:14-58) by
+    tests/golden/make_golden_tables.py: the 49-entry joint map, H36M_TO_J17 / J14.  The oracle reads THIS file, not the
+    product package's constants, so a wrong entry in `whmr_b200.constants` cannot hide."""
+    global _TABLES
+    if _TABLES is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'reference_tables.npz')
+        _TABLES = dict(np.load(path))
+    return _TABLES
 
 
 def regressor_readouts(model, verts, dtype=None):
@@ -161,8 +172,7 @@ def regressor_readouts(model, verts, dtype=None):
     (models/whmr.py:176-187, 240-251): H36M joints (17 -> pelvis-centred 14), the dense
     Dmap0/Dmap1 downsample, the SSM markers and smpl_kp_3d (J_regressor on POSED verts +
     selected vertices).  Dense matmuls, exactly as the reference computes them."""
-    import importlib
-    c = importlib.import_module('whmr_b200.constants')
+    h36m_to_j14 = [int(i) for i in reference_tables()['h36m_to_j14']]
     verts = torch.as_tensor(verts)
     dt = dtype or verts.dtype
     verts = verts.to(dt)
@@ -179,7 +189,7 @@ def regressor_readouts(model, verts, dtype=None):
     j17 = torch.matmul(t('J_regressor_h36m'), verts)               # whmr.py:177
     pelvis = j17[:, [0], :].clone()                                # :178
     out['h36m_j17'] = j17
-    out['kp_3d_h36m'] = j17[:, list(c.H36M_TO_J14), :] - pelvis    # :179-180
+    out['kp_3d_h36m'] = j17[:, h36m_to_j14, :] - pelvis    # :179-180
     out['sub_verts'] = torch.matmul(t('Dmap0'), verts)             # :182
     out['temp_verts'] = torch.matmul(t('Dmap1'), out['sub_verts'])  # :183
     out['markers'] = verts[:, torch.as_tensor(np.asarray(model['ssm']), dtype=torch.long).to(dev)]  # :184

@@ -27,6 +27,10 @@ def _worker(rank, world, port, total, q):
     idx = torch.arange(lo, hi, dtype=torch.float32)
     per_frame = torch.stack([idx * 2.0, idx + 0.5, idx * idx], dim=1)      # stand-in for [n_r, 3] errors
     g = all_gather_rows(per_frame, total)
+    g2 = all_gather_rows(per_frame)            # ragged path: sizes exchanged first
+    assert torch.equal(g, g2)
+    rag = all_gather_rows(per_frame[: (rank + 1) % 2 * per_frame.shape[0]])   # arbitrary ragged shards (some empty)
+    assert rag.shape[0] == sum(((r + 1) % 2) * (shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0]) for r in range(world))
     s = all_reduce_sum(per_frame.sum(0).clone())
     mx = max_over_ranks(float(rank + 1), torch.device("cpu"))
     if rank == 0:

@@ -222,3 +222,33 @@ def test_pkl_schema_roundtrip(tmp_path, smpl_model):
     for k in ('v_template', 'shapedirs', 'posedirs', 'J_regressor', 'weights'):
         np.testing.assert_array_equal(m2[k], smpl_model[k])
     assert list(m2['parents']) == list(smpl_model['parents'])
+
+
+def test_index_tables_equal_reference_module():
+    """whmr_b200.constants against the tables extracted by importing the reference's models/smpl.py
+    (tests/golden/make_golden_tables.py): every entry of the 49-joint map, the joint names, H36M_TO_J17 / J14, the focal."""
+    import numpy as np
+    from oracle.smpl_oracle import reference_tables
+    from whmr_b200 import constants as c
+    t = reference_tables()
+    assert list(c.JOINT_MAP_49) == [int(i) for i in t['joint_map_49']]
+    assert list(c.JOINT_NAMES) == [str(n) for n in t['joint_names']]
+    assert dict(c.JOINT_MAP) == {str(k): int(v) for k, v in zip(t['joint_map_keys'], t['joint_map_vals'])}
+    assert list(c.H36M_TO_J17) == [int(i) for i in t['h36m_to_j17']]
+    assert list(c.H36M_TO_J14) == [int(i) for i in t['h36m_to_j14']]
+    assert float(c.FOCAL_LENGTH) == float(t['focal_length'])
+    assert len(set(np.asarray(t['joint_map_49']).tolist())) <= 49 and int(np.max(t['joint_map_49'])) == 53
+
+
+def test_geometry_glue_on_cpu_matches_reference_golden(golden):
+    """The reference calls rot6d_to_rotmat on CPU tensors while it builds the model (models/whmr.py:65,285), so the drop-in
+    module must serve CPU (and autograd) callers: its torch path against the reference's own outputs."""
+    import torch
+    from whmr_b200 import geometry as geo
+    T = lambda k: torch.from_numpy(golden[k])  # noqa: E731
+    assert float((geo.rot6d_to_rotmat(T('rot6d_in')) - T('rot6d_out')).abs().max()) <= 1e-6
+    assert float((geo.unbiased_gram_schmidt(T('ugs_in')) - T('ugs_out')).abs().max()) <= 1e-6
+    assert float((geo.rotation_matrix_to_angle_axis(T('r2aa_in')) - T('r2aa_out')).abs().max()) <= 2e-6
+    x = T('ugs_in').clone().requires_grad_(True)
+    geo.rotation_matrix_to_angle_axis(geo.unbiased_gram_schmidt(x).reshape(-1, 3, 3)).sum().backward()
+    assert x.grad is not None and bool(torch.isfinite(x.grad).all())

@@ -214,6 +214,55 @@ def test_batch_rodrigues(dev):
     assert _maxabs(gpu_rod(aa.to(dev)), batch_rodrigues(aa)) <= 1e-6
 
 
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+def test_smpl_real_magnitude_stress(dev, gemm_mode):
+    """Blend-shape magnitudes of a real SMPL model: posedirs x10 (sigma 0.02) and shapedirs x3 (sigma 0.03) give pose
+    offsets up to ~0.7 m.  The split-operand tensor-core modes keep their margin: <= 1e-5 m against the fp32 oracle and
+    against the fp64 oracle."""
+    import whmr_b200.synthetic as syn
+    model = dict(syn.make_smpl_model(seed=0, weights="random"))
+    model['posedirs'] = (model['posedirs'] * 10.0).astype(np.float32)
+    model['shapedirs'] = (model['shapedirs'] * 3.0).astype(np.float32)
+    b = _bodies(48, seed=21)
+    smpl = _smpl(model, dev, gemm_mode)
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    out = smpl(betas=T(b['betas']), body_pose=T(b['rotmat'][:, 1:]), global_orient=T(b['rotmat'][:, :1]), pose2rot=False)
+    ref = _oracle(model)(b['betas'], b['rotmat'][:, 1:], b['rotmat'][:, :1], pose2rot=False)
+    ref64 = _oracle(model, torch.float64)(b['betas'], b['rotmat'][:, 1:].astype(np.float64),
+                                          b['rotmat'][:, :1].astype(np.float64), pose2rot=False)
+    off = float((ref64['vertices'] - ref64['vertices'].mean(1, keepdim=True)).abs().max())
+    e32, e64 = _maxabs(out.vertices, ref['vertices']), _maxabs(out.vertices, ref64['vertices'])
+    print("stress %s: |v| up to %.2f m, max err vs fp32 oracle %.2e m, vs fp64 %.2e m" % (gemm_mode, off, e32, e64))
+    assert e32 <= VERT_TOL and e64 <= VERT_TOL
+    assert _maxabs(out.joints, ref['joints']) <= VERT_TOL
+
+
+def test_smpl_65536_bodies_spot_check(dev, smpl_model):
+    """BASELINE configs[2]'s largest size in ONE call (16 chunks of 4,096 bodies, 5.4 GB of vertices): 48 bodies spread
+    over the call (incl. both sides of chunk boundaries and the last body) against the oracle, and position
+    independence (the same bodies as a 48-body batch are bitwise identical)."""
+    B = 65536
+    free, _ = torch.cuda.mem_get_info()
+    if free < 12 * 2**30:
+        pytest.skip("needs ~8 GB of free device memory")
+    b = _bodies(B, seed=17)
+    smpl = _smpl(smpl_model, dev, "bf16x3")
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    betas, rot = T(b['betas']), T(b['rotmat'])
+    big = smpl(betas=betas, body_pose=rot[:, 1:], global_orient=rot[:, :1], pose2rot=False)
+    rng = np.random.default_rng(0)
+    idx = sorted(set([0, 1, 4095, 4096, 8191, 8192, 32767, 32768, 61439, 61440, B - 2, B - 1] +
+                     rng.integers(0, B, size=36).tolist()))
+    ref = _oracle(smpl_model)(b['betas'][idx], b['rotmat'][idx, 1:], b['rotmat'][idx, :1], pose2rot=False)
+    sel = torch.tensor(idx, device=dev)
+    assert _maxabs(big.vertices[sel], ref['vertices']) <= VERT_TOL
+    assert _maxabs(big.joints[sel], ref['joints']) <= VERT_TOL
+    small = smpl(betas=betas[sel], body_pose=rot[sel, 1:], global_orient=rot[sel, :1], pose2rot=False)
+    assert torch.equal(big.vertices[sel], small.vertices) and torch.equal(big.joints[sel], small.joints)
+    del big, small
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------------------------------ read-outs
 @pytest.mark.parametrize("gemm_mode", ["fp32_simt", "bf16x3"])
 def test_body_model_head_matches_regressor_forward(dev, smpl_model, gemm_mode):
@@ -247,7 +296,7 @@ def test_body_model_head_matches_regressor_forward(dev, smpl_model, gemm_mode):
     np.testing.assert_allclose(out['focal_length'].cpu().numpy(), focal.numpy(), rtol=1e-6)
     assert _maxabs(out['pred_cam_t'], cam_t) <= 1e-5
     half = torch.from_numpy(b['orig_shape'][:, ::-1].copy()).unsqueeze(1) / 2
-    assert float(((out['kp_2d_w'].cpu() - kpn).abs() * half).max()) <= PX_TOL * 4   # px, large focal => 4e-3
+    assert float(((out['kp_2d_w'].cpu() - kpn).abs() * half).max()) <= PX_TOL
     # without H36M regressor 'kp_3d' is the 49 joints (models/whmr.py:140)
     out2 = head(T(b['rotmat']), T(b['betas']), T(b['cam']))
     assert out2['kp_3d'].shape == (B, 49, 3) and 'kp_2d_w' not in out2
@@ -287,17 +336,17 @@ def test_projection_matches_reference_golden(dev, golden):
     assert _maxabs(geo.projection(T('proj_points'), T('proj_cam')), g['proj_out']) * 128 <= PX_TOL
     kpn, focal, cam_t, px = geo.full_image_projection(T('proj_points'), T('proj_cam'), T('full_bbox_h'), T('full_center'),
                                                       T('full_orig_shape'), T('full_Tz'), want_px=True)
-    assert _maxabs(px, g['full_kp_px']) <= 4 * PX_TOL      # pixel coords ~2e3, fp32 ulp 2.4e-4
+    assert _maxabs(px, g['full_kp_px']) <= PX_TOL
     assert _maxabs(cam_t, g['full_cam_t']) <= 1e-5
     np.testing.assert_allclose(focal.cpu().numpy(), g['full_focal'], rtol=1e-6)
     assert _maxabs(kpn, g['full_kp_norm']) <= 1e-5
     cc = T('full_orig_shape')[:, [1, 0]] / 2.
     pp = geo.perspective_projection(T('proj_points'), T('pp_rot'), T('full_cam_t'), T('full_focal'), cc, retain_z=True)
-    assert _maxabs(pp, g['pp_retain_z']) <= 4 * PX_TOL
+    assert _maxabs(pp, g['pp_retain_z']) <= PX_TOL
     # keyword use + broadcast eye, exactly as models/whmr.py:157-163
     pp2 = geo.perspective_projection(T('proj_points'), rotation=torch.eye(3, device=dev).unsqueeze(0).expand(1, -1, -1),
                                      translation=T('full_cam_t'), focal_length=T('full_focal'), camera_center=cc)
-    assert _maxabs(pp2, g['full_kp_px']) <= 4 * PX_TOL
+    assert _maxabs(pp2, g['full_kp_px']) <= PX_TOL
     ct = geo.convert_pare_to_full_img_cam(T('proj_cam'), T('full_bbox_h'), T('full_center'), T('full_orig_shape')[:, 1],
                                           T('full_orig_shape')[:, 0], focal_length=5000.)
     assert _maxabs(ct, g['full_cam_t_f5000']) <= 1e-5
@@ -334,6 +383,82 @@ def test_projection_large_random(dev):
     assert _maxabs(kp, G.projection(pts, torch.from_numpy(b['cam']))) * 128 <= PX_TOL
 
 
+def test_geometry_dropins_carry_gradients(dev):
+    """The names INTEGRATION.md swaps into models/whmr.py:24-25 / core/trainer.py:27 sit inside the training graph
+    (kp_2d_w -> joints / Tz, core/trainer.py:518): perspective_projection, convert_pare_to_full_img_cam and projection
+    against autograd through the float64 oracle, in the exact composition of models/whmr.py:147-173."""
+    from oracle import geometry_oracle as G
+    from whmr_b200 import geometry as geo
+    b = _bodies(24, seed=9)
+    g = torch.Generator().manual_seed(3)
+    joints = (torch.randn(24, 49, 3, generator=g) * 0.4)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    cam, Tz, bh, ctr, osh = T(b['cam']), T(b['Tz']), T(b['bbox_height']), T(b['center']), T(b['orig_shape'])
+    w1, w2 = torch.randn(24, 49, 2, generator=g), torch.randn(24, 49, 2, generator=g)
+
+    def graph(mod, j, c, tz, dt, dv):
+        cv = lambda x: x.to(device=dv, dtype=dt)  # noqa: E731
+        s = c[:, 0].detach()
+        focal = s * cv(bh) * tz / 2.
+        cc = cv(osh)[:, [1, 0]] / 2.
+        cam_t = mod.convert_pare_to_full_img_cam(c.detach(), cv(bh), cv(ctr), cv(osh)[:, 1], cv(osh)[:, 0], Tz=tz)
+        eye = torch.eye(3, device=dv, dtype=dt).unsqueeze(0).expand(1, -1, -1)
+        kpw = mod.perspective_projection(j, rotation=eye, translation=cam_t, focal_length=focal, camera_center=cc)
+        kpw = kpw / cc.unsqueeze(1) - 1
+        kp = mod.projection(j.detach(), c)
+        return (kpw * cv(w1)).sum() + (kp * cv(w2)).sum()
+
+    leaf = lambda x, dt, dv: x.to(device=dv, dtype=dt).clone().requires_grad_(True)  # noqa: E731
+    j64, c64, t64 = leaf(joints, torch.float64, 'cpu'), leaf(cam, torch.float64, 'cpu'), leaf(Tz, torch.float64, 'cpu')
+    graph(G, j64, c64, t64, torch.float64, 'cpu').backward()
+    jg, cg, tg = leaf(joints, torch.float32, dev), leaf(cam, torch.float32, dev), leaf(Tz, torch.float32, dev)
+    graph(geo, jg, cg, tg, torch.float32, dev).backward()
+    rel = lambda a, r: float((a.detach().cpu().double() - r).abs().max() / (r.abs().max() + 1e-30))  # noqa: E731
+    assert jg.grad is not None and cg.grad is not None and tg.grad is not None
+    assert rel(jg.grad, j64.grad) <= 1e-4
+    assert rel(cg.grad, c64.grad) <= 1e-4
+    assert rel(tg.grad, t64.grad) <= 1e-4
+    # scalar focal + no rotation + retain_z, gradient to points and translation
+    pts = leaf(joints, torch.float32, dev)
+    tr = leaf(torch.tensor([[0.1, -0.2, 5.0]]).expand(24, 3).contiguous(), torch.float32, dev)
+    out = geo.perspective_projection(pts, None, tr, 1000., torch.zeros(24, 2, device=dev), retain_z=True)
+    out[..., :2].sum().backward()
+    p64 = leaf(joints, torch.float64, 'cpu')
+    t64b = leaf(torch.tensor([[0.1, -0.2, 5.0]]).expand(24, 3).contiguous(), torch.float64, 'cpu')
+    x = p64 + t64b.unsqueeze(1)
+    (1000. * x[..., :2] / x[..., 2:3]).sum().backward()
+    assert rel(pts.grad, p64.grad) <= 1e-4 and rel(tr.grad, t64b.grad) <= 1e-4
+
+
+def test_geometry_glue_cpu_and_grad_dispatch(dev, golden):
+    """init-time CPU use (models/whmr.py:65) and autograd use take the torch path; plain CUDA tensors the kernels"""
+    from whmr_b200 import geometry as geo
+    x = torch.from_numpy(golden['rot6d_in'])
+    assert _maxabs(geo.rot6d_to_rotmat(x), golden['rot6d_out']) <= 1e-6             # CPU tensor: no raise
+    assert _maxabs(geo.rot6d_to_rotmat(x.to(dev)), golden['rot6d_out']) <= 1e-6     # kernel
+    y = torch.from_numpy(golden['ugs_in']).to(dev).requires_grad_(True)
+    geo.unbiased_gram_schmidt(y).sum().backward()
+    assert y.grad is not None
+
+
+def test_handles_are_released_with_their_module(dev, smpl_model):
+    """ops._HANDLES / _READOUTS hold weak references: dropping the SMPL module frees the ~90 MB of device constants."""
+    import gc
+    from whmr_b200 import ops
+    smpl = _smpl(smpl_model, dev, "bf16x3")
+    b = _bodies(4)
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    smpl(betas=T(b['betas']), body_pose=T(b['rotmat'][:, 1:]), global_orient=T(b['rotmat'][:, :1]), pose2rot=False)
+    torch.cuda.synchronize()
+    n_h, n_r = len(ops._HANDLES), len(ops._READOUTS)
+    free0 = torch.cuda.mem_get_info()[0]
+    del smpl
+    gc.collect()
+    torch.cuda.synchronize()
+    assert len(ops._HANDLES) == n_h - 1 and len(ops._READOUTS) == n_r - 1
+    assert torch.cuda.mem_get_info()[0] - free0 >= 50 * 2**20      # cudaFree'd constants are back
+
+
 # ------------------------------------------------------------------------------------------ sampling
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_sampling_matches_reference_golden(dev, golden, tag):
@@ -353,7 +478,7 @@ def test_sampling_matches_reference_golden(dev, golden, tag):
     ext.im_feat = torch.from_numpy(g['fwd_feat']).to(dev)
     ext.cam = torch.from_numpy(g['fwd_cam']).to(dev)
     _, pf2 = ext(torch.from_numpy(g['fwd_p']).to(dev), None, None, None, None)
-    assert _maxabs(pf2, g['fwd_point_feat']) <= FEAT_RTOL * np.abs(g['fwd_point_feat']).max() * 4
+    assert _maxabs(pf2, g['fwd_point_feat']) <= FEAT_RTOL * np.abs(g['fwd_point_feat']).max()
 
 
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
@@ -377,6 +502,26 @@ def test_sampling_vs_grid_sample(dev, layout, H, W, N, C):
         out = ops.sample_bilinear(feat.permute(0, 2, 3, 1).contiguous().to(dev), pts.to(dev), ops.LAYOUT_NHWC)
     assert out.shape == (B, C, N)
     assert _maxabs(out, ref) <= FEAT_RTOL * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+@pytest.mark.parametrize("H,W", [(14, 14), (28, 28), (56, 56)])
+def test_sampling_config3_full_batch(dev, layout, H, W):
+    """BASELINE configs[3] at its full size (B = 1024, N = 431, C = 256; the 14x14 / 28x28 levels take the shared-memory
+    staged NCHW kernel): 24 bodies spread over the batch against grid_sample on the CPU."""
+    from oracle.sampling_oracle import grid_sample_points
+    from whmr_b200 import ops
+    import whmr_b200.synthetic as syn
+    B, N, C = 1024, 431, 256
+    g = torch.Generator(device=dev).manual_seed(H)
+    feat = torch.randn(B, C, H, W, generator=g, device=dev)
+    pts = torch.from_numpy(syn.make_sample_points(B, N, seed=3)).to(dev)
+    f_in = feat.contiguous(memory_format=torch.channels_last) if layout == "channels_last" else feat
+    out = ops.sample_bilinear(f_in, pts, ops.LAYOUT_NCHW)
+    assert out.shape == (B, C, N) and out.is_contiguous()
+    idx = sorted(set([0, 1, 511, 512, B - 1] + np.random.default_rng(H).integers(0, B, size=19).tolist()))
+    ref = grid_sample_points(feat[idx].cpu(), pts[idx].cpu())
+    assert _maxabs(out[idx], ref) <= FEAT_RTOL * float(ref.abs().max())
 
 
 @pytest.mark.parametrize("H,W", [(1, 1), (1, 9), (9, 1), (2, 2)])
@@ -428,12 +573,12 @@ def test_maf_project_matches_reference_golden(dev, golden):
     ext = MAF_Extractor(mesh_downsampling=None).to(dev)
     full, crop = ext.project(T('fwd_p'), T('fwd_cam'), T('mproj_center'), T('mproj_scale'), T('mproj_focal'),
                              T('mproj_img_center'), return_full=True)
-    assert _maxabs(full, g['mproj_full']) <= 4 * PX_TOL
-    assert _maxabs(crop, g['mproj_crop']) * 128 <= 20 * PX_TOL     # crop coords are scaled by 256/b (up to ~2.5x)
+    assert _maxabs(full, g['mproj_full']) <= PX_TOL
+    assert _maxabs(crop, g['mproj_crop']) * 128 <= PX_TOL
     tr = ext.get_trans(T('fwd_cam'), T('mproj_center'), T('mproj_scale'), T('mproj_focal'), T('mproj_img_center'))
     d = ext.perspective_projection(T('fwd_p') + tr, None, None, T('mproj_focal'), T('mproj_img_center'),
                                    distortion=T('mproj_kc'))
-    assert _maxabs(d, g['mproj_distorted']) <= 4 * PX_TOL
+    assert _maxabs(d, g['mproj_distorted']) <= PX_TOL
 
 
 # ------------------------------------------------------------------------------------------ metrics
@@ -645,17 +790,18 @@ def test_body_model_head_backward(dev, smpl_model):
     for stage in (None, 1, 2):
         head.train_stage = stage
         rm, be, cam, tz = T(b['rotmat'], True), T(b['betas'], True), T(b['cam'], True), T(b['Tz'], True)
-        out = head(rm, be, cam, T(b['bbox_height']), T(b['center']), T(b['orig_shape']), tz, J_regressor=True)
+        out = head(rm, be, cam, T(b['bbox_height']), T(b['center']), T(b['orig_shape']), tz, J_regressor=True, is_train=True)
         sum((out[k] * T(g)).sum() for k, g in gs.items()).backward()
         rm64, be64, cam64, tz64 = D(b['rotmat'], True), D(b['betas'], True), D(b['cam'], True), D(b['Tz'], True)
         ref = _oracle(smpl_model, torch.float64)(be64, rm64[:, 1:], rm64[:, :1], pose2rot=False)
         rr = regressor_readouts(smpl_model, ref['vertices'], torch.float64)
         j = ref['joints']
         # models/whmr.py:142-165: which projection sees the joints depends on cfg.TRAIN.STAGE; pred_cam is detached
-        # inside the predicted-focal block.  stage None: no detach anywhere (the op's full gradient)
-        jw = j if stage in (None, 1) else j.detach()
-        jf = j if stage in (None, 2) else j.detach()
-        camf = cam64 if stage is None else cam64.detach()
+        # inside the predicted-focal block.  stage None = the reference's configured default (TRAIN.STAGE: 2)
+        eff = 2 if stage is None else stage
+        jw = j if eff == 1 else j.detach()
+        jf = j if eff == 2 else j.detach()
+        camf = cam64.detach()
         with _default_f64():
             kp = G.projection(jw, cam64)
             kpn = G.full_projection(jf, camf, D(b['bbox_height']), D(b['center']), D(b['orig_shape']), tz64)[0]
@@ -720,15 +866,20 @@ def test_regressor_loop_matches_oracle_and_graph_replay(dev, smpl_model):
         assert _maxabs(got['markers'], ref['markers']) <= VERT_TOL
         assert _maxabs(got['kp_2d'], ref['kp_2d']) * 128 <= PX_TOL
         half = (bbox['orig_shape'].cpu()[:, [1, 0]] / 2).unsqueeze(1)
-        assert float(((got['kp_2d_w'].cpu() - ref['kp_2d_w']).abs() * half).max()) <= 4 * PX_TOL
+        assert float(((got['kp_2d_w'].cpu() - ref['kp_2d_w']).abs() * half).max()) <= PX_TOL
         for a, b in zip(got['point_feats'], ref['point_feats']):
             assert _maxabs(a, b) <= FEAT_RTOL * float(b.abs().max())
+        # rotation glue folded into the chain kernel (models/whmr.py:129-130, 174, 190, 632-633)
+        assert _maxabs(got['rotmat'], ref['rotmat']) <= 2e-6
+        assert _maxabs(got['pose'], ref['pose']) <= 2e-5 and got['pose'].shape == (B, 72)
+        assert _maxabs(got['theta'], ref['theta']) <= 2e-5 and got['theta'].shape == (B, 85)
+        assert _maxabs(got['global_pose'], ref['global_pose']) <= 2e-5
 
     check(loop.step(feats, params, bbox))
     loop.overlap = True
     check(loop.step(feats, params, bbox))
     g, outs = loop.capture(feats, params, bbox)
-    for k in ('verts', 'global_verts', 'kp_3d', 'markers', 'kp_2d', 'kp_2d_w'):   # (not the aliased inputs)
+    for k in ('verts', 'global_verts', 'kp_3d', 'markers', 'kp_2d', 'kp_2d_w', 'pose', 'theta', 'rotmat', 'global_pose'):   # (not the aliased inputs)
         outs[k].zero_()
     g.replay()
     torch.cuda.synchronize()

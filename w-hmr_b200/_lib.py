@@ -44,6 +44,11 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+class SmplGlue(C.Structure):
+    _fields_ = [("gram_schmidt", C.c_int32), ("rotmat_out", C.c_void_p), ("pose_aa_out", C.c_void_p),
+                ("theta_out", C.c_void_p), ("cam", C.c_void_p)]
+
+
 class SmplModelDesc(C.Structure):
     _fields_ = [("n_verts", C.c_int32), ("n_joints", C.c_int32), ("n_betas", C.c_int32),
                 ("v_template", C.c_void_p), ("shapedirs", C.c_void_p), ("posedirs", C.c_void_p),
@@ -68,6 +73,8 @@ SIGNATURES = {
     "whmr_smpl_forward": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "whmr_smpl_forward_readout": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i,
                                             C.POINTER(C.c_int), _vp, _sz, _vp]),
+    "whmr_smpl_forward_regressor": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i,
+                                              C.POINTER(C.c_int), _vp, _vp, _sz, _vp]),
     "whmr_readout_workspace_bytes": (_sz, [_vp, _i]),
     "whmr_smpl_chunk_bodies": (C.c_int, [_vp]),
     "whmr_smpl_is_fused": (C.c_int, [_vp]),
@@ -99,6 +106,7 @@ SIGNATURES = {
     "whmr_smpl_backward": (C.c_int, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "whmr_readout_backward": (C.c_int, [_vp, _vp, _i, _vp, _vp, _vp]),
     "whmr_project_weak_backward": (C.c_int, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
+    "whmr_perspective_projection_backward": (C.c_int, [_vp, _vp, _i, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "whmr_project_full_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "whmr_sample_bilinear_backward": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "whmr_joint_errors": (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

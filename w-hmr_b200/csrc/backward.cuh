@@ -66,6 +66,54 @@ project_weak_bwd_kernel(const float* __restrict__ points, const float* __restric
   }
 }
 
+// ---- utils/geometry.py:310-341 perspective_projection (no distortion): x = R p + t; u = f x/z + cx, v = f y/z + cy ------
+// grid = B, block 128.  Every output pointer may be null; the retained z column (z/z) has zero gradient.
+__global__ void __launch_bounds__(128)
+perspective_projection_bwd_kernel(const float* __restrict__ points, const float* __restrict__ rotation, int rot_batch,
+                                  const float* __restrict__ translation, const float* __restrict__ focal_dev,
+                                  float focal_scalar, const float* __restrict__ g_out, int N, int retain_z,
+                                  float* __restrict__ g_points, float* __restrict__ g_trans, float* __restrict__ g_focal,
+                                  float* __restrict__ g_center) {
+  __shared__ float red[6 * 128];
+  const int b = blockIdx.x;
+  const float* R = rotation ? rotation + (rot_batch > 1 ? (size_t)b * 9 : 0) : nullptr;
+  const float f = focal_dev ? focal_dev[b] : focal_scalar;
+  const float tx = translation ? translation[b * 3 + 0] : 0.f, ty = translation ? translation[b * 3 + 1] : 0.f,
+              tz = translation ? translation[b * 3 + 2] : 0.f;
+  const int ld = retain_z ? 3 : 2;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // d/d(tx, ty, tz), d/d focal, d/d(cx, cy)
+  for (int n = threadIdx.x; n < N; n += 128) {
+    const size_t i = (size_t)b * N + n;
+    float x = points[i * 3 + 0], y = points[i * 3 + 1], z = points[i * 3 + 2];
+    if (R) {
+      const float rx = R[0] * x + R[1] * y + R[2] * z, ry = R[3] * x + R[4] * y + R[5] * z, rz = R[6] * x + R[7] * y + R[8] * z;
+      x = rx; y = ry; z = rz;
+    }
+    x += tx; y += ty; z += tz;
+    const float gu = g_out[i * ld + 0], gv = g_out[i * ld + 1];
+    const float iz = 1.0f / z;
+    const float gx = gu * f * iz, gy = gv * f * iz, gz = -(gu * x + gv * y) * f * iz * iz;
+    if (g_points) {
+      if (R) {   // g_p = R^T g_x
+        g_points[i * 3 + 0] = R[0] * gx + R[3] * gy + R[6] * gz;
+        g_points[i * 3 + 1] = R[1] * gx + R[4] * gy + R[7] * gz;
+        g_points[i * 3 + 2] = R[2] * gx + R[5] * gy + R[8] * gz;
+      } else {
+        g_points[i * 3 + 0] = gx; g_points[i * 3 + 1] = gy; g_points[i * 3 + 2] = gz;
+      }
+    }
+    acc[0] += gx; acc[1] += gy; acc[2] += gz;
+    acc[3] += (gu * x + gv * y) * iz;
+    acc[4] += gu; acc[5] += gv;
+  }
+  block_sum<6, 128>(acc, red);
+  if (threadIdx.x == 0) {
+    if (g_trans) { g_trans[b * 3 + 0] = acc[0]; g_trans[b * 3 + 1] = acc[1]; g_trans[b * 3 + 2] = acc[2]; }
+    if (g_focal) g_focal[b] = acc[3];
+    if (g_center) { g_center[b * 2 + 0] = acc[4]; g_center[b * 2 + 1] = acc[5]; }
+  }
+}
+
 // ---- weak + predicted-focal block (models/whmr.py:142-173), the backward of project_full_kernel ------------------
 // upstream: g_kp_weak [B,N,2] (or null), g_kp_norm [B,N,2] (or null), g_focal [B] (or null), g_cam_t [B,3] (or null)
 // out: g_points [B,N,3] (or null), g_cam [B,3], g_Tz [B]

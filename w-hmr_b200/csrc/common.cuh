@@ -4,7 +4,10 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 
 #include "../../include/whmr_b200.h"
 
@@ -62,6 +65,26 @@ static inline void launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3
   cfg.attrs = attr;
   cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);   // errors surface through WHMR_LAUNCHED's cudaGetLastError
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: the largest value set so far is
+// remembered per (device, function), so a process that drives several GPUs (handles on cuda:1 after cuda:0,
+// nn.DataParallel, multi-device tests) raises it on every device it launches on.  Only ever raises.
+template <typename F>
+static inline cudaError_t ensure_dyn_smem(F* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> g(mu);
+  int& cur = done[std::make_pair(dev, reinterpret_cast<const void*>(func))];
+  if (bytes > cur) {
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    cur = bytes;
+  }
+  return cudaSuccess;
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -29,11 +29,8 @@ __global__ void __launch_bounds__(256) rot6d_to_rotmat_kernel(const float* __res
   o[6] = a1z; o[7] = b2z; o[8] = b3z;
 }
 
-__global__ void __launch_bounds__(256) unbiased_gram_schmidt_kernel(const float* __restrict__ x, int n,
-                                                                    float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* p = x + (size_t)i * 9;   // t_k = column k
+// utils/geometry.py:260-272 on one row-major 3x3 (in and out may alias)
+__device__ __forceinline__ void unbiased_gram_schmidt_dev(const float* p, float* o) {
   const float t1x = p[0], t1y = p[3], t1z = p[6], t2x = p[1], t2y = p[4], t2z = p[7], t3x = p[2], t3y = p[5], t3z = p[8];
   float r1x = ((t2y * t3z - t2z * t3y) + t1x) / 2.0f, r1y = ((t2z * t3x - t2x * t3z) + t1y) / 2.0f,
         r1z = ((t2x * t3y - t2y * t3x) + t1z) / 2.0f;
@@ -44,17 +41,23 @@ __global__ void __launch_bounds__(256) unbiased_gram_schmidt_kernel(const float*
   float r2x = qx - d * r1x, r2y = qy - d * r1y, r2z = qz - d * r1z;
   normalize3(r2x, r2y, r2z);
   const float r3x = r1y * r2z - r1z * r2y, r3y = r1z * r2x - r1x * r2z, r3z = r1x * r2y - r1y * r2x;
-  float* o = out + (size_t)i * 9;
   o[0] = r1x; o[1] = r2x; o[2] = r3x;
   o[3] = r1y; o[4] = r2y; o[5] = r3y;
   o[6] = r1z; o[7] = r2z; o[8] = r3z;
 }
 
-__global__ void __launch_bounds__(256) rotmat_to_axis_angle_kernel(const float* __restrict__ R, int n,
-                                                                   float* __restrict__ out) {
+__global__ void __launch_bounds__(256) unbiased_gram_schmidt_kernel(const float* __restrict__ x, int n,
+                                                                    float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float* p = R + (size_t)i * 9;
+  float r[9];
+  unbiased_gram_schmidt_dev(x + (size_t)i * 9, r);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) out[(size_t)i * 9 + k] = r[k];
+}
+
+// utils/geometry.py:54-83,86-136,160-240 on one row-major 3x3 -> axis-angle
+__device__ __forceinline__ void rotmat_to_axis_angle_dev(const float* p, float& ox, float& oy, float& oz) {
   // rmat_t = R^T  (utils/geometry.py:198); m[a][b] = R[b][a]
   const float m00 = p[0], m01 = p[3], m02 = p[6], m10 = p[1], m11 = p[4], m12 = p[7], m20 = p[2], m21 = p[5], m22 = p[8];
   const bool d2 = m22 < 1e-6f, d0_d1 = m00 > m11, d0_nd1 = m00 < -m11;
@@ -79,6 +82,15 @@ __global__ void __launch_bounds__(256) rotmat_to_axis_angle_kernel(const float* 
   if (isnan(ax)) ax = 0.0f;   // aa[torch.isnan(aa)] = 0.0 (:82)
   if (isnan(ay)) ay = 0.0f;
   if (isnan(az)) az = 0.0f;
+  ox = ax; oy = ay; oz = az;
+}
+
+__global__ void __launch_bounds__(256) rotmat_to_axis_angle_kernel(const float* __restrict__ R, int n,
+                                                                   float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float ax, ay, az;
+  rotmat_to_axis_angle_dev(R + (size_t)i * 9, ax, ay, az);
   out[(size_t)i * 3 + 0] = ax; out[(size_t)i * 3 + 1] = ay; out[(size_t)i * 3 + 2] = az;
 }
 

@@ -247,11 +247,7 @@ static int staged_channels(int C, int H, int W, int N) {
 template <bool kProject>
 static void launch_staged(const float* feat, const float* points, int pts_bstride, float* out, int B, int C, int H, int W,
                           int N, int cg, SampleProj pj, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(sample_bilinear_nchw_staged_kernel<kProject>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr_set = true;
-  }
+  ensure_dyn_smem(sample_bilinear_nchw_staged_kernel<kProject>, 64 * 1024);   // per device
   launch_pdl(kPdlSample, sample_bilinear_nchw_staged_kernel<kProject>, dim3(ceil_div(C, cg), B), dim3(256),
              (size_t)cg * H * W * sizeof(float), st, feat, points, pts_bstride, out, C, H, W, N, cg, pj);
 }

@@ -16,6 +16,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "rotations.cuh"
 
 namespace whmr {
 
@@ -37,6 +38,12 @@ struct ChainParams {
   float* pf_tf32;            // [B,2,KP] hi|lo tf32-valued floats or null
   float* At;                 // [2, At_rows, 32] tf32 hi|lo of A transposed: row (b*12+e), column = joint; or null
   size_t At_part_stride;     // floats between the hi and lo parts (= At_rows*32)
+  // Regressor.forward's rotation glue (models/whmr.py:129-130, 174, 190), folded in: no extra launches, no extra HBM pass
+  int gram_schmidt;          // rotmat mode: R <- unbiased_gram_schmidt(R) before anything else (eval mode)
+  float* rotmat_out;         // [B,J,9] the rotations actually used (the orthonormalised ones), or null
+  float* pose_aa_out;        // [B,J,3] rotation_matrix_to_angle_axis of them ('pose'), or null
+  float* theta_out;          // [B, 3+NB+3J] = cat(cam, betas, pose) ('theta'), or null; needs `cam`
+  const float* cam;          // [B,3]
   __half* At16;              // [At_rows, 64] fp16: A transposed, hi in columns 0..31, lo in 32..63, row = (b/2)*24 + e*2 + b%2 (fused kernel); or null
 };
 
@@ -84,6 +91,7 @@ __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(Ch
     const float* src = p.pose + ((size_t)b * p.J + j) * 9;
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = src[i];
+    if (p.gram_schmidt) unbiased_gram_schmidt_dev(R, R);
   } else {
     const float* src = p.pose + ((size_t)b * p.J + j) * 3;
     rodrigues_smplx(src[0], src[1], src[2], R);
@@ -174,9 +182,30 @@ __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(Ch
     }
   }
 
+  if (p.theta_out && lane < 3 + p.NB) {   // theta = [cam | betas | pose]; lanes 0..12 copy the head
+    p.theta_out[(size_t)b * (3 + p.NB + 3 * p.J) + lane] =
+        lane < 3 ? (p.cam ? p.cam[(size_t)b * 3 + lane] : 0.0f) : p.betas[(size_t)b * p.NB + (lane - 3)];
+  }
   if (!active) return;
 
   // ---- outputs ----------------------------------------------------------------------------
+  if (p.rotmat_out) {
+    float* ro = p.rotmat_out + ((size_t)b * p.J + j) * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) ro[i] = R[i];
+  }
+  if (p.pose_aa_out || p.theta_out) {
+    float ax, ay, az;
+    rotmat_to_axis_angle_dev(R, ax, ay, az);
+    if (p.pose_aa_out) {
+      float* o = p.pose_aa_out + ((size_t)b * p.J + j) * 3;
+      o[0] = ax; o[1] = ay; o[2] = az;
+    }
+    if (p.theta_out) {
+      float* o = p.theta_out + (size_t)b * (3 + p.NB + 3 * p.J) + 3 + p.NB + j * 3;
+      o[0] = ax; o[1] = ay; o[2] = az;
+    }
+  }
   if (p.joints) {
     float tx = 0.f, ty = 0.f, tz = 0.f;
     if (p.transl) {

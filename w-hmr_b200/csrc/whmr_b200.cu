@@ -383,7 +383,7 @@ static int get_ws(whmr_smpl_t h, int B, void* workspace, size_t bytes, SmplWorks
 
 static int chain_impl(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat, const float* transl,
                       int B, float* joints, float* rel_transforms, void* workspace, size_t workspace_bytes, void* stream,
-                      bool both_at_formats) {
+                      bool both_at_formats, const whmr_smpl_glue* glue = nullptr) {
   SmplWorkspace ws;
   int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
   if (rc) return rc;
@@ -403,6 +403,11 @@ static int chain_impl(whmr_smpl_t h, const float* betas, const float* pose, int 
   p.At = (h->skin_tc && (!f16 || both_at_formats)) ? ws.At : nullptr;
   p.At16 = f16 ? static_cast<__half*>(ws.At16) : nullptr;
   p.At_part_stride = ws.At_part_stride;
+  if (glue) {
+    WHMR_CHECK_ARG(!glue->gram_schmidt || pose_is_rotmat, "whmr_smpl_forward_regressor: gram_schmidt needs rotation-matrix input");
+    p.gram_schmidt = glue->gram_schmidt; p.rotmat_out = glue->rotmat_out; p.pose_aa_out = glue->pose_aa_out;
+    p.theta_out = glue->theta_out; p.cam = glue->cam;
+  }
   launch_pdl(kPdlChain, smpl_chain_kernel, dim3(ceil_div(B, kChainWarpsPerBlock)), dim3(kChainWarpsPerBlock * 32), 0, (cudaStream_t)stream, p);
   WHMR_LAUNCHED("smpl_chain_kernel");
   return WHMR_OK;
@@ -464,6 +469,7 @@ static int launch_readout_reduce(whmr_readout_t r, const float* verts, const flo
   q.rows = r->rows_reduce; q.n_rows = r->n_reduce; q.part_ptr = r->part_ptr; q.partial = partial;
   q.n_partial = r->n_partial; q.slot_of = r->slot_of; q.jt_ptr = r->jt_ptr; q.jt_col = r->jt_col; q.jt_val = r->jt_val;
   const size_t smem = (size_t)r->n_partial * 4 * sizeof(float);   // partials [n_partial,3] + slot list [n_partial]
+  if (smem > 48 * 1024) WHMR_CUDA(ensure_dyn_smem(readout_reduce_kernel, (int)smem));   // the launching device may not be the creating one
   launch_pdl(kPdlReadout, readout_reduce_kernel, dim3(nb), dim3(128), smem, st, q);
   WHMR_LAUNCHED("readout_reduce_kernel");
   return WHMR_OK;
@@ -604,17 +610,18 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, D>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st, h->tc.tmapA_bf16, \
              tmapPf, h->tc.tmapW16, tmapAt, p)
   if (instrumented) {
-    static bool attr_done = false;
-    if (!attr_done) {   // the instrumented instantiations are only ever launched from here
-      cudaFuncSetAttribute(smpl_fused_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<3>::kSmem);
-      cudaFuncSetAttribute(smpl_fused_tc_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<4>::kSmem);
-      cudaFuncSetAttribute(smpl_fused_tc_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<6>::kSmem);
-      cudaFuncSetAttribute(smpl_fused_tc_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FuTmem<8>::kSmem);
-      attr_done = true;
-    }
+    // the instrumented instantiations are only ever launched from here (per device)
+    ensure_dyn_smem(smpl_fused_tc_kernel<3, true>, FuTmem<3>::kSmem);
+    ensure_dyn_smem(smpl_fused_tc_kernel<4, true>, FuTmem<4>::kSmem);
+    ensure_dyn_smem(smpl_fused_tc_kernel<6, true>, FuTmem<6>::kSmem);
+    ensure_dyn_smem(smpl_fused_tc_kernel<8, true>, FuTmem<8>::kSmem);
     if (maxm == 3) WHMR_FUSED_LAUNCH(3, true); else if (maxm == 4) WHMR_FUSED_LAUNCH(4, true);
     else if (maxm == 6) WHMR_FUSED_LAUNCH(6, true); else WHMR_FUSED_LAUNCH(8, true);
   } else {
+    if (maxm == 3) ensure_dyn_smem(smpl_fused_tc_kernel<3, false>, FuTmem<3>::kSmem);
+    else if (maxm == 4) ensure_dyn_smem(smpl_fused_tc_kernel<4, false>, FuTmem<4>::kSmem);
+    else if (maxm == 6) ensure_dyn_smem(smpl_fused_tc_kernel<6, false>, FuTmem<6>::kSmem);
+    else ensure_dyn_smem(smpl_fused_tc_kernel<8, false>, FuTmem<8>::kSmem);
     if (maxm == 3) WHMR_FUSED_LAUNCH(3, false); else if (maxm == 4) WHMR_FUSED_LAUNCH(4, false);
     else if (maxm == 6) WHMR_FUSED_LAUNCH(6, false); else WHMR_FUSED_LAUNCH(8, false);
   }
@@ -713,6 +720,7 @@ int whmr_readout_finish_multi(whmr_readout_t ro, int n_calls, const float* const
     q.out_m[i] = ro_outs[i];
   }
   const size_t smem = (size_t)ro->n_partial * 4 * sizeof(float);
+  if (smem > 48 * 1024) WHMR_CUDA(ensure_dyn_smem(readout_reduce_kernel, (int)smem));
   launch_pdl(kPdlReadout, readout_reduce_kernel, dim3(B, n_calls), dim3(128), smem, (cudaStream_t)stream, q);
   WHMR_LAUNCHED("readout_reduce_kernel");
   return WHMR_OK;
@@ -723,6 +731,16 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
                               whmr_readout_t ro, float* ro_out, void* ro_workspace, size_t ro_workspace_bytes,
                               int defer_finish, int* finish_deferred, void* workspace, size_t workspace_bytes,
                               void* stream) {
+  return whmr_smpl_forward_regressor(h, betas, pose, pose_is_rotmat, transl, B, verts, joints, rel_transforms, ro, ro_out,
+                                     ro_workspace, ro_workspace_bytes, defer_finish, finish_deferred, nullptr, workspace,
+                                     workspace_bytes, stream);
+}
+
+int whmr_smpl_forward_regressor(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,
+                                const float* transl, int B, float* verts, float* joints, float* rel_transforms,
+                                whmr_readout_t ro, float* ro_out, void* ro_workspace, size_t ro_workspace_bytes,
+                                int defer_finish, int* finish_deferred, const whmr_smpl_glue* glue, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   if (finish_deferred) *finish_deferred = 0;
   SmplWorkspace ws;
   int rc = get_ws(h, B, workspace, workspace_bytes, &ws);
@@ -737,7 +755,7 @@ int whmr_smpl_forward_readout(whmr_smpl_t h, const float* betas, const float* po
   }
   cudaStream_t st = (cudaStream_t)stream;
   rc = chain_impl(h, betas, pose, pose_is_rotmat, transl, B, joints, rel_transforms, workspace, workspace_bytes, stream,
-                  false);
+                  false, glue);
   if (rc) return rc;
   if (h->probe_chain) WHMR_CUDA(cudaEventRecordWithFlags(h->probe_chain, st, cudaEventRecordExternal));
   // chunked so the [chunk, NP] pose-offset intermediate (and the chunk's vertices, for the read-outs)
@@ -986,13 +1004,7 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   up(jt_val, &h->jt_val);
   h->n_partial = n_partial; h->n_reduce = (int)rows_reduce.size();
   h->fusable = (size_t)n_partial * 16 <= 200 * 1024;   // one body's partial array + slot list must fit in shared memory
-  if (h->fusable) {
-    static int reduce_smem_max = 48 * 1024;   // the attribute is per function: only ever raise it
-    if (n_partial * 16 > reduce_smem_max) {
-      reduce_smem_max = n_partial * 16;
-      cudaFuncSetAttribute(readout_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, reduce_smem_max);
-    }
-  }
+  if (h->fusable && n_partial * 16 > 48 * 1024) ensure_dyn_smem(readout_reduce_kernel, n_partial * 16);   // again at launch
   if (e != cudaSuccess) {
     delete h;
     return set_error(WHMR_E_CUDA, "whmr_readout_create: device upload failed: %s", cudaGetErrorString(e));
@@ -1266,11 +1278,7 @@ int whmr_smpl_backward(whmr_smpl_t h, const float* betas, const float* pose, int
       q.g_offsets = c.g_off; q.g_A = c.g_A + (size_t)b0 * d.J * 12;
       q.B = nb; q.V = d.V; q.VP = d.VP; q.NP = d.NP; q.J = d.J; q.ell_k = d.ell_k;
       const size_t smem = skin_backward_smem_bytes(d.J);
-      static size_t smem_set = 0;
-      if (smem > smem_set) {
-        WHMR_CUDA(cudaFuncSetAttribute(skin_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-      }
+      WHMR_CUDA(ensure_dyn_smem(skin_backward_kernel, (int)smem));   // per device
       skin_backward_kernel<<<dim3(d.VP / kVertTile, ceil_div(nb, kBwdBodies)), kBwdThreads, smem, st>>>(q);
       WHMR_LAUNCHED("skin_backward_kernel");
       pose_blend_backward_kernel<<<dim3(ceil_div(d.KP, kPbTile), ceil_div(nb, kPbTile), ksplit), 256, 0, st>>>(
@@ -1312,6 +1320,21 @@ int whmr_project_weak_backward(const float* points, const float* cam, const floa
   WHMR_CHECK_ARG(points && cam && g_out && g_cam, "whmr_project_weak_backward: null pointer");
   project_weak_bwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(points, cam, g_out, N, focal, img_w, img_h, g_points, g_cam);
   WHMR_LAUNCHED("project_weak_bwd_kernel");
+  return WHMR_OK;
+}
+
+int whmr_perspective_projection_backward(const float* points, const float* rotation, int rot_batch,
+                                         const float* translation, const float* focal_dev, float focal_scalar,
+                                         const float* g_out, int B, int N, int retain_z, float* g_points,
+                                         float* g_translation, float* g_focal, float* g_center, void* stream) {
+  WHMR_CHECK_ARG(B >= 0 && N >= 0, "whmr_perspective_projection_backward: negative size");
+  if (B == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(points && g_out, "whmr_perspective_projection_backward: null pointer");
+  WHMR_CHECK_ARG(rot_batch == 0 || rot_batch == 1 || rot_batch == B, "whmr_perspective_projection_backward: bad rot_batch %d", rot_batch);
+  perspective_projection_bwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(points, rotation, rot_batch, translation, focal_dev,
+                                                                        focal_scalar, g_out, N, retain_z, g_points,
+                                                                        g_translation, g_focal, g_center);
+  WHMR_LAUNCHED("perspective_projection_bwd_kernel");
   return WHMR_OK;
 }
 

@@ -15,11 +15,15 @@ from .smpl import SMPL
 
 
 class EvalPass:
-    def __init__(self, smpl, J_regressor_h36m, joint_mapper=None):
+    def __init__(self, smpl, J_regressor_h36m, joint_mapper=None, smpl_male=None, smpl_female=None):
         """smpl: whmr_b200.smpl.SMPL (shared with the model, core/trainer.py:66); J_regressor_h36m [17,V]
-        (data/J_regressor_h36m.npy); joint_mapper: H36M_TO_J14 (default) or H36M_TO_J17 (mpi-inf-3dhp, :150)."""
+        (data/J_regressor_h36m.npy); joint_mapper: H36M_TO_J14 (default) or H36M_TO_J17 (mpi-inf-3dhp, :150).
+        smpl_male / smpl_female: the gendered models of the 3DPW protocol (core/trainer.py:58-64, 783-791): with them and a
+        per-frame `gender` vector the ground truth comes from the male model, overwritten by the female one where
+        gender == 1, exactly as the reference selects it."""
         assert isinstance(smpl, SMPL)
         self.smpl = smpl
+        self.smpl_male, self.smpl_female = smpl_male, smpl_female
         self._J = np.asarray(J_regressor_h36m, dtype=np.float64)
         self._map = list(constants.H36M_TO_J14 if joint_mapper is None else joint_mapper)
         self._ro = {}
@@ -37,9 +41,9 @@ class EvalPass:
             self._ro[str(device)] = ro
         return ro
 
-    def joints(self, betas, pose, pose_is_rotmat):
+    def joints(self, betas, pose, pose_is_rotmat, model=None):
         """SMPL forward + pelvis-centred evaluation joints in one pass -> (vertices [n,V,3], kp [n,14,3])."""
-        h, _ = self.smpl._state(betas.device)
+        h, _ = (model or self.smpl)._state(betas.device)
         ro = self._readout(betas.device)
         verts, _, flat = ops.smpl_lbs_readout(h.id, ro.id, betas, pose, bool(pose_is_rotmat))
         return verts, ro.split(flat, betas.shape[0])['kp']
@@ -47,11 +51,21 @@ class EvalPass:
     def joints_from_vertices(self, verts):
         return self._readout(verts.device).apply(verts)['kp']
 
-    def __call__(self, gt_pose, gt_betas, pred_rotmat=None, pred_betas=None, pred_vertices=None):
+    def __call__(self, gt_pose, gt_betas, pred_rotmat=None, pred_betas=None, pred_vertices=None, gender=None):
         """gt_pose [n,72] axis-angle, gt_betas [n,10]; prediction either as (pred_rotmat [n,24,3,3], pred_betas)
-        or as pred_vertices [n,V,3] (the model's `global_verts`, :181).  -> dict of per-frame errors in metres:
+        or as pred_vertices [n,V,3] (the model's `global_verts`, :181).  gender [n] (0 male, 1 female): ground truth from
+        the gendered models (core/trainer.py:783-791).  -> dict of per-frame errors in metres:
         mpjpe, pa_mpjpe, pve  (the reference multiplies by 1000 when printing, :262-266)."""
-        gt_verts, gt_kp = self.joints(gt_betas, gt_pose.reshape(gt_pose.shape[0], -1), False)
+        aa = gt_pose.reshape(gt_pose.shape[0], -1)
+        if gender is not None:
+            if self.smpl_male is None or self.smpl_female is None:
+                raise ValueError("EvalPass: gender given but no smpl_male / smpl_female models")
+            vm, km = self.joints(gt_betas, aa, False, self.smpl_male)
+            vf, kf = self.joints(gt_betas, aa, False, self.smpl_female)
+            fem = (gender.to(vm.device) == 1).view(-1, 1, 1)
+            gt_verts, gt_kp = torch.where(fem, vf, vm), torch.where(fem, kf, km)    # kp is linear in the vertices
+        else:
+            gt_verts, gt_kp = self.joints(gt_betas, aa, False)
         if pred_vertices is None:
             pred_vertices, pred_kp = self.joints(pred_betas, pred_rotmat.reshape(pred_rotmat.shape[0], -1, 3, 3), True)
         else:

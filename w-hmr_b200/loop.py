@@ -9,9 +9,11 @@ gets back what they would consume (sampled point features) plus the Regressor re
                 then Regressor.forward                                                     (:604-612)
     global    : 5th SMPL call with the re-estimated global orientation + H36M joints       (:641-651)
 
-`RegressorLoop.step` launches 41 kernels (5 x {chain, pose-blend, skin}, 4+1 x read-out pairs,
-4 weak + 3 full projections, 1 + 2x2 sampling); `capture()` wraps the step in a CUDA graph so a
-replay costs one launch from the host.
+`RegressorLoop.step` launches 18 kernels on the deferred schedule (5 x {chain with the rotation glue folded in, fused
+pose-blend + skinning}, 3 sampling, ONE finishing pass for the five read-outs, 4 projections) and 22 on the immediate
+one; `capture()` wraps the step in a CUDA graph so a replay costs one launch from the host.  Every call also produces
+the reference's `pose` / `theta` (rotation_matrix_to_angle_axis, :174,190) and, in eval mode, orthonormalises the
+predicted rotations first (unbiased_gram_schmidt, :129-130) -- inside the chain kernel, no extra launch.
 """
 import numpy as np
 import torch
@@ -46,6 +48,7 @@ class RegressorLoop:
         # finishing passes of the five read-outs + the joint projections after the loop, in one + four launches
         # (inference only: under autograd the immediate schedule is used); 0.389 -> see profiles/r01_notes.md
         self.defer = True
+        self.is_train = False   # eval mode: Regressor.forward orthonormalises the predicted rotations (models/whmr.py:129-130)
 
     def step(self, feats, params, bbox):
         """feats: 3 feature maps [B,256,H_i,W_i]; params: 5 dicts {rotmat [B,24,3,3], betas [B,10],
@@ -60,26 +63,31 @@ class RegressorLoop:
         self.head.side_stream = self._side if (self.overlap and self.head.probe is None) else None
         out = self.head(p[0]['rotmat'], p[0]['betas'], p[0]['cam'], J_regressor=J)           # forward_init
         point_feats = []
+        keep = [out]      # every iteration's result stays alive until the side stream has been joined (see BodyModelHead)
         for it in range(3):
             pf = self._sample(it, feats, out['markers'], p[it]['cam'])
             self.head._mark('sample_l%d' % it)
             point_feats.append(pf)
             q = p[it + 1]
             out = self.head(q['rotmat'], q['betas'], q['cam'], bbox['bbox_height'], bbox['center'],
-                            bbox['orig_shape'], bbox['Tz'], J_regressor=J)                   # :598 / :608
+                            bbox['orig_shape'], bbox['Tz'], J_regressor=J, is_train=self.is_train)   # :598 / :608
+            keep.append(out)
         g = p[4]
         h, _ = self.smpl._state(self.device)
         self.head._mark('pre_smpl')
         ro = self.head._readout(self.device, self.with_h36m)
-        gverts, gjoints24, flat = ops.smpl_lbs_readout(h.id, ro.id, g['betas'], g['rotmat'], True)  # :641-644
+        gverts, gjoints24, flat, _, _, gpose, _ = ops.smpl_regressor(h.id, ro.id, g['betas'], g['rotmat'], g['cam'],
+                                                                     False, False)   # :632-644
         r = ro.split(flat, gverts.shape[0])
         self.head._mark('skin_readout')
         if self.head.side_stream is not None:
             main.wait_stream(self._side)     # join: everything in the result dict is complete on the main stream
         res = dict(out)
+        res['_keep'] = keep
         res['point_feats'] = point_feats
         res['global_verts'] = gverts
         res['global_kp_3d'] = r['kp_3d_h36m'] if self.with_h36m else r['joints']            # :646-651
+        res['global_pose'] = gpose                                                          # :632-633
         return res
 
     def _sample(self, it, feats, markers, cam):
@@ -95,13 +103,14 @@ class RegressorLoop:
         kernel itself) and the camera, so the five finishing passes of the read-outs run as ONE launch after the loop,
         followed by the four joint projections (models/whmr.py:550-651 returns everything at the end as well)."""
         p = params
-        states = [self.head.begin(p[0]['rotmat'], p[0]['betas'], J)]
+        states = [self.head.begin(p[0]['rotmat'], p[0]['betas'], J, p[0]['cam'])]             # forward_init
         point_feats = []
         for it in range(3):
             point_feats.append(self._sample(it, feats, states[-1]['markers'], p[it]['cam']))
             q = p[it + 1]
-            states.append(self.head.begin(q['rotmat'], q['betas'], J))
-        states.append(self.head.begin(p[4]['rotmat'], p[4]['betas'], J))                     # global call, :641-644
+            states.append(self.head.begin(q['rotmat'], q['betas'], J, q['cam'], orthonormalize=not self.is_train))
+        # global call, :632-644: the axis-angle of [global_rotmat | last body rotations] IS global_pose
+        states.append(self.head.begin(p[4]['rotmat'], p[4]['betas'], J, p[4]['cam']))
         outs = self.head.complete_all(states, [p[0]['cam'], p[1]['cam'], p[2]['cam'], p[3]['cam'], None],
                                       bbox['bbox_height'], bbox['center'], bbox['orig_shape'], bbox['Tz'],
                                       full=[False, True, True, True, False])
@@ -109,6 +118,7 @@ class RegressorLoop:
         res['point_feats'] = point_feats
         res['global_verts'] = outs[4]['verts']
         res['global_kp_3d'] = outs[4]['r']['kp_3d_h36m'] if self.with_h36m else outs[4]['r']['joints']
+        res['global_pose'] = outs[4]['pose']
         return res
 
     # ---- CUDA-graph replay ------------------------------------------------------------------------

@@ -76,7 +76,10 @@ class MAF_Extractor(nn.Module):
         return self.reduce_dim(point_feat), point_feat
 
     def project(self, points, pred_cam, center, scale, img_focal, img_center, return_full=False):
-        """models/maf_extractor.py:145-173."""
+        """models/maf_extractor.py:145-173 (not called on the live path; forward-only)."""
+        if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in (points, pred_cam)):
+            raise NotImplementedError("MAF_Extractor.project has no backward (the reference never differentiates it: "
+                                      "models/whmr.py drives MAF_Extractor.forward); call it under torch.no_grad()")
         full, crop = ops.project_crop(points, pred_cam, center, scale, img_focal, img_center, self.crop_size,
                                       constants.IMG_RES_WIDTH, constants.IMG_RES_HEIGHT)
         return (full, crop) if return_full else crop

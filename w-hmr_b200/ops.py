@@ -5,6 +5,7 @@ allocates outputs / scratch through torch's caching allocator (so the C side nev
 No function in this file has a CPU or PyTorch-eager fallback.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -45,7 +46,10 @@ def _p(t):
 # ----------------------------------------------------------------------------------------------
 # SMPL handle
 # ----------------------------------------------------------------------------------------------
-_HANDLES = {}
+# id -> handle for the torch.library ops (which take plain ints).  WEAK: the owning SMPL / BodyModelHead module holds the
+# only strong reference, so dropping the module (or reloading its state dict, which rebuilds the handle) runs __del__ ->
+# whmr_smpl_destroy and frees the ~90 MB of re-arranged model constants on the device.
+_HANDLES = weakref.WeakValueDictionary()
 
 
 class SmplHandle:
@@ -79,7 +83,10 @@ class SmplHandle:
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.lib().whmr_smpl_destroy(self._h)
             self._h = C.c_void_p()
-        _HANDLES.pop(getattr(self, "id", None), None)
+        try:
+            _HANDLES.pop(getattr(self, "id", None), None)
+        except Exception:   # interpreter shutdown
+            pass
 
     def __del__(self):
         try:
@@ -113,10 +120,12 @@ class SmplHandle:
         return torch.empty(n, dtype=torch.uint8, device=self.device), n
 
     def forward(self, betas, pose, pose_is_rotmat, transl=None, want_transforms=False, readout=None,
-                defer_finish=False):
+                defer_finish=False, glue=None):
         """-> (verts [B,V,3], chain joints [B,J,3], A [B,J,12] or None[, flat read-out buffer, read-out scratch])
         With defer_finish the finishing pass of the read-outs may be left to the caller (`readout_finish`, any
-        stream); it was deferred iff the returned scratch tensor is non-empty."""
+        stream); it was deferred iff the returned scratch tensor is non-empty.
+        glue: dict(gram_schmidt=bool, cam=[B,3] or None) -> Regressor.forward's rotation glue runs inside the chain kernel
+        and three more tensors are appended to the result: rotmat [B,J,3,3] (the rotations used), pose [B,3J], theta."""
         betas = _req(betas, "betas", align=16)
         pose = _req(pose, "pose", align=16)
         transl = _req(transl, "transl")
@@ -129,21 +138,35 @@ class SmplHandle:
         joints = torch.empty(B, self.J, 3, dtype=torch.float32, device=self.device)
         A = torch.empty(B, self.J, 12, dtype=torch.float32, device=self.device) if want_transforms else None
         ws, n = self.workspace(B)
-        if readout is None:
+        g, extra = None, ()
+        if glue is not None:
+            cam = _req(glue.get("cam"), "cam")
+            rotmat = torch.empty(B, self.J, 3, 3, dtype=torch.float32, device=self.device)
+            pose_aa = torch.empty(B, self.J * 3, dtype=torch.float32, device=self.device)
+            theta = torch.empty(B, 3 + self.NB + self.J * 3, dtype=torch.float32, device=self.device)
+            g = _lib.SmplGlue(int(bool(glue.get("gram_schmidt"))), _p(rotmat), _p(pose_aa), _p(theta), _p(cam))
+            extra = (rotmat, pose_aa, theta)
+        if readout is None and g is None:
             with torch.cuda.device(self.device):
                 check(_lib.lib().whmr_smpl_forward(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl),
                                                    B, _p(verts), _p(joints), _p(A), _p(ws), n, _stream()))
             return verts, joints, A
-        ro_flat = torch.empty(B * readout.R * 3, dtype=torch.float32, device=self.device)
         L = _lib.lib()
-        nro = int(L.whmr_readout_workspace_bytes(readout._h, min(B, int(L.whmr_smpl_chunk_bodies(self._h)))))
-        ro_ws = torch.empty(max(nro, 1), dtype=torch.uint8, device=self.device)
+        ro_flat = ro_ws = None
+        nro = 0
+        if readout is not None:
+            ro_flat = torch.empty(B * readout.R * 3, dtype=torch.float32, device=self.device)
+            nro = int(L.whmr_readout_workspace_bytes(readout._h, min(B, int(L.whmr_smpl_chunk_bodies(self._h)))))
+            ro_ws = torch.empty(max(nro, 1), dtype=torch.uint8, device=self.device)
         deferred = C.c_int(0)
         with torch.cuda.device(self.device):
-            check(L.whmr_smpl_forward_readout(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl), B,
-                                              _p(verts), _p(joints), _p(A), readout._h, _p(ro_flat), _p(ro_ws), nro,
-                                              int(bool(defer_finish)), C.byref(deferred), _p(ws), n, _stream()))
-        return verts, joints, A, ro_flat, (ro_ws if deferred.value else ro_ws[:0])
+            check(L.whmr_smpl_forward_regressor(self._h, _p(betas), _p(pose), int(bool(pose_is_rotmat)), _p(transl), B,
+                                                _p(verts), _p(joints), _p(A), None if readout is None else readout._h,
+                                                _p(ro_flat), _p(ro_ws), nro, int(bool(defer_finish)), C.byref(deferred),
+                                                None if g is None else C.byref(g), _p(ws), n, _stream()))
+        if readout is None:
+            return (verts, joints, A) + extra
+        return (verts, joints, A, ro_flat, (ro_ws if deferred.value else ro_ws[:0])) + extra
 
     # per-stage launches (bench.py per-kernel timing, tests)
     def backward(self, betas, pose, g_verts=None, g_joints=None):
@@ -221,7 +244,7 @@ def rotation_matrix_to_angle_axis(R):
 # ----------------------------------------------------------------------------------------------
 # read-out
 # ----------------------------------------------------------------------------------------------
-_READOUTS = {}
+_READOUTS = weakref.WeakValueDictionary()   # weak for the same reason as _HANDLES
 
 
 class Readout:
@@ -601,6 +624,55 @@ def _(handle, readout, betas, pose, pose_is_rotmat):
             betas.new_empty(0, dtype=torch.uint8))
 
 
+@torch.library.custom_op("whmr::smpl_regressor", mutates_args=(), device_types="cuda")
+def smpl_regressor(handle: int, readout: int, betas: torch.Tensor, rotmat: torch.Tensor, cam: torch.Tensor,
+                   orthonormalize: bool, defer: bool) -> \
+        tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The SMPL part of Regressor.forward / forward_init in one chunked pass (models/whmr.py:128-190): optional
+    unbiased_gram_schmidt of the predicted rotations (eval mode), SMPL forward, every read-out of the table, `pose`
+    (rotation_matrix_to_angle_axis) and `theta` = cat(cam, betas, pose).
+    -> (verts, chain joints, flat read-outs, read-out scratch (non-empty iff the finishing pass was deferred),
+        rotmat used [B,J,3,3], pose [B,3J], theta [B,3+NB+3J]).  Differentiable w.r.t. betas / rotmat through verts, joints
+    and the read-outs when orthonormalize is False (training); pose / theta / rotmat carry no gradient."""
+    v, j, _, flat, ws, R, pose, theta = _HANDLES[handle].forward(
+        betas, rotmat, True, readout=_READOUTS[readout], defer_finish=defer,
+        glue={"gram_schmidt": orthonormalize, "cam": cam})
+    return v, j, flat, ws, R, pose, theta
+
+
+@smpl_regressor.register_fake
+def _(handle, readout, betas, rotmat, cam, orthonormalize, defer):
+    h, ro = _HANDLES[handle], _READOUTS[readout]
+    B = betas.shape[0]
+    return (betas.new_empty(B, h.V, 3), betas.new_empty(B, h.J, 3), betas.new_empty(B * ro.R * 3),
+            betas.new_empty(0, dtype=torch.uint8), betas.new_empty(B, h.J, 3, 3), betas.new_empty(B, h.J * 3),
+            betas.new_empty(B, 3 + h.NB + h.J * 3))
+
+
+def _smpl_reg_setup(ctx, inputs, output):
+    handle, readout, betas, rotmat, cam, orthonormalize, defer = inputs
+    ctx.save_for_backward(betas, rotmat)
+    ctx.handle, ctx.readout, ctx.orth = handle, readout, orthonormalize
+
+
+def _smpl_reg_bwd(ctx, g_v, g_j, g_flat, g_ws, g_R, g_pose, g_theta):
+    if ctx.orth:
+        raise NotImplementedError("whmr::smpl_regressor: no backward through unbiased_gram_schmidt (the reference applies it "
+                                  "in eval mode only, models/whmr.py:129-130)")
+    betas, pose = ctx.saved_tensors
+    h, ro = _HANDLES[ctx.handle], _READOUTS[ctx.readout]
+    B = betas.shape[0]
+    if g_flat is not None:
+        g_v = g_v.contiguous().clone() if g_v is not None else torch.zeros(B, h.V, 3, dtype=torch.float32, device=betas.device)
+        g_j = g_j.contiguous().clone() if g_j is not None else torch.zeros(B, h.J, 3, dtype=torch.float32, device=betas.device)
+        ro.backward(g_flat.contiguous(), g_v, g_j)
+    g_betas, g_pose_in = h.backward(betas, pose, g_v, g_j)
+    return None, None, g_betas, g_pose_in.view_as(pose), None, None, None
+
+
+smpl_regressor.register_autograd(_smpl_reg_bwd, setup_context=_smpl_reg_setup)
+
+
 @torch.library.custom_op("whmr::readout_finish", mutates_args=("flat",), device_types="cuda")
 def readout_finish(readout: int, joints: torch.Tensor, flat: torch.Tensor, scratch: torch.Tensor) -> None:
     ro = _READOUTS[readout]
@@ -788,3 +860,74 @@ def _pwf_bwd(ctx, g_kp, g_kpw, g_focal, g_cam_t):
 
 
 project_weak_full_op.register_autograd(_pwf_bwd, setup_context=_pwf_setup)
+
+
+# ----------------------------------------------------------------------------------------------
+# utils/geometry.py:310-341 perspective_projection as a differentiable op (the drop-in of whmr_b200.geometry): the
+# reference's training graph back-propagates through it into the joints (stage != 1), the translation (pred_cam_t -> Tz)
+# and the predicted focal length (-> Tz), models/whmr.py:147-173, core/trainer.py:518.
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op("whmr::perspective_projection", mutates_args=(), device_types="cuda")
+def perspective_projection_op(points: torch.Tensor, rotation: torch.Tensor, translation: torch.Tensor, focal: torch.Tensor,
+                              camera_center: torch.Tensor, retain_z: bool) -> torch.Tensor:
+    """rotation: [0] (none), [1,3,3] or [B,3,3]; translation: [0] (none) or [B,3]; focal: [1] or [B]."""
+    return perspective_projection(points, rotation if rotation.numel() else None,
+                                  translation if translation.numel() else None,
+                                  focal if focal.numel() > 1 else float(focal), camera_center, retain_z)
+
+
+@perspective_projection_op.register_fake
+def _(points, rotation, translation, focal, camera_center, retain_z):
+    return points.new_empty(points.shape[0], points.shape[1], 3 if retain_z else 2)
+
+
+@torch.library.custom_op("whmr::perspective_projection_backward", mutates_args=(), device_types="cuda")
+def perspective_projection_backward(points: torch.Tensor, rotation: torch.Tensor, translation: torch.Tensor,
+                                    focal: torch.Tensor, g_out: torch.Tensor, retain_z: bool) -> \
+        tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    points, g_out = _req(points, "points"), _req(g_out, "grad_out")
+    B, N = points.shape[0], points.shape[1]
+    dev = points.device
+    rot = _req(rotation, "rotation") if rotation.numel() else None
+    tr = _req(translation, "translation") if translation.numel() else None
+    f_dev = _req(focal.reshape(-1), "focal_length") if focal.numel() > 1 else None
+    g_points = torch.empty_like(points)
+    g_tr = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    g_f = torch.empty(B, dtype=torch.float32, device=dev)
+    g_c = torch.empty(B, 2, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().whmr_perspective_projection_backward(
+            _p(points), _p(rot), 0 if rot is None else (rot.shape[0] if rot.dim() == 3 else 1), _p(tr), _p(f_dev),
+            0.0 if f_dev is not None else float(focal), _p(g_out), B, N, int(bool(retain_z)), _p(g_points), _p(g_tr),
+            _p(g_f), _p(g_c), _stream()))
+    return g_points, g_tr, g_f, g_c
+
+
+@perspective_projection_backward.register_fake
+def _(points, rotation, translation, focal, g_out, retain_z):
+    B = points.shape[0]
+    return torch.empty_like(points), points.new_empty(B, 3), points.new_empty(B), points.new_empty(B, 2)
+
+
+def _pp_setup(ctx, inputs, output):
+    points, rotation, translation, focal, camera_center, retain_z = inputs
+    ctx.save_for_backward(points, rotation, translation, focal)
+    ctx.retain_z = retain_z
+    ctx.center_shape = tuple(camera_center.shape)
+
+
+def _pp_bwd(ctx, g):
+    points, rotation, translation, focal = ctx.saved_tensors
+    if rotation.numel() and ctx.needs_input_grad[1]:
+        raise NotImplementedError("whmr::perspective_projection: no gradient w.r.t. the rotation (the reference passes an "
+                                  "identity, models/whmr.py:157-163)")
+    g_points, g_tr, g_f, g_c = perspective_projection_backward(points, rotation, translation, focal, g.contiguous(),
+                                                               ctx.retain_z)
+    g_focal = None
+    if ctx.needs_input_grad[3]:
+        g_focal = g_f if focal.numel() > 1 else g_f.sum().reshape(focal.shape)
+    return (g_points, None, g_tr if translation.numel() else None, g_focal,
+            g_c.reshape(ctx.center_shape) if ctx.needs_input_grad[4] else None, None)
+
+
+perspective_projection_op.register_autograd(_pp_bwd, setup_context=_pp_setup)

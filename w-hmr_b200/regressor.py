@@ -2,10 +2,11 @@
 :225-269) -- everything between the regressor MLP's outputs (pred_rotmat, pred_shape, pred_cam) and
 the 17-key result dict -- as one module over the sm_100a kernels.
 
-Per call the reference issues: 1 SMPL forward (~100 launches), `projection`, the predicted-focal
-`perspective_projection`, the H36M matmul, two dense down-sampling matmuls (75 MFLOP/body), a
-marker gather, a dense vertices2joints and a VertexJointSelector.  Here that is 7 launches:
-chain, pose-blend, skin, read-out (short rows), read-out (long rows), weak projection, full projection.
+Per call the reference issues: unbiased_gram_schmidt (eval mode, ~25 launches), 1 SMPL forward (~100 launches),
+`projection`, the predicted-focal `perspective_projection`, rotation_matrix_to_angle_axis (~40 launches), the `theta`
+concatenation, the H36M matmul, two dense down-sampling matmuls (75 MFLOP/body), a marker gather, a dense
+vertices2joints and a VertexJointSelector.  Here that is 4 launches: chain (with the rotation glue folded in),
+fused pose-blend + skinning (+ read-out emits), read-out finishing pass, weak + full projection.
 """
 import numpy as np
 import torch
@@ -36,9 +37,11 @@ class BodyModelHead(nn.Module):
         self.side_stream = None
         # Gradient routing of the reference's training graph (models/whmr.py:142-165): cfg.TRAIN.STAGE == 1 -> `projection`
         # sees the joints, the predicted-focal block sees joints.detach(); any other stage the opposite; pred_cam is
-        # always detached inside the predicted-focal block (s and pred_cam_t).  None = no detach (forward-only use:
-        # one fused launch for both projections).
+        # always detached inside the predicted-focal block (s and pred_cam_t).  None = the reference's configured default
+        # (configs/pymaf_config.yaml:26, TRAIN.STAGE: 2) whenever a gradient is required; without autograd both
+        # projections run as one fused launch (no routing to do).
         self.train_stage = None
+        self.default_train_stage = 2
 
     def _mark(self, name):
         if self.probe is not None:
@@ -87,13 +90,15 @@ class BodyModelHead(nn.Module):
         return ro
 
     def _assemble(self, r, verts, rot, pred_rotmat, pred_shape, pred_cam, bbox_height, center, orig_shape, Tz, J_regressor,
-                  scale):
+                  scale, pose=None, theta=None):
         """projections of the 49 joints + the result dict of Regressor.forward / forward_init (models/whmr.py:142-208)"""
         B = rot.shape[0]
         pred_joints = r['joints']
-        if bbox_height is not None and self.train_stage is not None and torch.is_grad_enabled():
+        needs_grad = torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad
+                                                     for t in (pred_joints, pred_cam, Tz))
+        if bbox_height is not None and needs_grad:
             f, w, hgt = constants.FOCAL_LENGTH, float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT)
-            st1 = self.train_stage == 1
+            st1 = (self.default_train_stage if self.train_stage is None else self.train_stage) == 1
             kp_2d = ops.project_weak_op(pred_joints if st1 else pred_joints.detach(), pred_cam, f, w, hgt)
             _, kp_w, focal, cam_t = ops.project_weak_full_op(pred_joints.detach() if st1 else pred_joints, pred_cam.detach(),
                                                              bbox_height, center, orig_shape, Tz, f, w, hgt)
@@ -114,6 +119,8 @@ class BodyModelHead(nn.Module):
             'pred_pose': pred_rotmat.reshape(B, -1), 'pelvis': r['smpl_kp_3d'][:, :1, :], 'markers': r['markers'],
             'joints49': pred_joints,
         }
+        if pose is not None:      # models/whmr.py:174,190 (and :237,253 in forward_init)
+            out.update(pose=pose, theta=theta)
         if bbox_height is not None:
             out.update(kp_2d_w=kp_w, focal_length=focal, pred_cam_t=cam_t, scale=scale)
         return out
@@ -122,7 +129,9 @@ class BodyModelHead(nn.Module):
     #    only the markers / camera / shape / pose of a Regressor result; the regressor-row read-outs and the joint
     #    projections are read by the caller after the loop.  `begin` runs the SMPL kernels (vertices, one-hot read-outs
     #    such as the markers are complete on return), `complete_all` finishes every pending call in one launch.
-    def begin(self, pred_rotmat, pred_shape, J_regressor=None):
+    def begin(self, pred_rotmat, pred_shape, J_regressor=None, pred_cam=None, orthonormalize=False):
+        """orthonormalize: unbiased_gram_schmidt of the predicted rotations first (Regressor.forward in eval mode,
+        models/whmr.py:129-130); pred_cam: the head of `theta` (zeros if None)."""
         if torch.is_tensor(J_regressor):
             if self._h36m is None:
                 self.set_h36m_regressor(J_regressor)
@@ -132,10 +141,13 @@ class BodyModelHead(nn.Module):
         h, _ = self.smpl._state(dev)
         rot = pred_rotmat.reshape(B, -1, 3, 3)
         ro = self._readout(dev, bool(J_regressor))
-        verts, joints24, flat, scratch = ops.smpl_lbs_readout_deferred(h.id, ro.id, pred_shape, rot, True)
+        cam = pred_cam if pred_cam is not None else rot.new_zeros(B, 3)
+        verts, joints24, flat, scratch, rot_used, pose, theta = ops.smpl_regressor(h.id, ro.id, pred_shape, rot, cam,
+                                                                                   bool(orthonormalize), True)
         r = ro.split(flat, B)
-        return {'ro': ro, 'verts': verts, 'joints24': joints24, 'flat': flat, 'scratch': scratch, 'r': r, 'rot': rot,
-                'pred_rotmat': pred_rotmat, 'pred_shape': pred_shape, 'J': bool(J_regressor), 'markers': r['markers']}
+        return {'ro': ro, 'verts': verts, 'joints24': joints24, 'flat': flat, 'scratch': scratch, 'r': r, 'rot': rot_used,
+                'pred_rotmat': pred_rotmat, 'pred_shape': pred_shape, 'J': bool(J_regressor), 'markers': r['markers'],
+                'pose': pose, 'theta': theta}
 
     def complete_all(self, states, cams, bbox_height=None, center=None, orig_shape=None, Tz=None, full=None, scale=None):
         """states: list from `begin`; cams: pred_cam per state; full[i]: evaluate the predicted-focal block for state i
@@ -152,19 +164,23 @@ class BodyModelHead(nn.Module):
         outs = []
         for i, s in enumerate(states):
             if cams[i] is None:
-                outs.append({'verts': s['verts'], 'r': s['r']})
+                outs.append({'verts': s['verts'], 'r': s['r'], 'pose': s['pose'], 'rotmat': s['rot']})
                 continue
             use_full = bool(full[i]) if full is not None else bbox_height is not None
             outs.append(self._assemble(s['r'], s['verts'], s['rot'], s['pred_rotmat'], s['pred_shape'], cams[i],
-                                       bbox_height if use_full else None, center, orig_shape, Tz, s['J'], scale))
+                                       bbox_height if use_full else None, center, orig_shape, Tz, s['J'], scale,
+                                       pose=s['pose'], theta=s['theta']))
         return outs
 
     def forward(self, pred_rotmat, pred_shape, pred_cam, bbox_height=None, center=None, orig_shape=None,
-                Tz=None, J_regressor=None, scale=None):
+                Tz=None, J_regressor=None, scale=None, is_train=False, orthonormalize=None):
         """pred_rotmat [B,24,3,3]; pred_shape [B,10]; pred_cam [B,3].  With bbox_height/center/
         orig_shape/Tz the predicted-focal block (:147-173) is evaluated too (Regressor.forward);
         without them only the weak projection (forward_init).  J_regressor: None, True (use the
-        stored H36M regressor) or a tensor [17,V] / [B,17,V]."""
+        stored H36M regressor) or a tensor [17,V] / [B,17,V].
+        is_train: Regressor.forward's flag -- in eval mode the predicted rotations go through
+        unbiased_gram_schmidt first (:129-130); forward_init never does.  `orthonormalize` overrides.
+        The dict carries every tensor of the reference's (incl. `pose`, `theta`; `rotmat` = the rotations used)."""
         if torch.is_tensor(J_regressor):
             if self._h36m is None:
                 self.set_h36m_regressor(J_regressor)
@@ -177,10 +193,11 @@ class BodyModelHead(nn.Module):
         ro = self._readout(dev, bool(J_regressor))
         side = self.side_stream
         main = torch.cuda.current_stream(dev)
-        if side is None:
-            verts, joints24, flat = ops.smpl_lbs_readout(h.id, ro.id, pred_shape, rot, True)
-        else:
-            verts, joints24, flat, scratch = ops.smpl_lbs_readout_deferred(h.id, ro.id, pred_shape, rot, True)
+        if orthonormalize is None:
+            orthonormalize = bbox_height is not None and not is_train
+        verts, joints24, flat, scratch, rot, pose, theta = ops.smpl_regressor(
+            h.id, ro.id, pred_shape, rot, pred_cam, bool(orthonormalize), side is not None)
+        if side is not None:
             side.wait_stream(main)
             torch.cuda.set_stream(side)     # finishing pass + projections below go to the side stream
             if scratch.numel():
@@ -191,8 +208,11 @@ class BodyModelHead(nn.Module):
         r = ro.split(flat, B)
         self._mark('skin_readout')
         out = self._assemble(r, verts, rot, pred_rotmat, pred_shape, pred_cam, bbox_height, center, orig_shape, Tz,
-                             J_regressor, scale)
+                             J_regressor, scale, pose=pose, theta=theta)
         if side is not None:
+            # tensors the side stream still reads: under stream capture record_stream() is unavailable, so their blocks must
+            # not return to the capture pool before the caller joins the side stream -- the result keeps them alive
+            out['_side_keep'] = (joints24, flat, scratch)
             if not torch.cuda.is_current_stream_capturing():
                 for t in out.values():
                     if torch.is_tensor(t) and t.is_cuda:
