@@ -352,6 +352,13 @@ def run_ours(args):
         del g_cl, outs_cl, feats_cl
         torch.cuda.empty_cache()
 
+    # ---- the step INCLUDING the extractors' reduce_dim MLP: sampling + projection + Conv1d MLP as ONE
+    #      launch per level (maf_fused_kernel, 3xTF32 on tcgen05) against the two-step path (sampling kernel, [B,256,N]
+    #      round trip through HBM, PyTorch Conv1d MLP) --------------------------------------------------------------------
+    rd = None
+    if not args.skip_reduce_dim:
+        rd = reduce_dim_leg(args, model, dev, feats, params, bbox, rank, world, min(K, 300), W, gemm_mode)
+
     # ---- end to end through host buffers ------------------------------------------------------------
     e2e = None
     e2e_resident = None
@@ -514,13 +521,82 @@ def run_ours(args):
                        "launch": "one CUDA graph replay per step; schedule: finishing passes of the 5 read-outs + the 4 joint projections after the loop (1 + 4 launches), per-kernel probes taken on the immediate 22-launch schedule",
                        "feature_layout": "channels_last (NHWC memory)" if args.channels_last else "NCHW contiguous (reference layout)",
                        "rotation_glue": "unbiased_gram_schmidt (eval mode) + rotation_matrix_to_angle_axis + theta inside the chain kernel, every SMPL call"},
-            "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident, "channels_last": cl, "other_configs": other,
+            "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident, "channels_last": cl, "with_reduce_dim": rd, "other_configs": other,
             "gpu_launches": int(launches_per_step) * K, "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "torch_gpu_eager": eager, "smpl_at_scale": scale, "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def reduce_dim_leg(args, model, dev, feats, params, bbox, rank, world, K, W, gemm_mode):
+    """The loop step with the three MAF_Extractor modules in it (random-init Conv1d MLPs 256->128->64->32 with skip concats,
+    models/maf_extractor.py:75-101): fused (one maf_fused_kernel launch per level, no [B,256,N] tensor) vs two-step
+    (sampling kernel -> HBM -> PyTorch MLP), NCHW and channels_last maps; parity of the 'ref_features' of 16 bodies
+    against the oracle (grid_sample + reduce_dim on the CPU, fp32) at <= 1e-4 relative."""
+    import torch
+    import torch.distributed as dist
+    from whmr_b200 import _lib
+    from whmr_b200.loop import RegressorLoop
+    from whmr_b200.maf_extractor import MAF_Extractor
+    torch.manual_seed(1234)
+    exts = [MAF_Extractor(mesh_downsampling=None) for _ in range(3)]
+    convs = [[(c.weight.detach().clone(), c.bias.detach().clone()) for c in e.filters] for e in exts]
+    loop = RegressorLoop(model, dev, backbone=args.backbone, gemm_mode=gemm_mode, extractors=exts)
+    for e in loop.extractors:
+        e.return_point_feat = False
+    B = feats[0].shape[0]
+    res = {"mlp": "Conv1d(k=1) 256->128, [128;256]->64, [64;256]->32, leaky_relu x2 + relu, random init",
+           "arithmetic_fused": "3xTF32 (tcgen05 kind::tf32, hi/lo split of both operands)", "unit": UNIT}
+    if rank == 0 and not args.skip_parity:
+        from oracle.loop_oracle import LoopOracle, to_cpu_inputs
+        n = 16
+        sub = ([f[:n].contiguous() for f in feats], [{k: v[:n].contiguous() for k, v in q.items()} for q in params],
+               {k: v[:n].contiguous() for k, v in bbox.items()})
+        got = loop.step(*sub)
+        torch.cuda.synchronize()
+        ref = LoopOracle(model, args.backbone, convs=convs).step(*to_cpu_inputs(*sub))
+        err = max(float((a.cpu() - b).abs().max() / b.abs().max()) for a, b in zip(got["ref_features"], ref["ref_features"]))
+        res["parity_ref_features_rel"] = err
+        if not err <= 1e-4:
+            raise SystemExit("bench.py: fused sampling + reduce_dim differs from the oracle: %.3e relative" % err)
+
+    def timed(fs, fused):
+        for e in loop.extractors:
+            e.fused = fused
+        n0 = _lib.launch_count()
+        loop.step(fs, params, bbox)
+        ours = _lib.launch_count() - n0
+        g, _ = loop.capture(fs, params, bbox)
+        for _ in range(W):
+            g.replay()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t) / K
+        del g
+        return {"ms_per_step": ms, "value": world * B / (ms * 1e-3), "our_launches_per_step": int(ours)}
+
+    feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    res["fused_nchw"] = timed(feats, True)
+    res["two_step_nchw"] = timed(feats, False)
+    res["fused_channels_last"] = timed(feats_cl, True)
+    res["two_step_channels_last"] = timed(feats_cl, False)
+    res["two_step_note"] = ("sampling kernel + the module's PyTorch reduce_dim (cuDNN/cuBLAS convs, cat, leaky_relu: ~10 "
+                            "library launches per level, not counted in our_launches_per_step)")
+    del feats_cl
+    torch.cuda.empty_cache()
+    return res
 
 
 def ncu_traffic(kernel, B):
@@ -755,6 +831,10 @@ def run_extra(args):
         B, N, C = 1024, 431, 256
         pts = torch.from_numpy(syn.make_sample_points(B, N, seed=2, rank=rank)).to(dev)
         rows = {}
+        from whmr_b200.maf_extractor import MAF_Extractor
+        torch.manual_seed(1234)
+        ext = MAF_Extractor(mesh_downsampling=None).to(dev).eval()
+        mlp_flops = 2.0 * (256 * 128 + 384 * 64 + 320 * 32) * B * N       # algorithmic (fp32) flops of reduce_dim per level
         for (H, W) in ((14, 14), (28, 28), (56, 56)):
             feat = torch.randn(B, C, H, W, device=dev)
             alg = B * (4 * C * (min(4 * N, H * W) + N) + 8 * N)
@@ -765,6 +845,17 @@ def run_extra(args):
                                       "channels_last_ms": ms2, "channels_last_GBs_algorithmic": alg / ms2 / 1e6,
                                       "channels_last_frac": alg / ms2 / 1e6 / peaks["hbm_gbs"],
                                       "bodies_per_s_nchw": world * B / (ms * 1e-3)}
+            # MAF_Extractor.sampling incl. the reduce_dim MLP: fused kernel vs sampling kernel + PyTorch MLP
+            with torch.no_grad():
+                row = rows["%dx%d" % (H, W)]
+                for tag, f_in in (("nchw", feat), ("channels_last", fl)):
+                    ext.fused, ext.return_point_feat = True, False
+                    t_f = timed(lambda: ext.sampling(pts, im_feat=f_in), 20)
+                    ext.fused, ext.return_point_feat = False, True
+                    t_u = timed(lambda: ext.sampling(pts, im_feat=f_in), 10)
+                    row["with_reduce_dim_%s" % tag] = {
+                        "fused_ms": t_f, "two_step_ms": t_u, "fused_hbm_frac_algorithmic": alg / t_f / 1e6 / peaks["hbm_gbs"],
+                        "fused_tensor_frac_3xtf32": mlp_flops / (t_f * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] / 2 / 3)}
             del feat, fl
         res.update(metric="maf_sampling_431pts", unit="ms per level (1024 bodies per GPU)", levels=rows)
     elif args.workload == "eval_pass":
@@ -851,6 +942,7 @@ def main():
     ap.add_argument("--skip-sweep", action="store_true")
     ap.add_argument("--skip-other", action="store_true", help="skip the configs[2] / configs[4] legs")
     ap.add_argument("--skip-channels-last", action="store_true")
+    ap.add_argument("--skip-reduce-dim", action="store_true", help="skip the leg with the extractors' MLP fused into sampling")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--workload", default="regressor_loop", choices=["regressor_loop", "smpl_sweep", "maf_sampling", "eval_pass"],

@@ -258,6 +258,28 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
                         const float* cam, int N, float focal, float img_w, float img_h,
                         float* points2d_out, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * MAF_Extractor.sampling / .forward INCLUDING the `reduce_dim` MLP (models/maf_extractor.py:75-101,
+ * 103-143) as one kernel: grid_sample -> Conv1d(k=1) C_in->C1 -> [y;x]->C2 -> [y;x]->C3 with
+ * leaky_relu / leaky_relu / relu, 3xTF32 on the tensor cores; the [B,C_in,N] point features are
+ * written only when point_feat_out != NULL.  Weights are the module's conv0..2 parameters (Conv1d
+ * layout [C_out, C_in_total, 1], DEVICE pointers); set_weights re-splits them (call again after an
+ * optimizer step).  mesh_align_out [B, C3*N] (= y.view(B,-1) of [B,C3,N]).
+ * Widths: C_in, C1, C2 multiples of 32, C3 a multiple of 16, C1+C2+C3 <= 256 (reference: 256,128,64,32).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct whmr_maf_mlp_s* whmr_maf_mlp_t;
+int whmr_maf_mlp_create(int c_in, int c1, int c2, int c3, whmr_maf_mlp_t* out);
+int whmr_maf_mlp_destroy(whmr_maf_mlp_t m);
+int whmr_maf_mlp_set_weights(whmr_maf_mlp_t m, const float* w0, const float* b0, const float* w1,
+                             const float* b1, const float* w2, const float* b2, void* stream);
+int whmr_sample_reduce(whmr_maf_mlp_t m, const float* feat, int layout, int B, int H, int W,
+                       const float* points, int points_shared, int N, float* mesh_align_out,
+                       float* point_feat_out /*or NULL*/, void* stream);
+int whmr_project_sample_reduce(whmr_maf_mlp_t m, const float* feat, int layout, int B, int H, int W,
+                               const float* p, const float* cam, int N, float focal, float img_w,
+                               float img_h, float* points2d_out /*or NULL*/, float* mesh_align_out,
+                               float* point_feat_out /*or NULL*/, void* stream);
+
 /* verts[:, idx] (models/whmr.py:184 markers) -- verts [B,V,3], idx [n_idx] int32 DEVICE -> out [B,n_idx,3] */
 int whmr_gather_vertices(const float* verts, const int32_t* idx, int B, int V, int n_idx, float* out,
                          void* stream);

@@ -14,7 +14,10 @@ from .smpl_oracle import SMPLOracle, regressor_readouts
 
 
 class LoopOracle:
-    def __init__(self, model, backbone='vitpose', with_h36m=True, device='cpu'):
+    def __init__(self, model, backbone='vitpose', with_h36m=True, device='cpu', convs=None):
+        """convs: optional 3 x [(weight, bias)] x 3 of the extractors' Conv1d MLPs; then `step` also returns
+        'ref_features' = reduce_dim(point_feats[i]) (models/maf_extractor.py:75-101)."""
+        self.convs = convs
         import importlib
         syn = importlib.import_module('whmr_b200.synthetic')
         self.model = model
@@ -58,6 +61,9 @@ class LoopOracle:
         # models/whmr.py:632-633: global_pose = cat(axis-angle of the re-estimated global rotation, pose[:, 3:])
         res['global_pose'] = G.rotation_matrix_to_angle_axis(params[4]['rotmat'].reshape(-1, 3, 3)).reshape(-1, 72)
         res['point_feats'] = point_feats
+        if self.convs is not None:
+            from .sampling_oracle import reduce_dim
+            res['ref_features'] = [reduce_dim(pf, cv) for pf, cv in zip(point_feats, self.convs)]
         res['global_verts'] = g['vertices']
         if self.with_h36m:
             res['global_kp_3d'] = regressor_readouts(self.model, g['vertices'])['kp_3d_h36m']

@@ -889,3 +889,111 @@ def test_regressor_loop_matches_oracle_and_graph_replay(dev, smpl_model):
     g2.replay()
     torch.cuda.synchronize()
     check(outs2)
+
+
+# ------------------------------------------------------------------ sampling + reduce_dim in one kernel
+def _golden_extractor(g, dev):
+    from whmr_b200.maf_extractor import MAF_Extractor
+    ext = MAF_Extractor(mesh_downsampling=None).to(dev).eval()
+    sd = {k: torch.from_numpy(g['maf_' + k.replace('.', '_')]) for k in
+          ('conv0.weight', 'conv0.bias', 'conv1.weight', 'conv1.bias', 'conv2.weight', 'conv2.bias')}
+    ext.load_state_dict(sd, strict=False)
+    return ext
+
+
+def _launches():
+    from whmr_b200 import _lib
+    return _lib.launch_count()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_fused_sampling_mlp_matches_reference_golden(dev, golden, tag):
+    """MAF_Extractor.sampling / .forward under no_grad = one maf_fused_kernel launch; mesh_align_feat against the output
+    of the reference's own module (tests/golden/make_golden.py: models/maf_extractor.py:75-143) at <= 1e-4 relative."""
+    g = golden
+    ext = _golden_extractor(g, dev)
+    feat = torch.from_numpy(g['samp_%s_feat' % tag]).to(dev)
+    pts = torch.from_numpy(g['samp_%s_points' % tag]).to(dev)
+    with torch.no_grad():
+        ext.sampling(pts, im_feat=feat)           # first call also splits the weights (one more launch)
+        n0 = _launches()
+        maf, pf = ext.sampling(pts, im_feat=feat)
+        assert _launches() - n0 == 1
+    ref_m, ref_p = g['samp_%s_mesh_align' % tag], g['samp_%s_point_feat' % tag]
+    assert maf.shape == ref_m.shape and pf.shape == ref_p.shape
+    assert _maxabs(pf, ref_p) <= FEAT_RTOL * np.abs(ref_p).max()
+    assert _maxabs(maf, ref_m) <= FEAT_RTOL * np.abs(ref_m).max()
+    # channels_last maps take the NHWC instantiation: same numbers
+    with torch.no_grad():
+        maf_cl, pf_cl = ext.sampling(pts, im_feat=feat.contiguous(memory_format=torch.channels_last))
+    assert _maxabs(maf_cl, ref_m) <= FEAT_RTOL * np.abs(ref_m).max()
+    assert torch.equal(pf_cl, pf)
+    # without the [B,256,N] output
+    ext.return_point_feat = False
+    with torch.no_grad():
+        maf2, none = ext.sampling(pts, im_feat=feat)
+    assert none is None and torch.equal(maf2, maf)
+    ext.return_point_feat = True
+    # state-driven forward (projection fused in), models/maf_extractor.py:126-143
+    ext.im_feat = torch.from_numpy(g['fwd_feat']).to(dev)
+    ext.cam = torch.from_numpy(g['fwd_cam']).to(dev)
+    with torch.no_grad():
+        n0 = _launches()
+        maf3, pf3 = ext(torch.from_numpy(g['fwd_p']).to(dev), None, None, None, None)
+        assert _launches() - n0 == 1
+    assert _maxabs(pf3, g['fwd_point_feat']) <= FEAT_RTOL * np.abs(g['fwd_point_feat']).max()
+    assert _maxabs(maf3, g['fwd_mesh_align']) <= FEAT_RTOL * np.abs(g['fwd_mesh_align']).max()
+    # a parameter update is picked up (version counter), and the autograd path still gives the PyTorch MLP
+    with torch.no_grad():
+        ext.conv2.bias.add_(0.25)
+        maf4, _ = ext.sampling(pts, im_feat=feat)
+    maf5, _ = ext.sampling(pts, im_feat=feat)      # grad enabled + parameters require grad -> unfused path
+    assert maf5.requires_grad
+    assert _maxabs(maf4, maf5.detach().cpu()) <= 2e-3 * float(maf5.detach().abs().max())   # cuDNN runs the convs in TF32
+    assert _maxabs(maf4, ref_m) > 0.1
+
+
+@pytest.mark.parametrize("layout", ["nchw", "channels_last"])
+@pytest.mark.parametrize("B,N,H,W,mode", [(5, 67, 64, 48, "points"), (3, 63, 32, 24, "grid"), (4, 67, 128, 96, "project"),
+                                           (96, 431, 14, 14, "points"), (2, 431, 56, 56, "project"), (1, 1, 7, 5, "points")])
+def test_fused_sampling_mlp_vs_oracle(dev, layout, B, N, H, W, mode):
+    """maf_fused_kernel against grid_sample + the fp64 reduce_dim oracle: tile tails (B*N not a multiple of 128), tiles
+    spanning bodies, more tiles than CTAs (96 x 431 points = 324 tiles on 296 CTAs), the shared iteration-0 grid, the
+    projection-fused form, points outside the map, both memory layouts."""
+    from oracle import geometry_oracle as G
+    from oracle.sampling_oracle import grid_sample_points, reduce_dim
+    from whmr_b200 import constants
+    from whmr_b200.maf_extractor import MAF_Extractor
+    import whmr_b200.synthetic as syn
+    gen = torch.Generator().manual_seed(B * 1000 + N + H)
+    ext = MAF_Extractor(mesh_downsampling=None)
+    with torch.no_grad():
+        for p in ext.parameters():
+            p.copy_(torch.randn(p.shape, generator=gen) * (0.5 if p.dim() == 1 else 2.0 / np.sqrt(p.shape[1])))
+    convs = [(c.weight.detach().double(), c.bias.detach().double()) for c in ext.filters]
+    ext = ext.to(dev).eval()
+    feat = torch.randn(B, 256, H, W, generator=gen)
+    f_in = feat.to(dev)
+    if layout == "channels_last":
+        f_in = f_in.contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        if mode == "project":
+            b = syn.make_bodies(B, seed=7)
+            cam = torch.from_numpy(b['cam'])
+            p3 = torch.randn(B, N, 3, generator=gen) * torch.tensor([0.45, 0.45, 0.2])
+            pts = G.projection(p3, cam)
+            ext.im_feat, ext.cam = f_in, cam.to(dev)
+            maf, pf = ext(p3.to(dev), None, None, None, None)
+        elif mode == "grid":
+            pts1 = torch.from_numpy(syn.grid_points('vitpose'))[:N]
+            pts = pts1[None].expand(B, -1, -1)
+            maf, pf = ext.sampling(pts1.to(dev), im_feat=f_in)
+        else:
+            pts = torch.from_numpy(syn.make_sample_points(B, N, seed=H))
+            maf, pf = ext.sampling(pts.to(dev), im_feat=f_in)
+    ref_p = grid_sample_points(feat.double(), pts.double())
+    ref_m = reduce_dim(ref_p, convs)
+    assert pf.shape == (B, 256, N) and maf.shape == (B, 32 * N)
+    assert _maxabs(pf, ref_p) <= FEAT_RTOL * float(ref_p.abs().max())
+    assert _maxabs(maf, ref_m) <= FEAT_RTOL * float(ref_m.abs().max())
+    assert float(ref_m.abs().max()) > 0.5 and float((ref_m > 0).double().mean()) > 0.1     # the check is not vacuous

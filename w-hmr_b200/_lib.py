@@ -100,6 +100,11 @@ SIGNATURES = {
     "whmr_project_crop": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
     "whmr_sample_bilinear": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "whmr_project_sample": (C.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _f, _vp, _vp, _vp]),
+    "whmr_maf_mlp_create": (C.c_int, [_i, _i, _i, _i, C.POINTER(_vp)]),
+    "whmr_maf_mlp_destroy": (C.c_int, [_vp]),
+    "whmr_maf_mlp_set_weights": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "whmr_sample_reduce": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "whmr_project_sample_reduce": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "whmr_estimate_translation": (C.c_int, [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _vp]),
     "whmr_gather_vertices": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "whmr_smpl_backward_workspace_bytes": (C.c_size_t, [_vp, _i]),

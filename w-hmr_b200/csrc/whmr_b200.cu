@@ -18,6 +18,7 @@
 #include "readout.cuh"
 #include "rotations.cuh"
 #include "sampling.cuh"
+#include "maf_fused_tc.cuh"
 #include "skin_tc.cuh"
 #include "skinning.cuh"
 #include "smpl_fused_tc.cuh"
@@ -1171,6 +1172,109 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
              N, pj);
   WHMR_LAUNCHED("sample_bilinear_nhwc_kernel<project>");
   return WHMR_OK;
+}
+
+// =============================================================================================
+// sampling + reduce_dim MLP in one kernel (maf_fused_tc.cuh)
+// =============================================================================================
+struct whmr_maf_mlp_s {
+  MafDims d{};
+  int nx = 0, dev = 0, num_sms = 148;
+  float *wx = nullptr, *w1y = nullptr, *w2y = nullptr, *bias = nullptr;
+  CUtensorMap map_x, map_1, map_2;
+  bool weights_set = false;
+  DeviceArena arena;
+};
+
+int whmr_maf_mlp_create(int c_in, int c1, int c2, int c3, whmr_maf_mlp_t* out) {
+  WHMR_CHECK_ARG(out, "whmr_maf_mlp_create: null output");
+  WHMR_CHECK_ARG(c_in >= 32 && c_in % 32 == 0 && c1 >= 32 && c1 % 32 == 0 && c2 >= 32 && c2 % 32 == 0 && c3 >= 16 &&
+                     c3 % 16 == 0 && c1 + c2 + c3 <= kMafMaxOut,
+                 "whmr_maf_mlp_create: unsupported widths %d -> %d -> %d -> %d (need C_in, C1, C2 multiples of 32, C3 a "
+                 "multiple of 16, C1+C2+C3 <= %d)", c_in, c1, c2, c3, kMafMaxOut);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return set_error(WHMR_E_CUDA, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+  whmr_maf_mlp_s* m = new whmr_maf_mlp_s();
+  m->d = MafDims{c_in, c1, c2, c3};
+  m->nx = c1 + c2 + c3;
+  cudaGetDevice(&m->dev);
+  cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->dev);
+  void *a = nullptr, *b = nullptr, *c = nullptr, *bi = nullptr;
+  e = m->arena.alloc((size_t)2 * m->nx * c_in * 4, &a);
+  if (e == cudaSuccess) e = m->arena.alloc((size_t)2 * c2 * c1 * 4, &b);
+  if (e == cudaSuccess) e = m->arena.alloc((size_t)2 * c3 * c2 * 4, &c);
+  if (e == cudaSuccess) e = m->arena.alloc((size_t)kMafMaxOut * 4, &bi);
+  if (e != cudaSuccess) { delete m; return set_error(WHMR_E_CUDA, "whmr_maf_mlp_create: cudaMalloc failed: %s", cudaGetErrorString(e)); }
+  m->wx = (float*)a; m->w1y = (float*)b; m->w2y = (float*)c; m->bias = (float*)bi;
+  int rc = maf_encode_weights(fn, &m->map_x, m->wx, c_in, m->nx);
+  if (!rc) rc = maf_encode_weights(fn, &m->map_1, m->w1y, c1, c2);
+  if (!rc) rc = maf_encode_weights(fn, &m->map_2, m->w2y, c2, c3);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return WHMR_OK;
+}
+
+int whmr_maf_mlp_destroy(whmr_maf_mlp_t m) { delete m; return WHMR_OK; }
+
+int whmr_maf_mlp_set_weights(whmr_maf_mlp_t m, const float* w0, const float* b0, const float* w1, const float* b1,
+                             const float* w2, const float* b2, void* stream) {
+  WHMR_CHECK_ARG(m && w0 && w1 && w2, "whmr_maf_mlp_set_weights: null handle or weight pointer");
+  const int n = m->nx * m->d.c0 + m->d.c2 * m->d.c1 + m->d.c3 * m->d.c2 + m->nx;
+  maf_split_weights_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w0, b0, w1, b1, w2, b2, m->d, m->wx, m->w1y,
+                                                                                m->w2y, m->bias);
+  WHMR_LAUNCHED("maf_split_weights_kernel");
+  m->weights_set = true;
+  return WHMR_OK;
+}
+
+extern "C++" {
+template <bool kProject>
+static int maf_launch(whmr_maf_mlp_t m, const float* feat, int layout, int B, int H, int W, const float* points,
+                      int pts_bstride, int N, float* out, float* pf_out, SampleProj pj, cudaStream_t st, const char* who) {
+  WHMR_CHECK_ARG(m, "%s: null handle", who);
+  WHMR_CHECK_ARG(m->weights_set, "%s: whmr_maf_mlp_set_weights has not been called", who);
+  WHMR_CHECK_ARG(B >= 0 && N >= 0 && H > 0 && W > 0, "%s: bad sizes", who);
+  WHMR_CHECK_ARG(layout == WHMR_LAYOUT_NCHW || layout == WHMR_LAYOUT_NHWC, "%s: bad layout %d", who, layout);
+  if (B == 0 || N == 0) return WHMR_OK;
+  WHMR_CHECK_ARG(feat && points && out, "%s: null pointer", who);
+  WHMR_CHECK_ARG((long long)B * N < (1ll << 31) - kMafRows, "%s: B*N too large", who);
+  WHMR_CHECK_ARG(layout == WHMR_LAYOUT_NCHW || (reinterpret_cast<size_t>(feat) & 15) == 0, "%s: NHWC maps must be 16-byte aligned", who);
+  WHMR_CHECK_ARG(kProject || (reinterpret_cast<size_t>(points) & 7) == 0, "%s: points must be 8-byte aligned", who);
+  const int n_tiles = (int)(((long long)B * N + kMafRows - 1) / kMafRows);
+  const int grid = std::min(n_tiles, 2 * m->num_sms);
+  const size_t smem = maf_smem_bytes(m->d);
+#define WHMR_MAF_LAUNCH(L)                                                                                         \
+  do {                                                                                                             \
+    cudaError_t e_ = ensure_dyn_smem(maf_fused_kernel<L, kProject>, (int)smem);                                    \
+    if (e_ != cudaSuccess) return set_error(WHMR_E_CUDA, "%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(e_)); \
+    launch_pdl(kPdlSample, maf_fused_kernel<L, kProject>, dim3(grid), dim3(kMafThreads), smem, st, m->map_x, m->map_1, \
+               m->map_2, feat, points, pts_bstride, (const float*)m->bias, out, pf_out, B, N, H, W, m->d, n_tiles, pj); \
+  } while (0)
+  if (layout == WHMR_LAYOUT_NCHW) WHMR_MAF_LAUNCH(0); else WHMR_MAF_LAUNCH(1);
+#undef WHMR_MAF_LAUNCH
+  WHMR_LAUNCHED("maf_fused_kernel");
+  return WHMR_OK;
+}
+}  // extern "C++"
+
+int whmr_sample_reduce(whmr_maf_mlp_t m, const float* feat, int layout, int B, int H, int W, const float* points,
+                       int points_shared, int N, float* mesh_align_out, float* point_feat_out, void* stream) {
+  return maf_launch<false>(m, feat, layout, B, H, W, points, points_shared ? 0 : N * 2, N, mesh_align_out, point_feat_out,
+                           SampleProj{}, (cudaStream_t)stream, "whmr_sample_reduce");
+}
+
+int whmr_project_sample_reduce(whmr_maf_mlp_t m, const float* feat, int layout, int B, int H, int W, const float* p,
+                               const float* cam, int N, float focal, float img_w, float img_h, float* points2d_out,
+                               float* mesh_align_out, float* point_feat_out, void* stream) {
+  WHMR_CHECK_ARG(B == 0 || N == 0 || cam, "whmr_project_sample_reduce: null camera");
+  WHMR_CHECK_ARG(!points2d_out || (reinterpret_cast<size_t>(points2d_out) & 7) == 0,
+                 "whmr_project_sample_reduce: points2d_out must be 8-byte aligned");
+  return maf_launch<true>(m, feat, layout, B, H, W, p, N * 3, N, mesh_align_out, point_feat_out,
+                          SampleProj{cam, focal, img_w, img_h, points2d_out}, (cudaStream_t)stream,
+                          "whmr_project_sample_reduce");
 }
 
 // =============================================================================================

@@ -28,8 +28,12 @@ RES50_LEVELS = ((14, 14), (28, 28), (56, 56))
 
 
 class RegressorLoop:
-    def __init__(self, model, device, backbone='vitpose', gemm_mode=None, with_h36m=True):
+    def __init__(self, model, device, backbone='vitpose', gemm_mode=None, with_h36m=True, extractors=None):
+        """extractors: optional list of three `MAF_Extractor` modules (models/whmr.py:333-335).  With them the loop also runs
+        their `reduce_dim` MLP -- fused into the sampling launch (maf_fused_tc.cuh) -- and returns 'ref_features'
+        (3 x [B, 32*N], what `Regressor.forward` consumes, models/whmr.py:597-612) instead of the raw 'point_feats'."""
         self.device = torch.device(device)
+        self.extractors = None if extractors is None else [e.to(self.device).eval() for e in extractors]
         self.smpl = SMPL(model=model, gemm_mode=gemm_mode).to(self.device)
         self.head = BodyModelHead(self.smpl, model['Dmap0'], model['Dmap1'], model['ssm'],
                                   model.get('J_regressor_h36m'))
@@ -48,6 +52,7 @@ class RegressorLoop:
         # finishing passes of the five read-outs + the joint projections after the loop, in one + four launches
         # (inference only: under autograd the immediate schedule is used); 0.389 -> see profiles/r01_notes.md
         self.defer = True
+        self._needs_grad = False
         self.is_train = False   # eval mode: Regressor.forward orthonormalises the predicted rotations (models/whmr.py:129-130)
 
     def step(self, feats, params, bbox):
@@ -57,7 +62,9 @@ class RegressorLoop:
         J = True if self.with_h36m else None
         p = params
         main = torch.cuda.current_stream(self.device)
-        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for q in p for t in q.values())
+        needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for q in p for t in q.values()) or
+                                                  any(f.requires_grad for f in feats))
+        self._needs_grad = needs_grad
         if self.defer and self.head.probe is None and not self.overlap and not needs_grad:
             return self._step_deferred(feats, params, bbox, J)
         self.head.side_stream = self._side if (self.overlap and self.head.probe is None) else None
@@ -84,13 +91,23 @@ class RegressorLoop:
             main.wait_stream(self._side)     # join: everything in the result dict is complete on the main stream
         res = dict(out)
         res['_keep'] = keep
-        res['point_feats'] = point_feats
+        res['point_feats' if self.extractors is None else 'ref_features'] = point_feats
         res['global_verts'] = gverts
         res['global_kp_3d'] = r['kp_3d_h36m'] if self.with_h36m else r['joints']            # :646-651
         res['global_pose'] = gpose                                                          # :632-633
         return res
 
     def _sample(self, it, feats, markers, cam):
+        if self.extractors is not None:          # one launch: sampling (+ projection) + reduce_dim MLP
+            ext = self.extractors[it]
+            ext.layout = self.layout
+            # inference: no grad_fn is needed, so the extractor takes its fused kernel; a training step (parameters or
+            # inputs of the loop require a gradient) keeps autograd on and gets the sampling op + PyTorch MLP
+            with torch.set_grad_enabled(self._needs_grad):
+                if it == 0:
+                    return ext.sampling(self.grid, im_feat=feats[0])[0]                      # :596-597
+                ext.im_feat, ext.cam = feats[it], cam                                        # :564,593
+                return ext(markers, None, None, None, None)[0]                               # :606
         if it == 0:
             return ops.sample_bilinear_op(feats[0], self.grid, self.layout)                  # :596-597
         pf, _ = ops.project_sample_op(feats[it], markers, cam, constants.FOCAL_LENGTH,       # :606
@@ -115,7 +132,7 @@ class RegressorLoop:
                                       bbox['bbox_height'], bbox['center'], bbox['orig_shape'], bbox['Tz'],
                                       full=[False, True, True, True, False])
         res = dict(outs[3])
-        res['point_feats'] = point_feats
+        res['point_feats' if self.extractors is None else 'ref_features'] = point_feats
         res['global_verts'] = outs[4]['verts']
         res['global_kp_3d'] = outs[4]['r']['kp_3d_h36m'] if self.with_h36m else outs[4]['r']['joints']
         res['global_pose'] = outs[4]['pose']

@@ -4,8 +4,13 @@
 Kept: constructor spelling, mutable `im_feat` / `cam` attributes, parameter names `conv0..2`, the
 `Dmap` buffer, `sampling(points, im_feat=None, z_feat=None)`, `forward(p, center, scale, img_focal,
 img_center, s_feat=None, cam=None)`, `project`, `get_trans`, `perspective_projection`, `reduce_dim`.
-The grid_sample and the projections run in the sm_100a kernels; the Conv1d MLP (`reduce_dim`) stays
-PyTorch, as BASELINE.json's north star prescribes (regressor MLPs unchanged).
+
+Inference (under `torch.no_grad()`, or when neither the parameters nor the inputs require a gradient): `sampling` / `forward` are ONE launch -- grid_sample, the weak
+projection and the whole `reduce_dim` MLP run in `maf_fused_kernel` (3xTF32 on tcgen05; weights are
+this module's `conv0..2` parameters, so checkpoints load unchanged), and with `return_point_feat =
+False` the [B,256,N] point features the reference returns but never reads (models/whmr.py:597,606)
+are not written at all.  Under autograd (training) the sampling custom op (which has a backward) and
+the PyTorch `reduce_dim` below are used, as in the reference.  `fused = False` forces that path.
 """
 import os
 
@@ -43,9 +48,27 @@ class MAF_Extractor(nn.Module):
         self.register_buffer('Dmap', torch.as_tensor(np.asarray(Dmap), dtype=torch.float32))
         self.crop_size = constants.IMG_RES_WIDTH
         self.layout = ops.LAYOUT_NCHW
+        self.filter_channels = tuple(int(c) for c in filter_channels)
+        self.fused = True                # one-launch sampling + reduce_dim when no gradient is needed
+        self.return_point_feat = True    # False: the fused path skips the [B,C_s,N] output and returns None for it
+        self._mlp = None                 # ops.MafMlp, built lazily on the module's device
+
+    def _fused_mlp(self, im_feat, *others):
+        """The fused-kernel state, or None when this call must take the sampling op + PyTorch MLP path."""
+        if not self.fused or self.num_views != 1 or not ops.MafMlp.supported(self.filter_channels):
+            return None
+        if not (torch.is_tensor(im_feat) and im_feat.is_cuda and im_feat.dtype == torch.float32):
+            return None
+        if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad
+                                           for t in tuple(self.parameters()) + (im_feat,) + others):
+            return None      # the result must carry a grad_fn: sampling op with backward + PyTorch MLP
+        if self._mlp is None or self._mlp.device != im_feat.device:
+            self._mlp = ops.MafMlp(self.filter_channels, im_feat.device)
+        self._mlp.set_weights(self.filters)
+        return self._mlp
 
     def reduce_dim(self, feature):
-        """models/maf_extractor.py:75-101 (unchanged PyTorch MLP)."""
+        """models/maf_extractor.py:75-101 (the PyTorch MLP: training / autograd path and unsupported widths)."""
         y = feature
         tmpy = feature
         for i, f in enumerate(self.filters):
@@ -62,6 +85,9 @@ class MAF_Extractor(nn.Module):
         """models/maf_extractor.py:103-124.  points [B,N,2]; -> (mesh_align_feat [B,C_p*N], point_feat [B,C_s,N])"""
         if im_feat is None:
             im_feat = self.im_feat
+        mlp = self._fused_mlp(im_feat, points)
+        if mlp is not None:
+            return mlp.sample(im_feat, points, self.layout, self.return_point_feat)
         point_feat = ops.sample_bilinear_op(im_feat, points, self.layout)
         return self.reduce_dim(point_feat), point_feat
 
@@ -70,6 +96,10 @@ class MAF_Extractor(nn.Module):
         if cam is None:
             cam = self.cam
         im_feat = self.im_feat if s_feat is None else s_feat
+        mlp = self._fused_mlp(im_feat, p, cam)
+        if mlp is not None:
+            return mlp.project_sample(im_feat, p, cam, constants.FOCAL_LENGTH, float(constants.IMG_RES_WIDTH),
+                                      float(constants.IMG_RES_HEIGHT), self.layout, self.return_point_feat)[:2]
         point_feat, _ = ops.project_sample_op(im_feat, p, cam, constants.FOCAL_LENGTH,
                                            float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT),
                                            self.layout)

@@ -501,6 +501,91 @@ def project_sample(feat, p, cam, focal, img_w, img_h, layout=LAYOUT_NCHW):
     return out, pts2d
 
 
+class MafMlp:
+    """Device-side state of the fused sampling + `reduce_dim` kernel (whmr_maf_mlp_create): the tf32 hi|lo split of the
+    module's conv0..2 weights, re-split whenever a parameter's storage or version counter changes (optimizer step,
+    load_state_dict, .to())."""
+
+    def __init__(self, dims, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.WhmrError("MafMlp needs a CUDA device, got %s (no CPU fallback)" % (self.device,))
+        self.dims = tuple(int(d) for d in dims)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_lib.lib().whmr_maf_mlp_create(*self.dims, C.byref(self._h)))
+        self._key = None
+
+    @staticmethod
+    def supported(dims):
+        return len(dims) == 4 and dims[0] % 32 == 0 and dims[1] % 32 == 0 and dims[2] % 32 == 0 and dims[3] % 16 == 0 \
+            and min(dims) >= 16 and dims[1] + dims[2] + dims[3] <= 256
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().whmr_maf_mlp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, convs):
+        """convs: the three Conv1d modules (weight [C_out, C_in_total, 1], bias [C_out] or None)."""
+        ts = []
+        for c in convs:
+            ts += [c.weight, c.bias]
+        key = tuple((None if t is None else (t.data_ptr(), t._version, tuple(t.shape))) for t in ts)
+        if key == self._key:
+            return
+        c0, c1, c2, c3 = self.dims
+        want = [(c1, c0, 1), (c2, c1 + c0, 1), (c3, c2 + c0, 1)]
+        for c, w in zip(convs, want):
+            if tuple(c.weight.shape) != w:
+                raise ValueError("conv weight %s does not match the MLP widths %s" % (tuple(c.weight.shape), self.dims))
+        ts = [None if t is None else _req(t.detach(), "conv parameter") for t in ts]
+        with torch.cuda.device(self.device):
+            check(_lib.lib().whmr_maf_mlp_set_weights(self._h, *[_p(t) for t in ts], _stream()))
+        self._key = key
+
+    def sample(self, feat, points, layout=LAYOUT_NCHW, want_point_feat=True):
+        """MAF_Extractor.sampling in one launch -> (mesh_align_feat [B, C3*N], point_feat [B,C0,N] or None)"""
+        feat, layout, B, Cc, H, W = _feat_layout(feat, layout)
+        if Cc != self.dims[0]:
+            raise ValueError("feature maps have %d channels, the MLP expects %d" % (Cc, self.dims[0]))
+        points = _req(points, "points", align=8)
+        shared = points.dim() == 2 or (points.shape[0] == 1 and B != 1)
+        N = points.shape[-2]
+        if (not shared and points.shape[0] != B) or points.shape[-1] != 2:
+            raise ValueError("points %s do not match feature batch %d" % (tuple(points.shape), B))
+        out = torch.empty(B, self.dims[3] * N, dtype=torch.float32, device=feat.device)
+        pf = torch.empty(B, Cc, N, dtype=torch.float32, device=feat.device) if want_point_feat else None
+        with torch.cuda.device(feat.device):
+            check(_lib.lib().whmr_sample_reduce(self._h, _p(feat), int(layout), B, H, W, _p(points), int(shared), N,
+                                                _p(out), _p(pf), _stream()))
+        return out, pf
+
+    def project_sample(self, feat, p, cam, focal, img_w, img_h, layout=LAYOUT_NCHW, want_point_feat=True,
+                       want_points2d=False):
+        """MAF_Extractor.forward in one launch (weak projection + sampling + MLP)"""
+        feat, layout, B, Cc, H, W = _feat_layout(feat, layout)
+        if Cc != self.dims[0]:
+            raise ValueError("feature maps have %d channels, the MLP expects %d" % (Cc, self.dims[0]))
+        p = _req(p, "p")
+        cam = _req(cam, "cam")
+        N = p.shape[1]
+        out = torch.empty(B, self.dims[3] * N, dtype=torch.float32, device=feat.device)
+        pf = torch.empty(B, Cc, N, dtype=torch.float32, device=feat.device) if want_point_feat else None
+        pts2d = torch.empty(B, N, 2, dtype=torch.float32, device=feat.device) if want_points2d else None
+        with torch.cuda.device(feat.device):
+            check(_lib.lib().whmr_project_sample_reduce(self._h, _p(feat), int(layout), B, H, W, _p(p), _p(cam), N,
+                                                        float(focal), float(img_w), float(img_h), _p(pts2d), _p(out),
+                                                        _p(pf), _stream()))
+        return out, pf, pts2d
+
+
 # ----------------------------------------------------------------------------------------------
 # metrics
 # ----------------------------------------------------------------------------------------------
