@@ -232,7 +232,163 @@ sample_bilinear_nhwc_kernel(const float* __restrict__ feat, const float* __restr
   }
 }
 
+// Dense regime, both layouts (the default for NHWC maps; see dense_channels for the measured choice): a CTA stages the
+// WHOLE map of one body for CG channels in shared memory as tile[pixel][channel] -- NHWC input: a straight 16-byte-vector
+// copy; NCHW input: coalesced plane reads, transposed on the way in (row pitch CG+1, so both the staging stores and the
+// gather reads are bank-conflict free) -- and every byte of the map is read from HBM exactly once.  The gather then runs
+// with LANES = CHANNELS: the four taps of a point are four conflict-free shared-memory reads of CB = min(CG,32)
+// consecutive words (the plane-staged kernel has lanes = points, i.e. 32 random addresses per read: ~3.5 wavefronts
+// each, which is what bounds it), and the [32 points x CB channels] block is transposed through a per-warp tile so that
+// the [B,C,N] stores are 128 contiguous bytes per (channel, 32 points).  Same tap arithmetic and order as the other
+// kernels: bit-identical results.
+// grid = (ceil(C/CG), B), block 256; dynamic smem = H*W*pitch*4 + 8 warps x (32 points x 8 tap words + CB x 33 floats).
+template <int CG, bool kNchwIn, bool kProject>
+__global__ void __launch_bounds__(256)
+sample_bilinear_dense_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
+                             float* __restrict__ out, int C, int H, int W, int N, SampleProj pj) {
+  constexpr int CB = CG < 32 ? CG : 32;          // channels per warp block == lanes per point
+  constexpr int PPL = 32 / CB;                   // points handled per warp step
+  constexpr int kPitch = kNchwIn ? CG + 1 : CG;
+  extern __shared__ __align__(16) float dense_smem[];
+  const int HW = H * W;
+  float* tile = dense_smem;                                        // [HW][kPitch]
+  float* wtaps = dense_smem + (((size_t)HW * kPitch + 3) & ~(size_t)3);   // [8 warps][32 points][8]
+  float* wout = wtaps + 8 * 32 * 8;                                // [8 warps][CB][33]
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y, c0 = blockIdx.x * CG;
+  const int cg = min(CG, C - c0);
+  // staging with cp.async: every copy of a thread is in flight at once (a load->store loop keeps only a few KB per SM
+  // in flight and runs at a quarter of the HBM rate), no registers, and the 4-byte form does the NCHW transposition.
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  if (kNchwIn) {
+    const float* src = feat + ((size_t)b * C + c0) * HW;
+    const int total = cg * HW;
+    int c = threadIdx.x / HW, p = threadIdx.x - c * HW;
+    for (int i = threadIdx.x; i < total; i += 256) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_s + (uint32_t)(p * kPitch + c) * 4u), "l"(src + i) : "memory");
+      p += 256;
+      while (p >= HW) { p -= HW; ++c; }
+    }
+  } else {
+    const float* src = feat + (size_t)b * HW * C + c0;
+    if (cg == CG && (C & 3) == 0 && (reinterpret_cast<size_t>(feat) & 15) == 0) {
+      constexpr int V4 = CG / 4;
+      for (int i = threadIdx.x; i < HW * V4; i += 256) {
+        const int p = i / V4, j = i - p * V4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tile_s + (uint32_t)(p * kPitch + 4 * j) * 4u),
+                     "l"(src + (size_t)p * C + 4 * j) : "memory");
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW * cg; i += 256) {
+        const int p = i / cg, c = i - p * cg;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tile_s + (uint32_t)(p * kPitch + c) * 4u),
+                     "l"(src + (size_t)p * C + c) : "memory");
+      }
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  float ctx = 0.f, cty = 0.f, ctz = 0.f;
+  if (kProject) {   // utils/geometry.py:289-307
+    const float cs = pj.cam[b * 3 + 0];
+    ctx = pj.cam[b * 3 + 1]; cty = pj.cam[b * 3 + 2];
+    ctz = 2.0f * pj.focal / (pj.img_h * cs + 1e-9f);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / CB, cl = lane - sub * CB;      // point within the step, channel within the block
+  float* my_taps = wtaps + warp * (32 * 8);
+  float* my_out = wout + warp * (CB * 33);
+  const float* pb = points + (size_t)b * pts_bstride;
+  const int n_pblocks = (N + 31) >> 5;
+  constexpr int n_cblocks = CG / CB;
+  for (int blk = warp; blk < n_pblocks * n_cblocks; blk += 8) {
+    const int pblk = blk / n_cblocks, cblk = blk - pblk * n_cblocks;
+    const int n0 = pblk * 32, cb0 = cblk * CB;
+    {   // lane l: taps of point n0 + l -> the warp's tap table
+      const int n = min(n0 + lane, N - 1);
+      float2 g;
+      if (kProject) {
+        const float* q = pb + (size_t)n * 3;
+        const float px = q[0] + ctx, py = q[1] + cty, pz = q[2] + ctz;
+        g.x = (pj.focal * (px / pz)) / (pj.img_w * 0.5f);
+        g.y = (pj.focal * (py / pz)) / (pj.img_h * 0.5f);
+        if (pj.pts2d_out && blockIdx.x == 0 && cblk == 0 && n0 + lane < N)
+          *reinterpret_cast<float2*>(pj.pts2d_out + ((size_t)b * N + n) * 2) = g;
+      } else {
+        g = *reinterpret_cast<const float2*>(pb + (size_t)n * 2);
+      }
+      const Taps tp = make_taps(g.x, g.y, H, W);
+      __syncwarp();      // the previous block's reads of the tables are done
+      *reinterpret_cast<int4*>(my_taps + lane * 8) = make_int4(tp.o00 * kPitch, tp.o01 * kPitch, tp.o10 * kPitch, tp.o11 * kPitch);
+      *reinterpret_cast<float4*>(my_taps + lane * 8 + 4) = make_float4(tp.w00, tp.w01, tp.w10, tp.w11);
+      __syncwarp();
+    }
+    const float* tc = tile + cb0 + cl;
+#pragma unroll 4
+    for (int s = 0; s < CB; ++s) {
+      const int pt = s * PPL + sub;
+      const int4 o = *reinterpret_cast<const int4*>(my_taps + pt * 8);
+      const float4 w = *reinterpret_cast<const float4*>(my_taps + pt * 8 + 4);
+      float acc = tc[o.x] * w.x;
+      acc = fmaf(tc[o.y], w.y, acc);
+      acc = fmaf(tc[o.z], w.z, acc);
+      acc = fmaf(tc[o.w], w.w, acc);
+      my_out[cl * 33 + pt] = acc;
+    }
+    __syncwarp();
+    const int n = n0 + lane;
+    if (n < N) {
+      float* ob = out + ((size_t)b * C + c0 + cb0) * N + n;
+      const int cmax = min(CB, cg - cb0);
+#pragma unroll 4
+      for (int c = 0; c < cmax; ++c) ob[(size_t)c * N] = my_out[c * 33 + lane];
+    }
+  }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
+// Dense-regime plan: channels per CTA of sample_bilinear_dense_kernel (64, 32 or 16; two or more CTAs per SM), or 0.
+static inline size_t dense_smem_bytes(int cgp, int nchw_in, int HW) {
+  const int pitch = nchw_in ? cgp + 1 : cgp;
+  const int cb = cgp < 32 ? cgp : 32;
+  return ((((size_t)HW * pitch + 3) & ~(size_t)3) + 8 * 32 * 8 + 8 * cb * 33) * sizeof(float);
+}
+static int dense_channels(int C, int H, int W, int N, int nchw_in) {
+  static const int mode = getenv("WHMR_SAMPLE_DENSE") ? atoi(getenv("WHMR_SAMPLE_DENSE")) : -1;   // 0 never, 1 whenever it fits
+  if (mode == 0 || (C & 15)) return 0;
+  const long long HW = (long long)H * W;
+  if (mode != 1 && 4LL * N < HW) return 0;
+  // Measured at configs[3] (B=1024, N=431, fraction of the HBM roofline on algorithmic bytes, 14x14 / 28x28):
+  //   NHWC maps: this kernel 0.47 / 0.64 (CG=32; 0.42 / 0.63 at CG=64), direct NHWC gather 0.25 / 0.41;
+  //   NCHW maps: this kernel 0.42 / 0.41 (4-byte transposing copies), plane-staged kernel 0.47 / 0.59
+  // so NCHW input keeps the plane-staged kernel unless WHMR_SAMPLE_DENSE=1 asks for this one.
+  if (nchw_in && mode != 1) return 0;
+  if (HW > 16384) return 0;
+  static const int cap = getenv("WHMR_DENSE_CG") ? atoi(getenv("WHMR_DENSE_CG")) : 32;   // experiments: 64 / 32 / 16
+  for (int cgp = 64; cgp >= 16; cgp >>= 1)
+    if (cgp <= C && cgp <= cap && dense_smem_bytes(cgp, nchw_in, (int)HW) <= 100 * 1024) return cgp;
+  return 0;
+}
+
+template <bool kNchwIn, bool kProject>
+static cudaError_t launch_dense(int cgp, const float* feat, const float* points, int pts_bstride, float* out, int B, int C,
+                                int H, int W, int N, SampleProj pj, cudaStream_t st) {
+  const size_t smem = dense_smem_bytes(cgp, kNchwIn, H * W);
+  const dim3 grid(ceil_div(C, cgp), B);
+#define WHMR_DENSE(CGV)                                                                                            \
+  do {                                                                                                             \
+    cudaError_t e_ = ensure_dyn_smem(sample_bilinear_dense_kernel<CGV, kNchwIn, kProject>, 100 * 1024);            \
+    if (e_ != cudaSuccess) return e_;                                                                              \
+    launch_pdl(kPdlSample, sample_bilinear_dense_kernel<CGV, kNchwIn, kProject>, grid, dim3(256), smem, st, feat,  \
+               points, pts_bstride, out, C, H, W, N, pj);                                                          \
+  } while (0)
+  if (cgp == 64) WHMR_DENSE(64); else if (cgp == 32) WHMR_DENSE(32); else WHMR_DENSE(16);
+#undef WHMR_DENSE
+  return cudaSuccess;
+}
+
+
 // Dense regime of the NCHW sampler (sampling.cuh): channels per CTA for the shared-memory-staged kernel, or 0 when
 // the direct gather is the better kernel (sparse sampling, or planes too large to stage a useful number of).
 static int staged_channels(int C, int H, int W, int N) {

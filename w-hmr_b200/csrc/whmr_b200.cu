@@ -1125,6 +1125,13 @@ int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int
   WHMR_CHECK_ARG((reinterpret_cast<size_t>(points) & 7) == 0, "whmr_sample_bilinear: points must be 8-byte aligned");
   WHMR_CHECK_ARG((long long)C * N < (1ll << 31) && B < 65536, "whmr_sample_bilinear: C*N or B too large");
   cudaStream_t st = (cudaStream_t)stream;
+  if (const int cgp = dense_channels(C, H, W, N, layout == WHMR_LAYOUT_NCHW)) {   // dense regime: whole map through shared memory
+    WHMR_CUDA((layout == WHMR_LAYOUT_NCHW
+                   ? launch_dense<true, false>(cgp, feat, points, pts_bstride, out, B, C, H, W, N, SampleProj{}, st)
+                   : launch_dense<false, false>(cgp, feat, points, pts_bstride, out, B, C, H, W, N, SampleProj{}, st)));
+    WHMR_LAUNCHED("sample_bilinear_dense_kernel");
+    return WHMR_OK;
+  }
   if (layout == WHMR_LAYOUT_NCHW) {
     if (const int cg = staged_channels(C, H, W, N)) {
       launch_staged<false>(feat, points, pts_bstride, out, B, C, H, W, N, cg, SampleProj{}, st);
@@ -1151,6 +1158,11 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
     WHMR_CHECK_ARG((long long)C * N < (1ll << 31) && B < 65536, "whmr_project_sample: C*N or B too large");
     WHMR_CHECK_ARG(!points2d_out || (reinterpret_cast<size_t>(points2d_out) & 7) == 0, "whmr_project_sample: points2d_out must be 8-byte aligned");
     SampleProj pj{cam, focal, img_w, img_h, points2d_out};
+    if (const int cgp = dense_channels(C, H, W, N, 1)) {
+      WHMR_CUDA((launch_dense<true, true>(cgp, feat, p, N * 3, out, B, C, H, W, N, pj, (cudaStream_t)stream)));
+      WHMR_LAUNCHED("sample_bilinear_dense_kernel<project>");
+      return WHMR_OK;
+    }
     if (const int cg = staged_channels(C, H, W, N)) {
       launch_staged<true>(feat, p, N * 3, out, B, C, H, W, N, cg, pj, (cudaStream_t)stream);
       WHMR_LAUNCHED("sample_bilinear_nchw_staged_kernel<project>");
@@ -1167,6 +1179,11 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
   WHMR_CHECK_ARG(feat && p && cam && out, "whmr_project_sample: null pointer");
   WHMR_CHECK_ARG(!points2d_out || (reinterpret_cast<size_t>(points2d_out) & 7) == 0, "whmr_project_sample: points2d_out must be 8-byte aligned");
   SampleProj pj{cam, focal, img_w, img_h, points2d_out};
+  if (const int cgp = dense_channels(C, H, W, N, 0)) {
+    WHMR_CUDA((launch_dense<false, true>(cgp, feat, p, N * 3, out, B, C, H, W, N, pj, (cudaStream_t)stream)));
+    WHMR_LAUNCHED("sample_bilinear_dense_kernel<project>");
+    return WHMR_OK;
+  }
   dim3 grid(ceil_div(N, 32), ceil_div(C, 64), B);
   launch_pdl(kPdlSample, sample_bilinear_nhwc_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, feat, p, N * 3, out, C, H, W,
              N, pj);
