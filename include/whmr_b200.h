@@ -129,6 +129,9 @@ int whmr_batch_rodrigues(const float* aa, int n, float* R, void* stream);
 int whmr_rot6d_to_rotmat(const float* x, int n, float* R, void* stream);
 int whmr_unbiased_gram_schmidt(const float* x, int n, float* R, void* stream);
 int whmr_rotmat_to_axis_angle(const float* R, int n, float* aa, void* stream);
+/* utils/geometry.py:14-51 batch_rodrigues, the QUATERNION variant (half-angle -> quaternion -> normalise -> matrix) the
+ * trainer applies to ground-truth poses (core/trainer.py:244).  theta [n,3] -> R [n,3,3]. */
+int whmr_batch_rodrigues_quat(const float* theta, int n, float* R, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Sparse linear read-out of the posed vertices.  Replaces every "matrix x vertices" and

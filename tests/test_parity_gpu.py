@@ -206,7 +206,7 @@ def test_smpl_host_buffer_entry(dev, smpl_model):
 
 def test_batch_rodrigues(dev):
     from oracle.smpl_oracle import batch_rodrigues
-    from whmr_b200.geometry import batch_rodrigues as gpu_rod
+    from whmr_b200.geometry import batch_rodrigues_smplx as gpu_rod
     g = torch.Generator().manual_seed(0)
     aa = torch.randn(500, 3, generator=g) * 1.5
     aa[0] = 0
@@ -997,3 +997,14 @@ def test_fused_sampling_mlp_vs_oracle(dev, layout, B, N, H, W, mode):
     assert _maxabs(pf, ref_p) <= FEAT_RTOL * float(ref_p.abs().max())
     assert _maxabs(maf, ref_m) <= FEAT_RTOL * float(ref_m.abs().max())
     assert float(ref_m.abs().max()) > 0.5 and float((ref_m > 0).double().mean()) > 0.1     # the check is not vacuous
+
+
+def test_batch_rodrigues_quaternion_variant_matches_reference_golden(dev, golden):
+    """utils/geometry.py:14-51 (the variant `utils.geometry.batch_rodrigues` names; core/trainer.py:244) against the output
+    of the reference's own function, plus identity at theta = 0 (vendored KAT tests/test_losses/test_mesh_losses.py:24-25)."""
+    from whmr_b200 import geometry
+    R = geometry.batch_rodrigues(torch.from_numpy(golden['rodq_in']).to(dev))
+    assert R.shape == golden['rodq_out'].shape
+    assert _maxabs(R, golden['rodq_out']) <= 1e-6
+    I = geometry.batch_rodrigues(torch.zeros(5, 3, device=dev))
+    assert _maxabs(I, torch.eye(3).expand(5, 3, 3)) <= 1e-6

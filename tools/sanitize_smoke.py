@@ -25,6 +25,21 @@ for hw in ((14, 14), (56, 56)):
     o = ops.sample_bilinear(f, pts, ops.LAYOUT_NCHW)
     torch.cuda.synchronize()
     print("sample", hw, float(o.abs().max()))
+# channels_last maps: NHWC gather + the dense-regime kernel; fused sampling + reduce_dim MLP (tcgen05, both layouts, with
+# and without the projection, tile tail + more than one tile per CTA is covered by the GPU tests)
+from whmr_b200.maf_extractor import MAF_Extractor  # noqa: E402
+ext = MAF_Extractor(mesh_downsampling=None).to(dev).eval()
+for hw in ((14, 14), (64, 48)):
+    f = torch.randn(4, 256, *hw, device=dev)
+    fl = f.contiguous(memory_format=torch.channels_last)
+    o = ops.sample_bilinear(fl, pts, ops.LAYOUT_NCHW)
+    with torch.no_grad():
+        m1, p1 = ext.sampling(pts, im_feat=f)
+        m2, p2 = ext.sampling(pts, im_feat=fl)
+        ext.im_feat, ext.cam = f, torch.tensor([[0.9, 0.0, 0.1]], device=dev).repeat(4, 1)
+        m3, _ = ext(torch.randn(4, 67, 3, device=dev) * 0.3, None, None, None, None)
+    torch.cuda.synchronize()
+    print("maf fused", hw, float(o.abs().max()), float((m1 - m2).abs().max()), float(m3.abs().max()))
 # backward: SMPL (skin, pose-blend transpose, chain), transposed read-out
 from whmr_b200.smpl import SMPL  # noqa: E402
 smpl = SMPL(model=model).to(dev)

@@ -90,6 +90,7 @@ SIGNATURES = {
     "whmr_rot6d_to_rotmat": (C.c_int, [_vp, _i, _vp, _vp]),
     "whmr_unbiased_gram_schmidt": (C.c_int, [_vp, _i, _vp, _vp]),
     "whmr_rotmat_to_axis_angle": (C.c_int, [_vp, _i, _vp, _vp]),
+    "whmr_batch_rodrigues_quat": (C.c_int, [_vp, _i, _vp, _vp]),
     "whmr_readout_create": (C.c_int, [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, C.POINTER(_vp)]),
     "whmr_readout_destroy": (C.c_int, [_vp]),
     "whmr_readout_apply": (C.c_int, [_vp, _vp, _vp, _i, _vp, _vp]),

@@ -29,6 +29,30 @@ __global__ void __launch_bounds__(256) rot6d_to_rotmat_kernel(const float* __res
   o[6] = a1z; o[7] = b2z; o[8] = b3z;
 }
 
+// utils/geometry.py:14-51: the quaternion variant of batch_rodrigues (core/trainer.py:244 -- ground-truth poses of the
+// training step): angle = ||theta + 1e-8||, quat = (cos(angle/2), sin(angle/2) * theta/angle), normalised, -> matrix.
+// (The smplx variant inside SMPL.forward is whmr_batch_rodrigues; the two differ at ~1e-7.)
+__global__ void __launch_bounds__(256) batch_rodrigues_quat_kernel(const float* __restrict__ theta, int n,
+                                                                   float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float tx = theta[(size_t)i * 3 + 0], ty = theta[(size_t)i * 3 + 1], tz = theta[(size_t)i * 3 + 2];
+  const float ex = tx + 1e-8f, ey = ty + 1e-8f, ez = tz + 1e-8f;
+  const float angle = sqrtf(ex * ex + ey * ey + ez * ez);
+  const float nx = tx / angle, ny = ty / angle, nz = tz / angle;
+  const float half = angle * 0.5f;
+  const float vs = sinf(half);
+  float w = cosf(half), x = vs * nx, y = vs * ny, z = vs * nz;
+  const float qn = sqrtf(w * w + x * x + y * y + z * z);
+  w /= qn; x /= qn; y /= qn; z /= qn;
+  const float w2 = w * w, x2 = x * x, y2 = y * y, z2 = z * z;
+  const float wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+  float* o = out + (size_t)i * 9;
+  o[0] = w2 + x2 - y2 - z2; o[1] = 2 * xy - 2 * wz;    o[2] = 2 * wy + 2 * xz;
+  o[3] = 2 * wz + 2 * xy;    o[4] = w2 - x2 + y2 - z2; o[5] = 2 * yz - 2 * wx;
+  o[6] = 2 * xz - 2 * wy;    o[7] = 2 * wx + 2 * yz;    o[8] = w2 - x2 - y2 + z2;
+}
+
 // utils/geometry.py:260-272 on one row-major 3x3 (in and out may alias)
 __device__ __forceinline__ void unbiased_gram_schmidt_dev(const float* p, float* o) {
   const float t1x = p[0], t1y = p[3], t1z = p[6], t2x = p[1], t2y = p[4], t2z = p[7], t3x = p[2], t3y = p[5], t3z = p[8];

@@ -869,6 +869,7 @@ int whmr_batch_rodrigues(const float* aa, int n, float* R, void* stream) {
 WHMR_ROT_ENTRY(whmr_rot6d_to_rotmat, rot6d_to_rotmat_kernel)
 WHMR_ROT_ENTRY(whmr_unbiased_gram_schmidt, unbiased_gram_schmidt_kernel)
 WHMR_ROT_ENTRY(whmr_rotmat_to_axis_angle, rotmat_to_axis_angle_kernel)
+WHMR_ROT_ENTRY(whmr_batch_rodrigues_quat, batch_rodrigues_quat_kernel)
 #undef WHMR_ROT_ENTRY
 
 // =============================================================================================

@@ -114,8 +114,15 @@ def full_image_projection(pred_joints, pred_cam, bbox_height, center, orig_shape
     return ops.project_full(pred_joints, pred_cam, bbox_height, center, orig_shape, Tz, want_px=want_px)
 
 
-def batch_rodrigues(rot_vecs):
-    """smplx.lbs.batch_rodrigues (imported at models/whmr.py:9), the variant inside SMPL.forward."""
+def batch_rodrigues(theta):
+    """utils/geometry.py:14-51 -- what `from utils.geometry import batch_rodrigues` gives the trainer (core/trainer.py:244):
+    the QUATERNION variant (half-angle -> quaternion -> normalise -> matrix).  [N,3] -> [N,3,3]."""
+    return ops.batch_rodrigues_quat(theta)
+
+
+def batch_rodrigues_smplx(rot_vecs):
+    """smplx.lbs.batch_rodrigues (imported at models/whmr.py:9), the variant inside SMPL.forward (differs from the
+    quaternion one at ~1e-7)."""
     return ops.batch_rodrigues(rot_vecs)
 
 

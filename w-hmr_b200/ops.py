@@ -241,6 +241,11 @@ def rotation_matrix_to_angle_axis(R):
     return _rot_op("whmr_rotmat_to_axis_angle", R, 9, (3,))
 
 
+def batch_rodrigues_quat(theta):
+    """utils/geometry.py:14-51 (the quaternion variant, core/trainer.py:244): [N,3] -> [N,3,3]"""
+    return _rot_op("whmr_batch_rodrigues_quat", theta, 3, (3, 3))
+
+
 # ----------------------------------------------------------------------------------------------
 # read-out
 # ----------------------------------------------------------------------------------------------
