@@ -268,7 +268,7 @@ int whmr_project_sample(const float* feat, int layout, int B, int C, int H, int 
  * written only when point_feat_out != NULL.  Weights are the module's conv0..2 parameters (Conv1d
  * layout [C_out, C_in_total, 1], DEVICE pointers); set_weights re-splits them (call again after an
  * optimizer step).  mesh_align_out [B, C3*N] (= y.view(B,-1) of [B,C3,N]).
- * Widths: C_in, C1, C2 multiples of 32, C3 a multiple of 16, C1+C2+C3 <= 256 (reference: 256,128,64,32).
+ * Widths: C_in, C1, C2 multiples of 64, C3 a multiple of 16, C1+C2+C3 <= 256 (reference: 256,128,64,32).
  * ------------------------------------------------------------------------------------------ */
 typedef struct whmr_maf_mlp_s* whmr_maf_mlp_t;
 int whmr_maf_mlp_create(int c_in, int c1, int c2, int c3, whmr_maf_mlp_t* out);

@@ -1206,9 +1206,9 @@ struct whmr_maf_mlp_s {
 
 int whmr_maf_mlp_create(int c_in, int c1, int c2, int c3, whmr_maf_mlp_t* out) {
   WHMR_CHECK_ARG(out, "whmr_maf_mlp_create: null output");
-  WHMR_CHECK_ARG(c_in >= 32 && c_in % 32 == 0 && c1 >= 32 && c1 % 32 == 0 && c2 >= 32 && c2 % 32 == 0 && c3 >= 16 &&
+  WHMR_CHECK_ARG(c_in >= 64 && c_in % 64 == 0 && c1 >= 64 && c1 % 64 == 0 && c2 >= 64 && c2 % 64 == 0 && c3 >= 16 &&
                      c3 % 16 == 0 && c1 + c2 + c3 <= kMafMaxOut,
-                 "whmr_maf_mlp_create: unsupported widths %d -> %d -> %d -> %d (need C_in, C1, C2 multiples of 32, C3 a "
+                 "whmr_maf_mlp_create: unsupported widths %d -> %d -> %d -> %d (need C_in, C1, C2 multiples of 64, C3 a "
                  "multiple of 16, C1+C2+C3 <= %d)", c_in, c1, c2, c3, kMafMaxOut);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -1262,14 +1262,15 @@ static int maf_launch(whmr_maf_mlp_t m, const float* feat, int layout, int B, in
   WHMR_CHECK_ARG(layout == WHMR_LAYOUT_NCHW || (reinterpret_cast<size_t>(feat) & 15) == 0, "%s: NHWC maps must be 16-byte aligned", who);
   WHMR_CHECK_ARG(kProject || (reinterpret_cast<size_t>(points) & 7) == 0, "%s: points must be 8-byte aligned", who);
   const int n_tiles = (int)(((long long)B * N + kMafRows - 1) / kMafRows);
-  const int grid = std::min(n_tiles, 2 * m->num_sms);
-  const size_t smem = maf_smem_bytes(m->d);
+  const int grid = std::min(n_tiles, m->num_sms);
+  const size_t smem = maf_smem_bytes(m->d, layout == WHMR_LAYOUT_NHWC);
 #define WHMR_MAF_LAUNCH(L)                                                                                         \
   do {                                                                                                             \
     cudaError_t e_ = ensure_dyn_smem(maf_fused_kernel<L, kProject>, (int)smem);                                    \
     if (e_ != cudaSuccess) return set_error(WHMR_E_CUDA, "%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(e_)); \
     launch_pdl(kPdlSample, maf_fused_kernel<L, kProject>, dim3(grid), dim3(kMafThreads), smem, st, m->map_x, m->map_1, \
-               m->map_2, feat, points, pts_bstride, (const float*)m->bias, out, pf_out, B, N, H, W, m->d, n_tiles, pj); \
+               m->map_2, feat, points, pts_bstride, (const float*)m->bias, out, pf_out, B, N, H, W, m->d, n_tiles,     \
+               maf_w_stages(m->d), pj);                                                                            \
   } while (0)
   if (layout == WHMR_LAYOUT_NCHW) WHMR_MAF_LAUNCH(0); else WHMR_MAF_LAUNCH(1);
 #undef WHMR_MAF_LAUNCH

@@ -523,7 +523,7 @@ class MafMlp:
 
     @staticmethod
     def supported(dims):
-        return len(dims) == 4 and dims[0] % 32 == 0 and dims[1] % 32 == 0 and dims[2] % 32 == 0 and dims[3] % 16 == 0 \
+        return len(dims) == 4 and dims[0] % 64 == 0 and dims[1] % 64 == 0 and dims[2] % 64 == 0 and dims[3] % 16 == 0 \
             and min(dims) >= 16 and dims[1] + dims[2] + dims[3] <= 256
 
     def close(self):
