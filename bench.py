@@ -359,6 +359,12 @@ def run_ours(args):
     if not args.skip_reduce_dim:
         rd = reduce_dim_leg(args, model, dev, feats, params, bbox, rank, world, min(K, 300), W, gemm_mode)
 
+    # ---- training step: Regressor.forward body-model head forward + loss + backward at the reference's
+    #      TRAIN.BATCH_SIZE, custom ops with their CUDA backward kernels vs eager autograd of the dense path ----------------
+    train = None
+    if rank == 0 and not args.skip_train:
+        train = train_step_leg(model, loop, dev)
+
     # ---- end to end through host buffers ------------------------------------------------------------
     e2e = None
     e2e_resident = None
@@ -521,13 +527,76 @@ def run_ours(args):
                        "launch": "one CUDA graph replay per step; schedule: finishing passes of the 5 read-outs + the 4 joint projections after the loop (1 + 4 launches), per-kernel probes taken on the immediate 22-launch schedule",
                        "feature_layout": "channels_last (NHWC memory)" if args.channels_last else "NCHW contiguous (reference layout)",
                        "rotation_glue": "unbiased_gram_schmidt (eval mode) + rotation_matrix_to_angle_axis + theta inside the chain kernel, every SMPL call"},
-            "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident, "channels_last": cl, "with_reduce_dim": rd, "other_configs": other,
+            "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident, "channels_last": cl, "with_reduce_dim": rd, "train_step": train, "other_configs": other,
             "gpu_launches": int(launches_per_step) * K, "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "torch_gpu_eager": eager, "smpl_at_scale": scale, "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_leg(model, loop, dev, B=64, reps=30):
+    """core/trainer.py:380-636 back-propagates through the SMPL vertices, the 49 / H36M joints and both projections of
+    Regressor.forward (cfg.TRAIN.BATCH_SIZE = 64, configs/pymaf_config.yaml:28).  One head forward + a loss over those
+    tensors + backward: the torch.library ops of this repo (whmr_smpl_backward, whmr_readout_backward,
+    whmr_project_*_backward) against eager PyTorch autograd of the same dense path (the oracle restatement on cuda:0),
+    gradients w.r.t. rotmat / betas / cam / Tz compared between the two."""
+    import torch
+    import whmr_b200.synthetic as syn
+    from oracle.loop_oracle import LoopOracle
+    b = syn.make_bodies(B, seed=5)
+    T = lambda a, g=False: torch.from_numpy(a).to(dev).requires_grad_(g)  # noqa: E731
+    rm, be, cam, tz = T(b["rotmat"], True), T(b["betas"], True), T(b["cam"], True), T(b["Tz"], True)
+    bbox = {"bbox_height": T(b["bbox_height"]), "center": T(b["center"]), "orig_shape": T(b["orig_shape"]), "Tz": tz}
+    head = loop.head
+    keys = ("verts", "kp_3d", "kp_2d", "kp_2d_w", "smpl_kp_3d")
+    stage_before = head.train_stage
+    head.train_stage = 2          # both projections carry the joint gradient somewhere (models/whmr.py:143-173)
+
+    def loss_of(o):
+        return o["verts"].pow(2).sum() + o["kp_3d"].pow(2).sum() + o["kp_2d"].pow(2).sum() + o["kp_2d_w"].pow(2).sum() + \
+            o["smpl_kp_3d"].pow(2).sum()
+
+    def ours():
+        o = head(rm, be, cam, bbox["bbox_height"], bbox["center"], bbox["orig_shape"], tz, J_regressor=True, is_train=True)
+        loss_of(o).backward()
+
+    orc = LoopOracle(model, loop.backbone, device=str(dev))
+
+    def eager():
+        o = orc.regressor_outputs({"rotmat": rm, "betas": be, "cam": cam}, bbox, is_train=True, train_stage=2)
+        loss_of(o).backward()
+
+    def grads(fn):
+        for t in (rm, be, cam, tz):
+            t.grad = None
+        fn()
+        return [t.grad.clone() if t.grad is not None else torch.zeros_like(t) for t in (rm, be, cam, tz)]
+
+    def timed(fn):
+        for _ in range(5):
+            grads(fn)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    g_ours, g_ref = grads(ours), grads(eager)
+    rel = [float((a - r_).abs().max() / r_.abs().max().clamp_min(1e-30)) for a, r_ in zip(g_ours, g_ref)]
+    ms_ours, ms_eager = timed(ours), timed(eager)
+    head.train_stage = stage_before
+    for t in (rm, be, cam, tz):
+        t.grad = None
+    return {"batch": B, "ms_forward_loss_backward": ms_ours, "ms_eager_autograd_same_gpu": ms_eager,
+            "speedup_vs_eager": ms_eager / ms_ours,
+            "grad_rel_diff_vs_eager": dict(zip(("rotmat", "betas", "cam", "Tz"), rel)),
+            "loss": "sum of squares of verts, kp_3d (H36M), kp_2d, kp_2d_w, smpl_kp_3d; train stage 2 detach routing",
+            "note": "eager (host-launched) on both sides; backward kernels are CUDA-core (FFMA) kernels"}
 
 
 def reduce_dim_leg(args, model, dev, feats, params, bbox, rank, world, K, W, gemm_mode):
@@ -942,6 +1011,7 @@ def main():
     ap.add_argument("--skip-sweep", action="store_true")
     ap.add_argument("--skip-other", action="store_true", help="skip the configs[2] / configs[4] legs")
     ap.add_argument("--skip-channels-last", action="store_true")
+    ap.add_argument("--skip-train", action="store_true", help="skip the training-step (forward + backward) leg")
     ap.add_argument("--skip-reduce-dim", action="store_true", help="skip the leg with the extractors' MLP fused into sampling")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--quick", action="store_true")

@@ -25,7 +25,7 @@ class LoopOracle:
         self.grid = torch.from_numpy(syn.grid_points(backbone)).to(device)
         self.with_h36m = with_h36m
 
-    def regressor_outputs(self, p, bbox=None, is_train=False):
+    def regressor_outputs(self, p, bbox=None, is_train=False, train_stage=None):
         """Regressor.forward / forward_init after the MLP (models/whmr.py:128-209, 225-269).  Regressor.forward (bbox
         given) orthonormalises the predicted rotations in eval mode (:129-130); both compute `pose` / `theta` (:174,190)."""
         rotmat = p['rotmat']
@@ -35,12 +35,17 @@ class LoopOracle:
         verts, joints = o['vertices'], o['joints']
         r = regressor_readouts(self.model, verts)
         pose = G.rotation_matrix_to_angle_axis(rotmat.reshape(-1, 3, 3)).reshape(-1, 72)
-        out = {'verts': verts, 'joints49': joints, 'kp_2d': G.projection(joints, p['cam']), 'rotmat': rotmat, 'pose': pose,
+        # models/whmr.py:142-165: with cfg.TRAIN.STAGE given, one of the two projections sees detached joints and the
+        # predicted-focal block a detached camera (forward values are unchanged)
+        jw = joints if train_stage in (None, 1) else joints.detach()
+        out = {'verts': verts, 'joints49': joints, 'kp_2d': G.projection(jw, p['cam']), 'rotmat': rotmat, 'pose': pose,
                'theta': torch.cat([p['cam'], p['betas'], pose], dim=1),
                'sub_verts': r['sub_verts'], 'temp_verts': r['temp_verts'], 'markers': r['markers'],
                'smpl_kp_3d': r['smpl_kp_3d'], 'kp_3d': r['kp_3d_h36m'] if self.with_h36m else joints}
         if bbox is not None:
-            kpn, focal, cam_t, _ = G.full_projection(joints, p['cam'], bbox['bbox_height'], bbox['center'],
+            jf = joints if train_stage in (None, 2) else joints.detach()
+            camf = p['cam'] if train_stage is None else p['cam'].detach()
+            kpn, focal, cam_t, _ = G.full_projection(jf, camf, bbox['bbox_height'], bbox['center'],
                                                      bbox['orig_shape'], bbox['Tz'])
             out.update(kp_2d_w=kpn, focal_length=focal, pred_cam_t=cam_t)
         return out
