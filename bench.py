@@ -524,7 +524,7 @@ def run_ours(args):
                        "samplings_per_step": 3, "pose_blend_arithmetic": {0: "fp32_simt", 1: "tcgen05 bf16x3", 2: "tcgen05 3xtf32"}[loop.smpl.gemm_mode],
                        "parallelism": "dp%d (bodies sharded by rank, no data-path collective)" % world,
                        "l2": "inputs larger than L2: feature maps 4.2 GB/step/GPU + ~0.2 GB of outputs vs 126 MB L2",
-                       "launch": "one CUDA graph replay per step; schedule: finishing passes of the 5 read-outs + the 4 joint projections after the loop (1 + 4 launches), per-kernel probes taken on the immediate 22-launch schedule",
+                       "launch": "one CUDA graph replay per step; schedule: finishing passes of the 5 read-outs + the 4 joint projections after the loop in ONE launch, per-kernel probes taken on the immediate 22-launch schedule",
                        "feature_layout": "channels_last (NHWC memory)" if args.channels_last else "NCHW contiguous (reference layout)",
                        "rotation_glue": "unbiased_gram_schmidt (eval mode) + rotation_matrix_to_angle_axis + theta inside the chain kernel, every SMPL call"},
             "clocks": clocks, "e2e": e2e, "e2e_feat_resident": e2e_resident, "channels_last": cl, "with_reduce_dim": rd, "train_step": train, "other_configs": other,

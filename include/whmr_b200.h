@@ -199,6 +199,27 @@ int whmr_readout_finish(whmr_readout_t ro, const float* joints /*[B,J,3] or NULL
  * (models/whmr.py:550-651) nothing but the caller reads the finished rows, so the loop defers them to its end. */
 int whmr_readout_finish_multi(whmr_readout_t ro, int n_calls, const float* const* joints, const void* const* ro_workspaces,
                               float* const* ro_outs, int B, void* stream);
+/* The same with the joint projections of Regressor.forward / forward_init (models/whmr.py:142-173, 237) folded in: rows
+ * [row0, row0 + n_points) of the table (the 49 joints) are projected right after they are finished.  Per call: cam [B,3] or
+ * NULL (no projection: the global SMPL call); full != 0: weak projection + predicted-focal block (kp_weak, kp_norm [B,n,2],
+ * focal_out [B], cam_t_out [B,3]), else weak projection only (kp_weak).  All device pointers. */
+typedef struct whmr_finish_projection {
+  int32_t row0, n_points;
+  float focal, img_w, img_h;                 /* utils/geometry.py:289-307 constants */
+  const float* bbox_height;                  /* [B]   (needed when any call is full) */
+  const float* center;                       /* [B,2] */
+  const float* orig_shape;                   /* [B,2] (h, w) */
+  const float* Tz;                           /* [B] */
+  const float* cam[8];
+  int32_t full[8];
+  float* kp_weak[8];
+  float* kp_norm[8];
+  float* focal_out[8];
+  float* cam_t_out[8];
+} whmr_finish_projection;
+int whmr_readout_finish_project_multi(whmr_readout_t ro, int n_calls, const float* const* joints,
+                                      const void* const* ro_workspaces, float* const* ro_outs, int B,
+                                      const whmr_finish_projection* proj, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Projection.

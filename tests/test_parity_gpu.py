@@ -1008,3 +1008,32 @@ def test_batch_rodrigues_quaternion_variant_matches_reference_golden(dev, golden
     assert _maxabs(R, golden['rodq_out']) <= 1e-6
     I = geometry.batch_rodrigues(torch.zeros(5, 3, device=dev))
     assert _maxabs(I, torch.eye(3).expand(5, 3, 3)) <= 1e-6
+
+
+def test_loop_projections_folded_into_the_finishing_launch(dev, smpl_model):
+    """Deferred schedule: the four joint projections (models/whmr.py:142-173, 237) ride in the read-out finishing launch
+    (whmr_readout_finish_project_multi) -- 14 launches per pass instead of 18 -- and give the results of the stand-alone
+    projection kernels (same device functions) and of the oracle."""
+    from oracle.loop_oracle import LoopOracle, to_cpu_inputs
+    from whmr_b200.loop import RegressorLoop, make_loop_inputs
+    B = 9
+    loop = RegressorLoop(smpl_model, dev)
+    feats, params, bbox = make_loop_inputs(B, dev, seed=6)
+    loop.step(feats, params, bbox)
+    n0 = _launches()
+    a = loop.step(feats, params, bbox)
+    n_fused = _launches() - n0
+    loop.head.fuse_projection = False
+    n0 = _launches()
+    b = loop.step(feats, params, bbox)
+    n_separate = _launches() - n0
+    assert (n_fused, n_separate) == (14, 18)
+    for k in ('kp_2d', 'kp_2d_w', 'focal_length', 'pred_cam_t'):
+        assert a[k].shape == b[k].shape
+        assert _maxabs(a[k], b[k].cpu()) <= 1e-6 * max(1.0, float(b[k].abs().max())), k
+    ref = LoopOracle(smpl_model).step(*to_cpu_inputs(feats, params, bbox))
+    half = (bbox['orig_shape'].cpu()[:, [1, 0]] / 2).unsqueeze(1)
+    assert float(((a['kp_2d_w'].cpu() - ref['kp_2d_w']).abs() * half).max()) <= PX_TOL
+    assert _maxabs(a['kp_2d'], ref['kp_2d']) * 128 <= PX_TOL
+    assert _maxabs(a['focal_length'], ref['focal_length']) <= 1e-6 * float(ref['focal_length'].abs().max())
+    assert _maxabs(a['pred_cam_t'], ref['pred_cam_t']) <= 1e-5

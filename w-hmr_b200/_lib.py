@@ -49,6 +49,13 @@ class SmplGlue(C.Structure):
                 ("theta_out", C.c_void_p), ("cam", C.c_void_p)]
 
 
+class FinishProjection(C.Structure):     # whmr_finish_projection
+    _fields_ = [("row0", C.c_int32), ("n_points", C.c_int32), ("focal", C.c_float), ("img_w", C.c_float),
+                ("img_h", C.c_float), ("bbox_height", C.c_void_p), ("center", C.c_void_p), ("orig_shape", C.c_void_p),
+                ("Tz", C.c_void_p), ("cam", C.c_void_p * 8), ("full", C.c_int32 * 8), ("kp_weak", C.c_void_p * 8),
+                ("kp_norm", C.c_void_p * 8), ("focal_out", C.c_void_p * 8), ("cam_t_out", C.c_void_p * 8)]
+
+
 class SmplModelDesc(C.Structure):
     _fields_ = [("n_verts", C.c_int32), ("n_joints", C.c_int32), ("n_betas", C.c_int32),
                 ("v_template", C.c_void_p), ("shapedirs", C.c_void_p), ("posedirs", C.c_void_p),
@@ -80,6 +87,8 @@ SIGNATURES = {
     "whmr_smpl_is_fused": (C.c_int, [_vp]),
     "whmr_readout_finish": (C.c_int, [_vp, _vp, _i, _vp, _vp, _vp]),
     "whmr_readout_finish_multi": (C.c_int, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i, _vp]),
+    "whmr_readout_finish_project_multi": (C.c_int, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _i,
+                                                    C.POINTER(FinishProjection), _vp]),
     "whmr_smpl_stage_chain": (C.c_int, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "whmr_smpl_stage_pose_blend": (C.c_int, [_vp, _i, _vp, _sz, _vp]),
     "whmr_smpl_stage_skin": (C.c_int, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),

@@ -8,6 +8,52 @@
 
 namespace whmr {
 
+// utils/geometry.py:289-307 for one point (shared by the stand-alone kernels and the read-out finishing pass, so that
+// both schedules of the loop produce the same bits)
+__device__ __forceinline__ void project_weak_point(const float* __restrict__ pt, float s, float tx, float ty, float focal,
+                                                   float img_w, float img_h, float* __restrict__ out2) {
+  const float tz = 2.0f * focal / (img_h * s + 1e-9f);
+  const float px = pt[0] + tx;
+  const float py = pt[1] + ty;
+  const float pz = pt[2] + tz;
+  const float qx = px / pz, qy = py / pz;
+  out2[0] = (focal * qx) / (img_w * 0.5f);
+  out2[1] = (focal * qy) / (img_h * 0.5f);
+}
+
+// models/whmr.py:147-173 (+ utils/geometry.py:139-157) for point n of body b; n == 0 also writes focal / cam_t
+__device__ __forceinline__ void project_full_point(const float* __restrict__ pt, int b, int n, const float* __restrict__ cam,
+                                                   const float* __restrict__ bbox_height, const float* __restrict__ center,
+                                                   const float* __restrict__ orig_shape, const float* __restrict__ Tz,
+                                                   float* __restrict__ kp_norm2, float* __restrict__ kp_px2,
+                                                   float* __restrict__ focal_out, float* __restrict__ cam_t_out,
+                                                   float* __restrict__ kp_weak2, float wfocal, float wimg_w, float wimg_h) {
+  const float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
+  const float h = bbox_height[b], tz = Tz[b];
+  const float img_h = orig_shape[b * 2 + 0], img_w = orig_shape[b * 2 + 1];
+  const float focal = s * h * tz / 2.0f;                       // whmr.py:149
+  const float ccx = img_w / 2.0f, ccy = img_h / 2.0f;          // :152-153
+  const float sh = s * h;
+  const float ctx = tx + 2.0f * (center[b * 2 + 0] - (img_w / 2.0f)) / sh;   // geometry.py:152-155
+  const float cty = ty + 2.0f * (center[b * 2 + 1] - (img_h / 2.0f)) / sh;
+  if (n == 0) {
+    if (focal_out) focal_out[b] = focal;
+    if (cam_t_out) { cam_t_out[b * 3 + 0] = ctx; cam_t_out[b * 3 + 1] = cty; cam_t_out[b * 3 + 2] = tz; }
+  }
+  const float x = pt[0] + ctx, y = pt[1] + cty, z = pt[2] + tz;
+  const float qx = x / z, qy = y / z, qz = z / z;
+  const float u = focal * qx + ccx * qz;
+  const float v = focal * qy + ccy * qz;
+  if (kp_px2) { kp_px2[0] = u; kp_px2[1] = v; }
+  if (kp_norm2) { kp_norm2[0] = u / ccx - 1.0f; kp_norm2[1] = v / ccy - 1.0f; }   // :173
+  if (kp_weak2) {   // utils/geometry.py:289-307 on the same points (Regressor.forward evaluates both, :142-173)
+    const float wtz = 2.0f * wfocal / (wimg_h * s + 1e-9f);
+    const float wx = pt[0] + tx, wy = pt[1] + ty, wz = pt[2] + wtz;
+    kp_weak2[0] = (wfocal * (wx / wz)) / (wimg_w * 0.5f);
+    kp_weak2[1] = (wfocal * (wy / wz)) / (wimg_h * 0.5f);
+  }
+}
+
 // utils/geometry.py:289-307
 __global__ void __launch_bounds__(256)
 project_weak_kernel(const float* __restrict__ points, const float* __restrict__ cam, int B, int N,
@@ -17,14 +63,7 @@ project_weak_kernel(const float* __restrict__ points, const float* __restrict__ 
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * N) return;
   const int b = (int)(i / N);
-  const float s = cam[b * 3 + 0];
-  const float tz = 2.0f * focal / (img_h * s + 1e-9f);
-  const float px = points[i * 3 + 0] + cam[b * 3 + 1];
-  const float py = points[i * 3 + 1] + cam[b * 3 + 2];
-  const float pz = points[i * 3 + 2] + tz;
-  const float qx = px / pz, qy = py / pz;
-  out[i * 2 + 0] = (focal * qx) / (img_w * 0.5f);
-  out[i * 2 + 1] = (focal * qy) / (img_h * 0.5f);
+  project_weak_point(points + i * 3, cam[b * 3 + 0], cam[b * 3 + 1], cam[b * 3 + 2], focal, img_w, img_h, out + i * 2);
 }
 
 // utils/geometry.py:310-341
@@ -82,30 +121,9 @@ project_full_kernel(const float* __restrict__ points, const float* __restrict__ 
   if (i >= (long long)B * N) return;
   const int b = (int)(i / N);
   const int n = (int)(i % N);
-  const float s = cam[b * 3 + 0], tx = cam[b * 3 + 1], ty = cam[b * 3 + 2];
-  const float h = bbox_height[b], tz = Tz[b];
-  const float img_h = orig_shape[b * 2 + 0], img_w = orig_shape[b * 2 + 1];
-  const float focal = s * h * tz / 2.0f;                       // whmr.py:149
-  const float ccx = img_w / 2.0f, ccy = img_h / 2.0f;          // :152-153
-  const float sh = s * h;
-  const float ctx = tx + 2.0f * (center[b * 2 + 0] - (img_w / 2.0f)) / sh;   // geometry.py:152-155
-  const float cty = ty + 2.0f * (center[b * 2 + 1] - (img_h / 2.0f)) / sh;
-  if (n == 0) {
-    if (focal_out) focal_out[b] = focal;
-    if (cam_t_out) { cam_t_out[b * 3 + 0] = ctx; cam_t_out[b * 3 + 1] = cty; cam_t_out[b * 3 + 2] = tz; }
-  }
-  const float x = points[i * 3 + 0] + ctx, y = points[i * 3 + 1] + cty, z = points[i * 3 + 2] + tz;
-  const float qx = x / z, qy = y / z, qz = z / z;
-  const float u = focal * qx + ccx * qz;
-  const float v = focal * qy + ccy * qz;
-  if (kp_px) { kp_px[i * 2 + 0] = u; kp_px[i * 2 + 1] = v; }
-  if (kp_norm) { kp_norm[i * 2 + 0] = u / ccx - 1.0f; kp_norm[i * 2 + 1] = v / ccy - 1.0f; }   // :173
-  if (kp_weak) {   // utils/geometry.py:289-307 on the same points (Regressor.forward evaluates both, :142-173)
-    const float wtz = 2.0f * wfocal / (wimg_h * s + 1e-9f);
-    const float wx = points[i * 3 + 0] + tx, wy = points[i * 3 + 1] + ty, wz = points[i * 3 + 2] + wtz;
-    kp_weak[i * 2 + 0] = (wfocal * (wx / wz)) / (wimg_w * 0.5f);
-    kp_weak[i * 2 + 1] = (wfocal * (wy / wz)) / (wimg_h * 0.5f);
-  }
+  project_full_point(points + i * 3, b, n, cam, bbox_height, center, orig_shape, Tz, kp_norm ? kp_norm + i * 2 : nullptr,
+                     kp_px ? kp_px + i * 2 : nullptr, focal_out, cam_t_out, kp_weak ? kp_weak + i * 2 : nullptr, wfocal, wimg_w,
+                     wimg_h);
 }
 
 // models/maf_extractor.py:145-235 (project + get_trans + perspective_projection w/ distortion)

@@ -20,6 +20,7 @@
 //      (sub rows, joint-sourced terms).
 #pragma once
 #include "common.cuh"
+#include "projection.cuh"
 
 namespace whmr {
 
@@ -199,6 +200,10 @@ struct ReduceParams {
   const float* joints_m[8];
   const float* partial_m[8];
   float* out_m[8];
+  // projections of the finished rows [row0, row0 + n_points) (the 49 joints) folded into the finishing pass
+  // (whmr_readout_finish_project_multi): weak projection for every call with a camera, the predicted-focal block too
+  // where full[call] != 0 -- the loop's four projection launches disappear (models/whmr.py:142-173, 237)
+  whmr_finish_projection pj;
 };
 
 __device__ __forceinline__ void reduce_row(const ReduceParams& q, const float* joints, const float* ps, const int* slots,
@@ -259,6 +264,22 @@ __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
     }
     float* o = readout_dst(p, b, r);
     o[0] = x; o[1] = y; o[2] = z;
+  }
+  if (q.n_multi > 0 && q.pj.n_points > 0 && q.pj.cam[blockIdx.y]) {
+    __syncthreads();   // this body's rows written above are visible to the whole CTA (one-hot rows: by the SMPL kernel)
+    const int call = blockIdx.y;
+    const float* cam = q.pj.cam[call];
+    for (int n = threadIdx.x; n < q.pj.n_points; n += blockDim.x) {
+      const float* pt = readout_dst(p, b, q.pj.row0 + n);
+      const size_t i2 = ((size_t)b * q.pj.n_points + n) * 2;
+      if (q.pj.full[call])
+        project_full_point(pt, b, n, cam, q.pj.bbox_height, q.pj.center, q.pj.orig_shape, q.pj.Tz, q.pj.kp_norm[call] + i2,
+                           nullptr, q.pj.focal_out[call], q.pj.cam_t_out[call], q.pj.kp_weak[call] + i2, q.pj.focal,
+                           q.pj.img_w, q.pj.img_h);
+      else
+        project_weak_point(pt, cam[b * 3 + 0], cam[b * 3 + 1], cam[b * 3 + 2], q.pj.focal, q.pj.img_w, q.pj.img_h,
+                           q.pj.kp_weak[call] + i2);
+    }
   }
 }
 

@@ -703,7 +703,25 @@ int whmr_readout_finish(whmr_readout_t ro, const float* joints, int B, const voi
 
 int whmr_readout_finish_multi(whmr_readout_t ro, int n_calls, const float* const* joints, const void* const* ro_workspaces,
                               float* const* ro_outs, int B, void* stream) {
+  return whmr_readout_finish_project_multi(ro, n_calls, joints, ro_workspaces, ro_outs, B, nullptr, stream);
+}
+
+int whmr_readout_finish_project_multi(whmr_readout_t ro, int n_calls, const float* const* joints,
+                                      const void* const* ro_workspaces, float* const* ro_outs, int B,
+                                      const whmr_finish_projection* proj, void* stream) {
   WHMR_CHECK_ARG(ro && B >= 0 && n_calls >= 0 && n_calls <= 8, "whmr_readout_finish_multi: bad arguments (at most 8 calls)");
+  if (proj) {
+    WHMR_CHECK_ARG(proj->n_points >= 0 && proj->row0 >= 0 && proj->row0 + proj->n_points <= ro->R,
+                   "whmr_readout_finish_project_multi: rows [%d, %d) outside the table (%d rows)", proj->row0,
+                   proj->row0 + proj->n_points, ro->R);
+    for (int i = 0; i < n_calls && proj->n_points > 0; ++i) {
+      if (!proj->cam[i]) continue;
+      WHMR_CHECK_ARG(proj->kp_weak[i], "whmr_readout_finish_project_multi: call %d has a camera but no kp_weak output", i);
+      WHMR_CHECK_ARG(!proj->full[i] || (proj->kp_norm[i] && proj->bbox_height && proj->center && proj->orig_shape && proj->Tz),
+                     "whmr_readout_finish_project_multi: call %d is full but lacks kp_norm / bbox inputs", i);
+    }
+    WHMR_CHECK_ARG(ro->n_reduce > 0 || proj->n_points == 0, "whmr_readout_finish_project_multi: table has no finishing pass");
+  }
   if (B == 0 || n_calls == 0 || ro->n_reduce == 0) return WHMR_OK;
   WHMR_CHECK_ARG(joints && ro_workspaces && ro_outs, "whmr_readout_finish_multi: null pointer array");
   ReduceParams q{};
@@ -714,6 +732,7 @@ int whmr_readout_finish_multi(whmr_readout_t ro, int n_calls, const float* const
   q.rows = ro->rows_reduce; q.n_rows = ro->n_reduce; q.part_ptr = ro->part_ptr;
   q.n_partial = ro->n_partial; q.slot_of = ro->slot_of; q.jt_ptr = ro->jt_ptr; q.jt_col = ro->jt_col; q.jt_val = ro->jt_val;
   q.n_multi = n_calls;
+  if (proj) q.pj = *proj;
   for (int i = 0; i < n_calls; ++i) {
     WHMR_CHECK_ARG(ro_workspaces[i] && ro_outs[i] && (joints[i] || !ro->needs_joints), "whmr_readout_finish_multi: null buffer");
     q.joints_m[i] = joints[i];

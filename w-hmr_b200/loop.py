@@ -9,9 +9,9 @@ gets back what they would consume (sampled point features) plus the Regressor re
                 then Regressor.forward                                                     (:604-612)
     global    : 5th SMPL call with the re-estimated global orientation + H36M joints       (:641-651)
 
-`RegressorLoop.step` launches 18 kernels on the deferred schedule (5 x {chain with the rotation glue folded in, fused
-pose-blend + skinning}, 3 sampling, ONE finishing pass for the five read-outs, 4 projections) and 22 on the immediate
-one; `capture()` wraps the step in a CUDA graph so a replay costs one launch from the host.  Every call also produces
+`RegressorLoop.step` launches 14 kernels on the deferred schedule (5 x {chain with the rotation glue folded in, fused
+pose-blend + skinning}, 3 sampling, ONE finishing pass for the five read-outs with the four joint projections folded into
+it) and 22 on the immediate one; `capture()` wraps the step in a CUDA graph so a replay costs one launch from the host.  Every call also produces
 the reference's `pose` / `theta` (rotation_matrix_to_angle_axis, :174,190) and, in eval mode, orthonormalises the
 predicted rotations first (unbiased_gram_schmidt, :129-130) -- inside the chain kernel, no extra launch.
 """
@@ -116,9 +116,9 @@ class RegressorLoop:
         return pf
 
     def _step_deferred(self, feats, params, bbox, J):
-        """Same results, 18 launches instead of 22: the next iteration needs only the markers (written by the SMPL
-        kernel itself) and the camera, so the five finishing passes of the read-outs run as ONE launch after the loop,
-        followed by the four joint projections (models/whmr.py:550-651 returns everything at the end as well)."""
+        """Same results, 14 launches instead of 22: the next iteration needs only the markers (written by the SMPL
+        kernel itself) and the camera, so the five finishing passes of the read-outs AND the four joint projections run
+        as ONE launch after the loop (models/whmr.py:550-651 returns everything at the end as well)."""
         p = params
         states = [self.head.begin(p[0]['rotmat'], p[0]['betas'], J, p[0]['cam'])]             # forward_init
         point_feats = []

@@ -770,17 +770,54 @@ def readout_finish(readout: int, joints: torch.Tensor, flat: torch.Tensor, scrat
         check(_lib.lib().whmr_readout_finish(ro._h, _p(joints), joints.shape[0], _p(scratch), _p(flat), _stream()))
 
 
-def readout_finish_multi(readout, joints, flats, scratches):
+def readout_finish_multi(readout, joints, flats, scratches, proj=None):
     """The deferred finishing passes of several smpl_lbs_readout_deferred calls (same table, same batch) in one launch;
-    writes the regressor rows into each `flat` in place.  (Plain function: inference-side scheduling, no autograd.)"""
+    writes the regressor rows into each `flat` in place.  (Plain function: inference-side scheduling, no autograd.)
+
+    proj: fold the projections of one read-out group (the 49 joints) into the same launch -- dict(group=name, cams=[cam
+    [B,3] or None per call], full=[bool per call], bbox_height, center, orig_shape, Tz, focal, img_w, img_h).  Returns one
+    (kp_2d, kp_2d_w, focal_length, cam_t) tuple per call (kp_2d only / None where not full / no camera)."""
     ro = _READOUTS[readout]
     n = len(flats)
     if n == 0:
-        return
+        return []
     B = joints[0].shape[0]
+    dev = flats[0].device
     arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
-    with torch.cuda.device(flats[0].device):
-        check(_lib.lib().whmr_readout_finish_multi(ro._h, n, arr(joints), arr(scratches), arr(flats), B, _stream()))
+    outs = [None] * n
+    fp = None
+    keep = []
+    if proj is not None:
+        gi = ro.names.index(proj['group'])
+        fp = _lib.FinishProjection()
+        fp.row0, fp.n_points = int(sum(ro.sizes[:gi])), int(ro.sizes[gi])
+        fp.focal, fp.img_w, fp.img_h = float(proj['focal']), float(proj['img_w']), float(proj['img_h'])
+        if any(proj['full']):
+            bb = [_req(proj[k], k) for k in ('bbox_height', 'center', 'orig_shape', 'Tz')]
+            keep += bb
+            fp.bbox_height, fp.center, fp.orig_shape, fp.Tz = [t.data_ptr() for t in bb]
+        N = fp.n_points
+        for i in range(n):
+            cam = proj['cams'][i]
+            if cam is None:
+                continue
+            cam = _req(cam, "cam")
+            keep.append(cam)
+            fp.cam[i] = cam.data_ptr()
+            kp = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+            fp.kp_weak[i] = kp.data_ptr()
+            if proj['full'][i]:
+                kpw = torch.empty(B, N, 2, dtype=torch.float32, device=dev)
+                fl = torch.empty(B, dtype=torch.float32, device=dev)
+                ct = torch.empty(B, 3, dtype=torch.float32, device=dev)
+                fp.full[i], fp.kp_norm[i], fp.focal_out[i], fp.cam_t_out[i] = 1, kpw.data_ptr(), fl.data_ptr(), ct.data_ptr()
+                outs[i] = (kp, kpw, fl, ct)
+            else:
+                outs[i] = (kp, None, None, None)
+    with torch.cuda.device(dev):
+        check(_lib.lib().whmr_readout_finish_project_multi(ro._h, n, arr(joints), arr(scratches), arr(flats), B,
+                                                           None if fp is None else C.byref(fp), _stream()))
+    return outs
 
 
 @torch.library.custom_op("whmr::sample_bilinear", mutates_args=(), device_types="cuda")

@@ -31,6 +31,7 @@ class BodyModelHead(nn.Module):
         self._h36m = None if J_regressor_h36m is None else np.asarray(J_regressor_h36m, dtype=np.float64)
         self._ro = {}
         self.probe = None    # bench.py: callable(name) recording a CUDA event after each enqueued op
+        self.fuse_projection = True   # complete_all: the joint projections ride in the read-out finishing launch
         # optional torch.cuda.Stream: the read-out finishing pass and the joint projections of a call run on it,
         # concurrently with whatever the caller enqueues next on the main stream (the feature sampling only needs
         # the markers, which the skinning kernel itself writes).  The caller joins it (RegressorLoop.step does).
@@ -90,13 +91,15 @@ class BodyModelHead(nn.Module):
         return ro
 
     def _assemble(self, r, verts, rot, pred_rotmat, pred_shape, pred_cam, bbox_height, center, orig_shape, Tz, J_regressor,
-                  scale, pose=None, theta=None):
+                  scale, pose=None, theta=None, projected=None):
         """projections of the 49 joints + the result dict of Regressor.forward / forward_init (models/whmr.py:142-208)"""
         B = rot.shape[0]
         pred_joints = r['joints']
         needs_grad = torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad
                                                      for t in (pred_joints, pred_cam, Tz))
-        if bbox_height is not None and needs_grad:
+        if projected is not None:     # deferred schedule: computed inside the finishing launch (complete_all)
+            kp_2d, kp_w, focal, cam_t = projected
+        elif bbox_height is not None and needs_grad:
             f, w, hgt = constants.FOCAL_LENGTH, float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT)
             st1 = (self.default_train_stage if self.train_stage is None else self.train_stage) == 1
             kp_2d = ops.project_weak_op(pred_joints if st1 else pred_joints.detach(), pred_cam, f, w, hgt)
@@ -153,23 +156,36 @@ class BodyModelHead(nn.Module):
         """states: list from `begin`; cams: pred_cam per state; full[i]: evaluate the predicted-focal block for state i
         (Regressor.forward) or only the weak projection (forward_init); None entries in cams: no projection (the global
         SMPL call, models/whmr.py:641-651).  -> list of result dicts."""
-        pend = [s for s in states if s['scratch'].numel()]
+        use_full = [cams[i] is not None and (bool(full[i]) if full is not None else bbox_height is not None)
+                    for i in range(len(states))]
+        pend = [i for i, s in enumerate(states) if s['scratch'].numel()]
         by_ro = {}
-        for s in pend:
-            by_ro.setdefault(s['ro'].id, []).append(s)
-        for rid, group in by_ro.items():
-            for i in range(0, len(group), 8):
-                g = group[i:i + 8]
-                ops.readout_finish_multi(rid, [s['joints24'] for s in g], [s['flat'] for s in g], [s['scratch'] for s in g])
+        for i in pend:
+            by_ro.setdefault(states[i]['ro'].id, []).append(i)
+        projected = {}
+        for rid, idxs in by_ro.items():
+            for k in range(0, len(idxs), 8):
+                g = idxs[k:k + 8]
+                # the joint projections ride in the finishing launch (models/whmr.py:142-173, 237): no launch of their own
+                proj = None
+                if self.fuse_projection and any(cams[i] is not None for i in g):
+                    proj = dict(group='joints', cams=[cams[i] for i in g], full=[use_full[i] for i in g],
+                                bbox_height=bbox_height, center=center, orig_shape=orig_shape, Tz=Tz,
+                                focal=constants.FOCAL_LENGTH, img_w=float(constants.IMG_RES_WIDTH),
+                                img_h=float(constants.IMG_RES_HEIGHT))
+                res = ops.readout_finish_multi(rid, [states[i]['joints24'] for i in g], [states[i]['flat'] for i in g],
+                                               [states[i]['scratch'] for i in g], proj)
+                for i, r_ in zip(g, res):
+                    if r_ is not None:
+                        projected[i] = r_
         outs = []
         for i, s in enumerate(states):
             if cams[i] is None:
                 outs.append({'verts': s['verts'], 'r': s['r'], 'pose': s['pose'], 'rotmat': s['rot']})
                 continue
-            use_full = bool(full[i]) if full is not None else bbox_height is not None
             outs.append(self._assemble(s['r'], s['verts'], s['rot'], s['pred_rotmat'], s['pred_shape'], cams[i],
-                                       bbox_height if use_full else None, center, orig_shape, Tz, s['J'], scale,
-                                       pose=s['pose'], theta=s['theta']))
+                                       bbox_height if use_full[i] else None, center, orig_shape, Tz, s['J'], scale,
+                                       pose=s['pose'], theta=s['theta'], projected=projected.get(i)))
         return outs
 
     def forward(self, pred_rotmat, pred_shape, pred_cam, bbox_height=None, center=None, orig_shape=None,
