@@ -242,14 +242,18 @@ __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
   const float* partial = q.partial;
   if (q.n_multi > 0) { p.joints = q.joints_m[blockIdx.y]; p.out = q.out_m[blockIdx.y]; partial = q.partial_m[blockIdx.y]; }
   int* slots = reinterpret_cast<int*>(ps + q.n_partial * 3);   // [n_partial] emit slot of every vertex-sourced term
-  {
+  {   // cp.async: every 16-byte copy of a thread is in flight at once (a load -> store loop of 128 threads keeps ~8 KB in
+      // flight and made this ~50 KB staging the longest phase of the kernel: 25 us per 1280-CTA launch under ncu)
     const float4* src = reinterpret_cast<const float4*>(partial + (size_t)b * q.n_partial * 3);
-    float4* dst = reinterpret_cast<float4*>(ps);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ps);
     const int n4 = q.n_partial * 3 / 4;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < n4; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(src + i) : "memory");
     const int4* ssrc = reinterpret_cast<const int4*>(q.slot_of);   // padded to n_partial entries by the host
-    int4* sdst = reinterpret_cast<int4*>(slots);
-    for (int i = threadIdx.x; i < q.n_partial / 4; i += blockDim.x) sdst[i] = ssrc[i];
+    const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(slots);
+    for (int i = threadIdx.x; i < q.n_partial / 4; i += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)i * 16u), "l"(ssrc + i) : "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncthreads();
   for (int i = threadIdx.x; i < q.n_rows; i += blockDim.x) {
