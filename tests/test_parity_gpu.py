@@ -1037,3 +1037,42 @@ def test_loop_projections_folded_into_the_finishing_launch(dev, smpl_model):
     assert _maxabs(a['kp_2d'], ref['kp_2d']) * 128 <= PX_TOL
     assert _maxabs(a['focal_length'], ref['focal_length']) <= 1e-6 * float(ref['focal_length'].abs().max())
     assert _maxabs(a['pred_cam_t'], ref['pred_cam_t']) <= 1e-5
+
+
+def test_fused_sampling_mlp_random_shapes(dev):
+    """Randomised sweep of the fused sampling + reduce_dim kernel and the samplers behind it: tile boundaries (B*N below,
+    at and just above multiples of 128), one-pixel maps and map edges, more tiles than CTAs with a ragged tail, both memory
+    layouts, the [B,256,N] output on and off, against grid_sample + the fp64 MLP oracle."""
+    from oracle.sampling_oracle import grid_sample_points, reduce_dim
+    from whmr_b200.maf_extractor import MAF_Extractor
+    rng = np.random.default_rng(11)
+    gen = torch.Generator().manual_seed(11)
+    ext = MAF_Extractor(mesh_downsampling=None)
+    with torch.no_grad():
+        for p in ext.parameters():
+            p.copy_(torch.randn(p.shape, generator=gen) * (0.5 if p.dim() == 1 else 2.0 / np.sqrt(p.shape[1])))
+    convs = [(c.weight.detach().double(), c.bias.detach().double()) for c in ext.filters]
+    ext = ext.to(dev).eval()
+    cases = [(1, 128, 3, 3), (2, 64, 1, 9), (1, 129, 9, 1), (3, 43, 1, 1), (7, 55, 6, 4), (150, 130, 5, 5), (1, 127, 2, 2)]
+    for _ in range(9):
+        cases.append((int(rng.integers(1, 9)), int(rng.integers(1, 200)), int(rng.integers(1, 20)), int(rng.integers(1, 20))))
+    for ci, (B, N, H, W) in enumerate(cases):
+        feat = torch.randn(B, 256, H, W, generator=gen)
+        pts = (torch.rand(B, N, 2, generator=gen) * 2.6 - 1.3)
+        pts[0, 0] = torch.tensor([1.0, 1.0])
+        ref_p = grid_sample_points(feat.double(), pts.double())
+        ref_m = reduce_dim(ref_p, convs)
+        for lay in ("nchw", "channels_last"):
+            f_in = feat.to(dev)
+            if lay == "channels_last":
+                f_in = f_in.contiguous(memory_format=torch.channels_last)
+            ext.return_point_feat = bool(ci % 2)
+            with torch.no_grad():
+                maf, pf = ext.sampling(pts.to(dev), im_feat=f_in)
+            assert maf.shape == (B, 32 * N), (B, N, H, W, lay)
+            assert _maxabs(maf, ref_m) <= FEAT_RTOL * max(float(ref_m.abs().max()), 1e-3), (B, N, H, W, lay)
+            if pf is not None:
+                assert _maxabs(pf, ref_p) <= FEAT_RTOL * max(float(ref_p.abs().max()), 1e-3), (B, N, H, W, lay)
+            else:
+                assert not ext.return_point_feat
+    ext.return_point_feat = True
