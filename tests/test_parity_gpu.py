@@ -1076,3 +1076,43 @@ def test_fused_sampling_mlp_random_shapes(dev):
             else:
                 assert not ext.return_point_feat
     ext.return_point_feat = True
+
+
+@pytest.mark.parametrize("maxm", ["3", "4"])
+def test_smpl_fused_two_issuers_option(dev, maxm):
+    """WHMR_FUSED_ISSUERS=2 (two pose-blend issuing threads with per-issuer full barriers on the shared operand rings, the
+    skinning issuer loading its own A^T tiles; profiles/r02_notes.md section 4): same vertices, joints and read-outs as the
+    oracle at ragged batch sizes incl. a multi-chunk one.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import whmr_b200.synthetic as syn
+from whmr_b200 import ops
+from whmr_b200.loop import RegressorLoop
+from oracle.smpl_oracle import SMPLOracle, regressor_readouts
+dev = torch.device("cuda:0")
+model = syn.make_smpl_model(seed=0)
+loop = RegressorLoop(model, dev)
+h, _ = loop.smpl._state(dev)
+ro = loop.head._readout(dev, True)
+orc = SMPLOracle(model)
+for B in (1, 37, 300, 4096 + 130):
+    b = syn.make_bodies(B, seed=B)
+    betas, rot = torch.from_numpy(b["betas"]).to(dev), torch.from_numpy(b["rotmat"]).to(dev)
+    v, j, flat = ops.smpl_lbs_readout(h.id, ro.id, betas, rot, True)
+    torch.cuda.synchronize()
+    sel = sorted(set(list(range(min(B, 6))) + list(range(max(0, B - 6), B)) + ([4090, 4095, 4096, 4097] if B > 4100 else [])))
+    ref = orc(b["betas"][sel], b["rotmat"][sel][:, 1:], b["rotmat"][sel][:, :1], pose2rot=False)
+    ev = float((v[sel].cpu() - ref["vertices"]).abs().max())
+    rr = regressor_readouts(model, ref["vertices"])
+    got = ro.split(flat, B)
+    em = float((got["markers"][sel].cpu() - rr["markers"]).abs().max())
+    ek = float((got["kp_3d_h36m"][sel].cpu() - rr["kp_3d_h36m"]).abs().max())
+    assert ev <= 1e-5 and em <= 1e-5 and ek <= 1e-5, (B, ev, em, ek)
+print("two-issuer ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    env = dict(os.environ, WHMR_FUSED_ISSUERS="2", WHMR_FUSED_MAXM=maxm)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "two-issuer ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

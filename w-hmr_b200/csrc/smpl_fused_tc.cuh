@@ -90,7 +90,7 @@ template <int MAXM> struct FuTmem {
   static constexpr int kOffAt = kOffW + (kFuWTmem ? 0 : kFuWBytes);
   static constexpr int kOffStg = kOffAt + kFuAtStages * kFuAtBytes;
   static constexpr int kOffBars = kOffStg + kFuEpiWarps * 192 * 4;
-  static constexpr int kSmem = kOffBars + 256 + 1024;
+  static constexpr int kSmem = kOffBars + 512 + 1024;
   static_assert(kSmem <= 232448, "fused SMPL kernel exceeds the 227 KB shared-memory limit");
 };
 
@@ -172,7 +172,16 @@ __device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
 
 // kDbg: instrumented instantiation (WHMR_FUSED_DEBUG / WHMR_FUSED_DBGMODE); the production instantiation carries
 // none of the probes' predicates or branches (the epilogue is instruction-issue bound).
-template <int MAXM, bool kDbg>
+// kTwo: TWO pose-blend issuing threads (warps 1 and 2).  One thread gets a tcgen05.mma into the pipe every ~64-86 cycles
+// (profiles/r02_notes.md section 1), and a 48/64-body pose-blend MMA keeps the tensor core busy for 24/32: with one
+// issuer the pose blend costs 126 x ~86 cycles per item whatever the item's width.  The K chunks of an item alternate
+// between the two issuers (chunk kc of the n-th item of the CTA belongs to issuer (kc + n) & 1); both accumulate into the
+// same TMEM columns.  The operand rings stay shared and in global order, but every stage has one "full" barrier PER
+// ISSUER: a parity wait is only sound if the waiter sees every phase of its barrier, and an issuer that polled a stage
+// whose previous fill belonged to the other one would pass on a stale phase.  The issuer that does not own chunk 0 waits
+// for `first_issued` (the accumulate = 0 MMAs are in the pipe) before its first MMA; `off_full` takes both commits.  The
+// skinning issuer (warp 3) loads its own A^T tiles, one group ahead, so no warp is added.
+template <int MAXM, bool kDbg, bool kTwo = false>
 __global__ void __launch_bounds__(kFuThreads, 1)
 smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+shapedirs bf16 [NP, 2, KP]
                      const __grid_constant__ CUtensorMap tmapPf,   // pose feature bf16 [bodies, 2, KP], box rows = nbi
@@ -207,7 +216,10 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   uint64_t* off_empty = off_full + 2;              // [2]
   uint64_t* t_full = off_empty + 2;                // [2]
   uint64_t* t_empty = t_full + 2;                  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* a_full2 = t_empty + 2;                 // [4] kTwo: stage filled for issuer 1 (a_full: issuer 0)
+  uint64_t* pf_full2 = a_full2 + kFuMaxAStages;    // [3]
+  uint64_t* first_issued = pf_full2 + kFuMaxPfStages;   // [2] kTwo: chunk 0 of the item on this offset stage is in the pipe
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(first_issued + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work distribution: the (vertex tile, 16-body micro-item) grid is cut into gridDim.x contiguous, equal ranges
@@ -258,7 +270,12 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     for (int s = 0; s < kFuPfStages; ++s) { mbar_init(&pf_full[s], 1); mbar_init(&pf_empty[s], 1); }
     mbar_init(w_full, kFuWTmem ? 4 : 1); mbar_init(w_empty, 1);
     for (int s = 0; s < kFuAtStages; ++s) { mbar_init(&at_full[s], 1); mbar_init(&at_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&off_full[s], 1); mbar_init(&off_empty[s], kFuEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&off_full[s], kTwo ? 2 : 1); mbar_init(&off_empty[s], kFuEpiWarps); }
+    if (kTwo) {
+      for (int s = 0; s < kFuAStages; ++s) mbar_init(&a_full2[s], 1);
+      for (int s = 0; s < kFuPfStages; ++s) mbar_init(&pf_full2[s], 1);
+      for (int s = 0; s < 2; ++s) mbar_init(&first_issued[s], 1);
+    }
     for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kFuEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -291,25 +308,29 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         for (int i = 0; i < kFuAStages && i < 3 * p.kch; ++i) {
           const int kc = i / 3, c = i % 3;
           uint8_t* ast = a_ring + i * kFuABytes;
-          mbar_arrive_expect_tx(&a_full[i], kFuABytes);
-          tma_load_3d(ast, &tmapP, &a_full[i], kc * 64, 0, c * p.VP + it0.vt * kTcM);
-          tma_load_3d(ast + kTcM * 128, &tmapP, &a_full[i], kc * 64, 1, c * p.VP + it0.vt * kTcM);
+          uint64_t* fb = (kTwo && (kc & 1)) ? &a_full2[i] : &a_full[i];   // item 0: chunk kc belongs to issuer kc & 1
+          mbar_arrive_expect_tx(fb, kFuABytes);
+          tma_load_3d(ast, &tmapP, fb, kc * 64, 0, c * p.VP + it0.vt * kTcM);
+          tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * 64, 1, c * p.VP + it0.vt * kTcM);
           ++pre;
         }
       }
       pdl_wait();
+      int item_seq = 0;
       WHMR_FU_FOR_ITEMS {
         const Item it = item_at(m, seg_e[sg]);
         m += it.len;
         const int vt = it.vt, body0 = it.body0;
         const uint32_t pf_bytes = 2u * (uint32_t)it.len * 2048u;
         for (int kc = 0; kc < p.kch; ++kc) {
+          const bool second = kTwo && ((kc + item_seq) & 1);     // the issuer this chunk is filled for
           WHMR_FU_WAIT_R(&pf_empty[ps], pph ^ 1, d_pf);
           uint8_t* pst = pf_ring + ps * kFuPfBytes;
-          mbar_arrive_expect_tx(&pf_full[ps], pf_bytes);
+          uint64_t* pfb = second ? &pf_full2[ps] : &pf_full[ps];
+          mbar_arrive_expect_tx(pfb, pf_bytes);
           for (int u = 0; u < it.len; ++u) {   // 16-row boxes, stacked: same image as one (16*len)-row box
-            tma_load_3d(pst + u * 2048, &tmapPf, &pf_full[ps], kc * 64, 0, body0 + u * 16);
-            tma_load_3d(pst + kFuPfPart + u * 2048, &tmapPf, &pf_full[ps], kc * 64, 1, body0 + u * 16);
+            tma_load_3d(pst + u * 2048, &tmapPf, pfb, kc * 64, 0, body0 + u * 16);
+            tma_load_3d(pst + kFuPfPart + u * 2048, &tmapPf, pfb, kc * 64, 1, body0 + u * 16);
           }
           if (++ps == kFuPfStages) { ps = 0; pph ^= 1; }
           for (int c = 0; c < 3; ++c) {
@@ -318,22 +339,28 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             } else {
               WHMR_FU_WAIT_R(&a_empty[as], aph ^ 1, d_a);
               uint8_t* ast = a_ring + as * kFuABytes;
-              mbar_arrive_expect_tx(&a_full[as], kFuABytes);
-              tma_load_3d(ast, &tmapP, &a_full[as], kc * 64, 0, c * p.VP + vt * kTcM);
-              tma_load_3d(ast + kTcM * 128, &tmapP, &a_full[as], kc * 64, 1, c * p.VP + vt * kTcM);
+              uint64_t* fb = second ? &a_full2[as] : &a_full[as];
+              mbar_arrive_expect_tx(fb, kFuABytes);
+              tma_load_3d(ast, &tmapP, fb, kc * 64, 0, c * p.VP + vt * kTcM);
+              tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * 64, 1, c * p.VP + vt * kTcM);
             }
             if (++as == kFuAStages) { as = 0; aph ^= 1; }
           }
         }
+        ++item_seq;
       }
       if (dbgp) { long long* d = dbgp + blockIdx.x * 16; d[0] = d_pf; d[1] = d_a; d[2] = clock64() - k0; }
     }
-  } else if (warp == 1) {
-    // ============================ pose-blend MMA issuer ========================================
+  } else if (warp == 1 || (kTwo && warp == 2)) {
+    // ============================ pose-blend MMA issuer(s) =====================================
     if (elect_one()) {
-      int as = 0; uint32_t aph = 0;
+      const int me = warp - 1;          // kTwo: issuer 0 / 1
+      uint64_t* const my_a_full = (kTwo && me) ? a_full2 : a_full;
+      uint64_t* const my_pf_full = (kTwo && me) ? pf_full2 : pf_full;
+      int as = 0; uint32_t aph = 0;     // one issuer: ring phase; two: bit s = parity of MY next fill of stage s
       int ps = 0; uint32_t pph = 0;
       int buf = 0; uint32_t bph = 0;
+      int item_seq = 0;
       long long d_off = 0, d_pf = 0, d_a = 0;
       const long long k0 = dbgp ? clock64() : 0;
       WHMR_FU_FOR_ITEMS {
@@ -344,12 +371,34 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         WHMR_FU_WAIT_R(&off_empty[buf], bph ^ 1, d_off);
         tcgen05_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(buf * TM::kOffStage);
+        bool first_seen = !kTwo || ((item_seq & 1) == me);   // I own chunk 0 (or there is only one issuer)
         for (int kc = 0; kc < p.kch; ++kc) {
-          WHMR_FU_WAIT_R(&pf_full[ps], pph, d_pf);
+          const bool mine = !kTwo || (((kc + item_seq) & 1) == me);
+          if (!mine) {                  // the other issuer's chunk: only step over its stages
+            if (++ps == kFuPfStages) ps = 0;
+            for (int c = 0; c < 3; ++c) if (++as == kFuAStages) as = 0;
+            continue;
+          }
+          if (kTwo) {
+            WHMR_FU_WAIT_R(&my_pf_full[ps], (pph >> ps) & 1u, d_pf);
+            pph ^= 1u << ps;
+            if (!first_seen) {          // the accumulate = 0 MMAs of this item (chunk 0) must be in the pipe before mine
+              mbar_wait_backoff(&first_issued[buf], bph, p.backoff);
+              tcgen05_fence_after();
+              first_seen = true;
+            }
+          } else {
+            WHMR_FU_WAIT_R(&pf_full[ps], pph, d_pf);
+          }
           const uint32_t b_hi = smem_u32(pf_ring + ps * kFuPfBytes), b_lo = b_hi + kFuPfPart;
           const int nks = min(4, p.ksteps - kc * 4);
           for (int c = 0; c < 3; ++c) {
-            WHMR_FU_WAIT_R(&a_full[as], aph, d_a);
+            if (kTwo) {
+              WHMR_FU_WAIT_R(&my_a_full[as], (aph >> as) & 1u, d_a);
+              aph ^= 1u << as;
+            } else {
+              WHMR_FU_WAIT_R(&a_full[as], aph, d_a);
+            }
             tcgen05_fence_after();
             const uint32_t a_hi = smem_u32(a_ring + as * kFuABytes), a_lo = a_hi + kTcM * 128;
             const uint32_t d_tmem = d_base + (uint32_t)(c * TM::kNB);
@@ -361,17 +410,22 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
               umma<0, kFuCollector ? 3 : 0>(d_tmem, dA_hi, dB_hi, idesc, 1u);   //  ... and reused, see kFuCollector)
             }
             tcgen05_commit(&a_empty[as]);
-            if (++as == kFuAStages) { as = 0; aph ^= 1; }
+            if (++as == kFuAStages) { as = 0; if (!kTwo) aph ^= 1; }
           }
           tcgen05_commit(&pf_empty[ps]);
-          if (++ps == kFuPfStages) { ps = 0; pph ^= 1; }
+          if (++ps == kFuPfStages) { ps = 0; if (!kTwo) pph ^= 1; }
+          if (kTwo && kc == 0) {        // chunk 0 is in the pipe: the other issuer may follow
+            tcgen05_fence_before();
+            mbar_arrive(&first_issued[buf]);
+          }
         }
         tcgen05_commit(&off_full[buf]);
         if (++buf == TM::kOffStages) { buf = 0; bph ^= 1; }
+        ++item_seq;
       }
-      if (dbgp) { long long* d = dbgp + blockIdx.x * 16; d[3] = d_off; d[4] = d_pf; d[5] = d_a; d[6] = clock64() - k0; }
+      if (dbgp && me == 0) { long long* d = dbgp + blockIdx.x * 16; d[3] = d_off; d[4] = d_pf; d[5] = d_a; d[6] = clock64() - k0; }
     }
-  } else if (warp == 2) {
+  } else if (!kTwo && warp == 2) {
     // ============================ TMA producer: skinning operands ==============================
     if (elect_one()) {
       int s = 0; uint32_t ph = 0, w_par = 1;
@@ -416,6 +470,24 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       int ts = 0;
       long long d_t = 0, d_at = 0;
       const long long k0 = dbgp ? clock64() : 0;
+      // kTwo: this thread is also the TMA producer of its A^T tiles, one 8-body group ahead (the tile of group n+1 goes
+      // into the stage group n-1 used, whose MMAs retired a whole epilogue round trip ago)
+      int nsg = 0, nm = seg_b[0], ng_left = 0, nbody0 = 0, n_load = 0;   // cursor of the NEXT group to load
+      auto load_next = [&]() {
+        while (ng_left == 0) {
+          while (nsg < 2 && nm >= seg_e[nsg]) { ++nsg; if (nsg < 2) nm = seg_b[nsg]; }
+          if (nsg >= 2) return;
+          const Item nit = item_at(nm, seg_e[nsg]);
+          nm += nit.len;
+          ng_left = nit.ng; nbody0 = nit.body0;
+        }
+        const int st = n_load & 1;
+        if (n_load >= 2) mbar_wait_backoff(&at_empty[st], ((uint32_t)(n_load >> 1) - 1u) & 1u, p.backoff);
+        mbar_arrive_expect_tx(&at_full[st], kFuAtBytes);
+        tma_load_2d(at_ring + st * kFuAtBytes, &tmapAt, &at_full[st], 0, nbody0 * 12);
+        nbody0 += kFuGB; --ng_left; ++n_load;
+      };
+      if (kTwo) { pdl_wait(); load_next(); }
       WHMR_FU_FOR_ITEMS {
         const Item it = item_at(m, seg_e[sg]);
         m += it.len;
@@ -423,6 +495,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         if (vt != cur_vt) { mbar_wait_backoff(w_full, w_phase, p.backoff); w_phase ^= 1; cur_vt = vt; }
         const int ng = it.ng;
         for (int g = 0; g < ng; ++g) {
+          if (kTwo) load_next();       // tile of the next group
           WHMR_FU_WAIT_R(&t_empty[ts], t_ph ^ 1, d_t);
           WHMR_FU_WAIT_R(&at_full[s], ph, d_at);
           const uint32_t d_tmem = tmem_base + (uint32_t)(TM::kT + ts * kFuTN);

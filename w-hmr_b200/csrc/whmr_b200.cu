@@ -607,24 +607,33 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   p.backoff = (unsigned)backoff;
   if (dbg_on) { cudaMalloc(&p.dbg, sizeof(long long) * 32 * grid); cudaMemsetAsync(p.dbg, 0, sizeof(long long) * 32 * grid, st); }
   const bool instrumented = dbg_on || dbg_mode != 0;
-#define WHMR_FUSED_LAUNCH(M, D)                                                                                         \
-  launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, D>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st, h->tc.tmapA_bf16, \
+#define WHMR_FUSED_LAUNCH(M, D, T)                                                                                         \
+  launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, D, T>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st, h->tc.tmapA_bf16, \
              tmapPf, h->tc.tmapW16, tmapAt, p)
+  // two pose-blend issuing threads (smpl_fused_tc.cuh, kTwo): the 48- and 64-body plans only
+  static const int issuers_env = getenv("WHMR_FUSED_ISSUERS") ? atoi(getenv("WHMR_FUSED_ISSUERS")) : 1;
+  const bool two = issuers_env == 2 && (maxm == 3 || maxm == 4);
   if (instrumented) {
     // the instrumented instantiations are only ever launched from here (per device)
-    ensure_dyn_smem(smpl_fused_tc_kernel<3, true>, FuTmem<3>::kSmem);
-    ensure_dyn_smem(smpl_fused_tc_kernel<4, true>, FuTmem<4>::kSmem);
-    ensure_dyn_smem(smpl_fused_tc_kernel<6, true>, FuTmem<6>::kSmem);
-    ensure_dyn_smem(smpl_fused_tc_kernel<8, true>, FuTmem<8>::kSmem);
-    if (maxm == 3) WHMR_FUSED_LAUNCH(3, true); else if (maxm == 4) WHMR_FUSED_LAUNCH(4, true);
-    else if (maxm == 6) WHMR_FUSED_LAUNCH(6, true); else WHMR_FUSED_LAUNCH(8, true);
+    ensure_dyn_smem(smpl_fused_tc_kernel<3, true, false>, FuTmem<3>::kSmem);
+    ensure_dyn_smem(smpl_fused_tc_kernel<4, true, false>, FuTmem<4>::kSmem);
+    ensure_dyn_smem(smpl_fused_tc_kernel<6, true, false>, FuTmem<6>::kSmem);
+    ensure_dyn_smem(smpl_fused_tc_kernel<8, true, false>, FuTmem<8>::kSmem);
+    ensure_dyn_smem(smpl_fused_tc_kernel<3, true, true>, FuTmem<3>::kSmem);
+    ensure_dyn_smem(smpl_fused_tc_kernel<4, true, true>, FuTmem<4>::kSmem);
+    if (two) { if (maxm == 3) WHMR_FUSED_LAUNCH(3, true, true); else WHMR_FUSED_LAUNCH(4, true, true); }
+    else if (maxm == 3) WHMR_FUSED_LAUNCH(3, true, false); else if (maxm == 4) WHMR_FUSED_LAUNCH(4, true, false);
+    else if (maxm == 6) WHMR_FUSED_LAUNCH(6, true, false); else WHMR_FUSED_LAUNCH(8, true, false);
+  } else if (two) {
+    if (maxm == 3) { ensure_dyn_smem(smpl_fused_tc_kernel<3, false, true>, FuTmem<3>::kSmem); WHMR_FUSED_LAUNCH(3, false, true); }
+    else { ensure_dyn_smem(smpl_fused_tc_kernel<4, false, true>, FuTmem<4>::kSmem); WHMR_FUSED_LAUNCH(4, false, true); }
   } else {
-    if (maxm == 3) ensure_dyn_smem(smpl_fused_tc_kernel<3, false>, FuTmem<3>::kSmem);
-    else if (maxm == 4) ensure_dyn_smem(smpl_fused_tc_kernel<4, false>, FuTmem<4>::kSmem);
-    else if (maxm == 6) ensure_dyn_smem(smpl_fused_tc_kernel<6, false>, FuTmem<6>::kSmem);
-    else ensure_dyn_smem(smpl_fused_tc_kernel<8, false>, FuTmem<8>::kSmem);
-    if (maxm == 3) WHMR_FUSED_LAUNCH(3, false); else if (maxm == 4) WHMR_FUSED_LAUNCH(4, false);
-    else if (maxm == 6) WHMR_FUSED_LAUNCH(6, false); else WHMR_FUSED_LAUNCH(8, false);
+    if (maxm == 3) ensure_dyn_smem(smpl_fused_tc_kernel<3, false, false>, FuTmem<3>::kSmem);
+    else if (maxm == 4) ensure_dyn_smem(smpl_fused_tc_kernel<4, false, false>, FuTmem<4>::kSmem);
+    else if (maxm == 6) ensure_dyn_smem(smpl_fused_tc_kernel<6, false, false>, FuTmem<6>::kSmem);
+    else ensure_dyn_smem(smpl_fused_tc_kernel<8, false, false>, FuTmem<8>::kSmem);
+    if (maxm == 3) WHMR_FUSED_LAUNCH(3, false, false); else if (maxm == 4) WHMR_FUSED_LAUNCH(4, false, false);
+    else if (maxm == 6) WHMR_FUSED_LAUNCH(6, false, false); else WHMR_FUSED_LAUNCH(8, false, false);
   }
 #undef WHMR_FUSED_LAUNCH
   WHMR_LAUNCHED("smpl_fused_tc_kernel");
