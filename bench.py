@@ -379,10 +379,12 @@ def run_ours(args):
         s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         s_cmp = torch.cuda.current_stream(dev)
 
+        depth = max(2, int(args.e2e_depth))
+
         def make_sets(own_feats):
-            """two independent buffer sets (inputs, captured graph, outputs, pinned result buffers)"""
+            """`depth` independent buffer sets (inputs, captured graph, outputs, pinned result buffers)"""
             sets = []
-            for i in range(2):
+            for i in range(depth):
                 f_i = [torch.empty_like(f) for f in feats] if own_feats else feats
                 p_i = [{k: v.clone() for k, v in q.items()} for q in params]
                 b_i = {k: v.clone() for k, v in bbox.items()}
@@ -397,13 +399,15 @@ def run_ours(args):
 
         def run_pipeline(sets, with_feats, steps):
             """step k: H2D of its inputs (stream 1) -> graph replay (stream 2) -> D2H of its results (stream 3); buffer set
-            k % 2, so the copies of step k+1 run under the kernels of step k and the read-back of step k-1.  The host
-            waits for the results of step k-1 before it enqueues step k+1 (a caller that consumes every result)."""
+            k % depth, so the copies of step k+1 run under the kernels of step k and the read-back of step k-1.  The host
+            waits for the results of step k-(depth-1) before it enqueues step k+1 (a caller that consumes every result,
+            depth-1 steps behind the one it is submitting)."""
             for st in sets:
                 st["ev_cmp"].record(s_cmp)
                 st["ev_out"].record(s_d2h)
+            D = len(sets)
             for k in range(steps):
-                st = sets[k % 2]
+                st = sets[k % D]
                 with torch.cuda.stream(s_h2d):
                     s_h2d.wait_event(st["ev_cmp"])          # the previous replay on this set has consumed its inputs
                     if with_feats:
@@ -424,9 +428,10 @@ def run_ours(args):
                     for kk in out_keys:
                         st["h_out"][kk].copy_(st["outs"][kk], non_blocking=True)
                     st["ev_out"].record(s_d2h)
-                if k >= 1:
-                    sets[(k - 1) % 2]["ev_out"].synchronize()   # the caller reads step k-1's results now
-            sets[(steps - 1) % 2]["ev_out"].synchronize()
+                if k >= D - 1:
+                    sets[(k - (D - 1)) % D]["ev_out"].synchronize()   # the caller reads step k-(D-1)'s results now
+            for j in range(max(0, steps - (D - 1)), steps):
+                sets[j % D]["ev_out"].synchronize()
 
         def time_e2e(sets, with_feats, steps):
             run_pipeline(sets, with_feats, 3)
@@ -457,12 +462,12 @@ def run_ours(args):
         del sets
         torch.cuda.empty_cache()
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_small + h2d_feat,
-               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": ke, "pipeline": "3 streams x 2 buffer sets",
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": ke, "pipeline": "3 streams x %d buffer sets" % depth,
                "h2d_GBs_per_rank": (h2d_small + h2d_feat) / (ms_e2e * 1e-3) / 1e9, "numa": numa,
                "note": "ALL step inputs from pinned host memory, incl. the 3 feature-map levels (in the reference "
                        "these are produced on the device by the backbone and never cross PCIe)"}
         e2e_resident = {"value": world * B / (ms_e2e_res * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_small,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_res, "pipeline": "3 streams x 2 buffer sets",
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_res, "pipeline": "3 streams x %d buffer sets" % depth,
                         "d2h_GBs_per_rank": d2h / (ms_e2e_res * 1e-3) / 1e9,
                         "note": "same, feature maps device-resident as in the reference (backbone output)"}
     sampler.region = "idle"
@@ -1005,6 +1010,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None,
                     help="bodies per CPU pass (default: 64 for the cpu_baseline leg, the full batch for --impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-depth", type=int, default=3, help="buffer sets of the end-to-end pipeline (>= 2)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg")
