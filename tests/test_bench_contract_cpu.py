@@ -1,5 +1,5 @@
 """The reference arm of bench.py runs on the host only (the oracle port on CPU): its JSON line must carry the keys the
-driver's contract names.  (The GPU arm's line is produced on the B200 box; profiles/r01_bench_v*.json are its records.)"""
+driver's contract names.  (The GPU arm's line is produced on the B200 box; profiles/r02_bench_final.json is its latest record.)"""
 import json
 import os
 import subprocess
@@ -21,15 +21,23 @@ def test_reference_arm_json_line():
 
 
 def test_committed_gpu_bench_line_has_the_contract_keys():
-    """the last GPU bench line recorded under profiles/ (written on the B200 box)"""
-    recs = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("r01_bench_v") and f.endswith(".json")
-                  and "reference" not in f and "gpu" not in f and "channels" not in f)
-    assert recs
-    line = json.loads(open(os.path.join(ROOT, "profiles", recs[-1])).read().strip().splitlines()[-1])
+    """the last GPU bench line recorded under profiles/ (written on the B200 box by the default `python bench.py`)"""
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_final.json")).read().strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in line, k
-    assert line["vs_baseline"] is None and line["gpu_launches"] > 0
+    assert line["vs_baseline"] is None and line["gpu_launches"] > 0 and line["warmup"] >= 3
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # round-2 legs: the loop with the extractors' MLP fused into sampling, the training step, the other BASELINE configs
+    rd = line["with_reduce_dim"]
+    assert rd["parity_ref_features_rel"] <= 1e-4
+    assert rd["fused_nchw"]["ms_per_step"] < rd["two_step_nchw"]["ms_per_step"]
+    assert rd["fused_channels_last"]["ms_per_step"] < rd["two_step_channels_last"]["ms_per_step"]
+    assert line["train_step"]["ms_forward_loss_backward"] < line["train_step"]["ms_eager_autograd_same_gpu"]
+    assert max(line["train_step"]["grad_rel_diff_vs_eager"].values()) <= 1e-4
+    assert set(("smpl_sweep_65536", "eval_pass_35515")) <= set(line["other_configs"])
+    assert line["parity"]["verts_m"] <= 1e-5 and line["parity"]["kp2d_px"] <= 1e-3 and line["parity"]["sampled_rel"] <= 1e-4
