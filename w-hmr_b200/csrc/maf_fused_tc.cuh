@@ -230,7 +230,7 @@ maf_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             umma_ta_tf32(d_tmem, a_hi + ks * 8, dB_lo, idesc, 1u);
             umma_ta_tf32(d_tmem, a_hi + ks * 8, dB_hi, idesc, 1u);
           }
-          tcgen05_commit(&w_empty[st]);
+          if ((long long)g + wstages < total_ops) tcgen05_commit(&w_empty[st]);   // only where the refill below will wait for it
           if (g & 1) tcgen05_commit(&mma_done[rd & 1]);
           // weight chunk of op g + stages - 1 into the ring stage op g - 1 used, once that op has retired (the next
           // completion on that barrier is op g + stages - 1 itself: not issued yet, so the parity wait is safe)
@@ -347,8 +347,8 @@ maf_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll 1
         for (int k2 = 0; k2 < nrd; ++k2, ++rd) {
           // round 0 reads what the whole previous layer produced (round rd-1); later rounds only need their stage back
+          if (rd >= 2) WHMR_MAF_WAIT_OP(mma_done, rd - 2);
           if (k2 == 0) WHMR_MAF_WAIT_OP(mma_done, rd - 1);
-          else if (rd >= 2) WHMR_MAF_WAIT_OP(mma_done, rd - 2);
           tcgen05_fence_after();
           const int col = col0 + k2 * 64 + cq * 16;
           uint32_t z[16];
@@ -369,6 +369,7 @@ maf_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
       }
       // ---- output: relu(z + b2) -> mesh_align_feat[b, c*N + n] ----
+      if (rd >= 2) WHMR_MAF_WAIT_OP(mma_done, rd - 2);
       WHMR_MAF_WAIT_OP(mma_done, rd - 1);
       tcgen05_fence_after();
 #pragma unroll 1
