@@ -3,7 +3,8 @@
 //   1. whmr_smpl_forward_host with the identity pose returns v_template + shapedirs . beta   (host double reference);
 //   2. whmr_smpl_forward (device buffers, axis-angle) moves a single-joint-weighted vertex rigidly with the root;
 //   3. whmr_project_weak and whmr_sample_bilinear against straightforward host loops;
-//   4. argument errors come back as status codes with a message, never as exceptions.
+//   4. argument errors come back as status codes with a message, never as exceptions;
+//   5. whmr_maf_mlp_* + whmr_project_sample_reduce (sampling + projection + Conv1d MLP in one launch) against a host loop.
 // Build (tests/test_abi_gpu.py does this):  g++ -std=c++17 -I include -I $CUDA/include abi_smoke.cpp -L w-hmr_b200
 //   -lwhmr_b200 -L $CUDA/lib64 -lcudart -Wl,-rpath,... -o abi_smoke
 #include <cuda_runtime.h>
@@ -132,6 +133,81 @@ int main() {
     }
   printf("projection: %.3g px   sampling: %.3g\n", e3, e4);
   if (!(e3 <= 1e-3) || !(e4 <= 1e-4)) { printf("FAIL projection/sampling\n"); return 1; }
+  // 5. MAF_Extractor.forward as one call: weak projection + sampling + the reduce_dim MLP (3xTF32 tensor-core kernel),
+  //    weights in Conv1d layout, against a host double-precision loop; the [B,256,N] output is optional
+  {
+    const int C0 = 256, C1 = 128, C2 = 64, C3 = 32, Hm = 10, Wm = 6;
+    std::vector<float> fm((size_t)B * C0 * Hm * Wm), w0((size_t)C1 * C0), b0(C1), w1((size_t)C2 * (C1 + C0)), b1(C2),
+        w2((size_t)C3 * (C2 + C0)), b2(C3), maf((size_t)B * C3 * N), pfm((size_t)B * C0 * N);
+    for (auto& x : fm) x = frand();
+    for (auto& x : w0) x = frand() * 0.12f;
+    for (auto& x : w1) x = frand() * 0.10f;
+    for (auto& x : w2) x = frand() * 0.11f;
+    for (auto& x : b0) x = 0.3f * frand();
+    for (auto& x : b1) x = 0.3f * frand();
+    for (auto& x : b2) x = 0.3f * frand();
+    float *d_fm, *d_w0, *d_b0, *d_w1, *d_b1, *d_w2, *d_b2, *d_maf, *d_pfm;
+    CU(cudaMalloc(&d_fm, fm.size() * 4)); CU(cudaMalloc(&d_w0, w0.size() * 4)); CU(cudaMalloc(&d_b0, b0.size() * 4));
+    CU(cudaMalloc(&d_w1, w1.size() * 4)); CU(cudaMalloc(&d_b1, b1.size() * 4)); CU(cudaMalloc(&d_w2, w2.size() * 4));
+    CU(cudaMalloc(&d_b2, b2.size() * 4)); CU(cudaMalloc(&d_maf, maf.size() * 4)); CU(cudaMalloc(&d_pfm, pfm.size() * 4));
+    CU(cudaMemcpy(d_fm, fm.data(), fm.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_w0, w0.data(), w0.size() * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_b0, b0.data(), b0.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_w1, w1.data(), w1.size() * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_b1, b1.data(), b1.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_w2, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_b2, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
+    whmr_maf_mlp_t mlp = nullptr;
+    if (whmr_maf_mlp_create(256, 100, 64, 32, &mlp) == WHMR_OK) { printf("FAIL: unsupported MLP widths accepted\n"); return 1; }
+    CK(whmr_maf_mlp_create(C0, C1, C2, C3, &mlp));
+    if (whmr_sample_reduce(mlp, d_fm, WHMR_LAYOUT_NCHW, B, Hm, Wm, d_kp, 0, N, d_maf, nullptr, nullptr) == WHMR_OK) {
+      printf("FAIL: sample_reduce before set_weights accepted\n"); return 1;
+    }
+    CK(whmr_maf_mlp_set_weights(mlp, d_w0, d_b0, d_w1, d_b1, d_w2, d_b2, nullptr));
+    CK(whmr_project_sample_reduce(mlp, d_fm, WHMR_LAYOUT_NCHW, B, Hm, Wm, d_pts, d_cam, N, 1000.f, 256.f, 256.f, nullptr, d_maf,
+                                  d_pfm, nullptr));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(maf.data(), d_maf, maf.size() * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pfm.data(), d_pfm, pfm.size() * 4, cudaMemcpyDeviceToHost));
+    double e5 = 0, e6 = 0, ymax = 0;
+    std::vector<double> x(C0), y0(C1), y1(C2);
+    for (int b = 0; b < B; ++b)
+      for (int n = 0; n < N; ++n) {
+        const double gx = kp[((size_t)b * N + n) * 2], gy = kp[((size_t)b * N + n) * 2 + 1];   // weak projection checked in 3.
+        const double ix = (gx + 1.0) * 0.5 * (Wm - 1), iy = (gy + 1.0) * 0.5 * (Hm - 1);
+        const int x0 = (int)std::floor(ix), yy0 = (int)std::floor(iy);
+        for (int c = 0; c < C0; ++c) {
+          double acc = 0;
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) {
+              const int xx = x0 + dx, yy = yy0 + dy;
+              if (xx < 0 || xx >= Wm || yy < 0 || yy >= Hm) continue;
+              acc += (dx ? ix - x0 : 1.0 - (ix - x0)) * (dy ? iy - yy0 : 1.0 - (iy - yy0)) * fm[(((size_t)b * C0 + c) * Hm + yy) * Wm + xx];
+            }
+          x[c] = acc;
+          e5 = std::fmax(e5, std::fabs(acc - pfm[((size_t)b * C0 + c) * N + n]));
+        }
+        for (int o = 0; o < C1; ++o) {      // models/maf_extractor.py:75-101
+          double a = b0[o];
+          for (int c = 0; c < C0; ++c) a += (double)w0[(size_t)o * C0 + c] * x[c];
+          y0[o] = a > 0 ? a : 0.01 * a;
+        }
+        for (int o = 0; o < C2; ++o) {
+          double a = b1[o];
+          for (int c = 0; c < C1; ++c) a += (double)w1[(size_t)o * (C1 + C0) + c] * y0[c];
+          for (int c = 0; c < C0; ++c) a += (double)w1[(size_t)o * (C1 + C0) + C1 + c] * x[c];
+          y1[o] = a > 0 ? a : 0.01 * a;
+        }
+        for (int o = 0; o < C3; ++o) {
+          double a = b2[o];
+          for (int c = 0; c < C2; ++c) a += (double)w2[(size_t)o * (C2 + C0) + c] * y1[c];
+          for (int c = 0; c < C0; ++c) a += (double)w2[(size_t)o * (C2 + C0) + C2 + c] * x[c];
+          a = a > 0 ? a : 0.0;
+          ymax = std::fmax(ymax, a);
+          e6 = std::fmax(e6, std::fabs(a - maf[(size_t)b * C3 * N + (size_t)o * N + n]));
+        }
+      }
+    printf("fused sampling + MLP: point features %.3g, mesh_align_feat %.3g (max %.3g)\n", e5, e6, ymax);
+    if (!(e5 <= 1e-4) || !(e6 <= 1e-4 * ymax) || !(ymax > 0.1)) { printf("FAIL fused sampling + MLP\n"); return 1; }
+    CK(whmr_maf_mlp_destroy(mlp));
+  }
   CK(whmr_smpl_destroy(h));
   printf("launches: %llu\nABI SMOKE OK\n", (unsigned long long)whmr_launch_count());
   return 0;
