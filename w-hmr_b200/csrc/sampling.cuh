@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -121,7 +122,7 @@ sample_bilinear_nchw_kernel(const float* __restrict__ feat, const float* __restr
 // of the map is read exactly once -- and gathers the taps from shared memory.  A thread keeps the taps of its point(s)
 // in registers across the CG channels; for a fixed channel consecutive threads write consecutive n (coalesced).
 // Same arithmetic order as the gather kernel: results are bit-identical.
-// grid = (ceil(C / CG), B), block 256, dynamic smem = CG*H*W*4.
+// grid = (ceil(C / CG), B), block 256, dynamic smem = CG*H*W*4 (CG chosen by staged_channels: ~1120*sqrt(H*W) bytes).
 template <bool kProject>
 __global__ void __launch_bounds__(256)
 sample_bilinear_nchw_staged_kernel(const float* __restrict__ feat, const float* __restrict__ points, int pts_bstride,
@@ -134,13 +135,16 @@ sample_bilinear_nchw_staged_kernel(const float* __restrict__ feat, const float* 
   const int HW = H * W;
   const float* src = feat + ((size_t)b * C + c0) * HW;
   const int total = cg * HW;
+  // cp.async: all 16-byte copies of a thread in flight at once (a load -> store loop keeps ~16 KB per CTA in flight)
+  const uint32_t planes_s = (uint32_t)__cvta_generic_to_shared(planes);
   if ((reinterpret_cast<size_t>(src) & 15) == 0 && (total & 3) == 0) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(planes);
-    for (int i = threadIdx.x; i < (total >> 2); i += 256) d4[i] = __ldg(s4 + i);
+    for (int i = threadIdx.x; i < (total >> 2); i += 256)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(planes_s + (uint32_t)i * 16u), "l"(src + 4 * (size_t)i) : "memory");
   } else {
-    for (int i = threadIdx.x; i < total; i += 256) planes[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < total; i += 256)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(planes_s + (uint32_t)i * 4u), "l"(src + i) : "memory");
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   float cs = 0.f, ctx = 0.f, cty = 0.f, ctz = 0.f;
   if (kProject) {   // utils/geometry.py:289-307
@@ -395,15 +399,23 @@ static int staged_channels(int C, int H, int W, int N) {
   static const int mode = getenv("WHMR_SAMPLE_STAGED") ? atoi(getenv("WHMR_SAMPLE_STAGED")) : -1;   // 0 never, 1 whenever it fits
   if (mode == 0) return 0;
   const long long HW = (long long)H * W;
-  if (mode != 1 && 4LL * N < HW) return 0;
-  const int cg = (int)std::min<long long>(C, (64 * 1024) / (HW * 4));
+  // whole planes are cheaper than the gather's two 64-byte DRAM atoms per (point, channel) up to ~8N pixels per plane
+  // (configs[3], 56x56, N = 431: staged 0.648 ms vs gather 0.748 ms once the staging uses cp.async)
+  if (mode != 1 && 8LL * N < HW) return 0;
+  // planes per CTA: small planes want many small CTAs per SM, large planes need >= 4 planes per CTA to amortise the taps.
+  // Measured optimum (configs[3], fraction of the HBM roofline): 14x14 16 KB (0.57; 64 KB: 0.50), 28x28 32 KB (0.83; 64 KB:
+  // 0.77), 56x56 64 KB (0.54; gather 0.47)  =>  ~1120 * sqrt(H*W) bytes.  WHMR_STAGED_KB overrides.
+  static const long long budget_env = getenv("WHMR_STAGED_KB") ? atoll(getenv("WHMR_STAGED_KB")) * 1024 : 0;
+  long long budget = budget_env ? budget_env : (long long)(1120.0 * std::sqrt((double)HW));
+  budget = std::min<long long>(std::max<long long>(budget, 4 * HW * 4), 100 * 1024);
+  const int cg = (int)std::min<long long>(C, budget / (HW * 4));
   return cg >= 4 ? cg : 0;
 }
 
 template <bool kProject>
 static void launch_staged(const float* feat, const float* points, int pts_bstride, float* out, int B, int C, int H, int W,
                           int N, int cg, SampleProj pj, cudaStream_t st) {
-  ensure_dyn_smem(sample_bilinear_nchw_staged_kernel<kProject>, 64 * 1024);   // per device
+  ensure_dyn_smem(sample_bilinear_nchw_staged_kernel<kProject>, 112 * 1024);   // per device
   launch_pdl(kPdlSample, sample_bilinear_nchw_staged_kernel<kProject>, dim3(ceil_div(C, cg), B), dim3(256),
              (size_t)cg * H * W * sizeof(float), st, feat, points, pts_bstride, out, C, H, W, N, cg, pj);
 }
