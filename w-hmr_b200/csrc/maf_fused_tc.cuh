@@ -43,7 +43,6 @@ constexpr int kMafWorkerWarps = 16;
 constexpr int kMafWorkers = kMafWorkerWarps * 32;
 constexpr int kMafThreads = kMafWorkers + 32;    // + 1 control warp
 constexpr int kMafRows = 128;                    // points per tile (UMMA M)
-constexpr int kMafXBytes = kMafRows * 128;       // one 32-channel operand part (hi or lo)
 constexpr int kMafTmemCols = 512;                // accumulators [0, 256) + A-operand stages at 256 + 128 s: {64 hi | 64 lo}
 constexpr int kMafXCol = 256;
 constexpr int kMafXStage = 128;
