@@ -594,14 +594,52 @@ def train_step_leg(model, loop, dev, B=64, reps=30):
     g_ours, g_ref = grads(ours), grads(eager)
     rel = [float((a - r_).abs().max() / r_.abs().max().clamp_min(1e-30)) for a, r_ in zip(g_ours, g_ref)]
     ms_ours, ms_eager = timed(ours), timed(eager)
+
+    def graph_ms(fn):
+        """the same forward + loss + backward captured once as a CUDA graph and replayed: device time without the host's
+        per-op dispatch (both arms are host-bound at B = 64 when launched eagerly)"""
+        try:
+            for t in (rm, be, cam, tz):
+                t.grad = None
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fn()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            for t in (rm, be, cam, tz):
+                t.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.synchronize()
+            return "capture failed: %s" % (str(e).splitlines()[0][:160],)
+
+    ms_ours_graph, ms_eager_graph = graph_ms(ours), graph_ms(eager)
     head.train_stage = stage_before
     for t in (rm, be, cam, tz):
         t.grad = None
     return {"batch": B, "ms_forward_loss_backward": ms_ours, "ms_eager_autograd_same_gpu": ms_eager,
             "speedup_vs_eager": ms_eager / ms_ours,
+            "ms_graph_replay": ms_ours_graph, "ms_eager_autograd_graph_replay": ms_eager_graph,
             "grad_rel_diff_vs_eager": dict(zip(("rotmat", "betas", "cam", "Tz"), rel)),
             "loss": "sum of squares of verts, kp_3d (H36M), kp_2d, kp_2d_w, smpl_kp_3d; train stage 2 detach routing",
-            "note": "eager (host-launched) on both sides; backward kernels are CUDA-core (FFMA) kernels"}
+            "note": "ms_forward_loss_backward / ms_eager_autograd_same_gpu: host-launched (eager) on both sides; "
+                    "ms_graph_replay: the same forward + loss + backward of this repo's ops captured as one CUDA graph "
+                    "(the dense reference path builds tensors on the host inside the step and cannot be captured); backward "
+                    "kernels are CUDA-core (FFMA) kernels"}
 
 
 def reduce_dim_leg(args, model, dev, feats, params, bbox, rank, world, K, W, gemm_mode):
