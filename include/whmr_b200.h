@@ -185,6 +185,9 @@ typedef struct whmr_smpl_glue {
   float* pose_aa_out;     /* [B,J*3] axis-angle of them ('pose'), or NULL */
   float* theta_out;       /* [B, 3+n_betas+J*3] = cat(cam, betas, pose) ('theta'), or NULL */
   const float* cam;       /* [B,3] (theta's head), or NULL (zeros) */
+  const float* root_pose; /* NULL, or the root joint's rotation [B,9] / [B,3] (`global_orient`): `pose` then holds the
+                             other J-1 joints only ([B,J-1,9] / [B,J-1,3], `body_pose`) -- the reference's two SMPL.forward
+                             arguments go in as they are, without the concatenation smplx does (models/whmr.py:132-137) */
 } whmr_smpl_glue;
 /* whmr_smpl_forward_readout + the glue above (glue == NULL: identical to whmr_smpl_forward_readout; ro may be NULL). */
 int whmr_smpl_forward_regressor(whmr_smpl_t h, const float* betas, const float* pose, int pose_is_rotmat,

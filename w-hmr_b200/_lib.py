@@ -46,7 +46,7 @@ def build(force=False, verbose=False):
 
 class SmplGlue(C.Structure):
     _fields_ = [("gram_schmidt", C.c_int32), ("rotmat_out", C.c_void_p), ("pose_aa_out", C.c_void_p),
-                ("theta_out", C.c_void_p), ("cam", C.c_void_p)]
+                ("theta_out", C.c_void_p), ("cam", C.c_void_p), ("root_pose", C.c_void_p)]
 
 
 class FinishProjection(C.Structure):     # whmr_finish_projection

@@ -22,7 +22,8 @@ namespace whmr {
 
 struct ChainParams {
   const float* betas;   // [B,NB]
-  const float* pose;    // [B,J,9] or [B,J,3]
+  const float* pose;    // [B,J,9] or [B,J,3]  (root_pose != null: joints 1..J-1 only, [B,J-1,9] or [B,J-1,3])
+  const float* root_pose;   // [B,9] or [B,3] or null
   const float* transl;  // [B,3] or null
   int pose_is_rotmat;
   int B, J, NB, KP, max_depth;
@@ -87,13 +88,14 @@ __global__ void __launch_bounds__(kChainWarpsPerBlock * 32) smpl_chain_kernel(Ch
 
   // ---- local rotation -------------------------------------------------------------------
   float R[9];
+  const int pstride = p.pose_is_rotmat ? 9 : 3;
+  const float* src = !p.root_pose ? p.pose + ((size_t)b * p.J + j) * pstride
+                     : (j == 0 ? p.root_pose + (size_t)b * pstride : p.pose + ((size_t)b * (p.J - 1) + (j - 1)) * pstride);
   if (p.pose_is_rotmat) {
-    const float* src = p.pose + ((size_t)b * p.J + j) * 9;
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = src[i];
     if (p.gram_schmidt) unbiased_gram_schmidt_dev(R, R);
   } else {
-    const float* src = p.pose + ((size_t)b * p.J + j) * 3;
     rodrigues_smplx(src[0], src[1], src[2], R);
   }
 

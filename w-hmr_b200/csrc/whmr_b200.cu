@@ -407,7 +407,7 @@ static int chain_impl(whmr_smpl_t h, const float* betas, const float* pose, int 
   if (glue) {
     WHMR_CHECK_ARG(!glue->gram_schmidt || pose_is_rotmat, "whmr_smpl_forward_regressor: gram_schmidt needs rotation-matrix input");
     p.gram_schmidt = glue->gram_schmidt; p.rotmat_out = glue->rotmat_out; p.pose_aa_out = glue->pose_aa_out;
-    p.theta_out = glue->theta_out; p.cam = glue->cam;
+    p.theta_out = glue->theta_out; p.cam = glue->cam; p.root_pose = glue->root_pose;
   }
   launch_pdl(kPdlChain, smpl_chain_kernel, dim3(ceil_div(B, kChainWarpsPerBlock)), dim3(kChainWarpsPerBlock * 32), 0, (cudaStream_t)stream, p);
   WHMR_LAUNCHED("smpl_chain_kernel");

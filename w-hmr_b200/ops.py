@@ -120,17 +120,22 @@ class SmplHandle:
         return torch.empty(n, dtype=torch.uint8, device=self.device), n
 
     def forward(self, betas, pose, pose_is_rotmat, transl=None, want_transforms=False, readout=None,
-                defer_finish=False, glue=None):
+                defer_finish=False, glue=None, root_pose=None):
         """-> (verts [B,V,3], chain joints [B,J,3], A [B,J,12] or None[, flat read-out buffer, read-out scratch])
         With defer_finish the finishing pass of the read-outs may be left to the caller (`readout_finish`, any
         stream); it was deferred iff the returned scratch tensor is non-empty.
         glue: dict(gram_schmidt=bool, cam=[B,3] or None) -> Regressor.forward's rotation glue runs inside the chain kernel
-        and three more tensors are appended to the result: rotmat [B,J,3,3] (the rotations used), pose [B,3J], theta."""
+        and three more tensors are appended to the result: rotmat [B,J,3,3] (the rotations used), pose [B,3J], theta.
+        root_pose: the root rotation [B,9|3] (`global_orient`) as its own tensor; `pose` then holds the other J-1 joints
+        (`body_pose`) -- SMPL.forward's two arguments without the concatenation."""
         betas = _req(betas, "betas", align=16)
         pose = _req(pose, "pose", align=16)
+        root_pose = _req(root_pose, "root_pose")
         transl = _req(transl, "transl")
         B = betas.shape[0]
-        exp = self.J * (9 if pose_is_rotmat else 3)
+        exp = (self.J - (0 if root_pose is None else 1)) * (9 if pose_is_rotmat else 3)
+        if root_pose is not None and root_pose.numel() != B * (9 if pose_is_rotmat else 3):
+            raise ValueError("smpl forward: root_pose %s does not match B=%d" % (tuple(root_pose.shape), B))
         if pose.numel() != B * exp or betas.numel() != B * self.NB:
             raise ValueError("smpl forward: betas %s / pose %s do not match B=%d, J=%d, n_betas=%d, rotmat=%s"
                              % (tuple(betas.shape), tuple(pose.shape), B, self.J, self.NB, pose_is_rotmat))
@@ -139,12 +144,14 @@ class SmplHandle:
         A = torch.empty(B, self.J, 12, dtype=torch.float32, device=self.device) if want_transforms else None
         ws, n = self.workspace(B)
         g, extra = None, ()
+        if glue is None and root_pose is not None:
+            g = _lib.SmplGlue(0, None, None, None, None, _p(root_pose))
         if glue is not None:
             cam = _req(glue.get("cam"), "cam")
             rotmat = torch.empty(B, self.J, 3, 3, dtype=torch.float32, device=self.device)
             pose_aa = torch.empty(B, self.J * 3, dtype=torch.float32, device=self.device)
             theta = torch.empty(B, 3 + self.NB + self.J * 3, dtype=torch.float32, device=self.device)
-            g = _lib.SmplGlue(int(bool(glue.get("gram_schmidt"))), _p(rotmat), _p(pose_aa), _p(theta), _p(cam))
+            g = _lib.SmplGlue(int(bool(glue.get("gram_schmidt"))), _p(rotmat), _p(pose_aa), _p(theta), _p(cam), _p(root_pose))
             extra = (rotmat, pose_aa, theta)
         if readout is None and g is None:
             with torch.cuda.device(self.device):

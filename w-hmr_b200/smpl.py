@@ -148,6 +148,17 @@ class SMPL(nn.Module):
             betas = betas.expand(int(B / betas.shape[0]) * betas.shape[0], -1) if betas.shape[0] == 1 \
                 else betas.repeat(int(B / betas.shape[0]), 1)
         J = self.J_regressor.shape[0]
+        h, ro = self._state(betas.device)
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (betas, body_pose, global_orient))
+        if (not needs_grad and not return_full_pose and global_orient.shape[0] == B and body_pose.shape[0] == B
+                and betas.is_cuda):
+            # inference: the two pose arguments go to the kernel as they are (whmr_smpl_glue.root_pose) -- no concatenation
+            verts, joints24, A, flat, _ = h.forward(betas, body_pose, not pose2rot, transl=transl,
+                                                    want_transforms=return_transforms, readout=ro, root_pose=global_orient)
+            r = ro.split(flat, B)
+            return ModelOutput(vertices=verts if return_verts else None, joints=r['joints'], full_pose=None, betas=betas,
+                               global_orient=global_orient, body_pose=body_pose, smpl_joints=r['smpl_joints'],
+                               rel_transforms=A)
         if pose2rot:
             full_pose = torch.cat([global_orient.reshape(-1, 3).expand(B, -1) if global_orient.shape[0] != B
                                    else global_orient.reshape(B, 3),
@@ -155,7 +166,6 @@ class SMPL(nn.Module):
         else:
             full_pose = torch.cat([global_orient.reshape(-1, 1, 3, 3).expand(B, -1, -1, -1),
                                    body_pose.reshape(body_pose.shape[0], J - 1, 3, 3).expand(B, -1, -1, -1)], dim=1)
-        h, ro = self._state(betas.device)
         A = None
         if transl is None and not return_transforms:
             # torch.library op: differentiable w.r.t. betas / rotation matrices (core/trainer.py:380-636 back-propagates
