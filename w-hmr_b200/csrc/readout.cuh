@@ -193,7 +193,9 @@ struct ReduceParams {
   const int* slot_of;                   // [n_vertex_terms] emit slot of each vertex-sourced term, row-major
   const int* jt_ptr;                    // [R+1] range of each row's joint-sourced terms
   const int* jt_col; const float* jt_val;
-  const float* partial; int n_partial;  // [chunk, n_partial, 3], n_partial % 4 == 0
+  const float* partial; int n_partial;  // [chunk, n_partial, 3], n_partial % 4 == 0 (emit SLOTS per body)
+  int n_terms;                          // entries of slot_of (vertex-sourced TERMS, padded to 4): >= the slots when rows
+                                        // repeat (a row equal to an earlier one shares its slots: nothing emitted twice)
   // batched finish (whmr_readout_finish_multi): blockIdx.y selects one of n_multi independent (joints, partial, out)
   // triples of the same table and batch size -- the finishing passes of several SMPL calls in ONE launch
   int n_multi;
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
   const int b = blockIdx.x;
   const float* partial = q.partial;
   if (q.n_multi > 0) { p.joints = q.joints_m[blockIdx.y]; p.out = q.out_m[blockIdx.y]; partial = q.partial_m[blockIdx.y]; }
-  int* slots = reinterpret_cast<int*>(ps + q.n_partial * 3);   // [n_partial] emit slot of every vertex-sourced term
+  int* slots = reinterpret_cast<int*>(ps + q.n_partial * 3);   // [n_terms] emit slot of every vertex-sourced term
   {   // cp.async: every 16-byte copy of a thread is in flight at once (a load -> store loop of 128 threads keeps ~8 KB in
       // flight and made this ~50 KB staging the longest phase of the kernel: 25 us per 1280-CTA launch under ncu)
     const float4* src = reinterpret_cast<const float4*>(partial + (size_t)b * q.n_partial * 3);
@@ -249,9 +251,9 @@ __global__ void __launch_bounds__(128) readout_reduce_kernel(ReduceParams q) {
     const int n4 = q.n_partial * 3 / 4;
     for (int i = threadIdx.x; i < n4; i += blockDim.x)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)i * 16u), "l"(src + i) : "memory");
-    const int4* ssrc = reinterpret_cast<const int4*>(q.slot_of);   // padded to n_partial entries by the host
+    const int4* ssrc = reinterpret_cast<const int4*>(q.slot_of);   // padded to n_terms entries by the host
     const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(slots);
-    for (int i = threadIdx.x; i < q.n_partial / 4; i += blockDim.x)
+    for (int i = threadIdx.x; i < q.n_terms / 4; i += blockDim.x)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)i * 16u), "l"(ssrc + i) : "memory");
     asm volatile("cp.async.wait_all;" ::: "memory");
   }

@@ -130,6 +130,7 @@ struct whmr_readout_s {
   int *slot_of = nullptr, *jt_ptr = nullptr, *jt_col = nullptr;
   float* jt_val = nullptr;
   int n_partial = 0, n_reduce = 0;              // partial buffer [bodies, n_partial, 3] comes from the caller
+  int n_terms = 0;                              // entries of slot_of (>= n_partial when repeated rows share slots)
   bool fusable = false;                         // partial array of one body fits in shared memory
   int dst_VP = 0;
   float* vals = nullptr;
@@ -468,8 +469,8 @@ static int launch_readout_reduce(whmr_readout_t r, const float* verts, const flo
   p.R = r->R; p.V = r->V; p.J = r->J; p.B = nb; p.B_total = B_total; p.b0 = b0;
   p.verts = verts; p.joints = joints; p.out = out;
   q.rows = r->rows_reduce; q.n_rows = r->n_reduce; q.part_ptr = r->part_ptr; q.partial = partial;
-  q.n_partial = r->n_partial; q.slot_of = r->slot_of; q.jt_ptr = r->jt_ptr; q.jt_col = r->jt_col; q.jt_val = r->jt_val;
-  const size_t smem = (size_t)r->n_partial * 4 * sizeof(float);   // partials [n_partial,3] + slot list [n_partial]
+  q.n_partial = r->n_partial; q.n_terms = r->n_terms; q.slot_of = r->slot_of; q.jt_ptr = r->jt_ptr; q.jt_col = r->jt_col; q.jt_val = r->jt_val;
+  const size_t smem = ((size_t)r->n_partial * 3 + r->n_terms) * sizeof(float);   // partials [n_partial,3] + slot list [n_terms]
   if (smem > 48 * 1024) WHMR_CUDA(ensure_dyn_smem(readout_reduce_kernel, (int)smem));   // the launching device may not be the creating one
   launch_pdl(kPdlReadout, readout_reduce_kernel, dim3(nb), dim3(128), smem, st, q);
   WHMR_LAUNCHED("readout_reduce_kernel");
@@ -739,7 +740,7 @@ int whmr_readout_finish_project_multi(whmr_readout_t ro, int n_calls, const floa
   p.grp_prefix = ro->grp_prefix; p.grp_rows = ro->grp_rows;
   p.R = ro->R; p.V = ro->V; p.J = ro->J; p.B = B; p.B_total = B; p.b0 = 0;
   q.rows = ro->rows_reduce; q.n_rows = ro->n_reduce; q.part_ptr = ro->part_ptr;
-  q.n_partial = ro->n_partial; q.slot_of = ro->slot_of; q.jt_ptr = ro->jt_ptr; q.jt_col = ro->jt_col; q.jt_val = ro->jt_val;
+  q.n_partial = ro->n_partial; q.n_terms = ro->n_terms; q.slot_of = ro->slot_of; q.jt_ptr = ro->jt_ptr; q.jt_col = ro->jt_col; q.jt_val = ro->jt_val;
   q.n_multi = n_calls;
   if (proj) q.pj = *proj;
   for (int i = 0; i < n_calls; ++i) {
@@ -748,7 +749,7 @@ int whmr_readout_finish_project_multi(whmr_readout_t ro, int n_calls, const floa
     q.partial_m[i] = reinterpret_cast<const float*>(align_up(reinterpret_cast<size_t>(ro_workspaces[i]), 256));
     q.out_m[i] = ro_outs[i];
   }
-  const size_t smem = (size_t)ro->n_partial * 4 * sizeof(float);
+  const size_t smem = ((size_t)ro->n_partial * 3 + ro->n_terms) * sizeof(float);
   if (smem > 48 * 1024) WHMR_CUDA(ensure_dyn_smem(readout_reduce_kernel, (int)smem));
   launch_pdl(kPdlReadout, readout_reduce_kernel, dim3(B, n_calls), dim3(128), smem, (cudaStream_t)stream, q);
   WHMR_LAUNCHED("readout_reduce_kernel");
@@ -969,15 +970,27 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
     part_ptr[r + 1] = part_ptr[r] + nv;
   }
   const int n_terms = part_ptr[n_rows];
-  const int n_partial = (n_terms + 3) / 4 * 4;   // rows of the partial buffer start 16-byte aligned
+  const int n_terms_pad = std::max((n_terms + 3) / 4 * 4, 4);
   const int n_g32 = VP / 32;
+  // A row equal to an earlier regressor row (same columns, same values: e.g. kp_3d_h36m = h36m_j17[H36M_TO_J14],
+  // models/whmr.py:176-180) shares that row's partial slots: the skinning epilogue emits every distinct term once.
+  std::vector<int> alias_of(n_rows, -1);
+  for (int r = 0; r < n_rows; ++r) {
+    if (is_vert_onehot[r] || rp[r + 1] - rp[r] <= kShortRow) continue;
+    for (int r0 = 0; r0 < r; ++r0) {
+      if (is_vert_onehot[r0] || alias_of[r0] >= 0 || rp[r0 + 1] - rp[r0] != rp[r + 1] - rp[r]) continue;
+      bool same = true;
+      for (int k = 0; same && k < rp[r + 1] - rp[r]; ++k) same = ci[rp[r] + k] == ci[rp[r0] + k] && vv[rp[r] + k] == vv[rp[r0] + k];
+      if (same) { alias_of[r] = r0; break; }
+    }
+  }
   std::vector<std::vector<EmitEntry>> grp0(n_g32), grp1(n_g32);   // kind 0 (one-hot) / kind 1 (regressor terms)
   std::vector<std::vector<int>> grp1_term(n_g32);                  // row-major term index of each kind-1 entry
   for (int r = 0; r < n_rows; ++r) {
     if (is_vert_onehot[r]) {
       const int v = ci[rp[r]];
       grp0[v / 32].push_back(EmitEntry{(v % 32), 1.0f, gpre[r], grows[r], r - gpre[r]});
-    } else {
+    } else if (alias_of[r] < 0) {
       int t = part_ptr[r];
       for (int k = rp[r]; k < rp[r + 1]; ++k)
         if (ci[k] < n_verts) {
@@ -988,7 +1001,7 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   }
   // emit order: per group the one-hot entries sorted by destination (neighbouring lanes -> neighbouring output
   // slots), then the regressor terms, which get consecutive slots of the partial buffer
-  std::vector<int> emit_ptr(n_g32 + 1, 0), slot_of(std::max(n_partial, 4), 0);   // padded: staged with 16-byte loads
+  std::vector<int> emit_ptr(n_g32 + 1, 0), slot_of(n_terms_pad, 0);   // padded: staged with 16-byte loads
   std::vector<EmitEntry> emit_entries;
   int next_slot = 0;
   for (int g = 0; g < n_g32; ++g) {
@@ -1004,6 +1017,10 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
     }
     emit_ptr[g + 1] = (int)emit_entries.size();
   }
+  for (int r = 0; r < n_rows; ++r)      // repeated rows read the slots of the row they repeat
+    if (alias_of[r] >= 0)
+      for (int i = 0; i < part_ptr[r + 1] - part_ptr[r]; ++i) slot_of[part_ptr[r] + i] = slot_of[part_ptr[alias_of[r]] + i];
+  const int n_partial = std::max((next_slot + 3) / 4 * 4, 4);   // slots per body; rows of the partial buffer start 16-byte aligned
   // joint-sourced terms per row (handled by the reduce kernel: the skinning kernel only sees vertices)
   std::vector<int> jt_ptr(n_rows + 1, 0), jt_col;
   std::vector<float> jt_val;
@@ -1032,9 +1049,10 @@ int whmr_readout_create(int n_rows, int n_verts, int n_joints, const int32_t* ro
   up(emit_ptr, &h->emit_grp_ptr); up(emit_entries, &h->emit_entries); up(part_ptr, &h->part_ptr);
   up(rows_reduce, &h->rows_reduce); up(slot_of, &h->slot_of); up(jt_ptr, &h->jt_ptr); up(jt_col, &h->jt_col);
   up(jt_val, &h->jt_val);
-  h->n_partial = n_partial; h->n_reduce = (int)rows_reduce.size();
-  h->fusable = (size_t)n_partial * 16 <= 200 * 1024;   // one body's partial array + slot list must fit in shared memory
-  if (h->fusable && n_partial * 16 > 48 * 1024) ensure_dyn_smem(readout_reduce_kernel, n_partial * 16);   // again at launch
+  h->n_partial = n_partial; h->n_terms = n_terms_pad; h->n_reduce = (int)rows_reduce.size();
+  const size_t reduce_smem = ((size_t)n_partial * 3 + n_terms_pad) * 4;
+  h->fusable = reduce_smem <= 200 * 1024;   // one body's partial array + slot list must fit in shared memory
+  if (h->fusable && reduce_smem > 48 * 1024) ensure_dyn_smem(readout_reduce_kernel, (int)reduce_smem);   // again at launch
   if (e != cudaSuccess) {
     delete h;
     return set_error(WHMR_E_CUDA, "whmr_readout_create: device upload failed: %s", cudaGetErrorString(e));
