@@ -101,3 +101,31 @@ def test_joint_map_matches_reference_table():
     assert c.H36M_TO_J14 == (6, 5, 4, 1, 2, 3, 16, 15, 14, 11, 12, 13, 8, 10)
     assert len(c.vertex_joint_selector_ids()) == 21
     assert np.array_equal(np.asarray(c.SMPL_PARENTS)[1:] < np.arange(1, 24), np.ones(23, bool))
+
+
+def test_modules_deepcopy_and_pickle_without_native_handles():
+    """copy.deepcopy (EMA copies) and pickle (spawn-start DataLoader workers build an SMPL per dataset,
+    datasets/base_dataset.py:145) carry the drop-in modules; native handles are left behind and rebuilt lazily."""
+    import copy
+    import pickle
+
+    import numpy as np
+    import torch
+    import whmr_b200.synthetic as syn
+    from whmr_b200.maf_extractor import MAF_Extractor
+    from whmr_b200.regressor import BodyModelHead
+    from whmr_b200.smpl import SMPL
+    model = syn.make_smpl_model(seed=0)
+    smpl = SMPL(model=model)
+    smpl._dev['cuda:9'] = (object(), object())          # stands in for a live (SmplHandle, Readout) pair
+    ext = MAF_Extractor(mesh_downsampling=None)
+    ext._mlp = object()
+    head = BodyModelHead(smpl, model['Dmap0'], model['Dmap1'], model['ssm'], model['J_regressor_h36m'])
+    head._ro[('cuda:9', True)] = object()
+    for clone in (copy.deepcopy, lambda m: pickle.loads(pickle.dumps(m))):
+        s2, e2, h2 = clone(smpl), clone(ext), clone(head)
+        assert s2._dev == {} and e2._mlp is None and h2._ro == {} and h2.smpl._dev == {}
+        assert torch.equal(s2.v_template, smpl.v_template) and torch.equal(s2.joint_map, smpl.joint_map)
+        assert all(torch.equal(a, b) for a, b in zip(e2.state_dict().values(), ext.state_dict().values()))
+        assert np.array_equal(h2._ssm, head._ssm) and h2.fuse_projection == head.fuse_projection
+    assert len(smpl._dev) == 1 and ext._mlp is not None and len(head._ro) == 1     # the originals keep theirs

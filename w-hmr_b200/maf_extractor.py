@@ -53,6 +53,12 @@ class MAF_Extractor(nn.Module):
         self.return_point_feat = True    # False: the fused path skips the [B,C_s,N] output and returns None for it
         self._mlp = None                 # ops.MafMlp, built lazily on the module's device
 
+    def __getstate__(self):
+        """copy.deepcopy / pickle carry the module without the native handle of the fused kernel (rebuilt on first use)."""
+        d = self.__dict__.copy()
+        d['_mlp'] = None
+        return d
+
     def _fused_mlp(self, im_feat, *others):
         """The fused-kernel state, or None when this call must take the sampling op + PyTorch MLP path."""
         if not self.fused or self.num_views != 1 or not ops.MafMlp.supported(self.filter_channels):

@@ -44,6 +44,14 @@ class BodyModelHead(nn.Module):
         self.train_stage = None
         self.default_train_stage = 2
 
+    def __getstate__(self):
+        """copy.deepcopy / pickle: without the native read-out tables, streams and probes (rebuilt / reset on first use)."""
+        d = self.__dict__.copy()
+        d['_ro'] = {}
+        d['probe'] = None
+        d['side_stream'] = None
+        return d
+
     def _mark(self, name):
         if self.probe is not None:
             self.probe(name)

@@ -99,6 +99,13 @@ class SMPL(nn.Module):
         assert self.v_template.shape == (V, 3)
 
     # -- device-side state ---------------------------------------------------------------------
+    def __getstate__(self):
+        """copy.deepcopy / pickle (EMA copies, spawn-start DataLoader workers: datasets/base_dataset.py:145 builds an SMPL
+        per dataset) carry the module, not its native handles: those are rebuilt lazily on first use."""
+        d = self.__dict__.copy()
+        d['_dev'] = {}
+        return d
+
     def _load_from_state_dict(self, *a, **k):
         super()._load_from_state_dict(*a, **k)
         self._dev = {}   # model buffers may have changed: re-arrange lazily
