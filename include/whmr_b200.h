@@ -276,6 +276,11 @@ int whmr_project_crop(const float* points, const float* cam, const float* center
  * MAF_Extractor.sampling): bilinear, zero padding, align_corners=True, points[...,0] <-> W.
  *   feat [B,C,H,W] (NCHW) or [B,H,W,C] (NHWC); points [B,N,2], or [N,2] shared by every body when
  *   points_shared != 0 (the iteration-0 grid of models/whmr.py:338-347,596); out [B,C,N].
+ *   `feat` (here and in whmr_project_sample) is a device pointer OR a pointer into page-locked host memory
+ *   (cudaHostAlloc / cudaHostRegister / tensor.pin_memory(), unified addressing): a host-resident map is read in place,
+ *   so only the sectors its taps touch cross PCIe -- for the sparse regime (67 points on a 128x96 map: 1/11 of the map)
+ *   that is 2.4x faster than cudaMemcpyAsync of the map followed by the device gather (profiles/r02_notes.md 3.10).
+ *   points / cam / out are device pointers.
  * ------------------------------------------------------------------------------------------ */
 int whmr_sample_bilinear(const float* feat, int layout, int B, int C, int H, int W,
                          const float* points, int points_shared, int N, float* out, void* stream);

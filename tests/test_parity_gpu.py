@@ -566,6 +566,65 @@ def test_project_sample_channels_last_matches_nchw(dev):
     assert _maxabs(a_feat, ref) <= FEAT_RTOL * float(ref.abs().max())
 
 
+def test_sampling_from_pinned_host_maps_in_place(dev, smpl_model):
+    """A feature map in page-locked HOST memory is read in place by the sampling kernels (unified addressing; only the taps'
+    sectors cross PCIe): same bits as the device-resident map, for the plain sampler, the projection + sampling launch, the
+    drop-in MAF_Extractor and a whole loop pass (eager and as a CUDA graph) with the finest level host-resident.  A pageable
+    CPU tensor is still refused: there is no CPU path."""
+    from whmr_b200 import _lib, constants, ops
+    from whmr_b200.loop import RegressorLoop, make_loop_inputs
+    from whmr_b200.maf_extractor import MAF_Extractor
+    import whmr_b200.synthetic as syn
+    g = torch.Generator().manual_seed(31)
+    for (B, C, H, W, N) in ((3, 70, 24, 20, 67), (2, 64, 14, 14, 431), (2, 33, 128, 96, 67)):
+        feat = torch.randn(B, C, H, W, generator=g)
+        hfeat = feat.pin_memory()
+        assert ops.is_host_map(hfeat) and not ops.is_host_map(feat)
+        pts = (torch.rand(B, N, 2, generator=g) * 2.2 - 1.1).to(dev)
+        assert torch.equal(ops.sample_bilinear(hfeat, pts), ops.sample_bilinear(feat.to(dev), pts))
+        nhwc = feat.permute(0, 2, 3, 1).contiguous()
+        assert torch.equal(ops.sample_bilinear(nhwc.pin_memory(), pts, ops.LAYOUT_NHWC),
+                           ops.sample_bilinear(nhwc.to(dev), pts, ops.LAYOUT_NHWC))
+        hcl = nhwc.pin_memory().permute(0, 3, 1, 2)      # [B,C,H,W] view in channels_last strides of pinned memory
+        assert ops.is_host_map(hcl) and not hcl.is_contiguous()
+        assert torch.equal(ops.sample_bilinear(hcl, pts), ops.sample_bilinear(nhwc.to(dev), pts, ops.LAYOUT_NHWC))
+        p3 = (torch.randn(B, N, 3, generator=g) * 0.35).to(dev)
+        cam = torch.from_numpy(syn.make_bodies(B, seed=9)['cam']).to(dev)
+        a = ops.project_sample(hfeat, p3, cam, constants.FOCAL_LENGTH, 256., 256.)
+        b = ops.project_sample(feat.to(dev), p3, cam, constants.FOCAL_LENGTH, 256., 256.)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[0].device == p3.device
+        with pytest.raises(_lib.WhmrError):
+            ops.sample_bilinear(feat, pts)
+    # drop-in extractor (sampling op + the module's PyTorch MLP) on a host-resident map
+    ext = MAF_Extractor(mesh_downsampling=None).to(dev).eval()
+    feat = torch.randn(2, 256, 32, 24, generator=g)
+    p3 = (torch.randn(2, 67, 3, generator=g) * 0.35).to(dev)
+    cam = torch.from_numpy(syn.make_bodies(2, seed=3)['cam']).to(dev)
+    ext.fused = False
+    with torch.no_grad():
+        ext.im_feat, ext.cam = feat.pin_memory(), cam
+        y_h, pf_h = ext(p3, None, None, None, None)
+        ext.im_feat = feat.to(dev)
+        y_d, pf_d = ext(p3, None, None, None, None)
+    assert torch.equal(pf_h, pf_d) and torch.equal(y_h, y_d)
+    # loop pass with the finest level left on the host
+    B = 6
+    loop = RegressorLoop(smpl_model, dev)
+    feats, params, bbox = make_loop_inputs(B, dev, seed=8)
+    ref = loop.step(feats, params, bbox)
+    ref = {k: [t.clone() for t in v] if isinstance(v, list) else v.clone() for k, v in ref.items() if k in ('verts', 'point_feats', 'kp_2d_w')}
+    hf = [feats[0], feats[1], feats[2].cpu().pin_memory()]
+    got = loop.step(hf, params, bbox)
+    assert torch.equal(got['verts'], ref['verts']) and torch.equal(got['kp_2d_w'], ref['kp_2d_w'])
+    assert all(torch.equal(a, b) for a, b in zip(got['point_feats'], ref['point_feats']))
+    gr, outs = loop.capture(hf, params, bbox)
+    for t in outs['point_feats']:
+        t.zero_()
+    gr.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(outs['point_feats'], ref['point_feats']))
+
+
 def test_maf_project_matches_reference_golden(dev, golden):
     from whmr_b200.maf_extractor import MAF_Extractor
     g = golden

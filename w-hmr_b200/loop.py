@@ -108,6 +108,11 @@ class RegressorLoop:
                     return ext.sampling(self.grid, im_feat=feats[0])[0]                      # :596-597
                 ext.im_feat, ext.cam = feats[it], cam                                        # :564,593
                 return ext(markers, None, None, None, None)[0]                               # :606
+        if ops.is_host_map(feats[it]):   # pinned host map: gathered in place over PCIe (ops.is_host_map)
+            if it == 0:
+                return ops.sample_bilinear(feats[0], self.grid, self.layout)
+            return ops.project_sample(feats[it], markers.detach(), cam.detach(), constants.FOCAL_LENGTH,
+                                      float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT), self.layout)[0]
         if it == 0:
             return ops.sample_bilinear_op(feats[0], self.grid, self.layout)                  # :596-597
         pf, _ = ops.project_sample_op(feats[it], markers, cam, constants.FOCAL_LENGTH,       # :606

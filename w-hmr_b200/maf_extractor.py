@@ -94,7 +94,10 @@ class MAF_Extractor(nn.Module):
         mlp = self._fused_mlp(im_feat, points)
         if mlp is not None:
             return mlp.sample(im_feat, points, self.layout, self.return_point_feat)
-        point_feat = ops.sample_bilinear_op(im_feat, points, self.layout)
+        if ops.is_host_map(im_feat):     # pinned host map: taps gathered in place over PCIe (no gradient to the map)
+            point_feat = ops.sample_bilinear(im_feat, points.detach(), self.layout)
+        else:
+            point_feat = ops.sample_bilinear_op(im_feat, points, self.layout)
         return self.reduce_dim(point_feat), point_feat
 
     def forward(self, p, center, scale, img_focal, img_center, s_feat=None, cam=None, **kwargs):
@@ -106,9 +109,13 @@ class MAF_Extractor(nn.Module):
         if mlp is not None:
             return mlp.project_sample(im_feat, p, cam, constants.FOCAL_LENGTH, float(constants.IMG_RES_WIDTH),
                                       float(constants.IMG_RES_HEIGHT), self.layout, self.return_point_feat)[:2]
-        point_feat, _ = ops.project_sample_op(im_feat, p, cam, constants.FOCAL_LENGTH,
-                                           float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT),
-                                           self.layout)
+        if ops.is_host_map(im_feat):     # the reference detaches p and cam here (models/whmr.py:586-591)
+            point_feat, _ = ops.project_sample(im_feat, p.detach(), cam.detach(), constants.FOCAL_LENGTH,
+                                               float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT), self.layout)
+        else:
+            point_feat, _ = ops.project_sample_op(im_feat, p, cam, constants.FOCAL_LENGTH,
+                                                  float(constants.IMG_RES_WIDTH), float(constants.IMG_RES_HEIGHT),
+                                                  self.layout)
         return self.reduce_dim(point_feat), point_feat
 
     def project(self, points, pred_cam, center, scale, img_focal, img_center, return_full=False):

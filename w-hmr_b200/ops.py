@@ -467,11 +467,32 @@ def project_crop(points, cam, center, scale, img_focal, img_center, crop_size, i
 # ----------------------------------------------------------------------------------------------
 # sampling
 # ----------------------------------------------------------------------------------------------
+def is_host_map(feat):
+    """True for a feature map in PAGE-LOCKED host memory (`tensor.pin_memory()`): the sampling kernels read such a map in
+    place through unified addressing -- only the sectors the taps touch cross PCIe, never the whole map."""
+    return torch.is_tensor(feat) and feat.device.type == "cpu" and feat.is_pinned()
+
+
 def _feat_layout(feat, layout):
     """-> (tensor whose memory is contiguous in the kernel's layout, layout, B, C, H, W).
     A [B,C,H,W] tensor in torch.channels_last memory format IS an NHWC array in memory: it is
     handed to the NHWC kernel as is (no copy), so a backbone run in channels_last gets the 4x lower
-    sampling traffic for free."""
+    sampling traffic for free.
+    A pinned host tensor (is_host_map) is passed through as it is: it must already be fp32 and contiguous in the layout
+    named (nothing is copied or converted on the host: there is no CPU path)."""
+    if is_host_map(feat):
+        if feat.dtype != torch.float32 or feat.dim() != 4:
+            raise _lib.WhmrError("a host-resident feature map must be a pinned fp32 [B,C,H,W] / [B,H,W,C] tensor")
+        if layout == LAYOUT_NCHW and not feat.is_contiguous() and feat.is_contiguous(memory_format=torch.channels_last):
+            B, Cc, H, W = feat.shape
+            return feat, LAYOUT_NHWC, B, Cc, H, W
+        if not feat.is_contiguous():
+            raise _lib.WhmrError("a host-resident feature map must be contiguous (or channels_last): nothing is copied on the host")
+        if layout == LAYOUT_NCHW:
+            B, Cc, H, W = feat.shape
+        else:
+            B, H, W, Cc = feat.shape
+        return feat, layout, B, Cc, H, W
     if not torch.is_tensor(feat) or not feat.is_cuda:
         _req(feat, "im_feat")
     if layout == LAYOUT_NCHW:
@@ -485,29 +506,31 @@ def _feat_layout(feat, layout):
 
 
 def sample_bilinear(feat, points, layout=LAYOUT_NCHW):
-    """grid_sample(feat, points[:, :, None, :], align_corners=True)[..., 0]  ->  [B,C,N]"""
+    """grid_sample(feat, points[:, :, None, :], align_corners=True)[..., 0]  ->  [B,C,N]
+    `feat`: CUDA tensor, or a pinned host tensor gathered in place (is_host_map); the result lives on `points.device`."""
     feat, layout, B, Cc, H, W = _feat_layout(feat, layout)
     points = _req(points, "points", align=8)
     shared = points.dim() == 2 or (points.shape[0] == 1 and B != 1)   # one [N,2] grid for every body
     N = points.shape[-2]
     if (not shared and points.shape[0] != B) or points.shape[-1] != 2:
         raise ValueError("points %s do not match feature batch %d" % (tuple(points.shape), B))
-    out = torch.empty(B, Cc, N, dtype=torch.float32, device=feat.device)
-    with torch.cuda.device(feat.device):
+    out = torch.empty(B, Cc, N, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
         check(_lib.lib().whmr_sample_bilinear(_p(feat), int(layout), B, Cc, H, W, _p(points), int(shared), N,
                                               _p(out), _stream()))
     return out
 
 
 def project_sample(feat, p, cam, focal, img_w, img_h, layout=LAYOUT_NCHW):
-    """MAF_Extractor.forward's projection + sampling.  -> (point_feat [B,C,N], points2d [B,N,2])"""
+    """MAF_Extractor.forward's projection + sampling.  -> (point_feat [B,C,N], points2d [B,N,2])
+    `feat`: CUDA tensor, or a pinned host tensor gathered in place (is_host_map); the results live on `p.device`."""
     feat, layout, B, Cc, H, W = _feat_layout(feat, layout)
     p = _req(p, "p")
     cam = _req(cam, "cam")
     N = p.shape[1]
-    pts2d = torch.empty(B, N, 2, dtype=torch.float32, device=feat.device)
-    out = torch.empty(B, Cc, N, dtype=torch.float32, device=feat.device)
-    with torch.cuda.device(feat.device):
+    pts2d = torch.empty(B, N, 2, dtype=torch.float32, device=p.device)
+    out = torch.empty(B, Cc, N, dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
         check(_lib.lib().whmr_project_sample(_p(feat), int(layout), B, Cc, H, W, _p(p), _p(cam), N, float(focal),
                                              float(img_w), float(img_h), _p(pts2d), _p(out), _stream()))
     return out, pts2d
