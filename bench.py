@@ -384,11 +384,19 @@ def run_ours(args):
 
         depth = max(2, int(args.e2e_depth))
 
-        def make_sets(own_feats, host_levels=()):
+        cmp_streams = [s_cmp]
+        cmp_loops = [loop]
+
+        def make_sets(own_feats, host_levels=(), n_cs=1):
             """`depth` independent buffer sets (inputs, captured graph, outputs, pinned result buffers).  Levels in
-            `host_levels` stay in pinned host memory: the sampling kernel gathers their taps in place over PCIe."""
+            `host_levels` stay in pinned host memory: the sampling kernel gathers their taps in place over PCIe.
+            n_cs > 1: consecutive steps replay on n_cs compute streams, each with its own loop object (SMPL handle and
+            workspace), so the PCIe gathers of two steps overlap."""
+            while len(cmp_streams) < n_cs:
+                cmp_streams.append(torch.cuda.Stream(device=dev))
+                cmp_loops.append(RegressorLoop(model, dev, backbone=args.backbone, gemm_mode=gemm_mode))
             sets = []
-            for i in range(depth):
+            for i in range(depth if n_cs == 1 else max(depth, 2 * n_cs) // n_cs * n_cs):
                 f_i = [torch.empty_like(f) for f in feats] if own_feats else list(feats)
                 p_i = [{k: v.clone() for k, v in q.items()} for q in params]
                 b_i = {k: v.clone() for k, v in bbox.items()}
@@ -397,9 +405,10 @@ def run_ours(args):
                         d_.copy_(s_)
                 for lv in host_levels:
                     f_i[lv] = h_feats[lv]
-                g_i, o_i = loop.capture(f_i, p_i, b_i)
+                g_i, o_i = cmp_loops[i % n_cs].capture(f_i, p_i, b_i)
                 h_o = {k: torch.empty(o_i[k].shape, dtype=o_i[k].dtype, pin_memory=True) for k in out_keys}
                 sets.append({"feats": f_i, "params": p_i, "bbox": b_i, "graph": g_i, "outs": o_i, "h_out": h_o,
+                             "cmp": cmp_streams[i % n_cs],
                              "ev_in": torch.cuda.Event(), "ev_cmp": torch.cuda.Event(), "ev_out": torch.cuda.Event()})
             return sets
 
@@ -409,7 +418,7 @@ def run_ours(args):
             waits for the results of step k-(depth-1) before it enqueues step k+1 (a caller that consumes every result,
             depth-1 steps behind the one it is submitting)."""
             for st in sets:
-                st["ev_cmp"].record(s_cmp)
+                st["ev_cmp"].record(st["cmp"])
                 st["ev_out"].record(s_d2h)
             D = len(sets)
             for k in range(steps):
@@ -426,10 +435,12 @@ def run_ours(args):
                     for kk in st["bbox"]:
                         st["bbox"][kk].copy_(h_bbox[kk], non_blocking=True)
                     st["ev_in"].record(s_h2d)
-                s_cmp.wait_event(st["ev_in"])
-                s_cmp.wait_event(st["ev_out"])              # the previous results of this set have left the device
-                st["graph"].replay()
-                st["ev_cmp"].record(s_cmp)
+                s_c = st["cmp"]
+                s_c.wait_event(st["ev_in"])
+                s_c.wait_event(st["ev_out"])                # the previous results of this set have left the device
+                with torch.cuda.stream(s_c):
+                    st["graph"].replay()
+                st["ev_cmp"].record(s_c)
                 with torch.cuda.stream(s_d2h):
                     s_d2h.wait_event(st["ev_cmp"])
                     for kk in out_keys:
@@ -468,10 +479,12 @@ def run_ours(args):
         # in place (unified addressing), so only the sectors the taps touch cross PCIe instead of the whole map
         host_levels = [int(x) for x in args.e2e_host_levels.split(",") if x.strip() != ""]
         if host_levels:
-            sets = make_sets(True, host_levels)
+            n_cs = max(1, int(args.e2e_compute_streams))
+            sets = make_sets(True, host_levels, n_cs)
             ms_g = time_e2e(sets, True, ke)
-            pf_g = [t.clone() for t in sets[0]["outs"]["point_feats"]]
-            v_g = sets[0]["outs"]["verts"].clone()
+            sets_n = list(range(len(sets)))
+            pf_g = [t.clone() for t in sets[-1]["outs"]["point_feats"]]
+            v_g = sets[-1]["outs"]["verts"].clone()
             del sets
             torch.cuda.empty_cache()
             same = all(torch.equal(a_, b_) for a_, b_ in zip(pf_g, outs["point_feats"])) and torch.equal(v_g, outs["verts"])
@@ -484,7 +497,7 @@ def run_ours(args):
                           "h2d_bytes_per_step": copied + gathered, "h2d_bytes_copied": copied,
                           "h2d_bytes_gathered_in_place": gathered, "host_input_bytes_per_step": h2d_small + h2d_feat,
                           "d2h_bytes_per_step": d2h, "host_resident_levels": host_levels,
-                          "pipeline": "3 streams x %d buffer sets" % depth, "results_identical_to_device_resident_step": True,
+                          "pipeline": "H2D + %d compute + D2H streams x %d buffer sets" % (n_cs, len(sets_n)), "results_identical_to_device_resident_step": True,
                           "note": "ALL step inputs in pinned host memory; levels %s (%s) are NOT copied: the sampling kernel reads "
                                   "their taps in place through unified addressing (gathered bytes = 2 tap rows x one 32-byte "
                                   "sector per point and channel); the other levels and all parameters are cudaMemcpyAsync'd"
@@ -1109,6 +1122,8 @@ def main():
                     help="bodies per CPU pass (default: 64 for the cpu_baseline leg, the full batch for --impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-depth", type=int, default=3, help="buffer sets of the end-to-end pipeline (>= 2)")
+    ap.add_argument("--e2e-compute-streams", type=int, default=1,
+                    help="compute streams (each with its own loop object) of the e2e_host_gather leg")
     ap.add_argument("--e2e-host-levels", default="2",
                     help="feature levels left in pinned host memory and gathered in place by the sampling kernel in the "
                          "e2e_host_gather leg (comma separated; empty: leg off)")
