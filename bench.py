@@ -555,6 +555,11 @@ def run_ours(args):
     if not args.skip_other:
         other = other_configs(loop, model, dev, rank, world, peaks)
 
+    # ---- the path's share of the whole regressor loop, old vs new, rank 0, N == 1 ----------------
+    whole = None
+    if rank == 0 and world == 1 and not args.skip_whole_loop:
+        whole = whole_loop_leg(model, args.backbone, dev, B)
+
     # ---- CPU baseline (oracle on host cores), rank 0, N == 1 ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -605,7 +610,7 @@ def run_ours(args):
                        "launch": "one CUDA graph replay per step; schedule: finishing passes of the 5 read-outs + the 4 joint projections after the loop in ONE launch, per-kernel probes taken on the immediate 22-launch schedule",
                        "feature_layout": "channels_last (NHWC memory)" if args.channels_last else "NCHW contiguous (reference layout)",
                        "rotation_glue": "unbiased_gram_schmidt (eval mode) + rotation_matrix_to_angle_axis + theta inside the chain kernel, every SMPL call"},
-            "clocks": clocks, "e2e": e2e, "e2e_copy_all": e2e_copy, "e2e_host_gather": e2e_gather, "e2e_host_gather_channels_last": e2e_gather_cl, "e2e_feat_resident": e2e_resident, "channels_last": cl, "with_reduce_dim": rd, "train_step": train, "other_configs": other,
+            "clocks": clocks, "e2e": e2e, "e2e_copy_all": e2e_copy, "e2e_host_gather": e2e_gather, "e2e_host_gather_channels_last": e2e_gather_cl, "e2e_feat_resident": e2e_resident, "channels_last": cl, "with_reduce_dim": rd, "train_step": train, "whole_loop": whole, "other_configs": other,
             "gpu_launches": int(launches_per_step) * K, "gpu_launches_per_step": int(launches_per_step),
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "torch_gpu_eager": eager, "smpl_at_scale": scale, "parity": parity,
         }
@@ -956,6 +961,139 @@ def torch_gpu_eager_baseline(model, backbone, feats, params, bbox, B, reps=10):
                       "dense matmuls, allow_tf32=%s)" % (B, torch.__version__, torch.backends.cuda.matmul.allow_tf32)}
 
 
+def whole_loop_leg(model, backbone, dev, B, reps=5):
+    """the hot path's share of the WHOLE regressor loop, old vs new.  Around the path stand the
+    reference's unchanged PyTorch modules, random-init, eval mode, eager: the deconv stack that turns the backbone output into
+    the three feature levels (models/whmr.py:459-500, 560-564) and the three Regressor MLP heads (fc1 / fc2 / decpose /
+    decshape / deccam, models/whmr.py:46-55, 117-126).  The path between them -- MAF sampling + reduce_dim, gram-schmidt,
+    SMPL, read-outs, weak + full projection, global SMPL -- runs "old" as the oracle restatement of the reference's dense
+    eager-PyTorch code on this GPU and "new" through this repo's drop-in modules.  Rank 0, N = 1."""
+    import torch
+    import torch.nn as nn
+    import whmr_b200.synthetic as syn
+    from oracle import geometry_oracle as G
+    from oracle.loop_oracle import LoopOracle
+    from oracle.sampling_oracle import grid_sample_points, reduce_dim
+    from whmr_b200.loop import RegressorLoop
+    from whmr_b200.maf_extractor import MAF_Extractor
+    torch.manual_seed(0)
+    vit = backbone == "vitpose"
+    cin, (h0, w0) = (768, (16, 12)) if vit else (2048, (7, 7))
+    blocks = nn.ModuleList()
+    for i in range(3):     # ConvTranspose2d(k=4, s=2, p=1, no bias) + BatchNorm + ReLU, 256 filters each
+        blocks.append(nn.Sequential(nn.ConvTranspose2d(cin if i == 0 else 256, 256, 4, 2, 1, bias=False),
+                                    nn.BatchNorm2d(256), nn.ReLU(inplace=True)))
+    blocks = blocks.to(dev).eval()
+    exts = [MAF_Extractor(mesh_downsampling=None).to(dev).eval() for _ in range(3)]
+    n_grid = 63 if vit else 64
+    heads = nn.ModuleList()
+    for i in range(3):
+        fd = (n_grid if i == 0 else 67) * 32
+        m = nn.ModuleDict({"fc1": nn.Linear(fd + 216 + 13 + 5, 1024), "fc2": nn.Linear(1024, 1024),
+                           "decpose": nn.Linear(1024, 216), "decshape": nn.Linear(1024, 10), "deccam": nn.Linear(1024, 3)})
+        for k in ("decpose", "decshape", "deccam"):
+            nn.init.xavier_uniform_(m[k].weight, gain=0.01)
+        heads.append(m)
+    heads = heads.to(dev).eval()
+    b = syn.make_bodies(B, seed=21)
+    T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    init = {"rotmat": T(b["rotmat"]), "betas": T(b["betas"]), "cam": T(b["cam"])}
+    bbox = {k: T(b[k]) for k in ("bbox_height", "center", "orig_shape", "Tz")}
+    bbox_info = torch.randn(B, 5, device=dev)
+    s_feat = torch.randn(B, cin, h0, w0, device=dev)
+    loop = RegressorLoop(model, dev, backbone=backbone)
+    orc = LoopOracle(model, backbone, device="cuda")
+    convs = [[(c.weight.detach(), c.bias.detach()) for c in e.filters] for e in exts]
+    grid = loop.grid
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def mlp(i, feat, st):
+        m = heads[i]
+        xc = torch.cat([feat, bbox_info, st["rotmat"].reshape(B, -1), st["betas"], st["cam"]], 1)
+        xc = m["fc2"](m["fc1"](xc))
+        return {"rotmat": (m["decpose"](xc) + st["rotmat"].reshape(B, -1)).view(B, 24, 3, 3),
+                "betas": m["decshape"](xc) + st["betas"], "cam": m["deccam"](xc) + st["cam"]}
+
+    def run(new, acc):
+        """one pass; acc[k] += ms of section k (deconv / mlp / hot)"""
+        marks = []
+
+        def mark(k):
+            e = ev(); e.record(); marks.append((k, e))
+        torch.cuda.synchronize()     # sections are attributed cleanly: no backlog of the previous pass in the first one
+        mark(None)
+        feats, x = [], s_feat
+        for blk in blocks:
+            x = blk(x)
+            feats.append(x)
+        mark("deconv")
+        st = dict(init)
+        if new:
+            out = loop.head(st["rotmat"], st["betas"], st["cam"], J_regressor=True)
+        else:
+            out = orc.regressor_outputs(st)
+        for it in range(3):
+            if new:
+                e = exts[it]
+                if it == 0:
+                    feat = e.sampling(grid, im_feat=feats[0])[0]
+                else:
+                    e.im_feat, e.cam = feats[it], st["cam"]
+                    feat = e(out["markers"], None, None, None, None)[0]
+            else:
+                pts = grid.unsqueeze(0).expand(B, -1, -1) if it == 0 else G.projection(out["markers"], st["cam"])
+                feat = reduce_dim(grid_sample_points(feats[it], pts), convs[it])
+            mark("hot")
+            st = mlp(it, feat, st)
+            mark("mlp")
+            if new:
+                out = loop.head(st["rotmat"], st["betas"], st["cam"], bbox["bbox_height"], bbox["center"], bbox["orig_shape"],
+                                bbox["Tz"], J_regressor=True)
+            else:
+                out = orc.regressor_outputs(st, bbox)
+        if new:      # global call (models/whmr.py:628-651): SMPL + H36M joints of [global_rotmat | body rotations]
+            g = loop.head(out["rotmat"], st["betas"], st["cam"], J_regressor=True)
+        else:
+            g = orc.regressor_outputs({"rotmat": out["rotmat"], "betas": st["betas"], "cam": st["cam"]})
+        mark("hot")
+        torch.cuda.synchronize()
+        for (_, a), (k, e) in zip(marks[:-1], marks[1:]):
+            acc[k] = acc.get(k, 0.0) + a.elapsed_time(e)
+        return out, g
+
+    res = {}
+    with torch.no_grad():
+        outs = {}
+        for new in (False, True):
+            for _ in range(2):
+                run(new, {})
+            acc = {}
+            a, z = ev(), ev()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                outs[new] = run(new, acc)
+            z.record()
+            torch.cuda.synchronize()
+            tag = "new" if new else "old"
+            res["ms_whole_loop_" + tag] = a.elapsed_time(z) / reps
+            for k, v in acc.items():
+                res["ms_%s_%s" % (k, tag)] = v / reps
+        err = float((outs[True][0]["verts"] - outs[False][0]["verts"]).abs().max())
+    res["hot_path_share_old"] = res["ms_hot_old"] / res["ms_whole_loop_old"]
+    res["hot_path_share_new"] = res["ms_hot_new"] / res["ms_whole_loop_new"]
+    res["whole_loop_speedup"] = res["ms_whole_loop_old"] / res["ms_whole_loop_new"]
+    res["hot_path_speedup"] = res["ms_hot_old"] / res["ms_hot_new"]
+    res["verts_new_vs_old_m"] = err
+    res["batch"] = B
+    res["note"] = ("eager on both sides (host-launched); deconv stack %d->256->256->256 (ConvTranspose2d k4 s2 + BN + ReLU) from a "
+                   "[B,%d,%d,%d] backbone output and the three Regressor MLP heads are plain PyTorch in both arms; 'hot' = MAF "
+                   "sampling + reduce_dim, gram-schmidt, SMPL, read-outs, projections, global SMPL: 'old' = the oracle restatement "
+                   "of the reference's dense PyTorch code on this GPU, 'new' = this repo's drop-in modules; the ViT / ResNet "
+                   "encoder itself is not included" % (cin, cin, h0, w0))
+    return res
+
+
 def run_extra(args):
     """Non-default workloads = the other BASELINE.json configs (parity-test cases; measured here for the record):
       smpl_sweep   configs[2]: SMPL + H36M joint regression, 1k..64k bodies in total, sharded over the ranks
@@ -1128,6 +1266,7 @@ def main():
                     help="feature levels left in pinned host memory and gathered in place by the sampling kernel in the "
                          "e2e_host_gather leg (comma separated; empty: leg off)")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-whole-loop", action="store_true", help="skip the whole-loop (deconv stack + MLP heads around the path) leg")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg")
     ap.add_argument("--skip-sweep", action="store_true")
