@@ -866,6 +866,60 @@ def other_configs(loop, model, dev, rank, world, peaks):
 
     ev = EvalPass(loop.smpl, model["J_regressor_h36m"])
     res = {}
+    # ---- configs[0]: ONE SMPL forward at B = 64, axis-angle and rotation-matrix input (latency-bound: launch + one pass over
+    #      the posedirs tiles); rank 0, next to the CPU oracle on the host cores
+    if rank == 0:
+        from whmr_b200 import ops
+        b64 = syn.make_bodies(64, seed=11)
+        h, _ = loop.smpl._state(dev)
+        be, aa, rm = (torch.from_numpy(b64[k]).to(dev) for k in ("betas", "pose_aa", "rotmat"))
+        row = {"workload": "configs[0]: one SMPL forward (vertices + 24 joints), batch 64"}
+        for tag, pose, is_rot in (("axis_angle", aa, False), ("rotmat", rm, True)):
+            for _ in range(3):
+                h.forward(be, pose, is_rot)
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(200):
+                h.forward(be, pose, is_rot)
+            b_.record()
+            torch.cuda.synchronize()
+            us = a_.elapsed_time(b_) / 200 * 1e3
+            row[tag] = {"us_per_forward_eager": us, "bodies_per_s": 64 / (us * 1e-6)}
+        if world == 1:
+            from oracle.smpl_oracle import SMPLOracle
+            use_all_host_threads()
+            orc = SMPLOracle(model)
+            import time as _t
+            orc(b64["betas"], b64["pose_aa"][:, 3:], b64["pose_aa"][:, :3])
+            ts = []
+            for _ in range(5):
+                t0 = _t.perf_counter()
+                orc(b64["betas"], b64["pose_aa"][:, 3:], b64["pose_aa"][:, :3])
+                ts.append(_t.perf_counter() - t0)
+            ms_cpu = sorted(ts)[len(ts) // 2] * 1e3
+            row["cpu_oracle_axis_angle"] = {"ms_per_forward": ms_cpu, "bodies_per_s": 64 / (ms_cpu * 1e-3),
+                                            "threads": torch.get_num_threads()}
+        res["smpl_b64"] = row
+    # ---- configs[3]: MAF sampling of the 431 down-sampled vertices, B = 1024 per GPU, 14 / 28 / 56 maps, NCHW (contract) and
+    #      channels_last; fractions of the HBM roofline on algorithmic bytes
+    Bm, Nm, Cm = 1024, 431, 256
+    from whmr_b200 import ops as _ops
+    pts = torch.from_numpy(syn.make_sample_points(Bm, Nm, seed=2, rank=rank)).to(dev)
+    rows = {}
+    for (H, Wd) in ((14, 14), (28, 28), (56, 56)):
+        feat = torch.randn(Bm, Cm, H, Wd, device=dev)
+        alg = Bm * (4 * Cm * (min(4 * Nm, H * Wd) + Nm) + 8 * Nm)
+        ms_n = timed(lambda: _ops.sample_bilinear(feat, pts, _ops.LAYOUT_NCHW), 20)
+        fl = feat.contiguous(memory_format=torch.channels_last)
+        ms_c = timed(lambda: _ops.sample_bilinear(fl, pts, _ops.LAYOUT_NCHW), 20)
+        rows["%dx%d" % (H, Wd)] = {"nchw_ms": ms_n, "nchw_frac": alg / ms_n / 1e6 / peaks["hbm_gbs"],
+                                   "channels_last_ms": ms_c, "channels_last_frac": alg / ms_c / 1e6 / peaks["hbm_gbs"],
+                                   "algorithmic_bytes": alg}
+        del feat, fl
+    torch.cuda.empty_cache()
+    res["maf_sampling_1024x431"] = {"workload": "configs[3]: bilinear sampling of 431 points, 256 channels, %d bodies per GPU" % Bm,
+                                    "levels": rows, "scaling": "weak", "peak_GBs": peaks["hbm_gbs"]}
     total = 65536
     lo, hi = shard_bounds(total, rank, world)
     b = syn.make_bodies(hi - lo, seed=5, rank=rank)
