@@ -54,6 +54,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.stop_flag, self.region = index, period, [], False, "idle"
         self.ok = False
+        self.pcie = {}
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -76,9 +77,24 @@ class ClockSampler(threading.Thread):
                 except Exception:  # noqa: BLE001
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 self.samples.append((self.region, sm, int(r)))
+                if self.region.startswith("pcie:"):     # end-to-end legs: what really crosses the link (20 ms counter windows)
+                    rx = nv.nvmlDeviceGetPcieThroughput(self.h, nv.NVML_PCIE_UTIL_RX_BYTES)   # KB/s, host -> device
+                    tx = nv.nvmlDeviceGetPcieThroughput(self.h, nv.NVML_PCIE_UTIL_TX_BYTES)
+                    self.pcie.setdefault(self.region[5:], []).append((rx, tx))
             except Exception:  # noqa: BLE001
                 pass
             time.sleep(self.period)
+
+    def pcie_summary(self, tag, ms_per_step):
+        """median NVML PCIe counters over the leg `tag` -> measured GB/s and bytes per step (None without samples)"""
+        v = self.pcie.get(tag) or []
+        if len(v) < 3:
+            return None
+        rx = sorted(x[0] for x in v)[len(v) // 2] * 1024.0
+        tx = sorted(x[1] for x in v)[len(v) // 2] * 1024.0
+        return {"rx_GBs": rx / 1e9, "tx_GBs": tx / 1e9, "rx_bytes_per_step": rx * ms_per_step * 1e-3,
+                "tx_bytes_per_step": tx * ms_per_step * 1e-3, "samples": len(v),
+                "source": "nvmlDeviceGetPcieThroughput (median of 20 ms windows during the timed steps, rank 0's GPU)"}
 
     def summary(self):
         if not self.ok:
@@ -451,11 +467,15 @@ def run_ours(args):
             for j in range(max(0, steps - (D - 1)), steps):
                 sets[j % D]["ev_out"].synchronize()
 
-        def time_e2e(sets, with_feats, steps):
+        def time_e2e(sets, with_feats, steps, tag=None, _again=False):
             run_pipeline(sets, with_feats, 3)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
+            if tag:
+                if _again:
+                    sampler.pcie.pop(tag, None)
+                sampler.region = "pcie:" + tag
             t0 = time.perf_counter()
             a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a_.record(s_cmp)
@@ -464,15 +484,18 @@ def run_ours(args):
             b_.record(s_cmp)
             torch.cuda.synchronize()
             wall_ms = (time.perf_counter() - t0) * 1e3
+            sampler.region = "load"
             t = torch.tensor([max(a_.elapsed_time(b_), wall_ms)], device=dev)   # the slower of device and host clocks
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if tag and float(t) < 600.0 and not _again:    # long enough for the 20 ms PCIe counter windows (same on all ranks)
+                return time_e2e(sets, with_feats, int(steps * 700.0 / max(float(t), 1.0)) + 1, tag, True)
             return float(t) / steps
 
         ke = max(4, min(K, args.e2e_steps))
         sets = make_sets(True)
         d2h = sum(v.numel() * 4 for v in sets[0]["h_out"].values())
-        ms_e2e = time_e2e(sets, True, ke)
+        ms_e2e = time_e2e(sets, True, ke, "copy_all")
         del sets
         torch.cuda.empty_cache()
         # the same pass with the sparsely sampled levels left in pinned host memory: the sampling kernel gathers their taps
@@ -481,7 +504,7 @@ def run_ours(args):
         if host_levels:
             n_cs = max(1, int(args.e2e_compute_streams))
             sets = make_sets(True, host_levels, n_cs)
-            ms_g = time_e2e(sets, True, ke)
+            ms_g = time_e2e(sets, True, ke, "host_gather")
             sets_n = list(range(len(sets)))
             pf_g = [t.clone() for t in sets[-1]["outs"]["point_feats"]]
             v_g = sets[-1]["outs"]["verts"].clone()
@@ -512,7 +535,7 @@ def run_ours(args):
                 hb.copy_(f.permute(0, 2, 3, 1))
                 h_feats.append(hb.permute(0, 3, 1, 2))        # [B,C,H,W] view in channels_last strides, still pinned
             sets = make_sets(False, list(range(len(feats))))
-            ms_gc = time_e2e(sets, True, max(ke, min(K, 50)))
+            ms_gc = time_e2e(sets, True, max(ke, min(K, 50)), "host_gather_cl")
             e_cl = max(float((a_ - b_).abs().max() / b_.abs().max()) for a_, b_ in zip(sets[0]["outs"]["point_feats"], outs["point_feats"]))
             del sets
             torch.cuda.empty_cache()
@@ -527,7 +550,7 @@ def run_ours(args):
                                      "C contiguous floats per point (not the reference's NCHW layout: reported beside the "
                                      "headline, not as it)"}
         sets = make_sets(False)
-        ms_e2e_res = time_e2e(sets, False, max(ke, min(K, 200)))
+        ms_e2e_res = time_e2e(sets, False, max(ke, min(K, 200)), "feat_resident")
         del sets
         torch.cuda.empty_cache()
         e2e_copy = {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_small + h2d_feat,
@@ -541,6 +564,10 @@ def run_ours(args):
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_res, "pipeline": "3 streams x %d buffer sets" % depth,
                         "d2h_GBs_per_rank": d2h / (ms_e2e_res * 1e-3) / 1e9,
                         "note": "same, feature maps device-resident as in the reference (backbone output)"}
+        for d_, tag_ in ((e2e_copy, "copy_all"), (e2e_gather, "host_gather"), (e2e_gather_cl, "host_gather_cl"),
+                         (e2e_resident, "feat_resident")):
+            if d_ is not None:
+                d_["pcie_measured"] = sampler.pcie_summary(tag_, d_["ms_per_step"])
     sampler.region = "idle"
 
     # ---- kernel quality at scale: one SMPL forward at 16k bodies (BASELINE configs[2]) -------------
