@@ -575,6 +575,10 @@ def run_ours(args):
     if rank == 0 and not args.skip_sweep:
         scale = smpl_sweep(loop, dev, peaks, [4096, 16384] if not args.quick else [4096])
 
+    modes = None
+    if rank == 0 and not args.skip_sweep and gemm_mode is None:
+        modes = pose_blend_modes_leg(loop, model, dev, feats, params, bbox, B, peaks, reps=min(K, 300))
+
     # ---- BASELINE configs[2] and configs[4] on all ranks: a strong-scaling point and a pass that ends in a collective ----
     other = None
     if not args.skip_other:
@@ -637,7 +641,7 @@ def run_ours(args):
                        "rotation_glue": "unbiased_gram_schmidt (eval mode) + rotation_matrix_to_angle_axis + theta inside the chain kernel, every SMPL call"},
             "clocks": clocks, "e2e": e2e, "e2e_copy_all": e2e_copy, "e2e_host_gather": e2e_gather, "e2e_host_gather_channels_last": e2e_gather_cl, "e2e_feat_resident": e2e_resident, "channels_last": cl, "with_reduce_dim": rd, "train_step": train, "whole_loop": whole, "other_configs": other,
             "gpu_launches": int(launches_per_step) * K, "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "torch_gpu_eager": eager, "smpl_at_scale": scale, "parity": parity,
+            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "torch_gpu_eager": eager, "smpl_at_scale": scale, "pose_blend_modes": modes, "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
@@ -858,6 +862,59 @@ def smpl_sweep(loop, dev, peaks, sizes):
         res[str(Bs)] = {"ms": ms, "bodies_per_s": Bs / (ms * 1e-3), "hbm_GBs_algorithmic": gb,
                         "hbm_frac": gb / peaks["hbm_gbs"], "pose_blend_TFLOPs_algorithmic_if_alone": tf,
                         "tensor_frac_lower_bound": tf / tpeak}
+    return res
+
+
+def pose_blend_modes_leg(loop, model, dev, feats, params, bbox, B, peaks, reps=300):
+    """The two tensor-core arithmetics of the fused SMPL kernel side by side (the north star names TF32 / 3xTF32; bf16x3 is
+    the production default): loop step time at this batch, SMPL alone at 16,384 bodies against that arithmetic's own tensor
+    ceiling (sustained bf16 / 3 for bf16x3, sustained tf32 = bf16 / 2, / 3 for 3xTF32), and the measured vertex error
+    against the fp64 oracle.  Rank 0."""
+    import torch
+    import whmr_b200.synthetic as syn
+    from oracle.smpl_oracle import SMPLOracle
+    from whmr_b200 import ops
+    keep = loop.smpl.gemm_mode
+    orc = SMPLOracle(model, torch.float64)
+    bb = syn.make_bodies(32, seed=77)
+    ref = orc(bb["betas"], bb["rotmat"][:, 1:], bb["rotmat"][:, :1], pose2rot=False)["vertices"]
+    big = syn.make_bodies(16384, seed=5)
+    betas, rot = torch.from_numpy(big["betas"]).to(dev), torch.from_numpy(big["rotmat"]).to(dev)
+    res = {}
+    for name, mode, div in (("bf16x3", ops.GEMM_TC_BF16X3, 3.0), ("3xtf32", ops.GEMM_TC_3XTF32, 6.0)):
+        loop.smpl.set_gemm_mode(mode)
+        h, _ = loop.smpl._state(dev)
+        v = h.forward(torch.from_numpy(bb["betas"]).to(dev), torch.from_numpy(bb["rotmat"]).to(dev), True)[0]
+        err = float((v.double().cpu() - ref).abs().max())
+        g, _o = loop.capture(feats, params, bbox)
+        for _ in range(5):
+            g.replay()
+        torch.cuda.synchronize()
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        z.record()
+        torch.cuda.synchronize()
+        ms_step = a.elapsed_time(z) / reps
+        del g, _o
+        for _ in range(3):
+            h.forward(betas, rot, True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(10):
+            h.forward(betas, rot, True)
+        z.record()
+        torch.cuda.synchronize()
+        ms_big = a.elapsed_time(z) / 10
+        bps = 16384 / (ms_big * 1e-3)
+        tf = bps * 2.0 * KPOSE * 3 * V / 1e12
+        res[name] = {"fused_kernel": bool(h.is_fused()), "ms_per_step": ms_step, "step_bodies_per_s": B / (ms_step * 1e-3),
+                     "smpl_16384_bodies_per_s": bps, "pose_blend_TFLOPs_algorithmic": tf,
+                     "tensor_ceiling_TFLOPs": peaks["bf16_tflops_sustained"] / div,
+                     "tensor_frac": tf / (peaks["bf16_tflops_sustained"] / div), "verts_max_err_vs_fp64_m": err}
+    loop.smpl.set_gemm_mode(keep)
+    loop.smpl._state(dev)
     return res
 
 

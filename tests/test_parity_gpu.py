@@ -149,16 +149,19 @@ def test_smpl_chunked_large_batch_properties(dev, smpl_model, gemm_mode):
     assert ops is not None
 
 
-def test_smpl_fused_chunk_boundary_and_readouts(dev, smpl_model):
-    """The fused kernel runs in 4096-body chunks (the chunk bounds the read-out partial buffer): bodies on either side of
+@pytest.mark.parametrize("gemm_mode", ["bf16x3", "3xtf32"])
+def test_smpl_fused_chunk_boundary_and_readouts(dev, smpl_model, gemm_mode):
+    """(both arithmetics of the fused kernel: bf16 hi/lo and the kind::tf32 instantiation = 3xTF32)
+    The fused kernel runs in 4096-body chunks (the chunk bounds the read-out partial buffer): bodies on either side of
     the boundary, with the full BodyModelHead read-out table, are bitwise independent of their batch position and match
     the oracle; the flat group-major read-out buffer is laid out for the WHOLE batch, not per chunk."""
     from oracle.smpl_oracle import regressor_readouts
     from whmr_b200.regressor import BodyModelHead
     B = 4096 + 53
     b = _bodies(B, seed=13)
-    smpl = _smpl(smpl_model, dev, "bf16x3")
+    smpl = _smpl(smpl_model, dev, gemm_mode)
     head = BodyModelHead(smpl, smpl_model['Dmap0'], smpl_model['Dmap1'], smpl_model['ssm'], smpl_model['J_regressor_h36m'])
+    assert smpl._state(dev)[0].is_fused()
     T = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
     rot, betas, cam = T(b['rotmat']), T(b['betas']), T(b['cam'])
     big = head(rot, betas, cam, J_regressor=True)
@@ -172,6 +175,39 @@ def test_smpl_fused_chunk_boundary_and_readouts(dev, smpl_model):
     assert _maxabs(big['verts'][sel], ref['vertices']) <= VERT_TOL
     assert _maxabs(big['kp_3d'][sel], rr['kp_3d_h36m']) <= VERT_TOL
     assert _maxabs(big['temp_verts'][sel], rr['temp_verts']) <= VERT_TOL
+
+
+def test_smpl_two_kernel_paths_still_match(dev):
+    """WHMR_FUSED=0: pose blend (pose_blend_tc_kernel, bf16x3 and 3xTF32) and skinning (skin_tc_kernel) as two kernels with
+    the pose-offset intermediate in HBM -- the round-1 path the fused kernel replaced; kept as a switch, so kept tested.
+    The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import whmr_b200.synthetic as syn
+from whmr_b200.smpl import SMPL
+from oracle.smpl_oracle import SMPLOracle
+dev = torch.device("cuda:0")
+model = syn.make_smpl_model(seed=0)
+orc = SMPLOracle(model)
+for mode in ("bf16x3", "3xtf32"):
+    smpl = SMPL(model=model, gemm_mode=mode).to(dev)
+    assert not smpl._state(dev)[0].is_fused()
+    for B in (1, 37, 300):
+        b = syn.make_bodies(B, seed=B)
+        out = smpl(betas=torch.from_numpy(b["betas"]).to(dev), body_pose=torch.from_numpy(b["rotmat"][:, 1:]).to(dev),
+                   global_orient=torch.from_numpy(b["rotmat"][:, :1]).to(dev), pose2rot=False)
+        ref = orc(b["betas"], b["rotmat"][:, 1:], b["rotmat"][:, :1], pose2rot=False)
+        ev = float((out.vertices.cpu() - ref["vertices"]).abs().max())
+        ej = float((out.joints.cpu() - ref["joints"]).abs().max())
+        assert ev <= 1e-5 and ej <= 1e-5, (mode, B, ev, ej)
+print("two-kernel ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, WHMR_FUSED="0"), capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "two-kernel ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def test_smpl_transl_and_default_params(dev, smpl_model):

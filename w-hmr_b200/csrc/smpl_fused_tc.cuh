@@ -181,7 +181,7 @@ __device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
 // whose previous fill belonged to the other one would pass on a stale phase.  The issuer that does not own chunk 0 waits
 // for `first_issued` (the accumulate = 0 MMAs are in the pipe) before its first MMA; `off_full` takes both commits.  The
 // skinning issuer (warp 3) loads its own A^T tiles, one group ahead, so no warp is added.
-template <int MAXM, bool kDbg, bool kTwo = false>
+template <int MAXM, bool kDbg, bool kTwo = false, int kKind = 0>
 __global__ void __launch_bounds__(kFuThreads, 1)
 smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+shapedirs bf16 [NP, 2, KP]
                      const __grid_constant__ CUtensorMap tmapPf,   // pose feature bf16 [bodies, 2, KP], box rows = nbi
@@ -189,6 +189,12 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
                      const __grid_constant__ CUtensorMap tmapAt,   // A^T fp16 hi|lo [bodies*12, 64], box rows = 96
                      FusedParams p) {
   using TM = FuTmem<MAXM>;
+  // kKind: arithmetic of the POSE blend -- 0: bf16 hi/lo (kind::f16, 64 K elements per 128-byte chunk, K = 16 per MMA),
+  // 1: tf32 hi/lo = the north star's 3xTF32 (kind::tf32, 32 K elements per chunk, K = 8 per MMA: twice the chunks and MMAs
+  // per item, ~2^-21 instead of ~2^-16 relative error per product).  Stage sizes, rings, barriers, TMEM plan, the transform
+  // blend (fp16 hi/lo) and the epilogue are the same; the operands come from the tf32 copies (tmapP, tmapPf encoded for fp32).
+  constexpr int kChunkElems = kKind == 0 ? 64 : 32;
+  constexpr uint32_t kFmt = kKind == 0 ? 1u /*BF16*/ : 2u /*TF32*/;
   long long* const dbgp = kDbg ? p.dbg : nullptr;
   const int dbg_mode = kDbg ? p.dbg_mode : 0;
   extern __shared__ uint8_t smem_raw[];
@@ -310,8 +316,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           uint8_t* ast = a_ring + i * kFuABytes;
           uint64_t* fb = (kTwo && (kc & 1)) ? &a_full2[i] : &a_full[i];   // item 0: chunk kc belongs to issuer kc & 1
           mbar_arrive_expect_tx(fb, kFuABytes);
-          tma_load_3d(ast, &tmapP, fb, kc * 64, 0, c * p.VP + it0.vt * kTcM);
-          tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * 64, 1, c * p.VP + it0.vt * kTcM);
+          tma_load_3d(ast, &tmapP, fb, kc * kChunkElems, 0, c * p.VP + it0.vt * kTcM);
+          tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * kChunkElems, 1, c * p.VP + it0.vt * kTcM);
           ++pre;
         }
       }
@@ -329,8 +335,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           uint64_t* pfb = second ? &pf_full2[ps] : &pf_full[ps];
           mbar_arrive_expect_tx(pfb, pf_bytes);
           for (int u = 0; u < it.len; ++u) {   // 16-row boxes, stacked: same image as one (16*len)-row box
-            tma_load_3d(pst + u * 2048, &tmapPf, pfb, kc * 64, 0, body0 + u * 16);
-            tma_load_3d(pst + kFuPfPart + u * 2048, &tmapPf, pfb, kc * 64, 1, body0 + u * 16);
+            tma_load_3d(pst + u * 2048, &tmapPf, pfb, kc * kChunkElems, 0, body0 + u * 16);
+            tma_load_3d(pst + kFuPfPart + u * 2048, &tmapPf, pfb, kc * kChunkElems, 1, body0 + u * 16);
           }
           if (++ps == kFuPfStages) { ps = 0; pph ^= 1; }
           for (int c = 0; c < 3; ++c) {
@@ -341,8 +347,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
               uint8_t* ast = a_ring + as * kFuABytes;
               uint64_t* fb = second ? &a_full2[as] : &a_full[as];
               mbar_arrive_expect_tx(fb, kFuABytes);
-              tma_load_3d(ast, &tmapP, fb, kc * 64, 0, c * p.VP + vt * kTcM);
-              tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * 64, 1, c * p.VP + vt * kTcM);
+              tma_load_3d(ast, &tmapP, fb, kc * kChunkElems, 0, c * p.VP + vt * kTcM);
+              tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * kChunkElems, 1, c * p.VP + vt * kTcM);
             }
             if (++as == kFuAStages) { as = 0; aph ^= 1; }
           }
@@ -366,7 +372,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       WHMR_FU_FOR_ITEMS {
         const Item it = item_at(m, seg_e[sg]);
         m += it.len;
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(it.len * 2) << 17) |
+        const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(it.len * 2) << 17) |
                                ((uint32_t)(kTcM >> 4) << 24);   // bf16 x bf16 -> f32, M=128, N=16*len
         WHMR_FU_WAIT_R(&off_empty[buf], bph ^ 1, d_off);
         tcgen05_fence_after();
@@ -405,9 +411,9 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
             for (int ks = 0; ks < nks; ++ks) {
               const uint64_t dA_hi = umma_desc_sw128(a_hi + ks * 32), dA_lo = umma_desc_sw128(a_lo + ks * 32);
               const uint64_t dB_hi = umma_desc_sw128(b_hi + ks * 32), dB_lo = umma_desc_sw128(b_lo + ks * 32);
-              umma<0>(d_tmem, dA_lo, dB_hi, idesc, (kc | ks) != 0);   // small terms first
-              umma<0, kFuCollector ? 1 : 0>(d_tmem, dA_hi, dB_lo, idesc, 1u);   // (collector: hi tile kept ...
-              umma<0, kFuCollector ? 3 : 0>(d_tmem, dA_hi, dB_hi, idesc, 1u);   //  ... and reused, see kFuCollector)
+              umma<kKind>(d_tmem, dA_lo, dB_hi, idesc, (kc | ks) != 0);   // small terms first
+              umma<kKind, kFuCollector ? 1 : 0>(d_tmem, dA_hi, dB_lo, idesc, 1u);   // (collector: hi tile kept ...
+              umma<kKind, kFuCollector ? 3 : 0>(d_tmem, dA_hi, dB_hi, idesc, 1u);   //  ... and reused, see kFuCollector)
             }
             tcgen05_commit(&a_empty[as]);
             if (++as == kFuAStages) { as = 0; if (!kTwo) aph ^= 1; }

@@ -535,8 +535,14 @@ static int launch_skin(whmr_smpl_t h, const SmplWorkspace& ws, const float* beta
 }
 
 // pose blend + skinning of bodies [b0, b0+nb) in one kernel (smpl_fused_tc.cuh); bf16x3 pose blend only
+// (WHMR_GEMM_TC_3XTF32: the kind::tf32 instantiation, KP a multiple of the 32-element tf32 chunk; WHMR_FUSED_TF32=0 keeps
+//  that mode on the two-kernel path)
 static bool fused_applicable(const whmr_smpl_s* h) {
-  return h->d.J <= 32 && h->fused && h->skin_tc && h->gemm_mode == WHMR_GEMM_TC_BF16X3 && h->tc.ready && h->d.KP % 16 == 0;
+  static const bool tf32_ok = !(getenv("WHMR_FUSED_TF32") && atoi(getenv("WHMR_FUSED_TF32")) == 0);
+  if (!(h->d.J <= 32 && h->fused && h->skin_tc && h->tc.ready)) return false;
+  if (h->gemm_mode == WHMR_GEMM_TC_BF16X3) return h->d.KP % 16 == 0;
+  if (h->gemm_mode == WHMR_GEMM_TC_3XTF32) return tf32_ok && h->d.KP % 32 == 0;
+  return false;
 }
 
 static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* transl, int B, int b0, int nb, float* verts,
@@ -556,12 +562,14 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   const int n_vtiles = d.VP / kTcM;
   p.npv = ceil_div(nb, 16);
   p.n_micro = n_vtiles * p.npv;
-  p.ksteps = d.KP * 2 / 32;
+  const int kind = h->gemm_mode == WHMR_GEMM_TC_3XTF32 ? 1 : 0;   // pose-blend operands: bf16 hi|lo or tf32 hi|lo
+  const int elem = kind ? 4 : 2;
+  p.ksteps = d.KP * elem / 32;
   p.kch = ceil_div(p.ksteps, 4);
   p.jsteps = ceil_div(d.J, 16);
   CUtensorMap tmapPf, tmapAt;
-  char* pf_base = static_cast<char*>(ws.pf_split) + (size_t)b0 * 2 * d.KP * 2;
-  int rc = tc_encode(h->tc.encode_fn, &tmapPf, 0, pf_base, d.KP, ws.Bpad - b0, 16);
+  char* pf_base = static_cast<char*>(ws.pf_split) + (size_t)b0 * 2 * d.KP * elem;
+  int rc = tc_encode(h->tc.encode_fn, &tmapPf, kind, pf_base, d.KP, ws.Bpad - b0, 16);
   if (rc) return rc;
   rc = tc_encode_rows64h(h->tc.encode_fn, &tmapAt, static_cast<__half*>(ws.At16) + (size_t)b0 * 12 * 64,
                          (size_t)(ws.Bpad - b0) * 12, kFuTN);
@@ -578,6 +586,7 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   static const int split_env = getenv("WHMR_FUSED_SPLIT") ? atoi(getenv("WHMR_FUSED_SPLIT")) : -1;
   int maxm = p.n_micro <= 8 * h->tc.num_sms ? 3 : 4;
   if (maxm_env == 3 || maxm_env == 4 || maxm_env == 6 || maxm_env == 8) maxm = maxm_env;
+  if (kind == 1 && maxm > 4) maxm = 4;   // the tf32 instantiations exist for the 48- and 64-body plans
   p.split = 0;
   p.pieces = 0;
   // Small batches, optional (WHMR_FUSED_PIECES=-1 automatic, k > 0 forced): at most two items per CTA (see the kernel).
@@ -614,7 +623,17 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   // two pose-blend issuing threads (smpl_fused_tc.cuh, kTwo): the 48- and 64-body plans only
   static const int issuers_env = getenv("WHMR_FUSED_ISSUERS") ? atoi(getenv("WHMR_FUSED_ISSUERS")) : 1;
   const bool two = issuers_env == 2 && (maxm == 3 || maxm == 4);
-  if (instrumented) {
+  if (kind == 1) {   // 3xTF32 pose blend: the 48- and 64-body plans, one issuer, no instrumented build
+    const int m = (maxm == 3) ? 3 : 4;
+#define WHMR_FUSED_LAUNCH_TF32(M)                                                                                          \
+  do {                                                                                                                     \
+    ensure_dyn_smem(smpl_fused_tc_kernel<M, false, false, 1>, FuTmem<M>::kSmem);                                          \
+    launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, false, false, 1>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st,   \
+               h->tc.tmapA_tf32, tmapPf, h->tc.tmapW16, tmapAt, p);                                                       \
+  } while (0)
+    if (m == 3) WHMR_FUSED_LAUNCH_TF32(3); else WHMR_FUSED_LAUNCH_TF32(4);
+#undef WHMR_FUSED_LAUNCH_TF32
+  } else if (instrumented) {
     // the instrumented instantiations are only ever launched from here (per device)
     ensure_dyn_smem(smpl_fused_tc_kernel<3, true, false>, FuTmem<3>::kSmem);
     ensure_dyn_smem(smpl_fused_tc_kernel<4, true, false>, FuTmem<4>::kSmem);
