@@ -625,13 +625,15 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   const bool two = issuers_env == 2 && (maxm == 3 || maxm == 4);
   if (kind == 1) {   // 3xTF32 pose blend: the 48- and 64-body plans, one issuer, no instrumented build
     const int m = (maxm == 3) ? 3 : 4;
-#define WHMR_FUSED_LAUNCH_TF32(M)                                                                                          \
+#define WHMR_FUSED_LAUNCH_TF32(M, T)                                                                                       \
   do {                                                                                                                     \
-    ensure_dyn_smem(smpl_fused_tc_kernel<M, false, false, 1>, FuTmem<M>::kSmem);                                          \
-    launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, false, false, 1>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st,   \
+    ensure_dyn_smem(smpl_fused_tc_kernel<M, false, T, 1>, FuTmem<M>::kSmem);                                              \
+    launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, false, T, 1>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st,       \
                h->tc.tmapA_tf32, tmapPf, h->tc.tmapW16, tmapAt, p);                                                       \
   } while (0)
-    if (m == 3) WHMR_FUSED_LAUNCH_TF32(3); else WHMR_FUSED_LAUNCH_TF32(4);
+    static const int issuers_tf32 = getenv("WHMR_FUSED_ISSUERS_TF32") ? atoi(getenv("WHMR_FUSED_ISSUERS_TF32")) : issuers_env;
+    if (issuers_tf32 == 2) { if (m == 3) WHMR_FUSED_LAUNCH_TF32(3, true); else WHMR_FUSED_LAUNCH_TF32(4, true); }
+    else { if (m == 3) WHMR_FUSED_LAUNCH_TF32(3, false); else WHMR_FUSED_LAUNCH_TF32(4, false); }
 #undef WHMR_FUSED_LAUNCH_TF32
   } else if (instrumented) {
     // the instrumented instantiations are only ever launched from here (per device)
