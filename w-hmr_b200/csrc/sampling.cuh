@@ -407,7 +407,8 @@ static int staged_channels(int C, int H, int W, int N) {
   // 0.77), 56x56 64 KB (0.54; gather 0.47)  =>  ~1120 * sqrt(H*W) bytes.  WHMR_STAGED_KB overrides.
   static const long long budget_env = getenv("WHMR_STAGED_KB") ? atoll(getenv("WHMR_STAGED_KB")) * 1024 : 0;
   long long budget = budget_env ? budget_env : (long long)(1120.0 * std::sqrt((double)HW));
-  budget = std::min<long long>(std::max<long long>(budget, 4 * HW * 4), 100 * 1024);
+  // (cap 56 KB: at 56x56 four planes per CTA measured 0.565 of the roofline, five -- 62.7 KB -- 0.547)
+  budget = std::min<long long>(std::max<long long>(std::min<long long>(budget, 56 * 1024), 4 * HW * 4), 100 * 1024);
   const int cg = (int)std::min<long long>(C, budget / (HW * 4));
   return cg >= 4 ? cg : 0;
 }
