@@ -1398,7 +1398,7 @@ def main():
     ap.add_argument("--e2e-depth", type=int, default=3, help="buffer sets of the end-to-end pipeline (>= 2)")
     ap.add_argument("--e2e-compute-streams", type=int, default=1,
                     help="compute streams (each with its own loop object) of the e2e_host_gather leg")
-    ap.add_argument("--e2e-host-levels", default="2",
+    ap.add_argument("--e2e-host-levels", default="1,2",
                     help="feature levels left in pinned host memory and gathered in place by the sampling kernel in the "
                          "e2e_host_gather leg (comma separated; empty: leg off)")
     ap.add_argument("--skip-e2e", action="store_true")
