@@ -47,6 +47,8 @@ struct TcPlan {
   void* A_bf16 = nullptr;   // [NP,2,KP] bf16 hi|lo
   void* A_tf32 = nullptr;   // [NP,2,KP] fp32 holding tf32-representable hi|lo
   CUtensorMap tmapA_bf16, tmapA_tf32;
+  CUtensorMap tmapA_both[2];   // [kind] hi + lo of a 128-row tile in ONE box (tc_encode_both_parts), valid iff both_ok
+  int both_ok = 0;
   void* encode_fn = nullptr;   // cuTensorMapEncodeTiled
   int num_sms = 148;
   // tensor-core skinning: dense tf32 hi|lo weights [2, VP, 32 joints]
@@ -437,6 +439,21 @@ static inline int tc_encode(void* fn, CUtensorMap* map, int kind, void* base, in
   return WHMR_OK;
 }
 
+// The same [rows, 2, KP] hi|lo operand with the PART as the outermost box dimension: dims {KP, rows, 2}, strides {row, part},
+// box {128 bytes of K, box_rows, 2} -> shared-memory image [part][row][128 B] = the hi tile followed by the lo tile, by ONE copy.
+static inline int tc_encode_both_parts(void* fn, CUtensorMap* map, int kind, void* base, int KP, int rows, int box_rows) {
+  const int elem = kind == 0 ? 2 : 4;
+  cuuint64_t dims[3] = {(cuuint64_t)KP, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)2 * KP * elem, (cuuint64_t)KP * elem};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<PFN_encodeTiled>(fn)(
+      map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box,
+      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? WHMR_OK : WHMR_E_CUDA;    // the caller falls back to the per-part maps
+}
+
 template <typename Arena>
 static inline int tc_plan_create(const SmplDevice& d, const std::vector<float>& posedirs_p /*[KP,NP]*/, Arena& arena,
                                  TcPlan* plan) {
@@ -475,6 +492,8 @@ static inline int tc_plan_create(const SmplDevice& d, const std::vector<float>& 
   if (rc) return rc;
   rc = tc_encode(fn, &plan->tmapA_tf32, 1, dt, d.KP, d.NP, kTcM);
   if (rc) return rc;
+  plan->both_ok = tc_encode_both_parts(fn, &plan->tmapA_both[0], 0, db, d.KP, d.NP, kTcM) == WHMR_OK &&
+                  tc_encode_both_parts(fn, &plan->tmapA_both[1], 1, dt, d.KP, d.NP, kTcM) == WHMR_OK;
   cudaFuncSetAttribute(pose_blend_tc_kernel<0, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<256>::kTotal);
   cudaFuncSetAttribute(pose_blend_tc_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<256>::kTotal);
   cudaFuncSetAttribute(pose_blend_tc_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::kTotal);

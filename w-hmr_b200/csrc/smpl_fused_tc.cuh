@@ -109,6 +109,7 @@ struct FusedParams {
   int n_micro;                // (VP/128) * npv: the unit of work distribution
   int kch, ksteps;            // pose blend: 128-byte K chunks, 32-byte K steps (bf16: 16 elements)
   int jsteps;                 // skinning: ceil(J/16) fp16 K steps
+  int merged;                 // 1: tmapP / tmapPf are the {K chunk, rows, 2 parts} maps: ONE copy brings hi AND lo (and all 64 pose-feature rows)
   unsigned backoff;           // WHMR_FUSED_BACKOFF: ns between mbarrier polls of the single-thread roles
   int dbg_mode;               // WHMR_FUSED_DBGMODE bits (timing experiments only): 1 skip vertex stores, 2 skip read-out emits, 4 skip the transposes
   long long* dbg;             // WHMR_FUSED_DEBUG: [grid][16] per-role wait/total cycles, or null
@@ -316,8 +317,12 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           uint8_t* ast = a_ring + i * kFuABytes;
           uint64_t* fb = (kTwo && (kc & 1)) ? &a_full2[i] : &a_full[i];   // item 0: chunk kc belongs to issuer kc & 1
           mbar_arrive_expect_tx(fb, kFuABytes);
-          tma_load_3d(ast, &tmapP, fb, kc * kChunkElems, 0, c * p.VP + it0.vt * kTcM);
-          tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * kChunkElems, 1, c * p.VP + it0.vt * kTcM);
+          if (p.merged) {
+            tma_load_3d(ast, &tmapP, fb, kc * kChunkElems, c * p.VP + it0.vt * kTcM, 0);
+          } else {
+            tma_load_3d(ast, &tmapP, fb, kc * kChunkElems, 0, c * p.VP + it0.vt * kTcM);
+            tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * kChunkElems, 1, c * p.VP + it0.vt * kTcM);
+          }
           ++pre;
         }
       }
@@ -333,10 +338,15 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           WHMR_FU_WAIT_R(&pf_empty[ps], pph ^ 1, d_pf);
           uint8_t* pst = pf_ring + ps * kFuPfBytes;
           uint64_t* pfb = second ? &pf_full2[ps] : &pf_full[ps];
-          mbar_arrive_expect_tx(pfb, pf_bytes);
-          for (int u = 0; u < it.len; ++u) {   // 16-row boxes, stacked: same image as one (16*len)-row box
-            tma_load_3d(pst + u * 2048, &tmapPf, pfb, kc * kChunkElems, 0, body0 + u * 16);
-            tma_load_3d(pst + kFuPfPart + u * 2048, &tmapPf, pfb, kc * kChunkElems, 1, body0 + u * 16);
+          if (p.merged) {   // one box {K chunk, kFuPfPart / 128 rows, hi + lo}: rows past the item are never multiplied (N = 16 * len)
+            mbar_arrive_expect_tx(pfb, (uint32_t)kFuPfBytes);
+            tma_load_3d(pst, &tmapPf, pfb, kc * kChunkElems, body0, 0);
+          } else {
+            mbar_arrive_expect_tx(pfb, pf_bytes);
+            for (int u = 0; u < it.len; ++u) {   // 16-row boxes, stacked: same image as one (16*len)-row box
+              tma_load_3d(pst + u * 2048, &tmapPf, pfb, kc * kChunkElems, 0, body0 + u * 16);
+              tma_load_3d(pst + kFuPfPart + u * 2048, &tmapPf, pfb, kc * kChunkElems, 1, body0 + u * 16);
+            }
           }
           if (++ps == kFuPfStages) { ps = 0; pph ^= 1; }
           for (int c = 0; c < 3; ++c) {
@@ -347,8 +357,12 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
               uint8_t* ast = a_ring + as * kFuABytes;
               uint64_t* fb = second ? &a_full2[as] : &a_full[as];
               mbar_arrive_expect_tx(fb, kFuABytes);
-              tma_load_3d(ast, &tmapP, fb, kc * kChunkElems, 0, c * p.VP + vt * kTcM);
-              tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * kChunkElems, 1, c * p.VP + vt * kTcM);
+              if (p.merged) {
+                tma_load_3d(ast, &tmapP, fb, kc * kChunkElems, c * p.VP + vt * kTcM, 0);
+              } else {
+                tma_load_3d(ast, &tmapP, fb, kc * kChunkElems, 0, c * p.VP + vt * kTcM);
+                tma_load_3d(ast + kTcM * 128, &tmapP, fb, kc * kChunkElems, 1, c * p.VP + vt * kTcM);
+              }
             }
             if (++as == kFuAStages) { as = 0; aph ^= 1; }
           }

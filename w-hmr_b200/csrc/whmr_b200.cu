@@ -571,6 +571,13 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   char* pf_base = static_cast<char*>(ws.pf_split) + (size_t)b0 * 2 * d.KP * elem;
   int rc = tc_encode(h->tc.encode_fn, &tmapPf, kind, pf_base, d.KP, ws.Bpad - b0, 16);
   if (rc) return rc;
+  // merged copies (WHMR_FUSED_MERGED_TMA=1): hi and lo of an operand tile come with ONE TMA instruction, and the pose feature
+  // of a chunk as one 64-row box instead of 2 x len 16-row boxes: 4 copies per K chunk instead of 6 + 2 * len.  Measured
+  // neutral to -2 % in both arithmetics, with one or two issuers (profiles/r02_notes.md 4.8: the producer thread is not the
+  // limit), so it is off by default.
+  static const int merged_env = getenv("WHMR_FUSED_MERGED_TMA") ? atoi(getenv("WHMR_FUSED_MERGED_TMA")) : 0;
+  CUtensorMap tmapPfBoth;
+  bool merged = merged_env != 0 && h->tc.both_ok;
   rc = tc_encode_rows64h(h->tc.encode_fn, &tmapAt, static_cast<__half*>(ws.At16) + (size_t)b0 * 12 * 64,
                          (size_t)(ws.Bpad - b0) * 12, kFuTN);
   if (rc) return rc;
@@ -610,6 +617,13 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   if (p.split > 0 && (ceil_div(p.npv, p.split) > maxm || n_vtiles * p.split > h->tc.num_sms)) p.split = 0;
   const int grid = p.pieces > 0 ? std::min(h->tc.num_sms, n_vtiles * p.pieces)
                                 : (p.split > 0 ? n_vtiles * p.split : std::min(h->tc.num_sms, p.n_micro));
+  if (merged) {
+    const int pf_rows = std::max(64, 16 * maxm);      // FuTmem<MAXM>::kPfPart / 128
+    merged = tc_encode_both_parts(h->tc.encode_fn, &tmapPfBoth, kind, pf_base, d.KP, ws.Bpad - b0, pf_rows) == WHMR_OK;
+  }
+  p.merged = merged ? 1 : 0;
+  const CUtensorMap& mapP = merged ? h->tc.tmapA_both[kind] : (kind ? h->tc.tmapA_tf32 : h->tc.tmapA_bf16);
+  const CUtensorMap& mapPf = merged ? tmapPfBoth : tmapPf;
   static const bool dbg_on = getenv("WHMR_FUSED_DEBUG") != nullptr;
   static const int dbg_mode = getenv("WHMR_FUSED_DBGMODE") ? atoi(getenv("WHMR_FUSED_DBGMODE")) : 0;
   p.dbg_mode = dbg_mode;
@@ -618,8 +632,8 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   if (dbg_on) { cudaMalloc(&p.dbg, sizeof(long long) * 32 * grid); cudaMemsetAsync(p.dbg, 0, sizeof(long long) * 32 * grid, st); }
   const bool instrumented = dbg_on || dbg_mode != 0;
 #define WHMR_FUSED_LAUNCH(M, D, T)                                                                                         \
-  launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, D, T>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st, h->tc.tmapA_bf16, \
-             tmapPf, h->tc.tmapW16, tmapAt, p)
+  launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, D, T>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st, mapP, \
+             mapPf, h->tc.tmapW16, tmapAt, p)
   // two pose-blend issuing threads (smpl_fused_tc.cuh, kTwo): the 48- and 64-body plans only
   static const int issuers_env = getenv("WHMR_FUSED_ISSUERS") ? atoi(getenv("WHMR_FUSED_ISSUERS")) : 1;
   const bool two = issuers_env == 2 && (maxm == 3 || maxm == 4);
@@ -629,7 +643,7 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   do {                                                                                                                     \
     ensure_dyn_smem(smpl_fused_tc_kernel<M, false, T, 1>, FuTmem<M>::kSmem);                                              \
     launch_pdl(kPdlFused, smpl_fused_tc_kernel<M, false, T, 1>, dim3(grid), dim3(kFuThreads), FuTmem<M>::kSmem, st,       \
-               h->tc.tmapA_tf32, tmapPf, h->tc.tmapW16, tmapAt, p);                                                       \
+               mapP, mapPf, h->tc.tmapW16, tmapAt, p);                                                                   \
   } while (0)
     static const int issuers_tf32 = getenv("WHMR_FUSED_ISSUERS_TF32") ? atoi(getenv("WHMR_FUSED_ISSUERS_TF32")) : issuers_env;
     if (issuers_tf32 == 2) { if (m == 3) WHMR_FUSED_LAUNCH_TF32(3, true); else WHMR_FUSED_LAUNCH_TF32(4, true); }
