@@ -52,13 +52,22 @@ constexpr bool kFuWTmem = false;
 constexpr bool kFuWTmem = true;
 #endif
 constexpr int kFuWCol = 480;                  // TMEM column of the weight operand (all plans end at 480)
-constexpr int kFuGB = 8;                      // bodies per blended-transform tile
-constexpr int kFuTN = kFuGB * 12;             // 96 accumulator columns
+// Bodies per blended-transform tile.  8 (default): one 96-column accumulator in the 64-body plan, all sixteen epilogue warps
+// on every group.  4 (-DWHMR_FUSED_GB4): two 48-column accumulators in every plan and two TEAMS of eight epilogue warps, team t
+// on the groups that land in accumulator t -- the transform round trip of one group overlaps the arithmetic and stores of the
+// other (profiles/r02_notes.md section 4.9).
+#ifdef WHMR_FUSED_GB4
+constexpr int kFuGB = 4;
+#else
+constexpr int kFuGB = 8;
+#endif
+constexpr bool kFuTeams = kFuGB == 4;
+constexpr int kFuTN = kFuGB * 12;             // 96 (48) accumulator columns
 constexpr int kFuMaxAStages = 4;
 constexpr int kFuABytes = 2 * kTcM * 128;     // 32 KB: posedirs {hi,lo} of one (K chunk, plane)
 constexpr int kFuMaxPfStages = 3;
 constexpr int kFuWBytes = kTcM * 128;         // 16 KB: skinning weights, fp16 hi|lo along K (64 halfs per vertex)
-constexpr int kFuAtStages = 2;
+constexpr int kFuAtStages = kFuTeams ? 4 : 2;
 constexpr int kFuAtBytes = kFuTN * 128;       // 12 KB: A^T of 8 bodies, fp16 hi|lo along K
 constexpr int kFuEpiWarps = 16;
 constexpr int kFuThreads = (4 + kFuEpiWarps) * 32;
@@ -78,6 +87,7 @@ template <int MAXM> struct FuTmem {
   static constexpr int kT = kOffStages * kOffStage;  // first blended-transform column
   static constexpr int kTStages = (512 - kT) / kFuTN >= 2 ? 2 : 1;
   static_assert(kT + kTStages * kFuTN <= 512, "TMEM budget");
+  static_assert(!kFuTeams || kTStages == 2, "the two epilogue teams own one transform accumulator each");
   // shared memory
   static constexpr int kAStages = MAXM <= 4 ? 4 : 3;
   static constexpr int kPfPart = (kNB < 64 ? 64 : kNB) * 128;   // pose feature, one of {hi,lo}, one K chunk
@@ -283,7 +293,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       for (int s = 0; s < kFuPfStages; ++s) mbar_init(&pf_full2[s], 1);
       for (int s = 0; s < 2; ++s) mbar_init(&first_issued[s], 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kFuEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kFuTeams ? kFuEpiWarps / 2 : kFuEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -501,8 +511,8 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
           nm += nit.len;
           ng_left = nit.ng; nbody0 = nit.body0;
         }
-        const int st = n_load & 1;
-        if (n_load >= 2) mbar_wait_backoff(&at_empty[st], ((uint32_t)(n_load >> 1) - 1u) & 1u, p.backoff);
+        const int st = n_load % kFuAtStages;
+        if (n_load >= kFuAtStages) mbar_wait_backoff(&at_empty[st], ((uint32_t)(n_load / kFuAtStages) - 1u) & 1u, p.backoff);
         mbar_arrive_expect_tx(&at_full[st], kFuAtBytes);
         tma_load_2d(at_ring + st * kFuAtBytes, &tmapAt, &at_full[st], 0, nbody0 * 12);
         nbody0 += kFuGB; --ng_left; ++n_load;
@@ -548,7 +558,10 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
   } else {
     // ============================ epilogue =====================================================
     const int q = warp & 3;             // TMEM lane quarter
-    const int w4 = (warp - 4) >> 2;     // which 2 bodies of every 8-body group
+    const int w4 = (warp - 4) >> 2;     // which 2 bodies of every 8-body group (teams: team = w4 & 1, pair of the 4-body group = w4 >> 1)
+    const int team = kFuTeams ? (w4 & 1) : 0;
+    const int pair = kFuTeams ? (w4 >> 1) : w4;
+    int gcount = 0;                     // teams: groups of earlier items (the skinning issuer alternates the accumulators over ALL groups)
     float* stg = stage_out + (warp - 4) * 192;   // two 96-float transpose buffers, one per body of the group
     int cur_vt = -1;
     float tx = 0.f, ty = 0.f, tz = 0.f;
@@ -570,7 +583,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
     };
     const int V3 = p.V * 3;
     const bool has_transl = p.transl != nullptr;
-    int buf = 0, ts = 0; uint32_t bph = 0, t_ph = 0, w_par_e = 0;
+    int buf = 0, ts = kFuTeams ? team : 0; uint32_t bph = 0, t_ph = 0, w_par_e = 0;
     long long d_off = 0, d_t = 0, d_ld = 0, d_rel = 0;
 #ifdef WHMR_FUSED_FINE_PROBES   // per-section cycles of one epilogue warp (math+stage | vertex stores | read-out emits)
     long long d_math = 0, d_st = 0, d_emit = 0;
@@ -618,19 +631,28 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
       WHMR_FU_WAIT(&off_full[buf], bph, d_off);
       const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
       const uint32_t off_addr = tmem_base + lane_sel + (uint32_t)(buf * TM::kOffStage);
+      // teams: my groups of this item are those whose global number has my parity; the last of them releases the offsets
+      const int g_last = !kFuTeams ? ng - 1 : ((((gcount + ng - 1) & 1) == team) ? ng - 1 : ng - 2);
+      if (kFuTeams && g_last < 0) {        // a one-group item that belongs to the other team: nothing to read here
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&off_empty[buf]);
+      }
       for (int g = 0; g < ng; ++g) {
-        const int body_base = it.body0 + g * kFuGB + w4 * 2;       // first of this warp's two bodies
+        if (kFuTeams && (((gcount + g) & 1) != team)) continue;
+        const int body_base = it.body0 + g * kFuGB + pair * 2;     // first of this warp's two bodies
         const int n_valid = min(2, p.nb - body_base);              // may be <= 0
         WHMR_FU_WAIT(&t_full[ts], t_ph, d_t);
-        const uint32_t t_addr = tmem_base + lane_sel + (uint32_t)(TM::kT + ts * kFuTN + w4 * 24);
+        const uint32_t t_addr = tmem_base + lane_sel + (uint32_t)(TM::kT + ts * kFuTN + pair * 24);
         uint64_t* const t_rel = &t_empty[ts];
-        if (++ts == TM::kTStages) { ts = 0; t_ph ^= 1; }
+        if (kFuTeams) t_ph ^= 1;
+        else if (++ts == TM::kTStages) { ts = 0; t_ph ^= 1; }
         tcgen05_fence_after();
         const long long l0 = dbgp ? clock64() : 0;
         uint32_t T[24], O[6];
         tmem_ld_32x32b_x16(t_addr, T);
         tmem_ld_32x32b_x8(t_addr + 16, T + 16);
-        const uint32_t ocol = (uint32_t)(g * kFuGB + w4 * 2);
+        const uint32_t ocol = (uint32_t)(g * kFuGB + pair * 2);
         tmem_ld_32x32b_x2(off_addr + ocol, O);
         tmem_ld_32x32b_x2(off_addr + TM::kNB + ocol, O + 2);
         tmem_ld_32x32b_x2(off_addr + 2 * TM::kNB + ocol, O + 4);
@@ -641,7 +663,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(t_rel);
-          if (g == ng - 1) mbar_arrive(&off_empty[buf]);
+          if (g == g_last) mbar_arrive(&off_empty[buf]);
         }
         if (dbgp) { d_ld += l1 - l0; d_rel += clock64() - l1; }
         if (n_valid <= 0) continue;
@@ -736,6 +758,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
         };
         if (n_valid == 2 && !has_transl && full_tile) run(cuda::std::false_type{}); else run(cuda::std::true_type{});
       }
+      gcount += ng;
       if (++buf == TM::kOffStages) { buf = 0; bph ^= 1; }
     }
     if (dbgp && warp == 4 && lane == 0) { long long* d = dbgp + blockIdx.x * 16; d[10] = d_off; d[11] = d_t; d[12] = clock64() - k0; d[13] = d_ld; d[14] = d_rel;

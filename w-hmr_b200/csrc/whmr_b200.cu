@@ -593,7 +593,6 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   static const int split_env = getenv("WHMR_FUSED_SPLIT") ? atoi(getenv("WHMR_FUSED_SPLIT")) : -1;
   int maxm = p.n_micro <= 8 * h->tc.num_sms ? 3 : 4;
   if (maxm_env == 3 || maxm_env == 4 || maxm_env == 6 || maxm_env == 8) maxm = maxm_env;
-  if (kind == 1 && maxm > 4) maxm = 4;   // the tf32 instantiations exist for the 48- and 64-body plans
   p.split = 0;
   p.pieces = 0;
   // Small batches, optional (WHMR_FUSED_PIECES=-1 automatic, k > 0 forced): at most two items per CTA (see the kernel).
@@ -637,8 +636,8 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
   // two pose-blend issuing threads (smpl_fused_tc.cuh, kTwo): the 48- and 64-body plans only
   static const int issuers_env = getenv("WHMR_FUSED_ISSUERS") ? atoi(getenv("WHMR_FUSED_ISSUERS")) : 1;
   const bool two = issuers_env == 2 && (maxm == 3 || maxm == 4);
-  if (kind == 1) {   // 3xTF32 pose blend: the 48- and 64-body plans, one issuer, no instrumented build
-    const int m = (maxm == 3) ? 3 : 4;
+  if (kind == 1) {   // 3xTF32 pose blend: no instrumented build; two issuers for the 48- and 64-body plans only
+    const int m = maxm;
 #define WHMR_FUSED_LAUNCH_TF32(M, T)                                                                                       \
   do {                                                                                                                     \
     ensure_dyn_smem(smpl_fused_tc_kernel<M, false, T, 1>, FuTmem<M>::kSmem);                                              \
@@ -646,8 +645,9 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
                mapP, mapPf, h->tc.tmapW16, tmapAt, p);                                                                   \
   } while (0)
     static const int issuers_tf32 = getenv("WHMR_FUSED_ISSUERS_TF32") ? atoi(getenv("WHMR_FUSED_ISSUERS_TF32")) : issuers_env;
-    if (issuers_tf32 == 2) { if (m == 3) WHMR_FUSED_LAUNCH_TF32(3, true); else WHMR_FUSED_LAUNCH_TF32(4, true); }
-    else { if (m == 3) WHMR_FUSED_LAUNCH_TF32(3, false); else WHMR_FUSED_LAUNCH_TF32(4, false); }
+    if (issuers_tf32 == 2 && m <= 4) { if (m == 3) WHMR_FUSED_LAUNCH_TF32(3, true); else WHMR_FUSED_LAUNCH_TF32(4, true); }
+    else if (m == 3) WHMR_FUSED_LAUNCH_TF32(3, false); else if (m == 4) WHMR_FUSED_LAUNCH_TF32(4, false);
+    else if (m == 6) WHMR_FUSED_LAUNCH_TF32(6, false); else WHMR_FUSED_LAUNCH_TF32(8, false);
 #undef WHMR_FUSED_LAUNCH_TF32
   } else if (instrumented) {
     // the instrumented instantiations are only ever launched from here (per device)
