@@ -41,3 +41,19 @@ def test_committed_gpu_bench_line_has_the_contract_keys():
     assert max(line["train_step"]["grad_rel_diff_vs_eager"].values()) <= 1e-4
     assert set(("smpl_sweep_65536", "eval_pass_35515")) <= set(line["other_configs"])
     assert line["parity"]["verts_m"] <= 1e-5 and line["parity"]["kp2d_px"] <= 1e-3 and line["parity"]["sampled_rel"] <= 1e-4
+    # last session's legs: end to end with host-resident feature levels gathered in place (headline) beside the all-copies
+    # pass, both tensor-core arithmetics of the fused SMPL kernel, the share of the whole loop, every BASELINE config
+    e2e, copy_all = line["e2e"], line["e2e_copy_all"]
+    assert e2e["results_identical_to_device_resident_step"] is True and e2e["host_resident_levels"]
+    assert e2e["value"] > copy_all["value"] and e2e["h2d_bytes_per_step"] < copy_all["h2d_bytes_per_step"]
+    assert e2e["host_input_bytes_per_step"] == copy_all["h2d_bytes_per_step"]
+    assert line["e2e_host_gather_channels_last"]["sampled_rel_vs_nchw_step"] <= 1e-4
+    modes = line["pose_blend_modes"]
+    for name in ("bf16x3", "3xtf32"):
+        assert modes[name]["fused_kernel"] is True and modes[name]["verts_max_err_vs_fp64_m"] <= 1e-5
+        assert 0.0 < modes[name]["tensor_frac"] < 1.0
+    assert modes["3xtf32"]["verts_max_err_vs_fp64_m"] < modes["bf16x3"]["verts_max_err_vs_fp64_m"]
+    wl = line["whole_loop"]
+    assert wl["ms_whole_loop_new"] < wl["ms_whole_loop_old"] and wl["hot_path_share_new"] < wl["hot_path_share_old"]
+    assert wl["verts_new_vs_old_m"] <= 1e-5
+    assert set(("smpl_b64", "maf_sampling_1024x431")) <= set(line["other_configs"])
