@@ -51,3 +51,18 @@ for B in (1, 13):
     (o.vertices.sum() + o.joints.pow(2).sum()).backward()
     torch.cuda.synchronize()
     print("smpl backward B=%d" % B, float(rm.grad.abs().max()), float(be.grad.abs().max()))
+# last session: the kind::tf32 instantiation of the fused SMPL kernel (3xTF32) and sampling from pinned host maps
+smpl3 = SMPL(model=model, gemm_mode="3xtf32").to(dev)
+assert smpl3._state(dev)[0].is_fused()
+for B in (1, 37, 130):
+    b = syn.make_bodies(B, seed=7)
+    o = smpl3(betas=torch.from_numpy(b['betas']).to(dev), body_pose=torch.from_numpy(b['rotmat'][:, 1:]).to(dev),
+              global_orient=torch.from_numpy(b['rotmat'][:, :1]).to(dev), pose2rot=False)
+    torch.cuda.synchronize()
+    print("smpl 3xtf32 fused B=%d" % B, float(o.vertices.abs().max()))
+hf = torch.randn(3, 64, 128, 96).pin_memory()
+pts3 = torch.from_numpy(syn.make_sample_points(3, 67, seed=4)).to(dev)
+oh = ops.sample_bilinear(hf, pts3)
+od = ops.sample_bilinear(hf.to(dev), pts3)
+torch.cuda.synchronize()
+print("host-map sampling identical", bool(torch.equal(oh, od)))
