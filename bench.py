@@ -995,9 +995,11 @@ def other_configs(loop, model, dev, rank, world, peaks):
         ms_n = timed(lambda: _ops.sample_bilinear(feat, pts, _ops.LAYOUT_NCHW), 20)
         fl = feat.contiguous(memory_format=torch.channels_last)
         ms_c = timed(lambda: _ops.sample_bilinear(fl, pts, _ops.LAYOUT_NCHW), 20)
+        # what a caller pays who holds NCHW maps and converts them for the NHWC kernel ("conversion cost stated")
+        ms_conv = timed(lambda: feat.contiguous(memory_format=torch.channels_last), 10)
         rows["%dx%d" % (H, Wd)] = {"nchw_ms": ms_n, "nchw_frac": alg / ms_n / 1e6 / peaks["hbm_gbs"],
                                    "channels_last_ms": ms_c, "channels_last_frac": alg / ms_c / 1e6 / peaks["hbm_gbs"],
-                                   "algorithmic_bytes": alg}
+                                   "nchw_to_channels_last_conversion_ms": ms_conv, "algorithmic_bytes": alg}
         del feat, fl
     torch.cuda.empty_cache()
     res["maf_sampling_1024x431"] = {"workload": "configs[3]: bilinear sampling of 431 points, 256 channels, %d bodies per GPU" % Bm,
