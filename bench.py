@@ -1015,6 +1015,17 @@ def other_configs(loop, model, dev, rank, world, peaks):
                                "hbm_frac_algorithmic_per_gpu": bps / world * 84172 / 1e9 / peaks["hbm_gbs"],
                                "tensor_frac_bf16x3_per_gpu": bps / world * 2.0 * KPOSE * 3 * V / 1e12 / (peaks["bf16_tflops_sustained"] / 3)}
     del betas, rot
+    # the smaller points of the configs[2] sweep (1k .. 16k bodies in total, same sharding)
+    sweep = {}
+    for tot in (1024, 4096, 16384):
+        lo_s, hi_s = shard_bounds(tot, rank, world)
+        bs = syn.make_bodies(max(hi_s - lo_s, 1), seed=5, rank=rank)
+        be_s, ro_s = torch.from_numpy(bs["betas"]).to(dev), torch.from_numpy(bs["rotmat"]).to(dev)
+        ms_s = timed(lambda: ev.joints(be_s, ro_s, True), 10)
+        sweep[str(tot)] = {"ms": ms_s, "bodies_per_s": tot / (ms_s * 1e-3), "per_gpu_bodies": hi_s - lo_s}
+        del be_s, ro_s
+    sweep["65536"] = {"ms": ms, "bodies_per_s": bps, "per_gpu_bodies": hi - lo}
+    res["smpl_sweep"] = {"workload": "configs[2]: SMPL + H36M joint regression, total bodies sharded over the ranks", "points": sweep}
     torch.cuda.empty_cache()
     Nf = 35515
     lo, hi = shard_bounds(Nf, rank, world)
