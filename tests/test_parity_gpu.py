@@ -631,6 +631,8 @@ def test_sampling_from_pinned_host_maps_in_place(dev, smpl_model):
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and a[0].device == p3.device
         with pytest.raises(_lib.WhmrError):
             ops.sample_bilinear(feat, pts)
+        with pytest.raises(NotImplementedError):     # no silent loss of a gradient: a host map is inference-only
+            ops.sample_bilinear(feat.pin_memory().requires_grad_(True), pts)
     # drop-in extractor (sampling op + the module's PyTorch MLP) on a host-resident map
     ext = MAF_Extractor(mesh_downsampling=None).to(dev).eval()
     feat = torch.randn(2, 256, 32, 24, generator=g)

@@ -481,6 +481,9 @@ def _feat_layout(feat, layout):
     A pinned host tensor (is_host_map) is passed through as it is: it must already be fp32 and contiguous in the layout
     named (nothing is copied or converted on the host: there is no CPU path)."""
     if is_host_map(feat):
+        if feat.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("a host-resident (pinned) feature map is read in place and receives no gradient: "
+                                      "inference only -- move the map to the device to train through the sampling")
         if feat.dtype != torch.float32 or feat.dim() != 4:
             raise _lib.WhmrError("a host-resident feature map must be a pinned fp32 [B,C,H,W] / [B,H,W,C] tensor")
         if layout == LAYOUT_NCHW and not feat.is_contiguous() and feat.is_contiguous(memory_format=torch.channels_last):
