@@ -70,6 +70,11 @@ constexpr int kFuWBytes = kTcM * 128;         // 16 KB: skinning weights, fp16 h
 constexpr int kFuAtStages = kFuTeams ? 4 : 2;
 constexpr int kFuAtBytes = kFuTN * 128;       // 12 KB: A^T of 8 bodies, fp16 hi|lo along K
 constexpr int kFuEpiWarps = 16;
+#ifdef WHMR_FUSED_STORE32
+constexpr bool kFuStore64 = false;            // vertex stores of the epilogue as 4-byte (three per body and lane) ...
+#else
+constexpr bool kFuStore64 = true;             // ... or 8-byte accesses (one and a half): fewer LSU instructions in the busiest role
+#endif
 constexpr int kFuThreads = (4 + kFuEpiWarps) * 32;
 // TMEM / shared-memory plan, by the template parameter MAXM = micro-items (16 bodies) per item.
 // Measured (tools/microbench/umma_rate_bench.cu): a tcgen05.mma with M=128, K=16 costs max(~70, N/2) cycles -- the
@@ -714,6 +719,26 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
 #ifdef WHMR_FUSED_FINE_PROBES
           const long long e1c = dbgp ? clock64() : 0;
 #endif
+          if (!G && kFuStore64) {
+            // full tile, both bodies: the 96 floats of a (warp, body) leave as 48 aligned float2 -- one 8-byte load + store per
+            // lane and a second one on lanes 0..15 -- instead of three 4-byte pairs (a body row starts on an 8-byte boundary:
+            // 82,680 bytes per body; 16-byte stores would be misaligned on odd bodies)
+            float2 w0[2], w1[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float2* s2 = reinterpret_cast<const float2*>(stg + i * 96);
+              w0[i] = (dbg_mode & 4) ? make_float2(0.f, 0.f) : s2[lane];
+              w1[i] = (lane < 16 && !(dbg_mode & 4)) ? s2[32 + lane] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              float2* o2 = reinterpret_cast<float2*>(outp - lane + (size_t)i * V3);
+              if (!(dbg_mode & 1)) {
+                o2[lane] = w0[i];
+                if (lane < 16) o2[32 + lane] = w1[i];
+              }
+            }
+          } else {
           float v[6];
 #pragma unroll
           for (int i = 0; i < 2; ++i)
@@ -726,6 +751,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
 #pragma unroll
             for (int r = 0; r < 3; ++r)
               if ((!G || out_col + r * 32 < V3) && !(dbg_mode & 1)) ob[r * 32] = v[i * 3 + r];
+          }
           }
 #ifdef WHMR_FUSED_FINE_PROBES
           const long long e2c = dbgp ? clock64() : 0;
