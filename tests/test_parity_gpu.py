@@ -240,6 +240,31 @@ def test_smpl_host_buffer_entry(dev, smpl_model):
     assert _maxabs(joints, ref['joints24']) <= VERT_TOL
 
 
+def test_smpl_forward_into_4_byte_aligned_output(dev, smpl_model):
+    """The C ABI takes ANY float-aligned output pointer: a `verts` buffer that starts 4 bytes off an 8-byte boundary must not go
+    through the epilogue's float2 stores (smpl_fused_tc.cuh, store64)."""
+    from whmr_b200 import _lib
+    from whmr_b200._lib import check
+    smpl = _smpl(smpl_model, dev, "bf16x3")
+    h, _ = smpl._state(dev)
+    B = 37
+    b = _bodies(B, seed=19)
+    betas, rot = torch.from_numpy(b['betas']).to(dev), torch.from_numpy(b['rotmat']).to(dev).contiguous()
+    buf = torch.zeros(B * 6890 * 3 + 1, device=dev)
+    verts = buf[1:]
+    assert verts.data_ptr() % 8 == 4
+    joints = torch.empty(B, 24, 3, device=dev)
+    ws, n = h.workspace(B)
+    with torch.cuda.device(dev):
+        check(_lib.lib().whmr_smpl_forward(h._h, betas.data_ptr(), rot.data_ptr(), 1, None, B, verts.data_ptr(),
+                                           joints.data_ptr(), None, ws.data_ptr(), n,
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = _oracle(smpl_model)(b['betas'], b['rotmat'][:, 1:], b['rotmat'][:, :1], pose2rot=False)
+    assert _maxabs(verts.view(B, 6890, 3), ref['vertices']) <= VERT_TOL
+    assert float(buf[0]) == 0.0
+
+
 def test_batch_rodrigues(dev):
     from oracle.smpl_oracle import batch_rodrigues
     from whmr_b200.geometry import batch_rodrigues_smplx as gpu_rod

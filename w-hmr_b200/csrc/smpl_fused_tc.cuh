@@ -124,6 +124,7 @@ struct FusedParams {
   int n_micro;                // (VP/128) * npv: the unit of work distribution
   int kch, ksteps;            // pose blend: 128-byte K chunks, 32-byte K steps (bf16: 16 elements)
   int jsteps;                 // skinning: ceil(J/16) fp16 K steps
+  int store64;                // 1: `verts` is 8-byte aligned and 3 * V is even, so every body row is: the epilogue may store float2
   int merged;                 // 1: tmapP / tmapPf are the {K chunk, rows, 2 parts} maps: ONE copy brings hi AND lo (and all 64 pose-feature rows)
   unsigned backoff;           // WHMR_FUSED_BACKOFF: ns between mbarrier polls of the single-thread roles
   int dbg_mode;               // WHMR_FUSED_DBGMODE bits (timing experiments only): 1 skip vertex stores, 2 skip read-out emits, 4 skip the transposes
@@ -719,7 +720,7 @@ smpl_fused_tc_kernel(const __grid_constant__ CUtensorMap tmapP,    // posedirs+s
 #ifdef WHMR_FUSED_FINE_PROBES
           const long long e1c = dbgp ? clock64() : 0;
 #endif
-          if (!G && kFuStore64) {
+          if (!G && kFuStore64 && p.store64) {
             // full tile, both bodies: the 96 floats of a (warp, body) leave as 48 aligned float2 -- one 8-byte load + store per
             // lane and a second one on lanes 0..15 -- instead of three 4-byte pairs (a body row starts on an 8-byte boundary:
             // 82,680 bytes per body; 16-byte stores would be misaligned on odd bodies)

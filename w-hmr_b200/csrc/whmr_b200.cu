@@ -558,6 +558,7 @@ static int launch_fused(whmr_smpl_t h, const SmplWorkspace& ws, const float* tra
     p.ro_out = ro_out; p.ro_B = B; p.ro_b0 = b0;
   }
   p.nb = nb; p.V = d.V; p.VP = d.VP;
+  p.store64 = ((reinterpret_cast<size_t>(p.verts) & 7) == 0 && (3 * d.V) % 2 == 0) ? 1 : 0;   // any 4-byte aligned output is legal
   p.W16 = static_cast<const uint4*>(h->tc.W_f16);
   const int n_vtiles = d.VP / kTcM;
   p.npv = ceil_div(nb, 16);
